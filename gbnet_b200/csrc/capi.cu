@@ -1,0 +1,840 @@
+// C ABI of the B200-native OR-NOR sampler (include/gbnet_b200.h): the model layer.
+//
+// Replaces gbn::ModelBase / gbn::ModelORNOR (reference libgbnet/src/ModelBase.cpp:37-215,
+// ModelORNOR.cpp:13-29): owns the compiled topology, every chain's state and counters in HBM,
+// the sample / stop loop, Gelman-Rubin and the posterior summaries.  There is no CPU path: every
+// compute entry point launches kernels or fails with GBN_ERR_CUDA.
+#include "../../include/gbnet_b200.h"
+
+#include <atomic>
+#include <cmath>
+#include <csignal>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "topology.hpp"
+#include "kernels.cuh"
+#include "device_math.cuh"
+
+using namespace gbn;
+
+// ------------------------------------------------------------------------------ errors, signal
+static thread_local std::string g_error;
+
+static int fail(gbn_status s, const std::string &msg)
+{
+    g_error = msg;
+    return (int) s;
+}
+
+extern "C" const char *gbn_last_error(void) { return g_error.c_str(); }
+extern "C" int gbn_abi_version(void) { return GBN_ABI_VERSION; }
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(GBN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+// ModelBase.cpp:3-33: a process-global flag polled between batches of sweeps
+static volatile std::sig_atomic_t g_signal = 0;
+static void sigint_handler(int signum) { g_signal = signum; }
+extern "C" void gbn_set_signal(int signum) { g_signal = signum; }
+extern "C" void gbn_install_sigint_handler(void) { std::signal(SIGINT, sigint_handler); }
+
+extern "C" int gbn_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------ NCCL (dlopen)
+// Only the moment sums cross ranks; NCCL is resolved at run time so the library
+// loads on machines without it.
+namespace {
+struct NcclApi {
+    struct Uid { char b[128]; };         // ncclUniqueId (passed by value)
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, Uid, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool load(std::string &why)
+    {
+        if (lib) return true;
+        const char *names[] = { "libnccl.so.2", "libnccl.so" };
+        for (const char *n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { why = "cannot dlopen libnccl.so.2"; return false; }
+        GetUniqueId = (decltype(GetUniqueId)) dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank)) dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce)) dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy)) dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString)) dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { why = "NCCL symbols missing"; lib = nullptr; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+}  // namespace
+
+// ------------------------------------------------------------------------------ model
+struct gbn_model {
+    gbn_params p{};
+    Topology tp;
+    int device = 0;
+    int kernel = GBN_KERNEL_STRICT;
+    uint32_t n_datasets = 1, n_graphs = 0, n_graphs_local = 0, chain_offset = 0, n_chains = 0;
+    DevNet net{};
+    DevChains ch{};
+    std::vector<void *> owned;          // every cudaMalloc of this model
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t sweeps_total = 0;          // Philox counter word 1
+    uint32_t stat_n = 0;                // sweeps since burn_stats = RVNode::chain_length
+    uint64_t launches = 0;
+    double last_ms = 0.;
+    // device buffers
+    uint8_t *d_y = nullptr; double *d_yprob = nullptr;
+    double *d_inj_flat = nullptr, *d_inj_beta = nullptr, *d_inj_exp = nullptr;
+    double *d_sums = nullptr, *d_psums = nullptr, *d_dev = nullptr, *d_pdev = nullptr, *d_gr = nullptr, *d_max = nullptr;
+    double *d_scratch = nullptr; size_t scratch_bytes = 0;
+    bool moments_valid = false;
+    // comm
+    void *comm = nullptr; int rank = 0, world = 1;
+    // evidence kept for re-initialisation
+    std::vector<uint8_t> h_y; std::vector<double> h_yprob;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(gbn_model *m, T **out, size_t n)
+{
+    void *p = nullptr;
+    size_t bytes = sizeof(T) * (n ? n : 1);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(GBN_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
+    m->owned.push_back(p);
+    *out = (T *) p;
+    return 0;
+}
+
+template <class T>
+int dev_upload(gbn_model *m, T **out, const std::vector<T> &v)
+{
+    if (int rc = dev_alloc(m, out, v.size())) return rc;
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(*out, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+double host_keyed_u(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t node, uint32_t kind)
+{
+    u32x4 r = philox4x32_10(node >> 2, sweep, chain, kind, (uint32_t) seed, (uint32_t) (seed >> 32));
+    uint32_t w = (node & 3) == 0 ? r.x : ((node & 3) == 1 ? r.y : ((node & 3) == 2 ? r.z : r.w));
+    return (double) w * (1.0 / 4294967296.0);
+}
+
+// initial chain state (GraphORNOR.cpp:57-73, 223-224, 246): X drawn from its prior by the
+// Multinomial ctor (Multinomial.cpp:42-49), T at the prior mean, S at mor + 1; statistics zeroed
+int init_chains(gbn_model *m)
+{
+    const Topology &tp = m->tp;
+    const uint32_t nX = tp.nX, E = tp.E, C = m->n_chains;
+    std::vector<uint8_t> X((size_t) C * nX), S((size_t) C * E);
+    std::vector<double> T((size_t) C * nX);
+    const double xprob[2][2] = { { 0.99, 0.01 }, { 0.10, 0.90 } };
+    for (uint32_t c = 0; c < C; c++) {
+        const uint32_t gchain = chain_global_id(m->net, c);
+        for (uint32_t k = 0; k < nX; k++) {
+            const double *prob = xprob[tp.x_prior_active[k]];
+            double c0 = std::exp(std::log(prob[0]));
+            double c1 = c0 + std::exp(std::log(prob[1]));
+            double u = host_keyed_u(m->p.seed, gchain, 0, k, KIND_INIT);
+            double dice = 0. * (1 - u) + c1 * u;
+            X[(size_t) c * nX + k] = dice < c0 ? 0 : 1;
+            T[(size_t) c * nX + k] = tp.t_mean[k];
+        }
+        std::memcpy(&S[(size_t) c * E], tp.mor_idx.data(), E);
+    }
+    CUDA_TRY(cudaMemcpyAsync(m->ch.X, X.data(), X.size(), cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(m->ch.T, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(m->ch.S, S.data(), S.size(), cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int zero_stats(gbn_model *m)
+{
+    const size_t C = m->n_chains, nX = m->tp.nX, E = m->tp.E;
+    CUDA_TRY(cudaMemsetAsync(m->ch.cX1, 0, sizeof(uint32_t) * C * nX, m->stream));
+    CUDA_TRY(cudaMemsetAsync(m->ch.tMean, 0, sizeof(double) * C * nX, m->stream));
+    CUDA_TRY(cudaMemsetAsync(m->ch.tM2, 0, sizeof(double) * C * nX, m->stream));
+    CUDA_TRY(cudaMemsetAsync(m->ch.cS0, 0, sizeof(uint32_t) * C * E, m->stream));
+    CUDA_TRY(cudaMemsetAsync(m->ch.cS2, 0, sizeof(uint32_t) * C * E, m->stream));
+    m->stat_n = 0;
+    m->moments_valid = false;
+    return 0;
+}
+
+int refresh_fast(gbn_model *m)
+{
+    if (m->kernel != GBN_KERNEL_FAST) return 0;
+    const char *err = nullptr;
+    int n = launch_fast_refresh(m->net, m->ch, m->stream, &err);
+    if (n < 0) return fail(GBN_ERR_CUDA, std::string("fast refresh: ") + err);
+    m->launches += (uint64_t) n;
+    return 0;
+}
+
+int upload_evidence(gbn_model *m, const gbn_evidence *ev)
+{
+    const Topology &tp = m->tp;
+    if (!ev || ev->n_evid == 0 || ev->n_datasets == 0)
+        return fail(GBN_ERR_UNSUPPORTED, "empty evidence selects the reference's simulation mode (GraphORNOR.cpp:28), which is outside the sampling path");
+    if (ev->n_datasets != m->n_datasets) return fail(GBN_ERR_INVALID, "n_datasets differs from the model's");
+    m->h_y.assign((size_t) m->n_datasets * tp.nH, 1);
+    m->h_yprob.assign((size_t) m->n_datasets * 3, 0.);
+    try {
+        for (uint32_t d = 0; d < m->n_datasets; d++)
+            compile_evidence(tp, ev->n_evid, ev->evid_trg, ev->evid_val + (size_t) d * ev->n_evid, m->p.comp_yprob != 0,
+                             &m->h_y[(size_t) d * tp.nH], &m->h_yprob[(size_t) d * 3]);
+    } catch (const std::exception &ex) {
+        return fail(GBN_ERR_INVALID, ex.what());
+    }
+    CUDA_TRY(cudaMemcpy(m->d_y, m->h_y.data(), m->h_y.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->d_yprob, m->h_yprob.data(), sizeof(double) * m->h_yprob.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int ensure_scratch(gbn_model *m, size_t bytes)
+{
+    if (m->scratch_bytes >= bytes) return 0;
+    if (m->d_scratch) {
+        cudaFree(m->d_scratch);
+        for (auto &p : m->owned) if (p == m->d_scratch) p = nullptr;
+    }
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    m->owned.push_back(p);
+    m->d_scratch = (double *) p;
+    m->scratch_bytes = bytes;
+    return 0;
+}
+
+int use_device(const gbn_model *m)
+{
+    CUDA_TRY(cudaSetDevice(m->device));
+    return 0;
+}
+
+int allreduce(gbn_model *m, double *buf, size_t n, int op)
+{
+    if (!m->comm || m->world <= 1) return 0;
+    int rc = g_nccl.AllReduce(buf, buf, n, NCCL_FLOAT64, op, m->comm, m->stream);
+    if (rc != 0) return fail(GBN_ERR_COMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return 0;
+}
+
+// passes 1 and 2 of moments.cu with the all-reduce between them; results stay on the device
+int compute_moments(gbn_model *m)
+{
+    if (m->moments_valid) return 0;
+    const size_t ns = (size_t) m->n_datasets * n_stats_of(m->net);
+    const double N = (double) m->stat_n;
+    launch_moment_sums(m->net, m->ch, N, m->d_sums, m->d_psums, m->stream);
+    if (int rc = allreduce(m, m->d_sums, 2 * ns, NCCL_SUM)) return rc;
+    if (int rc = allreduce(m, m->d_psums, ns, NCCL_SUM)) return rc;
+    launch_moment_devs(m->net, m->ch, N, m->d_sums, m->d_psums, m->d_dev, m->d_pdev, m->stream);
+    if (int rc = allreduce(m, m->d_dev, ns, NCCL_SUM)) return rc;
+    if (int rc = allreduce(m, m->d_pdev, ns, NCCL_SUM)) return rc;
+    m->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    m->moments_valid = true;
+    return 0;
+}
+
+int max_gelman_rubin(gbn_model *m, double *out)
+{
+    if (m->stat_n == 0) { *out = std::numeric_limits<double>::infinity(); return 0; }   // ModelBase.cpp:96-101
+    if (int rc = compute_moments(m)) return rc;
+    CUDA_TRY(cudaMemsetAsync(m->d_max, 0, sizeof(double) * m->n_datasets, m->stream));
+    launch_gelman_rubin(m->net, (double) m->stat_n, m->d_sums, m->d_dev, UINT32_MAX, nullptr, m->d_max, m->stream);
+    m->launches += 1;
+    std::vector<double> h(m->n_datasets);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), m->d_max, sizeof(double) * m->n_datasets, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    double mx = 0.;
+    for (double v : h) mx = std::fmax(mx, v);
+    *out = mx;
+    return 0;
+}
+
+int sample_n(gbn_model *m, uint32_t n)
+{
+    if (n == 0) return 0;
+    if ((uint64_t) m->stat_n + n > 0xffffffffull) return fail(GBN_ERR_INVALID, "statistics counters would overflow 32 bits");
+    const char *err = nullptr;
+    CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
+    int launched;
+    if (m->kernel == GBN_KERNEL_FAST)
+        launched = launch_sweep_fast(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err);
+    else
+        launched = launch_sweep_strict(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err);
+    if (launched < 0) return fail(GBN_ERR_CUDA, std::string("sweep launch: ") + err);
+    CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
+    m->launches += (uint64_t) launched;
+    m->sweeps_total += n;
+    m->stat_n += n;
+    m->moments_valid = false;
+    if (m->ch.inj_flat) {
+        m->ch.inj_pos += n;
+        if (m->ch.inj_pos >= m->ch.inj_sweeps) { m->ch.inj_flat = m->ch.inj_beta = m->ch.inj_exp = nullptr; m->ch.inj_sweeps = m->ch.inj_pos = 0; }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" void gbn_params_default(gbn_params *p)
+{
+    std::memset(p, 0, sizeof *p);
+    const double sp[9] = { 0.40, 0.40, 0.20, 0.30, 0.40, 0.30, 0.20, 0.40, 0.40 };   // GraphORNOR.h:31-33
+    std::memcpy(p->sprior, sp, sizeof sp);
+    p->z_alpha = 25.; p->z_beta = 25.; p->z0_alpha = 25.; p->z0_beta = 25.;          // pyx:13-16, 20-23
+    p->t_alpha = 2.; p->t_beta = 2.;
+    p->n_graphs = 3;
+    p->noise_listen_children = 1; p->comp_yprob = 0; p->const_params = 0;
+    p->t_focus = 2.; p->t_lmargin = 2.; p->t_hmargin = 2.;
+    p->zn_focus = 2.; p->zn_lmargin = 8.; p->zn_hmargin = 2.;
+    p->seed = 0; p->device = 0; p->kernel = GBN_KERNEL_AUTO;
+    p->chain_offset = 0; p->n_graphs_local = 0;
+}
+
+extern "C" void gbn_model_destroy(gbn_model *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+    for (void *p : m->owned) if (p) cudaFree(p);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev, const gbn_params *p, gbn_model **out)
+{
+    if (!netin || !p || !out) return fail(GBN_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (p->n_graphs == 0) return fail(GBN_ERR_INVALID, "n_graphs must be positive");
+    if (!ev || ev->n_evid == 0 || ev->n_datasets == 0)
+        return fail(GBN_ERR_UNSUPPORTED, "empty evidence selects the reference's simulation mode (GraphORNOR.cpp:28), which is outside the sampling path");
+    for (int r = 0; r < 3; r++)
+        for (int v = 0; v < 3; v++)
+            if (!(p->sprior[3 * r + v] >= 0.)) return fail(GBN_ERR_INVALID, "sprior entries must be non-negative");   // Multinomial.cpp:39
+    if (!(p->z_alpha > 0.) || !(p->z_beta > 0.) || !(p->z0_alpha > 0.) || !(p->z0_beta > 0.))
+        return fail(GBN_ERR_INVALID, "Beta parameters must be positive");                                            // Beta.cpp:34
+
+    int ndev = gbn_device_count();
+    if (ndev <= 0) return fail(GBN_ERR_CUDA, "no CUDA device: gbnet_b200 has no CPU path");
+    if (p->device < 0 || p->device >= ndev) return fail(GBN_ERR_INVALID, "device ordinal out of range");
+
+    gbn_model *m = new gbn_model();
+    m->p = *p;
+    m->device = p->device;
+    auto bail = [&](int rc) { std::string keep = g_error; gbn_model_destroy(m); g_error = keep; return rc; };
+    if (int rc = use_device(m)) return bail(rc);
+
+    try {
+        m->tp = compile_topology(netin->n_edge, netin->src, netin->trg, netin->mor, netin->n_active, netin->active_tf,
+                                 p->t_focus, p->t_lmargin, p->t_hmargin);
+    } catch (const std::exception &ex) {
+        return bail(fail(GBN_ERR_INVALID, ex.what()));
+    }
+    const Topology &tp = m->tp;
+    m->n_datasets = ev->n_datasets;
+    m->n_graphs = p->n_graphs;
+    m->n_graphs_local = p->n_graphs_local ? p->n_graphs_local : p->n_graphs;
+    m->chain_offset = p->chain_offset;
+    if (m->chain_offset + m->n_graphs_local > m->n_graphs) return bail(fail(GBN_ERR_INVALID, "chain shard exceeds n_graphs"));
+    m->n_chains = m->n_datasets * m->n_graphs_local;
+    if (m->n_chains > 65535) return bail(fail(GBN_ERR_INVALID, "more than 65535 chains on one device"));
+
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
+        return bail(fail(GBN_ERR_CUDA, "cannot create stream / events"));
+
+    // ---- network
+    DevNet &n = m->net;
+    n.nX = tp.nX; n.nH = tp.nH; n.E = tp.E; n.Eu = tp.Eu; n.max_indeg = tp.max_indeg; n.max_outdeg = tp.max_outdeg;
+    {
+        uint32_t *u32 = nullptr; uint8_t *u8 = nullptr; double *f64 = nullptr;
+#define UP(field, vec, tmp) { if (int rc = dev_upload(m, &tmp, vec)) return bail(rc); n.field = tmp; }
+        UP(trg_ptr, tp.trg_ptr, u32) UP(par_tf, tp.par_tf, u32) UP(par_edge, tp.par_edge, u32)
+        UP(slot_of_edge, tp.slot_of_edge, u32) UP(slot_trg, tp.slot_trg, u32) UP(mor_idx, tp.mor_idx, u8)
+        UP(tf_ptr, tp.tf_ptr, u32) UP(tf_child, tp.tf_child, u32) UP(tf_slot, tp.tf_slot, u32)
+        UP(tfpos_of_slot, tp.tfpos_of_slot, u32) UP(trg_order, tp.trg_order, u32)
+        UP(x_prior_active, tp.x_prior_active, u8)
+        UP(t_a, tp.t_a, f64) UP(t_b, tp.t_b, f64) UP(t_mean, tp.t_mean, f64) UP(t_lnB, tp.t_lnB, f64)
+#undef UP
+    }
+    const double xprob[2][2] = { { 0.99, 0.01 }, { 0.10, 0.90 } };                    // GraphORNOR.h:40-41
+    const double ynoise[3][3] = { { 0.945, 0.050, 0.005 }, { 0.050, 0.900, 0.050 }, { 0.005, 0.050, 0.945 } };   // GraphORNOR.h:46-48
+    std::memcpy(n.xprob, xprob, sizeof xprob);
+    std::memcpy(n.ynoise, ynoise, sizeof ynoise);
+    std::memcpy(n.sprob, p->sprior, sizeof(double) * 9);                              // GraphORNOR.cpp:25
+    n.z_y = p->z_alpha / (p->z_alpha + p->z_beta);                                    // GraphORNOR.cpp:155-164
+    n.z_n = p->z0_alpha / (p->z0_alpha + p->z0_beta);
+    n.n_datasets = m->n_datasets; n.n_graphs_local = m->n_graphs_local; n.chain_offset = m->chain_offset; n.n_graphs = m->n_graphs;
+    n.listen = p->noise_listen_children ? 1 : 0;
+    n.const_params = p->const_params ? 1 : 0;
+    n.seed = p->seed;
+    {
+        // (1-z)^n by repeated multiplication, the way zcompl_pn is built (HNodeORNOR.cpp:57,61)
+        std::vector<double> zct((size_t) 2 * (tp.max_indeg + 2));
+        for (int cls = 0; cls < 2; cls++) {
+            double z = cls ? n.z_n : n.z_y, v = 1.;
+            for (uint32_t j = 0; j < tp.max_indeg + 2; j++) { zct[(size_t) cls * (tp.max_indeg + 2) + j] = v; v *= (1. - z); }
+        }
+        double *d = nullptr;
+        if (int rc = dev_upload(m, &d, zct)) return bail(rc);
+        n.zctab = d;
+    }
+    if (int rc = dev_alloc(m, &m->d_y, (size_t) m->n_datasets * tp.nH)) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_yprob, (size_t) m->n_datasets * 3)) return bail(rc);
+    n.y = m->d_y; n.yprob = m->d_yprob;
+    if (int rc = upload_evidence(m, ev)) return bail(rc);
+
+    // ---- kernel choice
+    const char *why = nullptr;
+    bool fast_ok = fast_supported(n, &why);
+    if (p->kernel == GBN_KERNEL_FAST && !fast_ok)
+        return bail(fail(GBN_ERR_UNSUPPORTED, std::string("fast kernel unavailable: ") + why));
+    m->kernel = (p->kernel == GBN_KERNEL_STRICT) ? GBN_KERNEL_STRICT : (fast_ok ? GBN_KERNEL_FAST : GBN_KERNEL_STRICT);
+    if (m->kernel == GBN_KERNEL_STRICT && strict_smem_bytes(n) > 227 * 1024)
+        return bail(fail(GBN_ERR_UNSUPPORTED, "strict kernel: n_tf too large for shared memory"));
+
+    // ---- chains
+    DevChains &ch = m->ch;
+    const size_t C = m->n_chains, nX = tp.nX, E = tp.E, nH = tp.nH;
+    ch.n_chains = m->n_chains;
+    if (int rc = dev_alloc(m, &ch.X, C * nX)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.T, C * nX)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.S, C * E)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.cX1, C * nX)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.tMean, C * nX)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.tM2, C * nX)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.cS0, C * E)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.cS2, C * E)) return bail(rc);
+    if (m->kernel == GBN_KERNEL_FAST) {
+        if (int rc = dev_alloc(m, &ch.tcache, C * nH)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.Stf, C * E)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.FX, C * nX)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.FXinv, C * nX)) return bail(rc);
+    }
+    const size_t ns = (size_t) m->n_datasets * n_stats_of(n);
+    if (int rc = dev_alloc(m, &m->d_sums, 2 * ns)) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_psums, ns)) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_dev, ns)) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_pdev, ns)) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_gr, (size_t) n_nodes_of(n))) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_max, (size_t) m->n_datasets)) return bail(rc);
+
+    if (int rc = init_chains(m)) return bail(rc);
+    if (int rc = zero_stats(m)) return bail(rc);
+    if (int rc = refresh_fast(m)) return bail(rc);
+    if (cudaStreamSynchronize(m->stream) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "initialisation failed on the device"));
+    *out = m;
+    return 0;
+}
+
+extern "C" int gbn_model_dims(const gbn_model *m, gbn_dims *out)
+{
+    if (!m || !out) return fail(GBN_ERR_INVALID, "null argument");
+    out->n_tf = m->tp.nX; out->n_trg = m->tp.nH; out->n_edge = m->tp.E;
+    out->n_nodes = n_nodes_of(m->net);
+    out->n_datasets = m->n_datasets; out->n_graphs = m->n_graphs;
+    out->n_graphs_local = m->n_graphs_local; out->chain_offset = m->chain_offset;
+    out->n_stats = n_stats_of(m->net);
+    return 0;
+}
+
+extern "C" int gbn_model_kernel(const gbn_model *m) { return m ? m->kernel : (int) GBN_ERR_INVALID; }
+
+extern "C" int gbn_model_tf_ids(const gbn_model *m, uint32_t *out)
+{
+    if (!m || !out) return fail(GBN_ERR_INVALID, "null argument");
+    std::memcpy(out, m->tp.tf_uid.data(), sizeof(uint32_t) * m->tp.nX);
+    return 0;
+}
+
+extern "C" int gbn_model_trg_ids(const gbn_model *m, uint32_t *out)
+{
+    if (!m || !out) return fail(GBN_ERR_INVALID, "null argument");
+    std::memcpy(out, m->tp.trg_uid.data(), sizeof(uint32_t) * m->tp.nH);
+    return 0;
+}
+
+extern "C" int gbn_model_sample_n(gbn_model *m, uint32_t n)
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (int rc = use_device(m)) return rc;
+    if (int rc = sample_n(m, n)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+    m->last_ms = ms;
+    return 0;
+}
+
+// ModelBase::sample (ModelBase.cpp:114-129).  The for-loop's increment expression clips dN
+// BEFORE adding it to n, so the batch that just ran is never clipped: sample(20, 30) draws 30.
+extern "C" int gbn_model_sample(gbn_model *m, uint32_t N, uint32_t dN)
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (int rc = use_device(m)) return rc;
+    double total_ms = 0.;
+    uint32_t n;
+    double gr = std::numeric_limits<double>::infinity();
+    for (n = 0; n < N && gr > 1.10 && g_signal == 0; ) {
+        if (int rc = sample_n(m, dN)) return rc;
+        CUDA_TRY(cudaStreamSynchronize(m->stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        total_ms += ms;
+        dN = std::min(dN, N - n);
+        n += dN;
+        if (int rc = max_gelman_rubin(m, &gr)) return rc;
+        if (dN == 0) break;        // the reference would spin forever on dN = 0; stop instead
+    }
+    g_signal = 0;                  // clearSignal(), ModelBase.cpp:126
+    m->last_ms = total_ms;
+    return 0;
+}
+
+extern "C" int gbn_model_burn_stats(gbn_model *m)
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (int rc = use_device(m)) return rc;
+    if (int rc = zero_stats(m)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+extern "C" int gbn_model_chain_length(const gbn_model *m, double *out)
+{
+    if (!m || !out) return fail(GBN_ERR_INVALID, "null argument");
+    *out = (double) m->stat_n;
+    return 0;
+}
+
+extern "C" int gbn_model_max_gelman_rubin(gbn_model *m, double *out)
+{
+    if (!m || !out) return fail(GBN_ERR_INVALID, "null argument");
+    if (int rc = use_device(m)) return rc;
+    return max_gelman_rubin(m, out);
+}
+
+extern "C" int gbn_model_gelman_rubin(gbn_model *m, uint32_t dataset, double *out)
+{
+    if (!m || !out) return fail(GBN_ERR_INVALID, "null argument");
+    if (dataset >= m->n_datasets) return fail(GBN_ERR_INVALID, "dataset out of range");
+    if (int rc = use_device(m)) return rc;
+    const uint32_t nn = n_nodes_of(m->net);
+    if (m->stat_n == 0) { for (uint32_t i = 0; i < nn; i++) out[i] = std::numeric_limits<double>::infinity(); return 0; }
+    if (int rc = compute_moments(m)) return rc;
+    CUDA_TRY(cudaMemsetAsync(m->d_max, 0, sizeof(double) * m->n_datasets, m->stream));
+    launch_gelman_rubin(m->net, (double) m->stat_n, m->d_sums, m->d_dev, dataset, m->d_gr, m->d_max, m->stream);
+    m->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(out, m->d_gr, sizeof(double) * nn, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+// ModelBase::get_posterior_means / sdevs (ModelBase.cpp:160-209): gsl_rstat over the per-chain
+// means of chains 1..M-1
+static int posterior(gbn_model *m, uint32_t dataset, char kind, double *out, uint32_t *n_out, bool want_sd)
+{
+    if (!m || !n_out) return fail(GBN_ERR_INVALID, "null argument");
+    if (dataset >= m->n_datasets) return fail(GBN_ERR_INVALID, "dataset out of range");
+    const uint32_t nX = m->tp.nX, E = m->tp.E, nT = m->net.const_params ? 0 : nX;
+    uint32_t off, cnt;
+    switch (kind) {
+    case 'X': off = 0; cnt = 2 * nX; break;
+    case 'T': off = 2 * nX; cnt = nT; break;
+    case 'S': off = 2 * nX + nT; cnt = 3 * E; break;
+    default: *n_out = 0; return 0;            // no node carries that name: empty result, as in the reference
+    }
+    *n_out = cnt;
+    if (!out || cnt == 0) return 0;
+    if (int rc = use_device(m)) return rc;
+    const double M = (double) m->n_graphs;
+    if (m->stat_n == 0) {
+        // every per-chain mean is gsl_rstat_mean of an empty accumulator = 0
+        for (uint32_t i = 0; i < cnt; i++) out[i] = 0.;
+        return 0;
+    }
+    if (int rc = compute_moments(m)) return rc;
+    const size_t base = (size_t) dataset * n_stats_of(m->net) + off;
+    std::vector<double> h(cnt);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), (want_sd ? m->d_pdev : m->d_psums) + base, sizeof(double) * cnt, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    const double n = M - 1.;
+    for (uint32_t i = 0; i < cnt; i++) {
+        if (want_sd) out[i] = n > 1. ? std::sqrt(h[i] / (n - 1.)) : 0.;
+        else out[i] = n > 0. ? h[i] / n : 0.;
+    }
+    return 0;
+}
+
+extern "C" int gbn_model_posterior_means(gbn_model *m, uint32_t dataset, char kind, double *out, uint32_t *n)
+{ return posterior(m, dataset, kind, out, n, false); }
+extern "C" int gbn_model_posterior_sdevs(gbn_model *m, uint32_t dataset, char kind, double *out, uint32_t *n)
+{ return posterior(m, dataset, kind, out, n, true); }
+
+// ModelBase::print_stats (ModelBase.cpp:144-158): "<id>_<stat>  mean(sd)" over chains 1..M-1
+extern "C" int gbn_model_print_stats(gbn_model *m)
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    const char kinds[3] = { 'X', 'T', 'S' };
+    const uint32_t per[3] = { 2, 1, 3 };
+    for (int t = 0; t < 3; t++) {
+        uint32_t cnt = 0;
+        if (int rc = posterior(m, 0, kinds[t], nullptr, &cnt, false)) return rc;
+        if (cnt == 0) continue;
+        std::vector<double> mu(cnt), sd(cnt);
+        if (int rc = posterior(m, 0, kinds[t], mu.data(), &cnt, false)) return rc;
+        if (int rc = posterior(m, 0, kinds[t], sd.data(), &cnt, true)) return rc;
+        for (uint32_t i = 0; i < cnt; i++) {
+            uint32_t node = i / per[t], j = i % per[t];
+            if (kinds[t] == 'S') {
+                uint32_t q = m->tp.slot_of_edge[node];
+                std::printf("S_%u-->%u_%u\t%.4f(%.4f)\n", m->tp.tf_uid[m->tp.par_tf[q]], m->tp.trg_uid[m->tp.slot_trg[q]], j, mu[i], sd[i]);
+            } else {
+                std::printf("%c_%u_%u\t%.4f(%.4f)\n", kinds[t], m->tp.tf_uid[node], j, mu[i], sd[i]);
+            }
+        }
+    }
+    std::fflush(stdout);
+    return 0;
+}
+
+extern "C" int gbn_model_set_evidence(gbn_model *m, const gbn_evidence *ev)
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (int rc = use_device(m)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (int rc = upload_evidence(m, ev)) return rc;
+    m->sweeps_total = 0;
+    m->ch.inj_flat = m->ch.inj_beta = m->ch.inj_exp = nullptr; m->ch.inj_sweeps = m->ch.inj_pos = 0;
+    if (int rc = init_chains(m)) return rc;
+    if (int rc = zero_stats(m)) return rc;
+    if (int rc = refresh_fast(m)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ multi-GPU
+extern "C" int gbn_comm_unique_id(void *id_out)
+{
+    std::string why;
+    if (!g_nccl.load(why)) return fail(GBN_ERR_COMM, why);
+    int rc = g_nccl.GetUniqueId(id_out);
+    if (rc != 0) return fail(GBN_ERR_COMM, "ncclGetUniqueId failed");
+    return 0;
+}
+
+extern "C" int gbn_model_attach_comm(gbn_model *m, int rank, int world, const void *id)
+{
+    if (!m || !id) return fail(GBN_ERR_INVALID, "null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(GBN_ERR_INVALID, "bad rank / world");
+    if (int rc = use_device(m)) return rc;
+    std::string why;
+    if (!g_nccl.load(why)) return fail(GBN_ERR_COMM, why);
+    NcclApi::Uid uid;
+    std::memcpy(uid.b, id, 128);
+    void *comm = nullptr;
+    int rc = g_nccl.CommInitRank(&comm, world, uid, rank);
+    if (rc != 0) return fail(GBN_ERR_COMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    m->comm = comm; m->rank = rank; m->world = world;
+    m->moments_valid = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ parity hooks
+extern "C" int gbn_model_get_state(gbn_model *m, uint32_t chain, double *out)
+{
+    if (!m || !out) return fail(GBN_ERR_INVALID, "null argument");
+    if (chain >= m->n_chains) return fail(GBN_ERR_INVALID, "chain out of range");
+    if (int rc = use_device(m)) return rc;
+    const uint32_t nX = m->tp.nX, E = m->tp.E;
+    std::vector<uint8_t> X(nX), S(E);
+    std::vector<double> T(nX);
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    CUDA_TRY(cudaMemcpy(X.data(), m->ch.X + (size_t) chain * nX, nX, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(T.data(), m->ch.T + (size_t) chain * nX, sizeof(double) * nX, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(S.data(), m->ch.S + (size_t) chain * E, E, cudaMemcpyDeviceToHost));
+    uint32_t o = 0;
+    for (uint32_t k = 0; k < nX; k++) out[o++] = X[k];
+    if (!m->net.const_params) for (uint32_t k = 0; k < nX; k++) out[o++] = T[k];
+    for (uint32_t e = 0; e < E; e++) out[o++] = S[m->tp.slot_of_edge[e]];
+    return 0;
+}
+
+extern "C" int gbn_model_set_state(gbn_model *m, uint32_t chain, const double *in)
+{
+    if (!m || !in) return fail(GBN_ERR_INVALID, "null argument");
+    if (chain >= m->n_chains) return fail(GBN_ERR_INVALID, "chain out of range");
+    if (int rc = use_device(m)) return rc;
+    const uint32_t nX = m->tp.nX, E = m->tp.E;
+    std::vector<uint8_t> X(nX), S(E);
+    std::vector<double> T(nX);
+    uint32_t o = 0;
+    for (uint32_t k = 0; k < nX; k++) { double v = in[o++]; if (v != 0. && v != 1.) return fail(GBN_ERR_INVALID, "X values must be 0 or 1"); X[k] = (uint8_t) v; }
+    if (!m->net.const_params) for (uint32_t k = 0; k < nX; k++) T[k] = in[o++];
+    for (uint32_t e = 0; e < E; e++) { double v = in[o++]; if (v != 0. && v != 1. && v != 2.) return fail(GBN_ERR_INVALID, "S values must be 0, 1 or 2"); S[m->tp.slot_of_edge[e]] = (uint8_t) v; }
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (!m->net.const_params)
+        CUDA_TRY(cudaMemcpy(m->ch.T + (size_t) chain * nX, T.data(), sizeof(double) * nX, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->ch.X + (size_t) chain * nX, X.data(), nX, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->ch.S + (size_t) chain * E, S.data(), E, cudaMemcpyHostToDevice));
+    if (int rc = refresh_fast(m)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+static int eval_to_host(gbn_model *m, uint32_t chain, double *out, size_t n, int which)
+{
+    if (!m || !out) return fail(GBN_ERR_INVALID, "null argument");
+    if (chain >= m->n_chains) return fail(GBN_ERR_INVALID, "chain out of range");
+    if (int rc = use_device(m)) return rc;
+    if (int rc = ensure_scratch(m, sizeof(double) * n)) return rc;
+    if (which == 0) launch_conditionals(m->net, m->ch, chain, m->d_scratch, m->stream);
+    else if (which == 1) launch_target_likelihoods(m->net, m->ch, chain, m->d_scratch, m->stream);
+    else launch_joint_logprob(m->net, m->ch, chain, m->d_scratch, m->stream);
+    m->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, m->d_scratch, sizeof(double) * n, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+extern "C" int gbn_model_eval_conditionals(gbn_model *m, uint32_t chain, double *out)
+{ return eval_to_host(m, chain, out, m ? (size_t) 3 * n_nodes_of(m->net) : 0, 0); }
+extern "C" int gbn_model_target_likelihoods(gbn_model *m, uint32_t chain, double *out)
+{ return eval_to_host(m, chain, out, m ? (size_t) m->tp.nH : 0, 1); }
+extern "C" int gbn_model_joint_logprob(gbn_model *m, uint32_t chain, double *out)
+{ return eval_to_host(m, chain, out, 1, 2); }
+
+extern "C" int gbn_model_inject_draws(gbn_model *m, uint32_t n_sweeps, const double *flat_u, const double *beta_v, const double *exp_v)
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (int rc = use_device(m)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    for (double **p : { &m->d_inj_flat, &m->d_inj_beta, &m->d_inj_exp })
+        if (*p) { for (auto &q : m->owned) if (q == *p) q = nullptr; cudaFree(*p); *p = nullptr; }
+    m->ch.inj_flat = m->ch.inj_beta = m->ch.inj_exp = nullptr; m->ch.inj_sweeps = m->ch.inj_pos = 0;
+    if (n_sweeps == 0) return 0;
+    if (!flat_u || !beta_v || !exp_v) return fail(GBN_ERR_INVALID, "null draw arrays");
+    const size_t C = m->n_chains, nX = m->tp.nX, E = m->tp.E;
+    const size_t nf = C * n_sweeps * (nX + E), nb = C * n_sweeps * nX;
+    if (int rc = dev_alloc(m, &m->d_inj_flat, nf)) return rc;
+    if (int rc = dev_alloc(m, &m->d_inj_beta, nb)) return rc;
+    if (int rc = dev_alloc(m, &m->d_inj_exp, nb)) return rc;
+    CUDA_TRY(cudaMemcpy(m->d_inj_flat, flat_u, sizeof(double) * nf, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->d_inj_beta, beta_v, sizeof(double) * nb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->d_inj_exp, exp_v, sizeof(double) * nb, cudaMemcpyHostToDevice));
+    m->ch.inj_flat = m->d_inj_flat; m->ch.inj_beta = m->d_inj_beta; m->ch.inj_exp = m->d_inj_exp;
+    m->ch.inj_sweeps = n_sweeps; m->ch.inj_pos = 0;
+    return 0;
+}
+
+extern "C" int gbn_model_export_draws(gbn_model *m, uint32_t chain, uint32_t sweep0, uint32_t n, double *flat_u, double *beta_v, double *exp_v)
+{
+    if (!m || !flat_u || !beta_v || !exp_v) return fail(GBN_ERR_INVALID, "null argument");
+    if (chain >= m->n_chains) return fail(GBN_ERR_INVALID, "chain out of range");
+    if (int rc = use_device(m)) return rc;
+    const size_t nX = m->tp.nX, E = m->tp.E;
+    const size_t nf = (size_t) n * (nX + E), nb = (size_t) n * nX;
+    if (int rc = ensure_scratch(m, sizeof(double) * (nf + 2 * nb))) return rc;
+    double *df = m->d_scratch, *db = df + nf, *de = db + nb;
+    launch_export_draws(m->net, chain_global_id(m->net, chain), sweep0, n, df, db, de, m->stream);
+    m->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(flat_u, df, sizeof(double) * nf, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(beta_v, db, sizeof(double) * nb, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(exp_v, de, sizeof(double) * nb, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+extern "C" int gbn_model_node_moments(gbn_model *m, uint32_t chain, double *mean, double *variance)
+{
+    if (!m || !mean || !variance) return fail(GBN_ERR_INVALID, "null argument");
+    if (chain >= m->n_chains) return fail(GBN_ERR_INVALID, "chain out of range");
+    if (int rc = use_device(m)) return rc;
+    const size_t ns = n_stats_of(m->net);
+    if (int rc = ensure_scratch(m, sizeof(double) * 2 * ns)) return rc;
+    if (m->stat_n == 0) { for (size_t i = 0; i < ns; i++) { mean[i] = 0.; variance[i] = 0.; } return 0; }
+    launch_node_moments(m->net, m->ch, chain, (double) m->stat_n, m->d_scratch, m->d_scratch + ns, m->stream);
+    m->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(mean, m->d_scratch, sizeof(double) * ns, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(variance, m->d_scratch + ns, sizeof(double) * ns, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+extern "C" int gbn_philox_kat(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    if (gbn_device_count() <= 0) return fail(GBN_ERR_CUDA, "no CUDA device: gbnet_b200 has no CPU path");
+    CUDA_TRY(cudaSetDevice(device));
+    uint32_t *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 16));
+    launch_philox_kat(ctr, key, d, 0);
+    cudaError_t e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(GBN_ERR_CUDA, cudaGetErrorString(e));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ measurement
+extern "C" int gbn_model_last_device_ms(const gbn_model *m, double *ms)
+{
+    if (!m || !ms) return fail(GBN_ERR_INVALID, "null argument");
+    *ms = m->last_ms;
+    return 0;
+}
+
+extern "C" int gbn_model_launch_count(const gbn_model *m, uint64_t *n)
+{
+    if (!m || !n) return fail(GBN_ERR_INVALID, "null argument");
+    *n = m->launches;
+    return 0;
+}
+
+extern "C" int gbn_model_sweep_count(const gbn_model *m, uint64_t *n)
+{
+    if (!m || !n) return fail(GBN_ERR_INVALID, "null argument");
+    *n = m->sweeps_total;
+    return 0;
+}
+
+extern "C" int gbn_model_synchronize(gbn_model *m)
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (int rc = use_device(m)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}

@@ -1,0 +1,81 @@
+// Device-resident model description passed by value to every kernel.
+//
+// HBM layout (all arrays chain-major so that one chain's data is contiguous):
+//   network (shared by all chains and datasets)      : CSR arrays, see topology.hpp
+//   per dataset   y[d][nH] u8, yprob[d][3] f64
+//   per chain     X[c][nX] u8 | T[c][nX] f64 | S[c][E] u8 in SLOT order
+//   statistics    cX1[c][nX] u32  (#sweeps with X=1; X=0 is N - cX1)
+//                 tMean[c][nX], tM2[c][nX] f64 (Welford, gsl_rstat order of operations)
+//                 cS0[c][E], cS2[c][E] u32 in slot order (S=1 is N - cS0 - cS2)
+//   fast kernel   tcache[c][nH] {pr0, pr2, zc, L} f64x4 (32 B = one DRAM sector per target)
+//                 Stf[c][E] u8   copy of S in by-TF CSR order (coalesced reads in the X phase)
+//                 FX[c][nX], FXinv[c][nX] f64   1 - t*x and its reciprocal
+// Integer counts replace the reference's gsl_rstat workspaces of 0/1 indicators
+// (Multinomial.cpp:101-105): mean = c/N, variance = N/(N-1) p (1-p).
+#pragma once
+
+#include <cstdint>
+
+namespace gbn {
+
+struct DevNet {
+    uint32_t nX, nH, E, Eu;
+    uint32_t max_indeg, max_outdeg;
+    const uint32_t *trg_ptr;      // [nH+1]
+    const uint32_t *par_tf;       // [E]  slot -> TF
+    const uint32_t *par_edge;     // [E]  slot -> edge input index
+    const uint32_t *slot_of_edge; // [E]
+    const uint32_t *slot_trg;     // [E]  slot -> target
+    const uint8_t *mor_idx;       // [E]  slot -> mor + 1
+    const uint32_t *tf_ptr;       // [nX+1]
+    const uint32_t *tf_child;     // [Eu]
+    const uint32_t *tf_slot;      // [Eu]
+    const uint32_t *tfpos_of_slot;// [E]  slot -> position in the by-TF CSR (fast kernel; needs Eu == E)
+    const uint32_t *trg_order;    // [nH] targets sorted by in-degree, descending (fast S phase)
+    const uint8_t *x_prior_active;// [nX]
+    const double *t_a, *t_b, *t_mean, *t_lnB;   // [nX]
+    const uint8_t *y;             // [n_datasets][nH]
+    const double *yprob;          // [n_datasets][3]
+    const double *zctab;          // [2][max_indeg+2]  (1-z)^n by repeated multiplication; row 0 = ZY, row 1 = ZN
+    double xprob[2][2];           // [prior_active][v]   GraphORNOR.h:40-41
+    double sprob[3][3];           // [mor+1][v]          GraphORNOR.cpp:25
+    double ynoise[3][3];          // [h][y]              GraphORNOR.h:46-48
+    double z_y, z_n;              // ZY / ZN constants   GraphORNOR.cpp:155-164
+    uint32_t n_datasets, n_graphs_local, chain_offset, n_graphs;
+    int32_t listen, const_params;
+    uint64_t seed;
+};
+
+// one 32-byte DRAM sector per target: products over the parents with S = 0 / S = 2, (1-z)^n, and
+// the target's current likelihood HNode::get_own_likelihood
+struct __align__(32) TargetCache { double pr0, pr2, zc, L; };
+
+struct DevChains {
+    uint32_t n_chains;            // local: n_datasets * n_graphs_local, dataset-major
+    uint8_t *X;
+    double *T;
+    uint8_t *S;
+    uint32_t *cX1;
+    double *tMean, *tM2;
+    uint32_t *cS0, *cS2;
+    // fast kernel only
+    TargetCache *tcache;
+    uint8_t *Stf;
+    double *FX, *FXinv;
+    // injected draws (NULL = keyed Philox streams)
+    const double *inj_flat;       // [chain][inj_sweeps][nX + E]  X then S in edge input order
+    const double *inj_beta;       // [chain][inj_sweeps][nX]
+    const double *inj_exp;        // [chain][inj_sweeps][nX]
+    uint32_t inj_sweeps;          // sweeps available
+    uint32_t inj_pos;             // first unconsumed injected sweep
+};
+
+// local chain index -> dataset and global chain id (Philox counter word 2)
+__host__ __device__ inline uint32_t chain_dataset(const DevNet &n, uint32_t c) { return c / n.n_graphs_local; }
+__host__ __device__ inline uint32_t chain_global_id(const DevNet &n, uint32_t c)
+{
+    uint32_t d = c / n.n_graphs_local, l = c % n.n_graphs_local;
+    return d * n.n_graphs + n.chain_offset + l;
+}
+
+}  // namespace gbn

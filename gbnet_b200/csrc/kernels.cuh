@@ -1,0 +1,59 @@
+// Launchers of every kernel in the library (host-callable; defined in the .cu files).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "device_model.cuh"
+
+namespace gbn {
+
+// ---- eval_kernels.cu (parity hooks)
+void launch_conditionals(const DevNet &net, const DevChains &ch, uint32_t c, double *out, cudaStream_t st);
+void launch_target_likelihoods(const DevNet &net, const DevChains &ch, uint32_t c, double *out, cudaStream_t st);
+void launch_joint_logprob(const DevNet &net, const DevChains &ch, uint32_t c, double *out, cudaStream_t st);
+void launch_philox_kat(const uint32_t ctr[4], const uint32_t key[2], uint32_t *out, cudaStream_t st);
+void launch_export_draws(const DevNet &net, uint32_t gchain, uint32_t sweep0, uint32_t n,
+                         double *flat_u, double *beta_v, double *exp_v, cudaStream_t st);
+
+// ---- sweep_strict.cu: n_sweeps full sweeps X -> T -> S of every local chain, one CTA per chain,
+// every likelihood recomputed from the state in the reference's operand order.
+// sweep0 = sweeps drawn since creation (Philox counter word), stat_n0 = sweeps since burn_stats.
+// Returns the number of kernels launched, or -1 with *err set.
+int launch_sweep_strict(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
+                        uint32_t stat_n0, cudaStream_t st, const char **err);
+size_t strict_smem_bytes(const DevNet &net);
+
+// ---- sweep_fast.cu: the throughput path (cached per-target products, speculative X windows)
+int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
+                      uint32_t stat_n0, cudaStream_t st, const char **err);
+// rebuild Stf / FX / FXinv / tcache from X, T, S (after creation and set_state)
+int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
+bool fast_supported(const DevNet &net, const char **why);
+
+// ---- moments.cu (K5): cross-chain moments -> Gelman-Rubin and posterior summaries
+struct MomentArgs {
+    uint32_t n_stats;             // per dataset: 2 nX + nT + 3 E
+    uint32_t n_nodes;
+    double N;                     // chain length (sweeps since burn)
+};
+// pass 1: sums[d][stat][0] = sum_k mean_k, [1] = sum_k var_k over the LOCAL chains of dataset d;
+//         psums[d][stat] = sum of mean_k over local chains whose GLOBAL index is >= 1
+void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double *sums, double *psums, cudaStream_t st);
+// pass 2: dev[d][stat] = sum_k (mean_k - mu)^2 with mu = sums[..][0] / M ;
+//         pdev[d][stat] = sum over global chains >= 1 of (mean_k - pmu)^2, pmu = psums / (M - 1)
+void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const double *sums, const double *psums,
+                        double *dev, double *pdev, cudaStream_t st);
+// finalize: Gelman-Rubin per node (random_nodes order) of dataset d, and its maximum
+void launch_gelman_rubin(const DevNet &net, double N, const double *sums, const double *dev,
+                         uint32_t dataset, double *gr_out /* [n_nodes] or NULL */, double *max_out /* [n_datasets] */,
+                         cudaStream_t st);
+// per-chain running moments in stat order (RVNode::mean / variance)
+void launch_node_moments(const DevNet &net, const DevChains &ch, uint32_t c, double N, double *mean, double *var, cudaStream_t st);
+
+// stat index helpers shared by host and device: per dataset, stats are laid out
+//   X: 2 per TF (outcome 0, 1) | T: 1 per TF (absent if const_params) | S: 3 per edge in EDGE INPUT order
+__host__ __device__ inline uint32_t n_stats_of(const DevNet &n) { return 2 * n.nX + (n.const_params ? 0 : n.nX) + 3 * n.E; }
+__host__ __device__ inline uint32_t n_nodes_of(const DevNet &n) { return n.nX + (n.const_params ? 0 : n.nX) + n.E; }
+
+}  // namespace gbn

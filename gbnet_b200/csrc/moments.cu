@@ -1,0 +1,206 @@
+// K5 — cross-chain moments: Gelman-Rubin (ModelBase.cpp:47-112) and posterior means / sdevs
+// (ModelBase.cpp:160-209) from the per-chain counters, without ever materialising per-chain
+// gsl_rstat workspaces.
+//
+// Per chain k and stat j the reference keeps mean_kj and variance_kj (RVNode.cpp:115-123).  For the
+// discrete nodes these follow exactly from the outcome counts: mean = c/N and
+// variance = sum (x - mean)^2 / (N-1) = c (N-c) / N / (N-1).  For T they are the Welford pair.
+// The cross-chain reduction is done in two passes so that it distributes over ranks:
+//   pass 1  sum_k mean_kj, sum_k variance_kj                     (-> all-reduce, sum)
+//   pass 2  sum_k (mean_kj - mu_j)^2                             (-> all-reduce, sum)
+//   final   B = N * pass2 / (M-1), W = pass1.var / M, Vhat, R    (every rank, redundantly)
+// The posterior getters skip GLOBAL chain 0 exactly as the reference does (ModelBase.cpp:172,197).
+//
+// Work items are "nodes in slot order": X_k (2 stats), T_k (1 stat), S at slot q (3 stats), so that
+// for every chain the counter reads are coalesced; results are written at the stat / node index
+// of the reference's random_nodes order (S in edge input order).
+#include "kernels.cuh"
+#include "device_math.cuh"
+
+namespace gbn {
+
+namespace {
+
+struct NodeRef {
+    uint32_t kind;      // 0 X, 1 T, 2 S
+    uint32_t idx;       // k or slot q
+    uint32_t n_stats;   // 2, 1, 3
+    uint32_t stat0;     // first stat index (reference order)
+    uint32_t node;      // node index (reference order)
+};
+
+__device__ __forceinline__ NodeRef node_ref(const DevNet &net, uint32_t n)
+{
+    const uint32_t nT = net.const_params ? 0 : net.nX;
+    NodeRef r;
+    if (n < net.nX) { r.kind = 0; r.idx = n; r.n_stats = 2; r.stat0 = 2 * n; r.node = n; }
+    else if (n < net.nX + nT) { r.kind = 1; r.idx = n - net.nX; r.n_stats = 1; r.stat0 = 2 * net.nX + r.idx; r.node = n; }
+    else {
+        r.kind = 2; r.idx = n - net.nX - nT; r.n_stats = 3;
+        const uint32_t e = net.par_edge[r.idx];
+        r.stat0 = 2 * net.nX + nT + 3 * e;
+        r.node = net.nX + nT + e;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void count_moment(double c, double N, double &mean, double &var)
+{
+    mean = c / N;
+    var = N > 1. ? (c * (N - c) / N) / (N - 1.) : 0.;
+}
+
+// mean / variance of every stat of node r in local chain c
+__device__ __forceinline__ void node_moments(const DevNet &net, const DevChains &ch, uint32_t c, const NodeRef &r,
+                                             double N, double mean[3], double var[3])
+{
+    if (r.kind == 0) {
+        double c1 = (double) ch.cX1[(size_t) c * net.nX + r.idx];
+        count_moment(N - c1, N, mean[0], var[0]);
+        count_moment(c1, N, mean[1], var[1]);
+    } else if (r.kind == 1) {
+        mean[0] = ch.tMean[(size_t) c * net.nX + r.idx];
+        var[0] = N > 1. ? ch.tM2[(size_t) c * net.nX + r.idx] / (N - 1.) : 0.;
+    } else {
+        double c0 = (double) ch.cS0[(size_t) c * net.E + r.idx];
+        double c2 = (double) ch.cS2[(size_t) c * net.E + r.idx];
+        count_moment(c0, N, mean[0], var[0]);
+        count_moment(N - c0 - c2, N, mean[1], var[1]);
+        count_moment(c2, N, mean[2], var[2]);
+    }
+}
+
+__global__ void k_moment_sums(DevNet net, DevChains ch, double N, double *sums, double *psums)
+{
+    const uint32_t n_nodes = n_nodes_of(net), n_stats = n_stats_of(net);
+    const uint32_t d = blockIdx.y;
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    const NodeRef r = node_ref(net, n);
+    double sm[3] = { 0., 0., 0. }, sv[3] = { 0., 0., 0. }, ps[3] = { 0., 0., 0. };
+    for (uint32_t l = 0; l < net.n_graphs_local; l++) {
+        double mean[3], var[3];
+        node_moments(net, ch, d * net.n_graphs_local + l, r, N, mean, var);
+        const bool post = (net.chain_offset + l) >= 1;
+        for (uint32_t j = 0; j < r.n_stats; j++) {
+            sm[j] += mean[j]; sv[j] += var[j];
+            if (post) ps[j] += mean[j];
+        }
+    }
+    for (uint32_t j = 0; j < r.n_stats; j++) {
+        size_t o = (size_t) d * n_stats + r.stat0 + j;
+        sums[2 * o] = sm[j]; sums[2 * o + 1] = sv[j];
+        psums[o] = ps[j];
+    }
+}
+
+__global__ void k_moment_devs(DevNet net, DevChains ch, double N, const double *sums, const double *psums,
+                              double *dev, double *pdev)
+{
+    const uint32_t n_nodes = n_nodes_of(net), n_stats = n_stats_of(net);
+    const uint32_t d = blockIdx.y;
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    const NodeRef r = node_ref(net, n);
+    const double M = (double) net.n_graphs;
+    double mu[3], pmu[3], dv[3] = { 0., 0., 0. }, pd[3] = { 0., 0., 0. };
+    for (uint32_t j = 0; j < r.n_stats; j++) {
+        size_t o = (size_t) d * n_stats + r.stat0 + j;
+        mu[j] = sums[2 * o] / M;
+        pmu[j] = M > 1. ? psums[o] / (M - 1.) : 0.;
+    }
+    for (uint32_t l = 0; l < net.n_graphs_local; l++) {
+        double mean[3], var[3];
+        node_moments(net, ch, d * net.n_graphs_local + l, r, N, mean, var);
+        const bool post = (net.chain_offset + l) >= 1;
+        for (uint32_t j = 0; j < r.n_stats; j++) {
+            double a = mean[j] - mu[j];
+            dv[j] += a * a;
+            if (post) { double b = mean[j] - pmu[j]; pd[j] += b * b; }
+        }
+    }
+    for (uint32_t j = 0; j < r.n_stats; j++) {
+        size_t o = (size_t) d * n_stats + r.stat0 + j;
+        dev[o] = dv[j];
+        pdev[o] = pd[j];
+    }
+}
+
+// ModelBase::get_gelman_rubin (ModelBase.cpp:72-92) from the globally reduced sums
+__global__ void k_gelman_rubin(DevNet net, double N, const double *sums, const double *dev, uint32_t d0, uint32_t nd,
+                               double *gr_out, unsigned long long *max_out)
+{
+    const uint32_t n_nodes = n_nodes_of(net), n_stats = n_stats_of(net);
+    const uint32_t d = d0 + blockIdx.y;
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    double max_gr = 0.;
+    if (n < n_nodes && blockIdx.y < nd) {
+        const NodeRef r = node_ref(net, n);
+        const double M = (double) net.n_graphs;
+        for (uint32_t j = 0; j < r.n_stats; j++) {
+            size_t o = (size_t) d * n_stats + r.stat0 + j;
+            double B = N * (M > 1. ? dev[o] / (M - 1.) : 0.);
+            double W = sums[2 * o + 1] / M;
+            double Vhat = W * (N - 1.) / N + B * (M + 1.) / (M * N);
+            double gr;
+            if (W > 0. && Vhat > 0.) gr = sqrt((N + 3.) / (N + 1.) * Vhat / W);
+            else if (Vhat > 0.) gr = INFINITY;
+            else gr = 1.;
+            max_gr = fmax(gr, max_gr);
+        }
+        if (gr_out) gr_out[(size_t) blockIdx.y * n_nodes + r.node] = max_gr;
+    }
+    // block maximum -> one atomic per block (non-negative doubles order like their bit patterns)
+    for (int o = 16; o > 0; o >>= 1) max_gr = fmax(max_gr, __shfl_xor_sync(0xffffffffu, max_gr, o));
+    __shared__ double wmax[32];
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = max_gr;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); w++) m = fmax(m, wmax[w]);
+        atomicMax(max_out + d, (unsigned long long) __double_as_longlong(m));
+    }
+}
+
+__global__ void k_node_moments(DevNet net, DevChains ch, uint32_t c, double N, double *mean_out, double *var_out)
+{
+    const uint32_t n_nodes = n_nodes_of(net);
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    const NodeRef r = node_ref(net, n);
+    double mean[3], var[3];
+    node_moments(net, ch, c, r, N, mean, var);
+    for (uint32_t j = 0; j < r.n_stats; j++) { mean_out[r.stat0 + j] = mean[j]; var_out[r.stat0 + j] = var[j]; }
+}
+
+}  // namespace
+
+void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double *sums, double *psums, cudaStream_t st)
+{
+    dim3 grid((n_nodes_of(net) + 127) / 128, net.n_datasets);
+    k_moment_sums<<<grid, 128, 0, st>>>(net, ch, N, sums, psums);
+}
+
+void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const double *sums, const double *psums,
+                        double *dev, double *pdev, cudaStream_t st)
+{
+    dim3 grid((n_nodes_of(net) + 127) / 128, net.n_datasets);
+    k_moment_devs<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, dev, pdev);
+}
+
+void launch_gelman_rubin(const DevNet &net, double N, const double *sums, const double *dev,
+                         uint32_t dataset, double *gr_out, double *max_out, cudaStream_t st)
+{
+    // dataset == UINT32_MAX: all datasets, maxima only
+    uint32_t d0 = dataset == UINT32_MAX ? 0 : dataset;
+    uint32_t nd = dataset == UINT32_MAX ? net.n_datasets : 1;
+    dim3 grid((n_nodes_of(net) + 127) / 128, nd);
+    k_gelman_rubin<<<grid, 128, 0, st>>>(net, N, sums, dev, d0, nd, gr_out, (unsigned long long *) max_out);
+}
+
+void launch_node_moments(const DevNet &net, const DevChains &ch, uint32_t c, double N, double *mean, double *var, cudaStream_t st)
+{
+    k_node_moments<<<(n_nodes_of(net) + 127) / 128, 128, 0, st>>>(net, ch, c, N, mean, var);
+}
+
+}  // namespace gbn

@@ -1,0 +1,321 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, on the GPU.
+
+Bars (BASELINE.json north_star):
+  * per-state conditional log-likelihoods and the joint log-probability: 1e-12 relative, fp64;
+  * discrete state updates: bit-exact under an identical injected draw stream (and under the
+    keyed Philox streams, which the oracle generates identically);
+  * T values: 1e-9 absolute (CUDA log/exp/lgamma differ from glibc in the last ulp, and the
+    random walk adds those differences up);
+  * Gelman-Rubin / posterior summaries: 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import make_problem, rel_err, sampler_from_problem
+
+pytestmark = pytest.mark.gpu
+
+import gbnet_b200  # noqa: E402
+from gbnet_b200 import KERNEL_FAST, KERNEL_STRICT  # noqa: E402
+
+LL_RTOL = 1e-12
+
+
+def _split_state(pb, P, st):
+    nX = P.n_tf()
+    nT = 0 if pb.const_params else nX
+    return st[:nX], st[nX:nX + nT], st[nX + nT:]
+
+
+def _assert_state_equal(pb, P, a, b, what=""):
+    xa, ta, sa = _split_state(pb, P, a)
+    xb, tb, sb = _split_state(pb, P, b)
+    assert np.array_equal(xa, xb), f"X differs {what}: {np.flatnonzero(xa != xb)[:10]}"
+    assert np.array_equal(sa, sb), f"S differs {what}: {np.flatnonzero(sa != sb)[:10]}"
+    if ta.size:
+        assert np.max(np.abs(ta - tb)) < 1e-9, f"T differs {what}: {np.max(np.abs(ta - tb))}"
+
+
+CASES = {
+    "cli": dict(),
+    "listen": dict(noise_listen_children=True),
+    "const": dict(const_params=True),
+    "yprob": dict(comp_yprob=True),
+    "pyx_defaults": dict(hyper="pyx"),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_conditionals_and_joint(case):
+    pb, _ = make_problem(NX=15, NY=80, AvgNTF=3.0, seed=7, **CASES[case])
+    P = oracle.PortModel(pb)
+    G = sampler_from_problem(pb, kernel=KERNEL_STRICT)
+    assert G.n_nodes() == P.n_nodes() and G.n_targets() == P.n_targets()
+    rng = np.random.default_rng(3)
+    for c in range(pb.n_graphs):
+        # same initial state by construction (keyed init draws)
+        assert np.array_equal(G.get_state(c), P.get_state(c))
+        # then a randomised state
+        st = P.get_state(c)
+        nX = P.n_tf()
+        nT = 0 if pb.const_params else nX
+        st[:nX] = rng.integers(0, 2, nX)
+        st[nX:nX + nT] = rng.uniform(0.02, 0.98, nT)
+        st[nX + nT:] = rng.integers(0, 3, st.size - nX - nT)
+        P.set_state(c, st)
+        G.set_state(c, st)
+        a, b = G.all_conditionals(c), P.all_conditionals(c)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        m = ~np.isnan(b)
+        assert rel_err(a[m], b[m]).max() < LL_RTOL
+        assert rel_err(G.target_likelihoods(c), P.target_likelihoods(c)).max() < LL_RTOL
+        assert rel_err(G.joint_logprob(c), P.joint_logprob(c)) < LL_RTOL
+
+
+def test_philox_and_keyed_draws():
+    for ctr, key in [((0, 0, 0, 0), (0, 0)), ((1, 2, 3, 4), (5, 6)),
+                     ((0xffffffff,) * 4, (0xffffffff,) * 2)]:
+        assert gbnet_b200.philox_kat(ctr, key) == oracle.philox4x32_10(ctr, key)
+    pb, _ = make_problem(NX=10, NY=40, seed=11)
+    P = oracle.PortModel(pb)
+    G = sampler_from_problem(pb, kernel=KERNEL_STRICT)
+    for c in (0, 2):
+        fg, bg, eg = G.export_draws(c, 3, 5)
+        fp, bp, ep = P.export_draws(c, 3, 5)
+        assert np.array_equal(fg, fp)                    # integer -> double conversion: exact
+        assert rel_err(bg, bp).max() < 1e-12             # gamma / beta samplers: libm ulps
+        assert rel_err(eg, ep).max() < 1e-12
+
+
+def _run_trajectory(pb, kernel, n_sweeps, injected, chunks=(1,)):
+    P = oracle.PortModel(pb)
+    G = sampler_from_problem(pb, kernel=kernel)
+    assert G.kernel() == kernel
+    M = pb.n_graphs
+    if injected:
+        draws = [P.export_draws(c, 1000, n_sweeps) for c in range(M)]     # any stream will do
+        for c in range(M):
+            P.inject(c, *draws[c])
+        G.inject(np.stack([d[0] for d in draws]), np.stack([d[1] for d in draws]),
+                 np.stack([d[2] for d in draws]))
+    done = 0
+    i = 0
+    while done < n_sweeps:
+        n = min(chunks[i % len(chunks)], n_sweeps - done)
+        P.sample_n(n)
+        G.sample_n(n)
+        done += n
+        i += 1
+        for c in range(M):
+            _assert_state_equal(pb, P, G.get_state(c), P.get_state(c), f"chain {c} after {done} sweeps")
+    return P, G
+
+
+@pytest.mark.parametrize("kernel", [KERNEL_STRICT, KERNEL_FAST])
+@pytest.mark.parametrize("injected", [True, False])
+def test_trajectory_bit_exact(kernel, injected):
+    pb, _ = make_problem(NX=20, NY=150, AvgNTF=3.0, seed=21, n_graphs=4)
+    P, G = _run_trajectory(pb, kernel, 40, injected, chunks=(1, 3, 7))
+    # per-chain running statistics
+    for c in range(pb.n_graphs):
+        mean, var = G.node_moments(c)
+        j = 0
+        for node in range(P.n_nodes()):
+            ns = 2 if node < P.n_tf() else (1 if node < 2 * P.n_tf() else 3)
+            for s in range(ns):
+                assert abs(mean[j] - P.node_mean(c, node, s)) < 1e-9
+                assert abs(var[j] - P.node_variance(c, node, s)) < 1e-9
+                j += 1
+    assert G.chain_length() == P.chain_length() == 40
+    gg, gp = G.gelman_rubin(), P.gelman_rubin()
+    fin = np.isfinite(gp)
+    assert np.array_equal(np.isfinite(gg), fin)
+    assert rel_err(gg[fin], gp[fin]).max() < 1e-9
+    assert rel_err(G.max_gelman_rubin(), P.max_gelman_rubin()) < 1e-9 or not np.isfinite(P.max_gelman_rubin())
+    for name in ("X", "T", "S"):
+        assert np.abs(G.posterior_means(name) - P.posterior_means(name)).max() < 1e-9
+        assert np.abs(G.posterior_sdevs(name) - P.posterior_sdevs(name)).max() < 1e-9
+    assert G.posterior_means("Q").size == 0
+
+
+@pytest.mark.parametrize("case", ["listen", "const", "yprob", "pyx_defaults"])
+def test_trajectory_variants_strict(case):
+    pb, _ = make_problem(NX=15, NY=100, AvgNTF=3.0, seed=33, **CASES[case])
+    _run_trajectory(pb, KERNEL_STRICT, 25, injected=False, chunks=(5,))
+    _run_trajectory(pb, KERNEL_STRICT, 10, injected=True, chunks=(2,))
+
+
+@pytest.mark.parametrize("case", ["const", "yprob"])
+def test_trajectory_variants_fast(case):
+    pb, _ = make_problem(NX=15, NY=100, AvgNTF=3.0, seed=34, **CASES[case])
+    _run_trajectory(pb, KERNEL_FAST, 25, injected=False, chunks=(5,))
+
+
+def test_fast_c1_shape_long():
+    """BASELINE config C1 (50 TFs / 2,000 targets / ~5,000 edges, 3 chains): the fast kernel
+    follows the oracle's chain bit for bit over 300 sweeps."""
+    pb, _ = make_problem(NX=50, NY=2000, AvgNTF=2.5, seed=1, n_graphs=3, num_active_tfs=3)
+    _run_trajectory(pb, KERNEL_FAST, 300, injected=False, chunks=(100,))
+
+
+def test_active_tf_prior_and_set_state_roundtrip():
+    pb, _ = make_problem(NX=12, NY=60, seed=9)
+    pb.active_tf = np.array([1, 5], np.uint32)
+    P, G = _run_trajectory(pb, KERNEL_FAST, 20, injected=False, chunks=(20,))
+    st = G.get_state(1)
+    G.set_state(0, st)
+    assert np.array_equal(G.get_state(0), st)
+
+
+def test_auto_kernel_selection_and_duplicates():
+    pb, _ = make_problem(NX=10, NY=50, seed=13)
+    assert sampler_from_problem(pb).kernel() == KERNEL_FAST
+    pbl, _ = make_problem(NX=10, NY=50, seed=13, noise_listen_children=True)
+    assert sampler_from_problem(pbl).kernel() == KERNEL_STRICT
+    # a duplicated (TF, target) edge with another sign: two S nodes, one child (HParentNode.h:18)
+    pb.src = np.concatenate([pb.src, pb.src[:3]])
+    pb.trg = np.concatenate([pb.trg, pb.trg[:3]])
+    pb.mor = np.concatenate([pb.mor, -pb.mor[:3]])
+    assert sampler_from_problem(pb).kernel() == KERNEL_STRICT
+    with pytest.raises(gbnet_b200.GbnError):
+        sampler_from_problem(pb, kernel=KERNEL_FAST)
+    _run_trajectory(pb, KERNEL_STRICT, 10, injected=False, chunks=(10,))
+    P = oracle.PortModel(pb)
+    G = sampler_from_problem(pb)
+    a, b = G.all_conditionals(0), P.all_conditionals(0)
+    m = ~np.isnan(b)
+    assert rel_err(a[m], b[m]).max() < LL_RTOL
+
+
+def test_sample_loop_quirks():
+    """ModelBase::sample (ModelBase.cpp:114-129): the batch just drawn is never clipped, R-hat is
+    INF before any sample, burn_stats resets the statistics but keeps the state."""
+    pb, _ = make_problem(NX=10, NY=50, seed=17)
+    P = oracle.PortModel(pb)
+    G = sampler_from_problem(pb)
+    assert np.isinf(G.max_gelman_rubin()) and np.all(np.isinf(G.gelman_rubin()))
+    G.sample(20, 30)
+    P.sample(20, 30)
+    assert G.chain_length() == P.chain_length() == 30
+    st = G.get_state(0)
+    G.burn_stats()
+    P.burn_stats()
+    assert G.chain_length() == 0 and np.isinf(G.max_gelman_rubin())
+    assert np.array_equal(G.get_state(0), st)
+    assert np.all(G.posterior_means("X") == 0)
+    G.sample(100, 30)
+    P.sample(100, 30)
+    assert G.chain_length() == P.chain_length()
+    for c in range(pb.n_graphs):
+        _assert_state_equal(pb, P, G.get_state(c), P.get_state(c))
+
+
+def test_single_chain_and_two_chains():
+    for M in (1, 2):
+        pb, _ = make_problem(NX=10, NY=50, seed=19, n_graphs=M)
+        P, G = _run_trajectory(pb, KERNEL_FAST, 15, injected=False, chunks=(15,))
+        assert rel_err(G.max_gelman_rubin(), P.max_gelman_rubin()) < 1e-9
+        assert np.abs(G.posterior_means("X") - P.posterior_means("X")).max() < 1e-12
+        assert np.abs(G.posterior_sdevs("X") - P.posterior_sdevs("X")).max() < 1e-12
+
+
+def test_batched_contrasts_match_single_models():
+    """n_datasets > 1 (BASELINE config C4): dataset d of a batched model is the same chain as a
+    single-dataset model built on evidence d with the same global chain ids."""
+    from gbnet_b200 import synth
+    pb, net = make_problem(NX=15, NY=100, AvgNTF=3.0, seed=41, n_graphs=2)
+    ev = [pb.evid_val] + [synth.redraw_evidence(net, seed=100 + i)[0] for i in range(2)]
+    G = sampler_from_problem(pb, evid_val=np.stack(ev))
+    assert G.n_chains() == 6 and G.n_datasets() == 3
+    G.sample_n(12)
+    # dataset 0 uses global chain ids 0,1 exactly like a single model
+    P = oracle.PortModel(pb)
+    P.sample_n(12)
+    for c in range(2):
+        _assert_state_equal(pb, P, G.get_state(c), P.get_state(c))
+    assert rel_err(G.gelman_rubin(0), P.gelman_rubin()).max() < 1e-9
+    # datasets 1, 2: conditionals of their current state against an oracle holding that evidence
+    for d in (1, 2):
+        pbd, _ = make_problem(NX=15, NY=100, AvgNTF=3.0, seed=41, n_graphs=2)
+        pbd.evid_val = ev[d]
+        Pd = oracle.PortModel(pbd)
+        c = d * 2 + 1
+        Pd.set_state(1, G.get_state(c))
+        a, b = G.all_conditionals(c), Pd.all_conditionals(1)
+        m = ~np.isnan(b)
+        assert rel_err(a[m], b[m]).max() < LL_RTOL
+    # replacing the evidence re-initialises like a fresh construction
+    G.set_evidence(pb.evid_trg, np.stack(ev))
+    G2 = sampler_from_problem(pb, evid_val=np.stack(ev))
+    G.sample_n(5)
+    G2.sample_n(5)
+    for c in range(6):
+        assert np.array_equal(G.get_state(c), G2.get_state(c))
+
+
+def test_chain_sharding_is_transparent():
+    """A model holding chains [2, 4) of 4 draws the same chains as the full model's chains 2, 3."""
+    pb, _ = make_problem(NX=12, NY=60, seed=43, n_graphs=4)
+    full = sampler_from_problem(pb)
+    part = sampler_from_problem(pb, chain_offset=2, n_graphs_local=2)
+    full.sample_n(10)
+    part.sample_n(10)
+    for c in range(2):
+        assert np.array_equal(part.get_state(c), full.get_state(2 + c))
+
+
+def test_errors():
+    pb, _ = make_problem(NX=8, NY=30, seed=23)
+    bad = pb.mor.copy()
+    bad[0] = 2
+    with pytest.raises(gbnet_b200.GbnError) as ei:
+        sampler_from_problem(pb, mor=bad)
+    assert "MOR values" in str(ei.value)
+    with pytest.raises(gbnet_b200.GbnError):
+        sampler_from_problem(pb, evid_trg=np.zeros(0, np.uint32), evid_val=np.zeros(0, np.int32))
+    G = sampler_from_problem(pb)
+    with pytest.raises(gbnet_b200.GbnError):
+        G.get_state(99)
+    with pytest.raises(gbnet_b200.GbnError):
+        G.gelman_rubin(5)
+
+
+@pytest.mark.parametrize("shape", ["C2", "C3"])
+def test_full_size_properties(shape):
+    """At BASELINE's full network sizes the oracle is too slow to follow for long, so: the fast
+    kernel against the strict kernel (same chain, bit for bit) for a few sweeps, the oracle for
+    one sweep on one chain, and counting invariants."""
+    from gbnet_b200 import synth
+    net = synth.shape(shape)
+    hy = synth.cli_default_hyper()
+    M = 4
+    pb = oracle.Problem(src=net.src, trg=net.trg, mor=net.mor, evid_trg=net.evid_trg, evid_val=net.evid_val,
+                        n_graphs=M, **hy)
+    F = sampler_from_problem(pb, kernel=KERNEL_FAST)
+    S = sampler_from_problem(pb, kernel=KERNEL_STRICT)
+    n = 6 if shape == "C2" else 3
+    F.sample_n(n)
+    S.sample_n(n)
+    for c in range(M):
+        a, b = F.get_state(c), S.get_state(c)
+        nX = F.n_tf()
+        assert np.array_equal(a[:nX], b[:nX]) and np.array_equal(a[2 * nX:], b[2 * nX:])
+        assert np.abs(a[nX:2 * nX] - b[nX:2 * nX]).max() < 1e-9
+    mean, var = F.node_moments(0)
+    nX, E = F.n_tf(), F.n_edges()
+    assert np.allclose(mean[:2 * nX].reshape(nX, 2).sum(1), 1.0, atol=1e-12)
+    assert np.allclose(mean[3 * nX:].reshape(E, 3).sum(1), 1.0, atol=1e-12)
+    # the oracle follows the same chains from the same initial state
+    P = oracle.PortModel(pb)
+    P.sample_n(n)
+    for c in range(M):
+        _assert_state_equal(pb, P, F.get_state(c), P.get_state(c), f"{shape} chain {c}")
+    assert rel_err(F.target_likelihoods(0), P.target_likelihoods(0)).max() < LL_RTOL
+    assert rel_err(F.joint_logprob(0), P.joint_logprob(0)) < 1e-11     # T differs by accumulated ulps
+    if shape == "C2":
+        P.set_state(0, F.get_state(0))
+        a, b = F.all_conditionals(0), P.all_conditionals(0)
+        m = ~np.isnan(b)
+        assert rel_err(a[m], b[m]).max() < LL_RTOL
+    assert F.launch_count() > 0 and F.last_device_ms() > 0
