@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the OR-NOR Gibbs hot path: edge-updates/sec on the STRING-scale network.
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one rank per GPU)
+  python bench.py --impl reference --steps K --warmup W    the reference's own C++ on the host cores
+
+Workload (BASELINE.json configs[2]): synthetic network following
+gbnet.tools.genData's law, 1,500 TFs / 20,000 targets / ~300,000 signed edges, CLI-default
+hyper-parameters, 256 chains per GPU (weak scaling: N GPUs run 256 N chains of ONE model, chains
+sharded over ranks, Gelman-Rubin moments all-reduced with NCCL).  One step = what one iteration of
+ModelBase::sample does (ModelBase.cpp:119-124): a batch of dN = 30 full sweeps X -> T -> S of every
+chain, followed by the max Gelman-Rubin evaluation.
+
+Printed JSON (one line, rank 0): see the task contract; `value` is device-timed (CUDA events on the
+model's stream, max over ranks) with everything resident in HBM; `e2e` goes through the public API
+with host buffers: per step new evidence from host memory -> chains re-initialised -> dN sweeps ->
+max R-hat and posterior X means read back to the host.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "edge-updates/sec (all chains, device-timed)"
+UNIT = "edge-updates/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--shape", default="C3", choices=["C1", "C2", "C3"])
+    ap.add_argument("--chains", type=int, default=256, help="chains per GPU")
+    ap.add_argument("--sweeps-per-step", type=int, default=30)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sweeps-per-step", type=int, default=1)
+    return ap.parse_args()
+
+
+def workload(shape):
+    from gbnet_b200 import synth
+    net = synth.shape(shape)
+    hy = synth.cli_default_hyper()
+    return net, hy
+
+
+def config_dict(args, net, world, chains_per_gpu):
+    r = net.realised()
+    return {"workload": f"{args.shape}: synthetic genData-law network {r['n_tf']} TFs / {r['n_trg']} targets / "
+                        f"{r['n_edge']} edges, {chains_per_gpu} chains per GPU, CLI-default hyper-parameters",
+            "n_tf": r["n_tf"], "n_targets": r["n_trg"], "n_edges": r["n_edge"],
+            "chains_per_gpu": chains_per_gpu, "chains_total": chains_per_gpu * world,
+            "sweeps_per_step": args.sweeps_per_step, "step": "dN sweeps of every chain + max Gelman-Rubin",
+            "parallelism": f"chains sharded over {world} GPU(s); NCCL all-reduce of R-hat moments",
+            "l2": "per-chain state + counters are larger than L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        if self.thread:
+            self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+def time_cpu(net, hy, n_graphs, sweeps, warm_sweeps, prefer_ref=True):
+    """edge-updates/s of the CPU sampler (the compiled reference when oracle/_ref exists, else
+    the C port) with one chain per host thread; construction is not timed."""
+    import oracle
+    cores = os.cpu_count() or 1
+    pb = oracle.Problem(src=net.src, trg=net.trg, mor=net.mor, evid_trg=net.evid_trg, evid_val=net.evid_val,
+                        n_graphs=n_graphs, **hy)
+    kind = "reference" if (prefer_ref and oracle.have_ref()) else "port"
+    M = oracle.RefModel(pb) if kind == "reference" else oracle.PortModel(pb)
+    M._f("omp_set_threads")(min(cores, n_graphs))
+    if warm_sweeps:
+        M.sample_n(warm_sweeps)
+    times = [M.time_sample_n(s) for s in sweeps]
+    M.close()
+    return kind, min(cores, n_graphs), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    net, hy = workload(args.shape)
+    cores = os.cpu_count() or 1
+    n_graphs = min(args.chains, cores)
+    s = args.ref_sweeps_per_step
+    kind, used, times = time_cpu(net, hy, n_graphs, [s] * args.steps, args.warmup * s)
+    total = sum(times)
+    value = n_graphs * s * args.steps * net.n_edges / total
+    cfg = config_dict(args, net, 1, args.chains)
+    cfg["sweeps_per_step"] = s
+    sample = (f"{n_graphs} of the workload's {args.chains} chains (one per host thread), {s} sweep(s) per step, "
+              f"ModelBase::sample_n timed with omp_get_wtime, construction excluded")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import gbnet_b200
+    from gbnet_b200 import synth
+    if gbnet_b200.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device (gbnet_b200 has no CPU path)")
+    net, hy = workload(args.shape)
+    E = net.n_edges
+    C = args.chains
+    dN = args.sweeps_per_step
+
+    G = gbnet_b200.Sampler(net.src, net.trg, net.mor, net.evid_trg, net.evid_val, n_graphs=C * world,
+                           chain_offset=rank * C, n_graphs_local=C, seed=2026, device=local_rank, **hy)
+    assert G.kernel() == gbnet_b200.KERNEL_FAST
+    if world > 1:
+        import torch
+        uid = [gbnet_b200.Sampler.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        G.attach_comm(rank, world, uid[0])
+
+    def barrier():
+        if world > 1:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+        G.synchronize()
+
+    def step():
+        G.sample_n(dN)
+        return G.max_gelman_rubin()
+
+    for _ in range(args.warmup):
+        step()
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    G.set_phase_timing(True)
+    launches0 = G.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    G.timer_start()
+    gr = None
+    for _ in range(args.steps):
+        gr = step()
+    dev_ms = G.timer_stop()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    launches = G.launch_count() - launches0
+    phase_ms, phase_sweeps = G.phase_ms()
+    G.set_phase_timing(False)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end to end through the public API with host buffers
+    evs = [synth.redraw_evidence(net, num_active_tfs=12, seed=500 + i)[0] for i in range(args.e2e_steps + 1)]
+    G.set_evidence(net.evid_trg, evs[-1])          # warm the path once
+    G.sample_n(dN)
+    barrier()
+    t1 = time.perf_counter()
+    post = None
+    for i in range(args.e2e_steps):
+        G.set_evidence(net.evid_trg, evs[i])       # host -> device: evidence; chains re-initialised
+        G.sample_n(dN)
+        gr_e2e = G.max_gelman_rubin()              # device -> host
+        post = G.posterior_means("X")              # device -> host
+    barrier()
+    e2e_s = time.perf_counter() - t1
+    h2d = int(net.evid_trg.nbytes + evs[0].nbytes)
+    d2h = int(post.nbytes + 8)
+
+    if world > 1:
+        import torch
+        t = torch.tensor([dev_ms, wall_ms, e2e_s, float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, e2e_s = float(t[0]), float(t[1]), float(t[2])
+        tl = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        launches = int(tl[0])
+
+    if rank == 0:
+        total_updates = world * C * dN * args.steps * E
+        value = total_updates / (dev_ms * 1e-3)
+        e2e_value = world * C * dN * args.e2e_steps * E / e2e_s
+
+        # roofline of the dominant kernel (algorithmic bytes: DESIGN.md §5)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        names = ["k_fast_x", "k_fast_t", "k_fast_s"]
+        # algorithmic bytes per edge-update of each kernel for C chains sharing one network:
+        #   X: by-TF target id 4 B + mor/sign 0.25 B shared by the chains, X/T terms amortised over the out-degree
+        #   T: folded into X's 0.2 B
+        #   S: S state 2 x 0.25 B + two u32 counters read+write 16 B, by-target parent id 4 B + prior row 0.25 B shared
+        per_unit = [0.2 + 8.25 / C, 0.0, 16.5 + 8.25 / C]
+        dom = int(np.argmax(phase_ms))
+        avg_ms = phase_ms[dom] / max(phase_sweeps, 1)
+        bytes_per_launch = per_unit[dom] * C * E
+        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(names[dom])
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+                    "kernel_ms_per_sweep": {n: phase_ms[i] / max(phase_sweeps, 1) for i, n in enumerate(names)},
+                    "kernel_share_of_step": {n: phase_ms[i] / dev_ms for i, n in enumerate(names)}}
+
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(args, net, world, C),
+                "wall_ms_per_step": wall_ms / args.steps, "max_gelman_rubin": gr,
+                "clocks": clk,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": args.e2e_steps,
+                        "what": "set_evidence(host arrays) + sample_n(dN) + max R-hat + posterior X means to host"},
+                "gpu_launches": launches,
+                "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_graphs = min(C, cores)
+            kind, used, times = time_cpu(net, hy, n_graphs, [1, 1, 1], 1)
+            line["cpu_baseline"] = {
+                "value": n_graphs * 3 * E / sum(times), "unit": UNIT, "cores": used, "kind": kind,
+                "sample": f"{n_graphs} of {C} chains (one per host thread), 3 sweeps after 1 warm-up sweep, "
+                          "ModelBase::sample_n timed with omp_get_wtime, construction excluded"}
+        print(json.dumps(line), flush=True)
+    G.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -90,8 +90,12 @@ SYMBOLS = {
     "gbn_model_node_moments": (C.c_int, [_vp, _u32, _P(_dbl), _P(_dbl)]),
     "gbn_philox_kat": (C.c_int, [C.c_int, _P(_u32), _P(_u32), _P(_u32)]),
     "gbn_model_last_device_ms": (C.c_int, [_vp, _P(_dbl)]),
+    "gbn_model_set_phase_timing": (C.c_int, [_vp, C.c_int]),
+    "gbn_model_phase_ms": (C.c_int, [_vp, _P(_dbl), _P(_u64)]),
     "gbn_model_launch_count": (C.c_int, [_vp, _P(_u64)]),
     "gbn_model_sweep_count": (C.c_int, [_vp, _P(_u64)]),
+    "gbn_model_timer_start": (C.c_int, [_vp]),
+    "gbn_model_timer_stop": (C.c_int, [_vp, _P(_dbl)]),
     "gbn_model_synchronize": (C.c_int, [_vp]),
 }
 

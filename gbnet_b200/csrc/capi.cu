@@ -98,17 +98,23 @@ struct gbn_model {
     DevChains ch{};
     std::vector<void *> owned;          // every cudaMalloc of this model
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
     uint64_t sweeps_total = 0;          // Philox counter word 1
     uint32_t stat_n = 0;                // sweeps since burn_stats = RVNode::chain_length
     uint64_t launches = 0;
     double last_ms = 0.;
     // device buffers
-    uint8_t *d_y = nullptr; double *d_yprob = nullptr;
+    uint8_t *d_y = nullptr; double *d_yprob = nullptr, *d_stab = nullptr;
     double *d_inj_flat = nullptr, *d_inj_beta = nullptr, *d_inj_exp = nullptr;
     double *d_sums = nullptr, *d_psums = nullptr, *d_dev = nullptr, *d_pdev = nullptr, *d_gr = nullptr, *d_max = nullptr;
     double *d_scratch = nullptr; size_t scratch_bytes = 0;
     bool moments_valid = false;
+    // per-kernel timing (gbn_model_set_phase_timing)
+    bool phase_timing = false;
+    std::vector<cudaEvent_t> phase_ev;
+    uint32_t phase_pending = 0;         // sweeps whose events are recorded but not yet read
+    double phase_ms[3] = { 0., 0., 0. };
+    uint64_t phase_launches = 0;        // sweeps accumulated in phase_ms
     // comm
     void *comm = nullptr; int rank = 0, world = 1;
     // evidence kept for re-initialisation
@@ -145,31 +151,21 @@ double host_keyed_u(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t node
 }
 
 // initial chain state (GraphORNOR.cpp:57-73, 223-224, 246): X drawn from its prior by the
-// Multinomial ctor (Multinomial.cpp:42-49), T at the prior mean, S at mor + 1; statistics zeroed
+// Multinomial ctor (Multinomial.cpp:42-49: inside the base-class ctor the blanket is prob[v]),
+// T at the prior mean, S at mor + 1.  The two cumulative likelihoods exp(log(prob[v])) are evaluated
+// here with the host libm so that the initial state is the oracle's bit for bit; the draw itself
+// (keyed Philox, kind INIT) happens on the device.
 int init_chains(gbn_model *m)
 {
-    const Topology &tp = m->tp;
-    const uint32_t nX = tp.nX, E = tp.E, C = m->n_chains;
-    std::vector<uint8_t> X((size_t) C * nX), S((size_t) C * E);
-    std::vector<double> T((size_t) C * nX);
     const double xprob[2][2] = { { 0.99, 0.01 }, { 0.10, 0.90 } };
-    for (uint32_t c = 0; c < C; c++) {
-        const uint32_t gchain = chain_global_id(m->net, c);
-        for (uint32_t k = 0; k < nX; k++) {
-            const double *prob = xprob[tp.x_prior_active[k]];
-            double c0 = std::exp(std::log(prob[0]));
-            double c1 = c0 + std::exp(std::log(prob[1]));
-            double u = host_keyed_u(m->p.seed, gchain, 0, k, KIND_INIT);
-            double dice = 0. * (1 - u) + c1 * u;
-            X[(size_t) c * nX + k] = dice < c0 ? 0 : 1;
-            T[(size_t) c * nX + k] = tp.t_mean[k];
-        }
-        std::memcpy(&S[(size_t) c * E], tp.mor_idx.data(), E);
+    double cum[2][2];
+    for (int a = 0; a < 2; a++) {
+        cum[a][0] = std::exp(std::log(xprob[a][0]));
+        cum[a][1] = cum[a][0] + std::exp(std::log(xprob[a][1]));
     }
-    CUDA_TRY(cudaMemcpyAsync(m->ch.X, X.data(), X.size(), cudaMemcpyHostToDevice, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(m->ch.T, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(m->ch.S, S.data(), S.size(), cudaMemcpyHostToDevice, m->stream));
-    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    launch_init_chains(m->net, m->ch, cum, m->stream);
+    m->launches += 1;
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -179,8 +175,7 @@ int zero_stats(gbn_model *m)
     CUDA_TRY(cudaMemsetAsync(m->ch.cX1, 0, sizeof(uint32_t) * C * nX, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->ch.tMean, 0, sizeof(double) * C * nX, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->ch.tM2, 0, sizeof(double) * C * nX, m->stream));
-    CUDA_TRY(cudaMemsetAsync(m->ch.cS0, 0, sizeof(uint32_t) * C * E, m->stream));
-    CUDA_TRY(cudaMemsetAsync(m->ch.cS2, 0, sizeof(uint32_t) * C * E, m->stream));
+    CUDA_TRY(cudaMemsetAsync(m->ch.cS, 0, sizeof(uint2) * C * E, m->stream));
     m->stat_n = 0;
     m->moments_valid = false;
     return 0;
@@ -210,6 +205,27 @@ int upload_evidence(gbn_model *m, const gbn_evidence *ev)
                              &m->h_y[(size_t) d * tp.nH], &m->h_yprob[(size_t) d * 3]);
     } catch (const std::exception &ex) {
         return fail(GBN_ERR_INVALID, ex.what());
+    }
+    {
+        // tables of the fast S phase (sweep_fast.cu): per dataset, over n = number of parents with S != 1
+        const uint32_t D = m->net.stab_D;
+        const double ynoise[3][3] = { { 0.945, 0.050, 0.005 }, { 0.050, 0.900, 0.050 }, { 0.005, 0.050, 0.945 } };
+        std::vector<double> tab((size_t) m->n_datasets * 7 * D);
+        for (uint32_t d = 0; d < m->n_datasets; d++) {
+            double *t = &tab[(size_t) d * 7 * D];
+            const double *yp = &m->h_yprob[(size_t) d * 3];
+            for (int cls = 0; cls < 2; cls++) {
+                double z = cls ? m->net.z_n : m->net.z_y, v = 1.;
+                for (uint32_t n = 0; n < D; n++) { t[(5 + cls) * D + n] = v; t[(3 + cls) * D + n] = 1. - v; v *= (1. - z); }
+            }
+            for (int y = 0; y < 3; y++) {
+                const int cls = (y != 1) ? 0 : 1;
+                const double K = yp[0] * ynoise[0][y] + yp[1] * ynoise[1][y] + yp[2] * ynoise[2][y];
+                for (uint32_t n = 0; n < D; n++)
+                    t[y * D + n] = t[(3 + cls) * D + n] * ynoise[0][y] + t[(5 + cls) * D + n] * K;
+            }
+        }
+        CUDA_TRY(cudaMemcpy(m->d_stab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemcpy(m->d_y, m->h_y.data(), m->h_y.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(m->d_yprob, m->h_yprob.data(), sizeof(double) * m->h_yprob.size(), cudaMemcpyHostToDevice));
@@ -286,9 +302,19 @@ int sample_n(gbn_model *m, uint32_t n)
     const char *err = nullptr;
     CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
     int launched;
-    if (m->kernel == GBN_KERNEL_FAST)
-        launched = launch_sweep_fast(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err);
-    else
+    if (m->kernel == GBN_KERNEL_FAST) {
+        cudaEvent_t *pev = nullptr;
+        if (m->phase_timing) {
+            while (m->phase_ev.size() < (size_t) 3 * n + 1) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreate(&e));
+                m->phase_ev.push_back(e);
+            }
+            pev = m->phase_ev.data();
+            m->phase_pending = n;
+        }
+        launched = launch_sweep_fast(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err, pev);
+    } else
         launched = launch_sweep_strict(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err);
     if (launched < 0) return fail(GBN_ERR_CUDA, std::string("sweep launch: ") + err);
     CUDA_TRY(cudaEventRecord(m->ev1, m->stream));
@@ -327,6 +353,9 @@ extern "C" void gbn_model_destroy(gbn_model *m)
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
     for (void *p : m->owned) if (p) cudaFree(p);
+    for (cudaEvent_t e : m->phase_ev) cudaEventDestroy(e);
+    if (m->tev0) cudaEventDestroy(m->tev0);
+    if (m->tev1) cudaEventDestroy(m->tev1);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -378,6 +407,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     // ---- network
     DevNet &n = m->net;
     n.nX = tp.nX; n.nH = tp.nH; n.E = tp.E; n.Eu = tp.Eu; n.max_indeg = tp.max_indeg; n.max_outdeg = tp.max_outdeg;
+    n.n_tiles = (uint32_t) tp.tile_trg0.size() - 1; n.tile_slots = tp.tile_slots;
     {
         uint32_t *u32 = nullptr; uint8_t *u8 = nullptr; double *f64 = nullptr;
 #define UP(field, vec, tmp) { if (int rc = dev_upload(m, &tmp, vec)) return bail(rc); n.field = tmp; }
@@ -385,6 +415,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         UP(slot_of_edge, tp.slot_of_edge, u32) UP(slot_trg, tp.slot_trg, u32) UP(mor_idx, tp.mor_idx, u8)
         UP(tf_ptr, tp.tf_ptr, u32) UP(tf_child, tp.tf_child, u32) UP(tf_slot, tp.tf_slot, u32)
         UP(tfpos_of_slot, tp.tfpos_of_slot, u32) UP(trg_order, tp.trg_order, u32)
+        UP(tile_trg0, tp.tile_trg0, u32) UP(par_pack, tp.par_pack, u32)
         UP(x_prior_active, tp.x_prior_active, u8)
         UP(t_a, tp.t_a, f64) UP(t_b, tp.t_b, f64) UP(t_mean, tp.t_mean, f64) UP(t_lnB, tp.t_lnB, f64)
 #undef UP
@@ -413,7 +444,9 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     }
     if (int rc = dev_alloc(m, &m->d_y, (size_t) m->n_datasets * tp.nH)) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_yprob, (size_t) m->n_datasets * 3)) return bail(rc);
-    n.y = m->d_y; n.yprob = m->d_yprob;
+    n.stab_D = (tp.max_indeg + 2 + 1) & ~1u;     // even: the arrays behind the tables stay 16-byte aligned in shared memory
+    if (int rc = dev_alloc(m, &m->d_stab, (size_t) m->n_datasets * 7 * n.stab_D)) return bail(rc);
+    n.y = m->d_y; n.yprob = m->d_yprob; n.stab = m->d_stab;
     if (int rc = upload_evidence(m, ev)) return bail(rc);
 
     // ---- kernel choice
@@ -435,13 +468,12 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     if (int rc = dev_alloc(m, &ch.cX1, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.tMean, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.tM2, C * nX)) return bail(rc);
-    if (int rc = dev_alloc(m, &ch.cS0, C * E)) return bail(rc);
-    if (int rc = dev_alloc(m, &ch.cS2, C * E)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.cS, C * E)) return bail(rc);
     if (m->kernel == GBN_KERNEL_FAST) {
-        if (int rc = dev_alloc(m, &ch.tcache, C * nH)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.tc2, C * nH)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.ny, C * nH)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.Stf, C * E)) return bail(rc);
-        if (int rc = dev_alloc(m, &ch.FX, C * nX)) return bail(rc);
-        if (int rc = dev_alloc(m, &ch.FXinv, C * nX)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.FXp, C * nX)) return bail(rc);
     }
     const size_t ns = (size_t) m->n_datasets * n_stats_of(n);
     if (int rc = dev_alloc(m, &m->d_sums, 2 * ns)) return bail(rc);
@@ -486,6 +518,20 @@ extern "C" int gbn_model_trg_ids(const gbn_model *m, uint32_t *out)
     return 0;
 }
 
+// after a stream synchronize: fold the recorded per-kernel events into phase_ms
+static int collect_phase_times(gbn_model *m)
+{
+    for (uint32_t sw = 0; sw < m->phase_pending; sw++)
+        for (int ph = 0; ph < 3; ph++) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, m->phase_ev[3 * sw + ph], m->phase_ev[3 * sw + ph + 1]));
+            m->phase_ms[ph] += ms;
+        }
+    m->phase_launches += m->phase_pending;
+    m->phase_pending = 0;
+    return 0;
+}
+
 extern "C" int gbn_model_sample_n(gbn_model *m, uint32_t n)
 {
     if (!m) return fail(GBN_ERR_INVALID, "null model");
@@ -495,6 +541,24 @@ extern "C" int gbn_model_sample_n(gbn_model *m, uint32_t n)
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
     m->last_ms = ms;
+    return collect_phase_times(m);
+}
+
+extern "C" int gbn_model_set_phase_timing(gbn_model *m, int on)
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    m->phase_timing = on != 0;
+    m->phase_ms[0] = m->phase_ms[1] = m->phase_ms[2] = 0.;
+    m->phase_launches = 0;
+    m->phase_pending = 0;
+    return 0;
+}
+
+extern "C" int gbn_model_phase_ms(const gbn_model *m, double ms_out[3], uint64_t *sweeps)
+{
+    if (!m || !ms_out || !sweeps) return fail(GBN_ERR_INVALID, "null argument");
+    for (int i = 0; i < 3; i++) ms_out[i] = m->phase_ms[i];
+    *sweeps = m->phase_launches;
     return 0;
 }
 
@@ -513,6 +577,7 @@ extern "C" int gbn_model_sample(gbn_model *m, uint32_t N, uint32_t dN)
         float ms = 0.f;
         CUDA_TRY(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
         total_ms += ms;
+        if (int rc = collect_phase_times(m)) return rc;
         dN = std::min(dN, N - n);
         n += dN;
         if (int rc = max_gelman_rubin(m, &gr)) return rc;
@@ -828,6 +893,29 @@ extern "C" int gbn_model_sweep_count(const gbn_model *m, uint64_t *n)
 {
     if (!m || !n) return fail(GBN_ERR_INVALID, "null argument");
     *n = m->sweeps_total;
+    return 0;
+}
+
+// device time between two points of the caller's choosing, on the model's stream
+extern "C" int gbn_model_timer_start(gbn_model *m)
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (int rc = use_device(m)) return rc;
+    if (!m->tev0) { CUDA_TRY(cudaEventCreate(&m->tev0)); CUDA_TRY(cudaEventCreate(&m->tev1)); }
+    CUDA_TRY(cudaEventRecord(m->tev0, m->stream));
+    return 0;
+}
+
+extern "C" int gbn_model_timer_stop(gbn_model *m, double *ms)
+{
+    if (!m || !ms) return fail(GBN_ERR_INVALID, "null argument");
+    if (!m->tev0) return fail(GBN_ERR_INVALID, "timer not started");
+    if (int rc = use_device(m)) return rc;
+    CUDA_TRY(cudaEventRecord(m->tev1, m->stream));
+    CUDA_TRY(cudaEventSynchronize(m->tev1));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, m->tev0, m->tev1));
+    *ms = f;
     return 0;
 }
 

@@ -56,6 +56,18 @@ __device__ __forceinline__ double keyed_u(uint64_t seed, uint32_t chain, uint32_
     return unit_from_word(pick_word(r, node & 3));
 }
 
+// S nodes: the uniform of the j-th parent edge (append_parent order) of target i; four consecutive
+// edges of one target share one Philox block, so a thread walking a target's edges refreshes its
+// block every fourth step, in step with the other lanes of its warp
+__device__ __forceinline__ u32x4 keyed_s_block(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t target, uint32_t j)
+{
+    return philox4x32_10(target, sweep, chain, KIND_S | ((j >> 2) << 8), (uint32_t) seed, (uint32_t) (seed >> 32));
+}
+__device__ __forceinline__ double keyed_s(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t target, uint32_t j)
+{
+    return unit_from_word(pick_word(keyed_s_block(seed, chain, sweep, target, j), j & 3));
+}
+
 // sequential word stream private to one T update
 struct WordStream {
     uint32_t k0, k1, tf, sweep, chain, block, have;

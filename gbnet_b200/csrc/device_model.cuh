@@ -6,15 +6,16 @@
 //   per chain     X[c][nX] u8 | T[c][nX] f64 | S[c][E] u8 in SLOT order
 //   statistics    cX1[c][nX] u32  (#sweeps with X=1; X=0 is N - cX1)
 //                 tMean[c][nX], tM2[c][nX] f64 (Welford, gsl_rstat order of operations)
-//                 cS0[c][E], cS2[c][E] u32 in slot order (S=1 is N - cS0 - cS2)
-//   fast kernel   tcache[c][nH] {pr0, pr2, zc, L} f64x4 (32 B = one DRAM sector per target)
+//                 cS[c][E] u32x2 in slot order: #sweeps with S=0 and with S=2 (S=1 is N - both)
+//   fast kernel   tc2[c][nH] {pr0, pr2} f64x2 and ny[c][nH] u16 (n | y << 14): the per-target product cache
 //                 Stf[c][E] u8   copy of S in by-TF CSR order (coalesced reads in the X phase)
-//                 FX[c][nX], FXinv[c][nX] f64   1 - t*x and its reciprocal
+//                 FXp[c][nX] f64x2   1 - t*x and its reciprocal
 // Integer counts replace the reference's gsl_rstat workspaces of 0/1 indicators
 // (Multinomial.cpp:101-105): mean = c/N, variance = N/(N-1) p (1-p).
 #pragma once
 
 #include <cstdint>
+#include <cuda_runtime.h>
 
 namespace gbn {
 
@@ -31,11 +32,16 @@ struct DevNet {
     const uint32_t *tf_child;     // [Eu]
     const uint32_t *tf_slot;      // [Eu]
     const uint32_t *tfpos_of_slot;// [E]  slot -> position in the by-TF CSR (fast kernel; needs Eu == E)
-    const uint32_t *trg_order;    // [nH] targets sorted by in-degree, descending (fast S phase)
+    const uint32_t *tile_trg0;    // [n_tiles+1] fast S phase: tiles of consecutive targets
+    const uint32_t *trg_order;    // [nH] inside a tile, targets by descending in-degree
+    const uint32_t *par_pack;     // [E]  slot -> par_tf | (mor+1) << 30
+    uint32_t n_tiles, tile_slots;
     const uint8_t *x_prior_active;// [nX]
     const double *t_a, *t_b, *t_mean, *t_lnB;   // [nX]
     const uint8_t *y;             // [n_datasets][nH]
     const double *yprob;          // [n_datasets][3]
+    const double *stab;           // [n_datasets][7][stab_D] fast S phase tables over n: c0[y=0..2], omz[cls], zc[cls]
+    uint32_t stab_D;              // max_indeg + 2 rounded up to even
     const double *zctab;          // [2][max_indeg+2]  (1-z)^n by repeated multiplication; row 0 = ZY, row 1 = ZN
     double xprob[2][2];           // [prior_active][v]   GraphORNOR.h:40-41
     double sprob[3][3];           // [mor+1][v]          GraphORNOR.cpp:25
@@ -46,10 +52,6 @@ struct DevNet {
     uint64_t seed;
 };
 
-// one 32-byte DRAM sector per target: products over the parents with S = 0 / S = 2, (1-z)^n, and
-// the target's current likelihood HNode::get_own_likelihood
-struct __align__(32) TargetCache { double pr0, pr2, zc, L; };
-
 struct DevChains {
     uint32_t n_chains;            // local: n_datasets * n_graphs_local, dataset-major
     uint8_t *X;
@@ -57,11 +59,12 @@ struct DevChains {
     uint8_t *S;
     uint32_t *cX1;
     double *tMean, *tM2;
-    uint32_t *cS0, *cS2;
+    uint2 *cS;                    // {count S=0, count S=2}
     // fast kernel only
-    TargetCache *tcache;
+    double2 *tc2;                 // [c][nH] {pr0, pr2}: products over the parents with S = 0 / S = 2
+    uint16_t *ny;                 // [c][nH] n | y << 14, n = number of parents with S != 1
     uint8_t *Stf;
-    double *FX, *FXinv;
+    double2 *FXp;                 // {1 - t*x, 1 / (1 - t*x)}
     // injected draws (NULL = keyed Philox streams)
     const double *inj_flat;       // [chain][inj_sweeps][nX + E]  X then S in edge input order
     const double *inj_beta;       // [chain][inj_sweeps][nX]

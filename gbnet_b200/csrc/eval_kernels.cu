@@ -141,12 +141,36 @@ __global__ void k_export_draws(DevNet net, uint32_t gchain, uint32_t sweep0, uin
             exp_v[(size_t) i * net.nX + j] = draw_exp(net.seed, gchain, sw, j);
         } else {
             uint32_t e = j - net.nX;
-            flat_u[idx] = keyed_u(net.seed, gchain, sw, net.slot_of_edge[e], KIND_S);
+            const uint32_t q = net.slot_of_edge[e], i = net.slot_trg[q];
+            flat_u[idx] = keyed_s(net.seed, gchain, sw, i, q - net.trg_ptr[i]);
         }
     }
 }
 
+// Multinomial ctor draw for X (Multinomial.cpp:42-49), T = prior mean, S = mor + 1
+__global__ void k_init_chains(DevNet net, DevChains ch, double c00, double c01, double c10, double c11)
+{
+    const uint32_t c = blockIdx.y;
+    const uint32_t gchain = chain_global_id(net, c);
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < net.nX) {
+        const bool act = net.x_prior_active[j] != 0;
+        const double c0 = act ? c10 : c00, c1 = act ? c11 : c01;
+        const double u = keyed_u(net.seed, gchain, 0, j, KIND_INIT);
+        const double dice = 0. * (1 - u) + c1 * u;
+        ch.X[(size_t) c * net.nX + j] = dice < c0 ? 0 : 1;
+        ch.T[(size_t) c * net.nX + j] = net.t_mean[j];
+    }
+    if (j < net.E) ch.S[(size_t) c * net.E + j] = net.mor_idx[j];
+}
+
 }  // namespace
+
+void launch_init_chains(const DevNet &net, const DevChains &ch, const double cum[2][2], cudaStream_t st)
+{
+    uint32_t n = net.nX > net.E ? net.nX : net.E;
+    k_init_chains<<<dim3((n + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch, cum[0][0], cum[0][1], cum[1][0], cum[1][1]);
+}
 
 void launch_conditionals(const DevNet &net, const DevChains &ch, uint32_t c, double *out, cudaStream_t st)
 {

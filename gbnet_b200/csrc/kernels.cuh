@@ -16,6 +16,9 @@ void launch_philox_kat(const uint32_t ctr[4], const uint32_t key[2], uint32_t *o
 void launch_export_draws(const DevNet &net, uint32_t gchain, uint32_t sweep0, uint32_t n,
                          double *flat_u, double *beta_v, double *exp_v, cudaStream_t st);
 
+// initial state of every local chain; cum[a][v] = cumulative prior likelihood of X (host libm)
+void launch_init_chains(const DevNet &net, const DevChains &ch, const double cum[2][2], cudaStream_t st);
+
 // ---- sweep_strict.cu: n_sweeps full sweeps X -> T -> S of every local chain, one CTA per chain,
 // every likelihood recomputed from the state in the reference's operand order.
 // sweep0 = sweeps drawn since creation (Philox counter word), stat_n0 = sweeps since burn_stats.
@@ -25,8 +28,10 @@ int launch_sweep_strict(const DevNet &net, const DevChains &ch, uint32_t n_sweep
 size_t strict_smem_bytes(const DevNet &net);
 
 // ---- sweep_fast.cu: the throughput path (cached per-target products, speculative X windows)
+// phase_ev: NULL, or 3 * n_sweeps + 1 events recorded before the X, T, S kernels of every sweep and after the
+// last kernel (per-kernel device times for the roofline report)
 int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
-                      uint32_t stat_n0, cudaStream_t st, const char **err);
+                      uint32_t stat_n0, cudaStream_t st, const char **err, cudaEvent_t *phase_ev = nullptr);
 // rebuild Stf / FX / FXinv / tcache from X, T, S (after creation and set_state)
 int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
 bool fast_supported(const DevNet &net, const char **why);

@@ -62,8 +62,9 @@ __device__ __forceinline__ void node_moments(const DevNet &net, const DevChains 
         mean[0] = ch.tMean[(size_t) c * net.nX + r.idx];
         var[0] = N > 1. ? ch.tM2[(size_t) c * net.nX + r.idx] / (N - 1.) : 0.;
     } else {
-        double c0 = (double) ch.cS0[(size_t) c * net.E + r.idx];
-        double c2 = (double) ch.cS2[(size_t) c * net.E + r.idx];
+        const uint2 cs = ch.cS[(size_t) c * net.E + r.idx];
+        double c0 = (double) cs.x;
+        double c2 = (double) cs.y;
         count_moment(c0, N, mean[0], var[0]);
         count_moment(N - c0 - c2, N, mean[1], var[1]);
         count_moment(c2, N, mean[2], var[2]);

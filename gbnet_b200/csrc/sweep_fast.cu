@@ -36,7 +36,7 @@ namespace gbn {
 namespace {
 
 constexpr int FX_NT = 512;           // X kernel: 16 warps = 16-TF speculative window
-constexpr int FS_NT = 128;           // S kernel
+constexpr int FS_NT = 256;           // S kernel: one thread per target of a tile (= TILE_TARGETS)
 constexpr int FT_NT = 128;           // T kernel
 
 struct SweepArgs {
@@ -53,18 +53,31 @@ __device__ __forceinline__ void normalise(double &m, int &e)
     e += ex;
 }
 
-__device__ __forceinline__ TargetCache load_cache(const TargetCache *p)
+// the per-target likelihood from the cached products and the tables over n (see the S phase):
+//   L = c0[n] + omz[n] * pr0 * (a + pr2 * b)
+struct TargetConst { const double *c0t, *omzt; double ca, cb; };
+
+__device__ __forceinline__ TargetConst target_const(const DevNet &net, const double *sTab, uint32_t D, uint32_t y)
 {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    double2 a = q[0], b = q[1];
-    return TargetCache{ a.x, a.y, b.x, b.y };
+    const uint32_t cls = (y != 1) ? 0 : 1;                         // ZY for DE targets, ZN otherwise
+    return TargetConst{ sTab + y * D, sTab + (3 + cls) * D,
+                        net.ynoise[2][y] - net.ynoise[0][y], net.ynoise[1][y] - net.ynoise[2][y] };
 }
 
-__device__ __forceinline__ void store_cache(TargetCache *p, double pr0, double pr2, double zc, double L)
+// likelihood of a child of X_k now (Lc) and with X_k flipped (Lf): the flip multiplies the product
+// that holds the edge's factor by fac
+__device__ __forceinline__ void child_likelihoods(const DevNet &net, const double *sTab, uint32_t D, double2 pr, uint32_t ny,
+                                                  uint32_t s, double fac, double &Lc, double &Lf)
 {
-    double2 *q = reinterpret_cast<double2 *>(p);
-    q[0] = make_double2(pr0, pr2);
-    q[1] = make_double2(zc, L);
+    const uint32_t n = ny & 0x3fffu;
+    const TargetConst k = target_const(net, sTab, D, ny >> 14);
+    const double c0 = k.c0t[n], om = k.omzt[n];
+    const double w = pr.y * k.cb;
+    const double B = pr.x * (k.ca + w);
+    Lc = c0 + om * B;
+    const double f0 = c0 + om * (B * fac);                          // the edge feeds pr0
+    const double f2 = c0 + om * (pr.x * (k.ca + w * fac));          // the edge feeds pr2
+    Lf = s == 0 ? f0 : (s == 2 ? f2 : Lc);
 }
 
 // ---------------------------------------------------------------------------------- X phase
@@ -72,24 +85,26 @@ template <int NT>
 __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, SweepArgs a)
 {
     constexpr int NW = NT / 32;
-    extern __shared__ uint8_t sX[];              // [nX]
+    extern __shared__ __align__(16) unsigned char smem_x[];
     __shared__ int s_dec[NW];
+    const uint32_t nX = net.nX, E = net.E, nH = net.nH, D = net.stab_D;
+    double *sTab = reinterpret_cast<double *>(smem_x);       // [7][D]
+    uint8_t *sX = reinterpret_cast<uint8_t *>(sTab + 7 * D); // [nX]
 
     const uint32_t c = blockIdx.x;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nX = net.nX, E = net.E, nH = net.nH;
     const uint32_t d = chain_dataset(net, c);
     const uint32_t gchain = chain_global_id(net, c);
     uint8_t *gX = ch.X + (size_t) c * nX;
     const double *gT = ch.T + (size_t) c * nX;
     const uint8_t *gStf = ch.Stf + (size_t) c * E;
-    TargetCache *tcache = ch.tcache + (size_t) c * nH;
+    double2 *tc2 = ch.tc2 + (size_t) c * nH;
+    const uint16_t *gny = ch.ny + (size_t) c * nH;
     uint32_t *cX1 = ch.cX1 + (size_t) c * nX;
-    const uint8_t *gy = net.y + (size_t) d * nH;
-    const double yp[3] = { net.yprob[3 * d], net.yprob[3 * d + 1], net.yprob[3 * d + 2] };
     const double *inj_flat = a.use_inj ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + E) : nullptr;
 
     for (uint32_t k = tid; k < nX; k += NT) sX[k] = gX[k];
+    for (uint32_t j = tid; j < 7 * D; j += NT) sTab[j] = net.stab[(size_t) d * 7 * D + j];
     __syncthreads();
 
     uint32_t k0 = 0;
@@ -105,21 +120,19 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
             cbeg = net.tf_ptr[kw]; cend = net.tf_ptr[kw + 1];
             double mc = 1., mf = 1.;
             int ec = 0, ef = 0, cnt = 0;
-            for (uint32_t cc = cbeg + lane; cc < cend; cc += 32) {
-                const uint32_t i = net.tf_child[cc];
-                const uint32_t s = gStf[cc];
-                const TargetCache tc = load_cache(tcache + i);
-                double Lf = tc.L;
-                if (s != 1) {
-                    const uint32_t y = gy[i];
-                    const double col[3] = { net.ynoise[0][y], net.ynoise[1][y], net.ynoise[2][y] };
-                    const double pr0 = s == 0 ? tc.pr0 * fac : tc.pr0;
-                    const double pr2 = s == 2 ? tc.pr2 * fac : tc.pr2;
-                    Lf = lik_from_products(pr0, pr2, tc.zc, yp, col);
-                }
-                mc *= tc.L;
-                mf *= Lf;
-                if (++cnt == 16) { normalise(mc, ec); normalise(mf, ef); cnt = 0; }
+            // two children per lane and iteration: both cache entries are requested before either is used
+            for (uint32_t cc = cbeg + lane; cc < cend; cc += 64) {
+                const bool two = cc + 32 < cend;
+                const uint32_t ia = net.tf_child[cc], ib = two ? net.tf_child[cc + 32] : ia;
+                const uint32_t sa = __ldcs(gStf + cc), sb = two ? (uint32_t) __ldcs(gStf + cc + 32) : 1u;
+                const double2 pa = tc2[ia], pb = tc2[ib];
+                const uint32_t na = gny[ia], nb = gny[ib];
+                double Lca, Lfa, Lcb, Lfb;
+                child_likelihoods(net, sTab, D, pa, na, sa, fac, Lca, Lfa);
+                child_likelihoods(net, sTab, D, pb, nb, sb, fac, Lcb, Lfb);
+                mc *= Lca; mf *= Lfa;
+                if (two) { mc *= Lcb; mf *= Lfb; }
+                if (++cnt == 8) { normalise(mc, ec); normalise(mf, ef); cnt = 0; }
             }
             normalise(mc, ec);
             normalise(mf, ef);
@@ -150,17 +163,14 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
         if (warp < ncommit && kw < nX) {
             if (lane == 0) { sX[kw] = (uint8_t) (dec & 1); cX1[kw] += (uint32_t) (dec & 1); }
             if (dec & 2) {
-                // apply the flip of X_kw to the cache of each child that depends on it
+                // apply the flip of X_kw to the cached product of each child that depends on it
                 for (uint32_t cc = cbeg + lane; cc < cend; cc += 32) {
                     const uint32_t s = gStf[cc];
                     if (s == 1) continue;
                     const uint32_t i = net.tf_child[cc];
-                    const TargetCache tc = load_cache(tcache + i);
-                    const uint32_t y = gy[i];
-                    const double col[3] = { net.ynoise[0][y], net.ynoise[1][y], net.ynoise[2][y] };
-                    const double pr0 = s == 0 ? tc.pr0 * fac : tc.pr0;
-                    const double pr2 = s == 2 ? tc.pr2 * fac : tc.pr2;
-                    store_cache(tcache + i, pr0, pr2, tc.zc, lik_from_products(pr0, pr2, tc.zc, yp, col));
+                    double2 pr = tc2[i];
+                    if (s == 0) pr.x *= fac; else pr.y *= fac;
+                    tc2[i] = pr;
                 }
             }
         }
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
 
 // ---------------------------------------------------------------------------------- T phase
 // Beta::sample (Beta.cpp:60-104) for T nodes that do not listen to their children: the blanket is
-// the Beta prior alone.  Also publishes FX = 1 - t*x (HNodeORNOR.cpp:59) and its reciprocal for
+// the Beta prior alone.  Also publishes FXp = {1 - t*x, 1 / (1 - t*x)} (HNodeORNOR.cpp:59) for
 // the S phase.
 __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, SweepArgs a, int update_t)
 {
@@ -200,97 +210,149 @@ __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, Swee
         ch.tMean[o] = m; ch.tM2[o] = m2;
     }
     const double fx = 1. - t * (double) ch.X[o];
-    ch.FX[o] = fx;
-    ch.FXinv[o] = 1. / fx;
+    ch.FXp[o] = make_double2(fx, 1. / fx);
 }
 
 // ---------------------------------------------------------------------------------- S phase
-// mode 0: sweep (draw every S of the target, count, refresh the cache)
-// mode 1: refresh only (rebuild the cache from X, T, S; no draws, no counts)
-template <int MODE>
-__global__ void __launch_bounds__(FS_NT) k_fast_s(DevNet net, DevChains ch, SweepArgs a)
+// One CTA per (tile of consecutive targets, chain).  The tile's slots are one contiguous range:
+// S bytes and the packed parent ids are staged in shared memory with coalesced loads; warps then
+// take GROUPS of 32 targets (tile-local descending in-degree order, so the lanes of a warp finish
+// together and the longest groups start first) from a shared counter, each lane walking its
+// target's edges in input order out of shared memory; finally the new S values and the counters go
+// back with one coalesced pass over the tile's slots.
+//
+// Likelihood algebra.  With N_h = YNOISE[h][y], K = sum_h YPROB[h] N_h, zc = (1-z)^n, omz = 1 - zc
+// (HNodeORNOR.cpp:64,82,96 and HNode.cpp:40-46 expanded):
+//     L(pr0, pr2, n) = c0[n] + omz[n] * pr0 * (a + pr2 * b),
+//     c0[n] = omz[n] N_0 + zc[n] K,   a = N_2 - N_0,   b = N_1 - N_2.
+// c0 / omz / zc are per-dataset tables over n (net.stab, built on the host with zc by repeated
+// multiplication as in the reference).  The three candidates of one edge share R0, R2 (the products
+// without the edge) and differ only in which product takes the factor f and in n.
+// MODE 0: sweep (draw every S of the target, count, refresh the cache)
+// MODE 1: refresh only (rebuild the cache from X, T, S; no draws, no counts)
+template <int MODE, bool STAGE_FX>
+__global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, SweepArgs a)
 {
-    const uint32_t nX = net.nX, E = net.E, nH = net.nH;
-    const uint32_t c = blockIdx.y;
-    const uint32_t idx = blockIdx.x * FS_NT + threadIdx.x;
-    if (idx >= nH) return;
-    const uint32_t i = net.trg_order[idx];
-    const uint32_t d = chain_dataset(net, c);
-    const uint32_t gchain = chain_global_id(net, c);
-    uint8_t *gS = ch.S + (size_t) c * E;
-    uint8_t *gStf = ch.Stf + (size_t) c * E;
-    const double *FX = ch.FX + (size_t) c * nX;
-    const double *FXinv = ch.FXinv + (size_t) c * nX;
-    uint32_t *cS0 = ch.cS0 + (size_t) c * E;
-    uint32_t *cS2 = ch.cS2 + (size_t) c * E;
-    const double yp[3] = { net.yprob[3 * d], net.yprob[3 * d + 1], net.yprob[3 * d + 2] };
-    const uint32_t y = net.y[(size_t) d * nH + i];
-    const double col[3] = { net.ynoise[0][y], net.ynoise[1][y], net.ynoise[2][y] };
-    const uint32_t cls = (y != 1) ? 0 : 1;                     // ZY for DE targets, ZN otherwise
-    const double z = cls ? net.z_n : net.z_y;
-    const double rz = 1. / z;
-    const double *zct = net.zctab + (size_t) cls * (net.max_indeg + 2);
-    const uint32_t q0 = net.trg_ptr[i], q1 = net.trg_ptr[i + 1];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_next;
+    const uint32_t nX = net.nX, E = net.E, nH = net.nH, D = net.stab_D;
+    double *sTab = reinterpret_cast<double *>(smem_raw);                       // [7][D]
+    double2 *sFX = reinterpret_cast<double2 *>(sTab + 7 * D);                   // [nX] if staged
+    uint32_t *sPar = reinterpret_cast<uint32_t *>(sFX + (STAGE_FX ? nX : 0));  // [tile_slots]
+    uint8_t *sS = reinterpret_cast<uint8_t *>(sPar + net.tile_slots);           // [tile_slots]
 
-    // products over the parents in append_parent order (HNodeORNOR.cpp:55-62, 72-81)
-    double P0 = 1., P2 = 1.;
-    uint32_t n = 0;
-    for (uint32_t q = q0; q < q1; q++) {
-        const uint32_t s = gS[q];
-        if (s != 1) {
-            const double f = FX[net.par_tf[q]] * z;
-            n++;
-            if (s == 0) P0 *= f; else P2 *= f;
-        }
-    }
-    double Lfin = lik_from_products(P0, P2, zct[n], yp, col);
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t c = blockIdx.y;
+    const uint32_t d = chain_dataset(net, c);
+    const uint32_t t0 = net.tile_trg0[blockIdx.x], t1 = net.tile_trg0[blockIdx.x + 1];
+    const uint32_t qb = net.trg_ptr[t0], nslot = net.trg_ptr[t1] - qb;
+    uint8_t *gS = ch.S + (size_t) c * E + qb;
+    const double2 *gFX = ch.FXp + (size_t) c * nX;
+
+    if (tid == 0) s_next = 0;
     if (MODE == 0) {
-        const double *inj_flat = a.use_inj ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + E) + nX : nullptr;
-        uint32_t blk = 0xffffffffu;
-        u32x4 rnd = { 0, 0, 0, 0 };
-        for (uint32_t q = q0; q < q1; q++) {
-            const uint32_t kk = net.par_tf[q];
-            const uint32_t s = gS[q];
-            const double *sp = net.sprob[net.mor_idx[q]];
-            const double f = FX[kk] * z;
-            const double finv = FXinv[kk] * rz;
-            const double R0 = s == 0 ? P0 * finv : P0;          // products without this edge
-            const double R2 = s == 2 ? P2 * finv : P2;
-            const uint32_t nR = n - (s != 1);
-            const double zc0 = zct[nR], zc1 = zct[nR + 1];
-            double L[3];
-            L[0] = lik_from_products(R0 * f, R2, zc1, yp, col);
-            L[1] = lik_from_products(R0, R2, zc0, yp, col);
-            L[2] = lik_from_products(R0, R2 * f, zc1, yp, col);
-            // exp(log prior + log L) of Multinomial.cpp:66-75 as a product
-            double cum0 = 0. + sp[0] * L[0];
-            double cum1 = cum0 + sp[1] * L[1];
-            double cum2 = cum1 + sp[2] * L[2];
-            if (!(cum2 > 0.)) { cum0 = 0. + sp[0]; cum1 = cum0 + sp[1]; cum2 = cum1 + sp[2]; }
-            double u;
-            if (a.use_inj) u = inj_flat[net.par_edge[q]];
-            else {
-                if ((q >> 2) != blk) {
-                    blk = q >> 2;
-                    rnd = philox4x32_10(blk, a.sweep, gchain, KIND_S, (uint32_t) net.seed, (uint32_t) (net.seed >> 32));
+        // the tile's counters are only touched by the final pass: start pulling their lines into L2 now
+        const char *cs = reinterpret_cast<const char *>(ch.cS + (size_t) c * E + qb);
+        for (uint32_t off = tid * 128u; off < nslot * 8u; off += FS_NT * 128u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(cs + off));
+    }
+    for (uint32_t j = tid; j < nslot; j += FS_NT) { sS[j] = __ldcs(gS + j); sPar[j] = net.par_pack[qb + j]; }
+    for (uint32_t j = tid; j < 7 * D; j += FS_NT) sTab[j] = net.stab[(size_t) d * 7 * D + j];
+    if (STAGE_FX) for (uint32_t k = tid; k < nX; k += FS_NT) sFX[k] = gFX[k];
+    __syncthreads();
+
+    const uint32_t gchain = chain_global_id(net, c);
+    const uint32_t n_groups = (t1 - t0 + 31) / 32;
+    const double *inj_flat = (MODE == 0 && a.use_inj) ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + E) + nX : nullptr;
+    uint8_t *gStf = ch.Stf + (size_t) c * E;
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&s_next, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= n_groups) break;
+        const uint32_t ti = t0 + 32 * g + lane;
+        if (ti >= t1) continue;
+        const uint32_t i = net.trg_order[ti];
+        const uint32_t y = net.y[(size_t) d * nH + i];
+        const uint32_t cls = (y != 1) ? 0 : 1;                     // ZY for DE targets, ZN otherwise
+        const double z = cls ? net.z_n : net.z_y;
+        const double rz = 1. / z;
+        const double ca = net.ynoise[2][y] - net.ynoise[0][y];     // a
+        const double cb = net.ynoise[1][y] - net.ynoise[2][y];     // b
+        const double *c0t = sTab + y * D, *omzt = sTab + (3 + cls) * D;
+        const uint32_t q0 = net.trg_ptr[i], deg = net.trg_ptr[i + 1] - q0;
+        const uint32_t l0 = q0 - qb;                               // first local slot
+
+        // products over the parents in append_parent order (HNodeORNOR.cpp:55-62, 72-81)
+        double P0 = 1., P2 = 1.;
+        uint32_t n = 0;
+        for (uint32_t j = 0; j < deg; j++) {
+            const uint32_t s = sS[l0 + j];
+            const uint32_t kk = sPar[l0 + j] & 0x3fffffffu;
+            const double f = (STAGE_FX ? sFX[kk].x : gFX[kk].x) * z;
+            n += (s != 1);
+            P0 *= (s == 0) ? f : 1.;
+            P2 *= (s == 2) ? f : 1.;
+        }
+        if (MODE == 0) {
+            u32x4 rnd = { 0, 0, 0, 0 };
+            for (uint32_t j = 0; j < deg; j++) {
+                const uint32_t q = q0 + j;
+                const uint32_t pk = sPar[l0 + j];
+                const uint32_t kk = pk & 0x3fffffffu;
+                const uint32_t s = sS[l0 + j];
+                const double *sp = net.sprob[pk >> 30];
+                const double2 fx = STAGE_FX ? sFX[kk] : gFX[kk];
+                const double f = fx.x * z;
+                const double finv = fx.y * rz;
+                const double R0 = s == 0 ? P0 * finv : P0;          // products without this edge
+                const double R2 = s == 2 ? P2 * finv : P2;
+                const uint32_t nR = n - (s != 1);
+                const double w = R2 * cb;
+                const double B = R0 * (ca + w);
+                const double om1 = omzt[nR + 1], c01 = c0t[nR + 1];
+                const double L0 = c01 + om1 * (B * f);              // S = 0: the factor joins pr0
+                const double L1 = c0t[nR] + omzt[nR] * B;           // S = 1: edge off
+                const double L2 = c01 + om1 * (R0 * (ca + w * f));  // S = 2: the factor joins pr2
+                // exp(log prior + log L) of Multinomial.cpp:66-75 as a product
+                double cum0 = 0. + sp[0] * L0;
+                double cum1 = cum0 + sp[1] * L1;
+                double cum2 = cum1 + sp[2] * L2;
+                if (!(cum2 > 0.)) { cum0 = 0. + sp[0]; cum1 = cum0 + sp[1]; cum2 = cum1 + sp[2]; }
+                double u;
+                if (a.use_inj) u = inj_flat[net.par_edge[q]];
+                else {
+                    if ((j & 3) == 0) rnd = keyed_s_block(net.seed, gchain, a.sweep, i, j);
+                    u = unit_from_word(pick_word(rnd, j & 3));
                 }
-                u = unit_from_word(pick_word(rnd, q & 3));
+                const double dice = 0. * (1 - u) + cum2 * u;
+                const uint32_t ns = dice < cum0 ? 0u : (dice < cum1 ? 1u : (dice < cum2 ? 2u : s));
+                if (ns != s) {
+                    sS[l0 + j] = (uint8_t) ns;
+                    gStf[net.tfpos_of_slot[q]] = (uint8_t) ns;
+                    P0 = ns == 0 ? R0 * f : R0;
+                    P2 = ns == 2 ? R2 * f : R2;
+                    n = nR + (ns != 1);
+                }
             }
-            const double dice = 0. * (1 - u) + cum2 * u;
-            const uint32_t ns = dice < cum0 ? 0u : (dice < cum1 ? 1u : (dice < cum2 ? 2u : s));
-            if (ns != s) {
-                gS[q] = (uint8_t) ns;
-                gStf[net.tfpos_of_slot[q]] = (uint8_t) ns;
-                P0 = ns == 0 ? R0 * f : R0;
-                P2 = ns == 2 ? R2 * f : R2;
-                n = nR + (ns != 1);
-            }
-            cS0[q] += (ns == 0);
-            cS2[q] += (ns == 2);
-            Lfin = L[ns];
+        }
+        ch.tc2[(size_t) c * nH + i] = make_double2(P0, P2);
+        ch.ny[(size_t) c * nH + i] = (uint16_t) (n | (y << 14));
+    }
+    if (MODE == 0) {
+        __syncthreads();
+        // Multinomial.cpp:101-105 as counts: one coalesced pass over the tile's slots
+        uint2 *cS = ch.cS + (size_t) c * E + qb;
+#pragma unroll 8
+        for (uint32_t j = tid; j < nslot; j += FS_NT) {
+            const uint32_t v = sS[j];
+            __stcs(gS + j, (uint8_t) v);
+            uint2 cs = __ldcs(cS + j);                   // streamed: keep the product cache in L2 instead
+            cs.x += (v == 0);
+            cs.y += (v == 2);
+            __stcs(cS + j, cs);
         }
     }
-    store_cache(ch.tcache + (size_t) c * nH + i, P0, P2, zct[n], Lfin);
 }
 
 // Stf from S (refresh only)
@@ -304,18 +366,45 @@ __global__ void k_fast_stf(DevNet net, DevChains ch)
 
 }  // namespace
 
-bool fast_supported(const DevNet &net, const char **why)
-{
-    if (net.Eu != net.E) { *why = "duplicate (TF, target) edges"; return false; }
-    if (net.listen && !net.const_params) { *why = "T nodes listen to their children"; return false; }
-    if ((size_t) net.nX + 64 > 200 * 1024) { *why = "n_tf too large for the X window kernel"; return false; }
-    return true;
-}
-
 static int check(cudaError_t e, const char **err)
 {
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
     return 0;
+}
+
+// shared memory of the S kernel: FXp of the chain (when it fits), packed parents and S bytes of a tile
+static size_t s_smem_bytes(const DevNet &net, bool stage_fx)
+{
+    return sizeof(double) * 7 * (size_t) net.stab_D + (stage_fx ? sizeof(double2) * (size_t) net.nX : 0) + (size_t) net.tile_slots * 5 + 16;
+}
+
+static bool s_stage_fx(const DevNet &net) { return sizeof(double2) * (size_t) net.nX <= 32 * 1024; }
+
+bool fast_supported(const DevNet &net, const char **why)
+{
+    if (net.nX >= (1u << 30)) { *why = "n_tf does not fit the packed parent id"; return false; }
+    if (s_smem_bytes(net, s_stage_fx(net)) > 200 * 1024) { *why = "in-degree too large for the S tile"; return false; }
+    if (net.Eu != net.E) { *why = "duplicate (TF, target) edges"; return false; }
+    if (net.listen && !net.const_params) { *why = "T nodes listen to their children"; return false; }
+    if (sizeof(double) * 7 * (size_t) net.stab_D + net.nX + 64 > 200 * 1024) { *why = "n_tf too large for the X window kernel"; return false; }
+    if (net.max_indeg >= (1u << 14)) { *why = "in-degree does not fit the packed (n, y) word"; return false; }
+    return true;
+}
+
+template <int MODE, bool STAGE>
+static int launch_s_t(const DevNet &net, const DevChains &ch, const SweepArgs &a, cudaStream_t st, const char **err)
+{
+    const size_t smem = s_smem_bytes(net, STAGE);
+    if (check(cudaFuncSetAttribute(k_fast_s<MODE, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), err)) return -1;
+    k_fast_s<MODE, STAGE><<<dim3(net.n_tiles, ch.n_chains), FS_NT, smem, st>>>(net, ch, a);
+    return 0;
+}
+
+static int launch_s(const DevNet &net, const DevChains &ch, const SweepArgs &a, int mode, cudaStream_t st, const char **err)
+{
+    const bool stage = s_stage_fx(net);
+    if (mode == 0) return stage ? launch_s_t<0, true>(net, ch, a, st, err) : launch_s_t<0, false>(net, ch, a, st, err);
+    return stage ? launch_s_t<1, true>(net, ch, a, st, err) : launch_s_t<1, false>(net, ch, a, st, err);
 }
 
 int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err)
@@ -324,22 +413,18 @@ int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st,
     SweepArgs a{ 0, 0, 0, 0 };
     k_fast_stf<<<dim3((net.E + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
     k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, 0);
-    k_fast_s<1><<<dim3((net.nH + FS_NT - 1) / FS_NT, ch.n_chains), FS_NT, 0, st>>>(net, ch, a);
+    if (launch_s(net, ch, a, 1, st, err)) return -1;
     if (check(cudaGetLastError(), err)) return -1;
     return 3;
 }
 
 int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
-                      uint32_t stat_n0, cudaStream_t st, const char **err)
+                      uint32_t stat_n0, cudaStream_t st, const char **err, cudaEvent_t *phase_ev)
 {
     if (n_sweeps == 0 || ch.n_chains == 0) return 0;
-    static bool attr_set = false;
-    const size_t smem_x = net.nX;
-    if (!attr_set || smem_x > 48 * 1024) {
-        if (check(cudaFuncSetAttribute(k_fast_x<FX_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int) (smem_x > 48 * 1024 ? smem_x : 48 * 1024)), err)) return -1;
-        attr_set = true;
-    }
+    const size_t smem_x = sizeof(double) * 7 * (size_t) net.stab_D + net.nX;
+    if (check(cudaFuncSetAttribute(k_fast_x<FX_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) (smem_x > 48 * 1024 ? smem_x : 48 * 1024)), err)) return -1;
     int launches = 0;
     for (uint32_t sw = 0; sw < n_sweeps; sw++) {
         SweepArgs a;
@@ -347,11 +432,15 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         a.stat_n = stat_n0 + sw + 1;
         a.use_inj = (ch.inj_flat != nullptr && (ch.inj_pos + sw) < ch.inj_sweeps) ? 1 : 0;
         a.inj_row = ch.inj_pos + sw;
+        if (phase_ev) cudaEventRecord(phase_ev[3 * sw], st);
         k_fast_x<FX_NT><<<ch.n_chains, FX_NT, smem_x, st>>>(net, ch, a);
+        if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
         k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, net.const_params ? 0 : 1);
-        k_fast_s<0><<<dim3((net.nH + FS_NT - 1) / FS_NT, ch.n_chains), FS_NT, 0, st>>>(net, ch, a);
+        if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 2], st);
+        if (launch_s(net, ch, a, 0, st, err)) return -1;
         launches += 3;
     }
+    if (phase_ev) cudaEventRecord(phase_ev[3 * n_sweeps], st);
     if (check(cudaGetLastError(), err)) return -1;
     return launches;
 }

@@ -38,8 +38,7 @@ __global__ void __launch_bounds__(NT) k_sweep_strict(DevNet net, DevChains ch, u
     uint32_t *cX1 = ch.cX1 + (size_t) c * nX;
     double *tMean = ch.tMean + (size_t) c * nX;
     double *tM2 = ch.tM2 + (size_t) c * nX;
-    uint32_t *cS0 = ch.cS0 + (size_t) c * E;
-    uint32_t *cS2 = ch.cS2 + (size_t) c * E;
+    uint2 *cS = ch.cS + (size_t) c * E;
     const uint8_t *gy = net.y + (size_t) d * nH;
     const double *yp = net.yprob + 3 * (size_t) d;
 
@@ -173,11 +172,10 @@ __global__ void __launch_bounds__(NT) k_sweep_strict(DevNet net, DevChains ch, u
                     }
                     llik[v] = (0. + log(net.sprob[mi][v])) + log(ps.likelihood(yp, col));
                 }
-                const double u = inj ? inj_flat[nX + net.par_edge[q]] : keyed_u(net.seed, gchain, sweep, q, KIND_S);
+                const double u = inj ? inj_flat[nX + net.par_edge[q]] : keyed_s(net.seed, gchain, sweep, i, q - q0);
                 const uint32_t ns = multinomial_draw<3>(llik, net.sprob[mi], u, cur);
                 gS[q] = (uint8_t) ns;
-                cS0[q] += (ns == 0);
-                cS2[q] += (ns == 2);
+                { uint2 cs = cS[q]; cs.x += (ns == 0); cs.y += (ns == 2); cS[q] = cs; }
             }
         }
         __syncthreads();

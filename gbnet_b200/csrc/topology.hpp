@@ -25,6 +25,9 @@
 
 namespace gbn {
 
+constexpr uint32_t TILE_TARGETS = 512;     // fast S kernel: 16 groups of 32 targets per tile
+constexpr uint32_t TILE_SLOTS = 8192;
+
 struct Topology {
     uint32_t nX = 0, nH = 0, E = 0, Eu = 0;
     uint32_t max_indeg = 0, max_outdeg = 0;
@@ -33,7 +36,13 @@ struct Topology {
     std::vector<uint8_t> mor_idx;                   // per slot, mor + 1
     std::vector<uint32_t> tf_ptr, tf_child, tf_slot;
     std::vector<uint32_t> tfpos_of_slot;            // slot -> position in the by-TF CSR (UINT32_MAX for a duplicate edge)
-    std::vector<uint32_t> trg_order;                // targets by in-degree, descending (stable)
+    // fast S phase: targets are cut into TILES of consecutive targets (<= TILE_TARGETS targets and
+    // <= tile_slots slots, so one tile's slots are one contiguous, coalescible range); inside a tile
+    // threads take targets in descending in-degree order (trg_order) so a warp's lanes finish together
+    std::vector<uint32_t> tile_trg0;                // [n_tiles+1] first target of each tile
+    std::vector<uint32_t> trg_order;                // [nH] tile-local order
+    std::vector<uint32_t> par_pack;                 // [E] slot -> par_tf | (mor+1) << 30
+    uint32_t tile_slots = 0;                        // slot capacity of a tile
     std::vector<uint32_t> n_h_child;                // edges per TF (GraphORNOR.cpp:206-211)
     std::vector<uint8_t> x_prior_active;            // per TF
     std::vector<double> t_a, t_b, t_mean, t_lnB;    // per TF
@@ -123,11 +132,25 @@ inline Topology compile_topology(uint32_t n_edge, const uint32_t *src, const uin
                 }
             }
     }
+    // tiles for the fast S phase
+    tp.tile_slots = std::max<uint32_t>(TILE_SLOTS, tp.max_indeg);
+    tp.tile_trg0.assign(1, 0);
+    {
+        uint32_t cnt = 0, slots = 0;
+        for (uint32_t i = 0; i < nH; i++) {
+            uint32_t d = tp.trg_ptr[i + 1] - tp.trg_ptr[i];
+            if (cnt == TILE_TARGETS || slots + d > tp.tile_slots) { tp.tile_trg0.push_back(i); cnt = 0; slots = 0; }
+            cnt++; slots += d;
+        }
+        tp.tile_trg0.push_back(nH);
+    }
     tp.trg_order.resize(nH);
     for (uint32_t i = 0; i < nH; i++) tp.trg_order[i] = i;
-    std::stable_sort(tp.trg_order.begin(), tp.trg_order.end(), [&](uint32_t a, uint32_t b) {
-        return tp.trg_ptr[a + 1] - tp.trg_ptr[a] > tp.trg_ptr[b + 1] - tp.trg_ptr[b];
-    });
+    for (size_t t = 0; t + 1 < tp.tile_trg0.size(); t++)
+        std::stable_sort(tp.trg_order.begin() + tp.tile_trg0[t], tp.trg_order.begin() + tp.tile_trg0[t + 1],
+                         [&](uint32_t a, uint32_t b) { return tp.trg_ptr[a + 1] - tp.trg_ptr[a] > tp.trg_ptr[b + 1] - tp.trg_ptr[b]; });
+    tp.par_pack.resize(E);
+    for (uint32_t q = 0; q < E; q++) tp.par_pack[q] = tp.par_tf[q] | ((uint32_t) tp.mor_idx[q] << 30);
     tp.x_prior_active.assign(nX, 0);
     for (uint32_t i = 0; i < n_active; i++) {
         uint32_t k = rank_of(tp.tf_uid, active_tf[i]);

@@ -237,6 +237,16 @@ class Sampler:
         _capi.check(self._lib.gbn_model_last_device_ms(self._h, C.byref(v)))
         return v.value
 
+    def set_phase_timing(self, on=True):
+        _capi.check(self._lib.gbn_model_set_phase_timing(self._h, int(bool(on))))
+
+    def phase_ms(self):
+        """(ms in the X, T, S kernels, sweeps covered) since set_phase_timing(True)"""
+        ms = (C.c_double * 3)()
+        n = C.c_uint64()
+        _capi.check(self._lib.gbn_model_phase_ms(self._h, ms, C.byref(n)))
+        return [float(v) for v in ms], int(n.value)
+
     def launch_count(self):
         v = C.c_uint64()
         _capi.check(self._lib.gbn_model_launch_count(self._h, C.byref(v)))
@@ -246,6 +256,14 @@ class Sampler:
         v = C.c_uint64()
         _capi.check(self._lib.gbn_model_sweep_count(self._h, C.byref(v)))
         return int(v.value)
+
+    def timer_start(self):
+        _capi.check(self._lib.gbn_model_timer_start(self._h))
+
+    def timer_stop(self):
+        v = C.c_double()
+        _capi.check(self._lib.gbn_model_timer_stop(self._h, C.byref(v)))
+        return v.value
 
     def synchronize(self):
         _capi.check(self._lib.gbn_model_synchronize(self._h))

@@ -165,10 +165,18 @@ int gbn_philox_kat(int device, const uint32_t ctr[4], const uint32_t key[2], uin
 /* ---- measurement ---- */
 /* device time (CUDA events on the model's stream) of the last sample_n / sample call, in ms */
 int gbn_model_last_device_ms(const gbn_model *m, double *ms);
+/* per-kernel device times of the fast path: when switched on, CUDA events are recorded on the
+ * model's stream around the X, T and S kernels of every sweep; gbn_model_phase_ms returns the
+ * accumulated milliseconds per kernel and the number of sweeps they cover */
+int gbn_model_set_phase_timing(gbn_model *m, int on);
+int gbn_model_phase_ms(const gbn_model *m, double ms_out[3], uint64_t *sweeps);
 /* number of kernels this library launched on behalf of the model since creation */
 int gbn_model_launch_count(const gbn_model *m, uint64_t *n);
 /* total sweeps drawn since creation (Philox counter word) */
 int gbn_model_sweep_count(const gbn_model *m, uint64_t *n);
+/* device time between two points chosen by the caller (CUDA events on the model's stream) */
+int gbn_model_timer_start(gbn_model *m);
+int gbn_model_timer_stop(gbn_model *m, double *ms);
 int gbn_model_synchronize(gbn_model *m);
 
 #ifdef __cplusplus

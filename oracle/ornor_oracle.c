@@ -48,7 +48,8 @@ void orn_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 /* stream kinds (counter word 3, low byte) */
 enum { KIND_X = 0, KIND_S = 1, KIND_TBETA = 2, KIND_TEXP = 3, KIND_INIT = 4 };
 
-/* One 32-bit uniform per discrete node; four neighbouring nodes share one Philox block.
+/* One 32-bit uniform per discrete node; four neighbouring X nodes share one Philox block
+ * (S nodes: keyed_s below).
  * u = w / 2^32 in [0,1): the same resolution gsl_rng_uniform has for mt19937. */
 static double keyed_u(uint64_t seed, unsigned int chain, unsigned int sweep, unsigned int node,
                       unsigned int kind)
@@ -58,6 +59,18 @@ static double keyed_u(uint64_t seed, unsigned int chain, unsigned int sweep, uns
     uint32_t out[4];
     orn_philox4x32_10(ctr, key, out);
     return (double) out[node & 3] * (1.0 / 4294967296.0);
+}
+
+/* S nodes: the uniform of the j-th parent edge (append_parent order) of target i; four consecutive
+ * edges of one target share one Philox block: counter (i, sweep, chain, KIND_S | (j/4) << 8) */
+static double keyed_s(uint64_t seed, unsigned int chain, unsigned int sweep, unsigned int target,
+                      unsigned int j)
+{
+    uint32_t ctr[4] = { target, sweep, chain, KIND_S | ((j >> 2) << 8) };
+    uint32_t key[2] = { (uint32_t) seed, (uint32_t) (seed >> 32) };
+    uint32_t out[4];
+    orn_philox4x32_10(ctr, key, out);
+    return (double) out[j & 3] * (1.0 / 4294967296.0);
 }
 
 double orn_draw_u(uint64_t seed, unsigned int chain, unsigned int sweep, unsigned int node,
@@ -670,7 +683,10 @@ void orn_export_draws(const orn_model *m, unsigned int chain, unsigned int sweep
         unsigned int sw = sweep0 + i;
         double *f = flat_u + (size_t) i * (nX + E);
         for (unsigned int k = 0; k < nX; k++) f[k] = keyed_u(m->p.seed, chain, sw, k, KIND_X);
-        for (unsigned int e = 0; e < E; e++) f[nX + e] = keyed_u(m->p.seed, chain, sw, m->slot_of_edge[e], KIND_S);
+        for (unsigned int e = 0; e < E; e++) {
+            unsigned int q = m->slot_of_edge[e], i = m->slot_trg[q];
+            f[nX + e] = keyed_s(m->p.seed, chain, sw, i, q - m->trg_ptr[i]);
+        }
         for (unsigned int k = 0; k < nX; k++) {
             beta_v[(size_t) i * nX + k] = orn_draw_beta(m->p.seed, chain, sw, k, m->t_a[k], m->t_b[k]);
             exp_v[(size_t) i * nX + k] = orn_draw_exp(m->p.seed, chain, sw, k);
@@ -686,6 +702,9 @@ static double flat_draw(const orn_model *m, chain_t *ch, unsigned int chain, uns
     if (ch->inj_flat) {
         if (ch->i_flat >= ch->n_flat) { fprintf(stderr, "ornor_oracle: flat queue exhausted\n"); abort(); }
         u = ch->inj_flat[ch->i_flat++];
+    } else if (kind == KIND_S) {
+        unsigned int i = m->slot_trg[node];
+        u = keyed_s(m->p.seed, chain, ch->sweep, i, node - m->trg_ptr[i]);
     } else {
         u = keyed_u(m->p.seed, chain, ch->sweep, node, kind);
     }
