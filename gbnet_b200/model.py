@@ -21,6 +21,72 @@ def _rank(symbols):
     return {s: i for i, s in enumerate(order)}, order
 
 
+def marshal_frames(ents, rels, evid=None, active_tf_set_py=frozenset()):
+    """pandas -> integer problem: what ModelORNOR.pyx:18-66 does before calling the C++ ctor.
+
+    Returns a dict with the integer edge list (edge order = insertion order of the reference's
+    ``network_py`` dict, duplicates collapsed with the last sign winning), the evidence restricted to
+    targets of the network, the active-TF ids, and the symbol tables in std::set<string> order."""
+    assertion_msg = ("Please make sure that provided ents file is a "
+                     "Pandas Dataframe with column 'uid' available")
+    ents = ents[["uid", "name"]].dropna()                         # pyx:25-28
+    if 'uid' in ents.columns:
+        ents = ents.set_index('uid')
+    assert ents.index.name == 'uid', assertion_msg
+
+    # pyx:32-36 (the reference writes the symbol columns into the caller's frame as well)
+    rels["srcsymbol"] = ents.loc[rels.srcuid, "name"].values
+    rels["trgsymbol"] = ents.loc[rels.trguid, "name"].values
+    trg_set = set(rels["trgsymbol"].values)
+    network_py = {(src, trg): mor for src, trg, mor in rels[["srcsymbol", "trgsymbol", "type"]].values}
+
+    assertion_msg = ("Please make sure that provided DEG file is either a "
+                     "dictionary or a Pandas Series with uids as keys/index")
+    if evid is not None:                                          # pyx:41-54
+        if isinstance(evid, pd.DataFrame):
+            assert 'uid' in evid.columns, assertion_msg
+            evid = evid[["uid", "val"]].dropna()
+        elif isinstance(evid, dict):
+            evid = pd.DataFrame([dict(uid=k, val=v) for k, v in evid.items()]).dropna()
+        else:
+            raise TypeError(assertion_msg)
+        evid = evid.copy()
+        evid["symbol"] = ents.loc[evid.uid, "name"].values
+        evid = evid[evid["symbol"].isin(trg_set)]
+        evidence_py = dict(zip(evid["symbol"].values, evid["val"].values))
+    else:
+        evidence_py = {}
+
+    for mor in network_py.values():                               # GraphORNOR.cpp:39-41
+        if mor not in (-1, 0, 1):
+            raise IndexError("MOR values can only be either -1, 0 or 1")
+
+    src_rank, tf_symbols = _rank(s for s, _ in network_py)
+    trg_rank, trg_symbols = _rank(t for _, t in network_py)
+    edges = list(network_py.keys())
+    ev_items = [(trg_rank[s], int(v)) for s, v in evidence_py.items() if s in trg_rank]
+    return dict(
+        src=np.fromiter((src_rank[s] for s, _ in edges), np.uint32, len(edges)),
+        trg=np.fromiter((trg_rank[t] for _, t in edges), np.uint32, len(edges)),
+        mor=np.fromiter((int(m) for m in network_py.values()), np.int32, len(edges)),
+        evid_trg=np.array([k for k, _ in ev_items], np.uint32),
+        evid_val=np.array([v for _, v in ev_items], np.int32),
+        active=sorted(src_rank[s] for s in active_tf_set_py if s in src_rank),
+        tf_symbols=tf_symbols, trg_symbols=trg_symbols, edges=edges)
+
+
+def check_sprior(sprior):
+    """pyx:70-82"""
+    if sprior is None:
+        return [0.40, 0.40, 0.20,
+                0.30, 0.40, 0.30,
+                0.20, 0.40, 0.40]
+    sprior = np.array(sprior)
+    assert sprior.shape == (3, 3), 'wrong shape for sprior'
+    assert (sprior.sum(axis=1) == 1).all(), 'bad sprior, rowsums != 1'
+    return sprior.flatten().tolist()
+
+
 class ModelORNOR:
     def __init__(self, ents, rels, evid=None, active_tf_set_py=set(),
                  sprior=None, z_alpha=25., z_beta=25., z0_alpha=None, z0_beta=None, t_alpha=2., t_beta=2.,
@@ -29,61 +95,10 @@ class ModelORNOR:
                  seed=0, device=0, kernel=KERNEL_AUTO):
         z0_alpha = z_alpha if z0_alpha is None else z0_alpha          # pyx:18-19
         z0_beta = z_beta if z0_beta is None else z0_beta
-
-        assertion_msg = ("Please make sure that provided ents file is a "
-                         "Pandas Dataframe with column 'uid' available")
-        ents = ents[["uid", "name"]].dropna()                         # pyx:25-28
-        if 'uid' in ents.columns:
-            ents = ents.set_index('uid')
-        assert ents.index.name == 'uid', assertion_msg
-
-        # pyx:32-36 (the reference writes the symbol columns into the caller's frame as well)
-        rels["srcsymbol"] = ents.loc[rels.srcuid, "name"].values
-        rels["trgsymbol"] = ents.loc[rels.trguid, "name"].values
-        trg_set = set(rels["trgsymbol"].values)
-        network_py = {(src, trg): mor for src, trg, mor in rels[["srcsymbol", "trgsymbol", "type"]].values}
-
-        assertion_msg = ("Please make sure that provided DEG file is either a "
-                         "dictionary or a Pandas Series with uids as keys/index")
-        if evid is not None:                                          # pyx:41-54
-            if isinstance(evid, pd.DataFrame):
-                assert 'uid' in evid.columns, assertion_msg
-                evid = evid[["uid", "val"]].dropna()
-            elif isinstance(evid, dict):
-                evid = pd.DataFrame([dict(uid=k, val=v) for k, v in evid.items()]).dropna()
-            else:
-                raise TypeError(assertion_msg)
-            evid = evid.copy()
-            evid["symbol"] = ents.loc[evid.uid, "name"].values
-            evid = evid[evid["symbol"].isin(trg_set)]
-            evidence_py = dict(zip(evid["symbol"].values, evid["val"].values))
-        else:
-            evidence_py = {}
-
-        if sprior is None:                                            # pyx:70-82
-            sprior_py = [0.40, 0.40, 0.20,
-                         0.30, 0.40, 0.30,
-                         0.20, 0.40, 0.40]
-        else:
-            sprior = np.array(sprior)
-            assert sprior.shape == (3, 3), 'wrong shape for sprior'
-            assert (sprior.sum(axis=1) == 1).all(), 'bad sprior, rowsums != 1'
-            sprior_py = sprior.flatten().tolist()
-
-        for mor in network_py.values():                               # GraphORNOR.cpp:39-41
-            if mor not in (-1, 0, 1):
-                raise IndexError("MOR values can only be either -1, 0 or 1")
-
-        src_rank, self._tf_symbols = _rank(s for s, _ in network_py)
-        trg_rank, self._trg_symbols = _rank(t for _, t in network_py)
-        self._edges = list(network_py.keys())
-        src = np.fromiter((src_rank[s] for s, _ in self._edges), np.uint32, len(self._edges))
-        trg = np.fromiter((trg_rank[t] for _, t in self._edges), np.uint32, len(self._edges))
-        mor = np.fromiter((int(m) for m in network_py.values()), np.int32, len(self._edges))
-        ev_items = [(trg_rank[s], int(v)) for s, v in evidence_py.items() if s in trg_rank]
-        evid_trg = np.array([k for k, _ in ev_items], np.uint32)
-        evid_val = np.array([v for _, v in ev_items], np.int32)
-        active = [src_rank[s] for s in active_tf_set_py if s in src_rank]
+        m = marshal_frames(ents, rels, evid, active_tf_set_py)
+        sprior_py = check_sprior(sprior)
+        self._tf_symbols, self._trg_symbols, self._edges = m["tf_symbols"], m["trg_symbols"], m["edges"]
+        src, trg, mor, evid_trg, evid_val, active = m["src"], m["trg"], m["mor"], m["evid_trg"], m["evid_val"], m["active"]
 
         self._sampler = Sampler(src, trg, mor, evid_trg, evid_val, active_tf=active, sprior=sprior_py,
                                 z_alpha=z_alpha, z_beta=z_beta, z0_alpha=z0_alpha, z0_beta=z0_beta,
