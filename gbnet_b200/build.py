@@ -12,7 +12,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libgbnet_b200.so")
+# GBN_LIB_VARIANT=fma builds / loads a second library whose fast path is compiled with FMA contraction
+# (an experiment knob: the shipped default keeps -fmad=false everywhere)
+VARIANT = os.environ.get("GBN_LIB_VARIANT", "")
+LIB = os.path.join(HERE, "libgbnet_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 SOURCES = ["capi.cu", "eval_kernels.cu", "sweep_strict.cu", "sweep_fast.cu", "moments.cu"]
 HEADERS = ["device_math.cuh", "device_model.cuh", "kernels.cuh", "topology.hpp",
            os.path.join("..", "..", "include", "gbnet_b200.h")]
@@ -41,7 +44,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu for sm_100a into gbnet_b200/libgbnet_b200.so; returns its path."""
     if not force and not _stale():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
     os.makedirs(objdir, exist_ok=True)
     nvcc = nvcc_path()
     procs = []
@@ -49,7 +52,10 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        flags = list(NVCC_FLAGS)
+        if VARIANT == "fma" and src == "sweep_fast.cu":
+            flags[flags.index("-fmad=false")] = "-fmad=true"
+        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, pr in procs:

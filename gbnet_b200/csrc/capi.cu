@@ -171,7 +171,7 @@ int init_chains(gbn_model *m)
 
 int zero_stats(gbn_model *m)
 {
-    const size_t C = m->n_chains, nX = m->tp.nX, E = m->tp.E;
+    const size_t C = m->n_chains, nX = m->tp.nX, E = m->tp.Ep;
     CUDA_TRY(cudaMemsetAsync(m->ch.cX1, 0, sizeof(uint32_t) * C * nX, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->ch.tMean, 0, sizeof(double) * C * nX, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->ch.tM2, 0, sizeof(double) * C * nX, m->stream));
@@ -407,15 +407,15 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     // ---- network
     DevNet &n = m->net;
     n.nX = tp.nX; n.nH = tp.nH; n.E = tp.E; n.Eu = tp.Eu; n.max_indeg = tp.max_indeg; n.max_outdeg = tp.max_outdeg;
-    n.n_tiles = (uint32_t) tp.tile_trg0.size() - 1; n.tile_slots = tp.tile_slots;
+    n.Ep = tp.Ep; n.n_groups = tp.n_groups;
     {
         uint32_t *u32 = nullptr; uint8_t *u8 = nullptr; double *f64 = nullptr;
 #define UP(field, vec, tmp) { if (int rc = dev_upload(m, &tmp, vec)) return bail(rc); n.field = tmp; }
-        UP(trg_ptr, tp.trg_ptr, u32) UP(par_tf, tp.par_tf, u32) UP(par_edge, tp.par_edge, u32)
+        UP(deg, tp.deg, u32) UP(gbase, tp.gbase, u32) UP(ref_of_dt, tp.ref_of_dt, u32)
+        UP(par_tf, tp.par_tf, u32) UP(par_edge, tp.par_edge, u32)
         UP(slot_of_edge, tp.slot_of_edge, u32) UP(slot_trg, tp.slot_trg, u32) UP(mor_idx, tp.mor_idx, u8)
         UP(tf_ptr, tp.tf_ptr, u32) UP(tf_child, tp.tf_child, u32) UP(tf_slot, tp.tf_slot, u32)
-        UP(tfpos_of_slot, tp.tfpos_of_slot, u32) UP(trg_order, tp.trg_order, u32)
-        UP(tile_trg0, tp.tile_trg0, u32) UP(par_pack, tp.par_pack, u32)
+        UP(tfpos_of_slot, tp.tfpos_of_slot, u32) UP(par_pack, tp.par_pack, u32)
         UP(x_prior_active, tp.x_prior_active, u8)
         UP(t_a, tp.t_a, f64) UP(t_b, tp.t_b, f64) UP(t_mean, tp.t_mean, f64) UP(t_lnB, tp.t_lnB, f64)
 #undef UP
@@ -460,15 +460,15 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
 
     // ---- chains
     DevChains &ch = m->ch;
-    const size_t C = m->n_chains, nX = tp.nX, E = tp.E, nH = tp.nH;
+    const size_t C = m->n_chains, nX = tp.nX, E = tp.E, Ep = tp.Ep, nH = tp.nH;
     ch.n_chains = m->n_chains;
     if (int rc = dev_alloc(m, &ch.X, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.T, C * nX)) return bail(rc);
-    if (int rc = dev_alloc(m, &ch.S, C * E)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.S, C * Ep)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.cX1, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.tMean, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.tM2, C * nX)) return bail(rc);
-    if (int rc = dev_alloc(m, &ch.cS, C * E)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.cS, C * Ep)) return bail(rc);
     if (m->kernel == GBN_KERNEL_FAST) {
         if (int rc = dev_alloc(m, &ch.tc2, C * nH)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.ny, C * nH)) return bail(rc);
@@ -685,7 +685,7 @@ extern "C" int gbn_model_print_stats(gbn_model *m)
             uint32_t node = i / per[t], j = i % per[t];
             if (kinds[t] == 'S') {
                 uint32_t q = m->tp.slot_of_edge[node];
-                std::printf("S_%u-->%u_%u\t%.4f(%.4f)\n", m->tp.tf_uid[m->tp.par_tf[q]], m->tp.trg_uid[m->tp.slot_trg[q]], j, mu[i], sd[i]);
+                std::printf("S_%u-->%u_%u\t%.4f(%.4f)\n", m->tp.tf_uid[m->tp.par_tf[q]], m->tp.trg_uid[m->tp.ref_of_dt[m->tp.slot_trg[q]]], j, mu[i], sd[i]);
             } else {
                 std::printf("%c_%u_%u\t%.4f(%.4f)\n", kinds[t], m->tp.tf_uid[node], j, mu[i], sd[i]);
             }
@@ -743,13 +743,13 @@ extern "C" int gbn_model_get_state(gbn_model *m, uint32_t chain, double *out)
     if (!m || !out) return fail(GBN_ERR_INVALID, "null argument");
     if (chain >= m->n_chains) return fail(GBN_ERR_INVALID, "chain out of range");
     if (int rc = use_device(m)) return rc;
-    const uint32_t nX = m->tp.nX, E = m->tp.E;
-    std::vector<uint8_t> X(nX), S(E);
+    const uint32_t nX = m->tp.nX, E = m->tp.E, Ep = m->tp.Ep;
+    std::vector<uint8_t> X(nX), S(Ep);
     std::vector<double> T(nX);
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     CUDA_TRY(cudaMemcpy(X.data(), m->ch.X + (size_t) chain * nX, nX, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(T.data(), m->ch.T + (size_t) chain * nX, sizeof(double) * nX, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(S.data(), m->ch.S + (size_t) chain * E, E, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(S.data(), m->ch.S + (size_t) chain * Ep, Ep, cudaMemcpyDeviceToHost));
     uint32_t o = 0;
     for (uint32_t k = 0; k < nX; k++) out[o++] = X[k];
     if (!m->net.const_params) for (uint32_t k = 0; k < nX; k++) out[o++] = T[k];
@@ -762,8 +762,8 @@ extern "C" int gbn_model_set_state(gbn_model *m, uint32_t chain, const double *i
     if (!m || !in) return fail(GBN_ERR_INVALID, "null argument");
     if (chain >= m->n_chains) return fail(GBN_ERR_INVALID, "chain out of range");
     if (int rc = use_device(m)) return rc;
-    const uint32_t nX = m->tp.nX, E = m->tp.E;
-    std::vector<uint8_t> X(nX), S(E);
+    const uint32_t nX = m->tp.nX, E = m->tp.E, Ep = m->tp.Ep;
+    std::vector<uint8_t> X(nX), S(Ep, 1);             // pad slots stay at 1 (edge off)
     std::vector<double> T(nX);
     uint32_t o = 0;
     for (uint32_t k = 0; k < nX; k++) { double v = in[o++]; if (v != 0. && v != 1.) return fail(GBN_ERR_INVALID, "X values must be 0 or 1"); X[k] = (uint8_t) v; }
@@ -773,7 +773,7 @@ extern "C" int gbn_model_set_state(gbn_model *m, uint32_t chain, const double *i
     if (!m->net.const_params)
         CUDA_TRY(cudaMemcpy(m->ch.T + (size_t) chain * nX, T.data(), sizeof(double) * nX, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(m->ch.X + (size_t) chain * nX, X.data(), nX, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(m->ch.S + (size_t) chain * E, S.data(), E, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(m->ch.S + (size_t) chain * Ep, S.data(), Ep, cudaMemcpyHostToDevice));
     if (int rc = refresh_fast(m)) return rc;
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     return 0;

@@ -217,7 +217,7 @@ __device__ __forceinline__ uint32_t multinomial_draw(const double (&llik)[N], co
 
 namespace gbn {
 
-// HNode::get_own_likelihood (HNode.cpp:33-53) of target i: one scan over the parents in
+// HNode::get_own_likelihood (HNode.cpp:33-53) of DEVICE target i: one scan over the parents in
 // append_parent order.  xf(kk, q), tf(kk, q), sf(q) give X, T of parent TF kk and S of slot q,
 // so callers can override one node (candidate evaluation) without touching memory.
 template <class XF, class TF, class SF>
@@ -227,8 +227,9 @@ __device__ __forceinline__ double target_likelihood(const DevNet &net, uint32_t 
     const uint32_t y = net.y[(size_t) dataset * net.nH + i];
     const double z = (y != 1) ? net.z_y : net.z_n;                    // GraphORNOR.cpp:257-260
     ParentScan ps;
-    const uint32_t q1 = net.trg_ptr[i + 1];
-    for (uint32_t q = net.trg_ptr[i]; q < q1; q++) {
+    const uint32_t deg = net.deg[i];
+    uint32_t q = slot0(net, i);
+    for (uint32_t j = 0; j < deg; j++, q += 32) {
         const uint32_t kk = net.par_tf[q];
         ps.add(tf(kk, q), xf(kk, q), sf(q), z);
     }

@@ -3,10 +3,10 @@
 // HBM layout (all arrays chain-major so that one chain's data is contiguous):
 //   network (shared by all chains and datasets)      : CSR arrays, see topology.hpp
 //   per dataset   y[d][nH] u8, yprob[d][3] f64
-//   per chain     X[c][nX] u8 | T[c][nX] f64 | S[c][E] u8 in SLOT order
+//   per chain     X[c][nX] u8 | T[c][nX] f64 | S[c][Ep] u8 in (padded, transposed) SLOT order
 //   statistics    cX1[c][nX] u32  (#sweeps with X=1; X=0 is N - cX1)
 //                 tMean[c][nX], tM2[c][nX] f64 (Welford, gsl_rstat order of operations)
-//                 cS[c][E] u32x2 in slot order: #sweeps with S=0 and with S=2 (S=1 is N - both)
+//                 cS[c][Ep] u32x2 in slot order: #sweeps with S=0 and with S=2 (S=1 is N - both)
 //   fast kernel   tc2[c][nH] {pr0, pr2} f64x2 and ny[c][nH] u16 (n | y << 14): the per-target product cache
 //                 Stf[c][E] u8   copy of S in by-TF CSR order (coalesced reads in the X phase)
 //                 FXp[c][nX] f64x2   1 - t*x and its reciprocal
@@ -21,21 +21,21 @@ namespace gbn {
 
 struct DevNet {
     uint32_t nX, nH, E, Eu;
+    uint32_t Ep, n_groups;        // padded slot count, groups of 32 device targets (topology.hpp)
     uint32_t max_indeg, max_outdeg;
-    const uint32_t *trg_ptr;      // [nH+1]
-    const uint32_t *par_tf;       // [E]  slot -> TF
-    const uint32_t *par_edge;     // [E]  slot -> edge input index
+    const uint32_t *deg;          // [nH]   in-degree per device target
+    const uint32_t *gbase;        // [n_groups+1] first slot of each group; slot(dt, j) = gbase[dt/32] + 32 j + dt%32
+    const uint32_t *ref_of_dt;    // [nH]   device target -> reference target index (Philox key of S draws)
+    const uint32_t *par_tf;       // [Ep]  slot -> TF (0 for pads)
+    const uint32_t *par_edge;     // [Ep]  slot -> edge input index (UINT32_MAX for pads)
     const uint32_t *slot_of_edge; // [E]
-    const uint32_t *slot_trg;     // [E]  slot -> target
-    const uint8_t *mor_idx;       // [E]  slot -> mor + 1
+    const uint32_t *slot_trg;     // [Ep]  slot -> device target
+    const uint8_t *mor_idx;       // [Ep]  slot -> mor + 1 (1 for pads)
     const uint32_t *tf_ptr;       // [nX+1]
-    const uint32_t *tf_child;     // [Eu]
+    const uint32_t *tf_child;     // [Eu]  device target ids, ascending reference target order
     const uint32_t *tf_slot;      // [Eu]
-    const uint32_t *tfpos_of_slot;// [E]  slot -> position in the by-TF CSR (fast kernel; needs Eu == E)
-    const uint32_t *tile_trg0;    // [n_tiles+1] fast S phase: tiles of consecutive targets
-    const uint32_t *trg_order;    // [nH] inside a tile, targets by descending in-degree
-    const uint32_t *par_pack;     // [E]  slot -> par_tf | (mor+1) << 30
-    uint32_t n_tiles, tile_slots;
+    const uint32_t *tfpos_of_slot;// [Ep]  slot -> position in the by-TF CSR (fast kernel; needs Eu == E)
+    const uint32_t *par_pack;     // [Ep]  slot -> par_tf | (mor+1) << 30 (TF 0, mor+1 = 1 for pads)
     const uint8_t *x_prior_active;// [nX]
     const double *t_a, *t_b, *t_mean, *t_lnB;   // [nX]
     const uint8_t *y;             // [n_datasets][nH]
@@ -74,6 +74,9 @@ struct DevChains {
 };
 
 // local chain index -> dataset and global chain id (Philox counter word 2)
+// first slot of device target dt; its j-th parent is 32 j further
+__device__ __forceinline__ uint32_t slot0(const DevNet &n, uint32_t dt) { return n.gbase[dt >> 5] + (dt & 31); }
+
 __host__ __device__ inline uint32_t chain_dataset(const DevNet &n, uint32_t c) { return c / n.n_graphs_local; }
 __host__ __device__ inline uint32_t chain_global_id(const DevNet &n, uint32_t c)
 {

@@ -17,7 +17,7 @@ struct ChainPtrs {
 
 __device__ __forceinline__ ChainPtrs chain_ptrs(const DevNet &net, const DevChains &ch, uint32_t c)
 {
-    return ChainPtrs{ ch.X + (size_t) c * net.nX, ch.T + (size_t) c * net.nX, ch.S + (size_t) c * net.E };
+    return ChainPtrs{ ch.X + (size_t) c * net.nX, ch.T + (size_t) c * net.nX, ch.S + (size_t) c * net.Ep };
 }
 
 // XNode/TNode::get_children_loglikelihood (XNode.cpp:16-22, TNode.cpp:15-25) with X_k or T_k
@@ -88,7 +88,7 @@ __global__ void k_target_likelihoods(DevNet net, DevChains ch, uint32_t c, doubl
     const uint32_t d = chain_dataset(net, c);
     const ChainPtrs p = chain_ptrs(net, ch, c);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < net.nH; i += gridDim.x * blockDim.x)
-        out[i] = target_likelihood(net, d, i,
+        out[net.ref_of_dt[i]] = target_likelihood(net, d, i,
             [&](uint32_t kk, uint32_t) -> uint32_t { return p.X[kk]; },
             [&](uint32_t kk, uint32_t) -> double { return p.T[kk]; },
             [&](uint32_t q) -> uint32_t { return p.S[q]; });
@@ -107,8 +107,8 @@ __global__ void k_joint_logprob(DevNet net, DevChains ch, uint32_t c, double *ou
     if (!net.const_params)
         for (uint32_t k = threadIdx.x; k < net.nX; k += blockDim.x)
             lp += log(beta_pdf(p.T[k], net.t_a[k], net.t_b[k], net.t_lnB[k]));
-    for (uint32_t q = threadIdx.x; q < net.E; q += blockDim.x)
-        lp += log(net.sprob[net.mor_idx[q]][p.S[q]]);
+    for (uint32_t q = threadIdx.x; q < net.Ep; q += blockDim.x)
+        if (net.par_edge[q] != 0xffffffffu) lp += log(net.sprob[net.mor_idx[q]][p.S[q]]);
     for (uint32_t i = threadIdx.x; i < net.nH; i += blockDim.x) {
         double L = target_likelihood(net, d, i,
             [&](uint32_t kk, uint32_t) -> uint32_t { return p.X[kk]; },
@@ -142,7 +142,7 @@ __global__ void k_export_draws(DevNet net, uint32_t gchain, uint32_t sweep0, uin
         } else {
             uint32_t e = j - net.nX;
             const uint32_t q = net.slot_of_edge[e], i = net.slot_trg[q];
-            flat_u[idx] = keyed_s(net.seed, gchain, sw, i, q - net.trg_ptr[i]);
+            flat_u[idx] = keyed_s(net.seed, gchain, sw, net.ref_of_dt[i], (q - slot0(net, i)) >> 5);
         }
     }
 }
@@ -161,14 +161,14 @@ __global__ void k_init_chains(DevNet net, DevChains ch, double c00, double c01, 
         ch.X[(size_t) c * net.nX + j] = dice < c0 ? 0 : 1;
         ch.T[(size_t) c * net.nX + j] = net.t_mean[j];
     }
-    if (j < net.E) ch.S[(size_t) c * net.E + j] = net.mor_idx[j];
+    if (j < net.Ep) ch.S[(size_t) c * net.Ep + j] = net.mor_idx[j];     // pads: 1 = edge off
 }
 
 }  // namespace
 
 void launch_init_chains(const DevNet &net, const DevChains &ch, const double cum[2][2], cudaStream_t st)
 {
-    uint32_t n = net.nX > net.E ? net.nX : net.E;
+    uint32_t n = net.nX > net.Ep ? net.nX : net.Ep;
     k_init_chains<<<dim3((n + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch, cum[0][0], cum[0][1], cum[1][0], cum[1][1]);
 }
 

@@ -60,5 +60,7 @@ void launch_node_moments(const DevNet &net, const DevChains &ch, uint32_t c, dou
 //   X: 2 per TF (outcome 0, 1) | T: 1 per TF (absent if const_params) | S: 3 per edge in EDGE INPUT order
 __host__ __device__ inline uint32_t n_stats_of(const DevNet &n) { return 2 * n.nX + (n.const_params ? 0 : n.nX) + 3 * n.E; }
 __host__ __device__ inline uint32_t n_nodes_of(const DevNet &n) { return n.nX + (n.const_params ? 0 : n.nX) + n.E; }
+// work items of the moment kernels: nodes in slot order, pad slots included (and skipped)
+__host__ __device__ inline uint32_t n_work_of(const DevNet &n) { return n.nX + (n.const_params ? 0 : n.nX) + n.Ep; }
 
 }  // namespace gbn

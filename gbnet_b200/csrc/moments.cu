@@ -11,7 +11,7 @@
 //   final   B = N * pass2 / (M-1), W = pass1.var / M, Vhat, R    (every rank, redundantly)
 // The posterior getters skip GLOBAL chain 0 exactly as the reference does (ModelBase.cpp:172,197).
 //
-// Work items are "nodes in slot order": X_k (2 stats), T_k (1 stat), S at slot q (3 stats), so that
+// Work items are "nodes in slot order": X_k (2 stats), T_k (1 stat), S at (padded) slot q (3 stats), so that
 // for every chain the counter reads are coalesced; results are written at the stat / node index
 // of the reference's random_nodes order (S in edge input order).
 #include "kernels.cuh"
@@ -36,8 +36,9 @@ __device__ __forceinline__ NodeRef node_ref(const DevNet &net, uint32_t n)
     if (n < net.nX) { r.kind = 0; r.idx = n; r.n_stats = 2; r.stat0 = 2 * n; r.node = n; }
     else if (n < net.nX + nT) { r.kind = 1; r.idx = n - net.nX; r.n_stats = 1; r.stat0 = 2 * net.nX + r.idx; r.node = n; }
     else {
-        r.kind = 2; r.idx = n - net.nX - nT; r.n_stats = 3;
+        r.kind = 2; r.idx = n - net.nX - nT;
         const uint32_t e = net.par_edge[r.idx];
+        r.n_stats = e == 0xffffffffu ? 0 : 3;              // pad slot: nothing to report
         r.stat0 = 2 * net.nX + nT + 3 * e;
         r.node = net.nX + nT + e;
     }
@@ -62,7 +63,7 @@ __device__ __forceinline__ void node_moments(const DevNet &net, const DevChains 
         mean[0] = ch.tMean[(size_t) c * net.nX + r.idx];
         var[0] = N > 1. ? ch.tM2[(size_t) c * net.nX + r.idx] / (N - 1.) : 0.;
     } else {
-        const uint2 cs = ch.cS[(size_t) c * net.E + r.idx];
+        const uint2 cs = ch.cS[(size_t) c * net.Ep + r.idx];
         double c0 = (double) cs.x;
         double c2 = (double) cs.y;
         count_moment(c0, N, mean[0], var[0]);
@@ -73,10 +74,10 @@ __device__ __forceinline__ void node_moments(const DevNet &net, const DevChains 
 
 __global__ void k_moment_sums(DevNet net, DevChains ch, double N, double *sums, double *psums)
 {
-    const uint32_t n_nodes = n_nodes_of(net), n_stats = n_stats_of(net);
+    const uint32_t n_stats = n_stats_of(net);
     const uint32_t d = blockIdx.y;
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_nodes) return;
+    if (n >= n_work_of(net)) return;
     const NodeRef r = node_ref(net, n);
     double sm[3] = { 0., 0., 0. }, sv[3] = { 0., 0., 0. }, ps[3] = { 0., 0., 0. };
     for (uint32_t l = 0; l < net.n_graphs_local; l++) {
@@ -98,10 +99,10 @@ __global__ void k_moment_sums(DevNet net, DevChains ch, double N, double *sums, 
 __global__ void k_moment_devs(DevNet net, DevChains ch, double N, const double *sums, const double *psums,
                               double *dev, double *pdev)
 {
-    const uint32_t n_nodes = n_nodes_of(net), n_stats = n_stats_of(net);
+    const uint32_t n_stats = n_stats_of(net);
     const uint32_t d = blockIdx.y;
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_nodes) return;
+    if (n >= n_work_of(net)) return;
     const NodeRef r = node_ref(net, n);
     const double M = (double) net.n_graphs;
     double mu[3], pmu[3], dv[3] = { 0., 0., 0. }, pd[3] = { 0., 0., 0. };
@@ -135,8 +136,8 @@ __global__ void k_gelman_rubin(DevNet net, double N, const double *sums, const d
     const uint32_t d = d0 + blockIdx.y;
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     double max_gr = 0.;
-    if (n < n_nodes && blockIdx.y < nd) {
-        const NodeRef r = node_ref(net, n);
+    const NodeRef r = (n < n_work_of(net)) ? node_ref(net, n) : NodeRef{ 0, 0, 0, 0, 0 };
+    if (r.n_stats > 0 && blockIdx.y < nd) {
         const double M = (double) net.n_graphs;
         for (uint32_t j = 0; j < r.n_stats; j++) {
             size_t o = (size_t) d * n_stats + r.stat0 + j;
@@ -165,10 +166,10 @@ __global__ void k_gelman_rubin(DevNet net, double N, const double *sums, const d
 
 __global__ void k_node_moments(DevNet net, DevChains ch, uint32_t c, double N, double *mean_out, double *var_out)
 {
-    const uint32_t n_nodes = n_nodes_of(net);
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_nodes) return;
+    if (n >= n_work_of(net)) return;
     const NodeRef r = node_ref(net, n);
+    if (r.n_stats == 0) return;
     double mean[3], var[3];
     node_moments(net, ch, c, r, N, mean, var);
     for (uint32_t j = 0; j < r.n_stats; j++) { mean_out[r.stat0 + j] = mean[j]; var_out[r.stat0 + j] = var[j]; }
@@ -178,14 +179,14 @@ __global__ void k_node_moments(DevNet net, DevChains ch, uint32_t c, double N, d
 
 void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double *sums, double *psums, cudaStream_t st)
 {
-    dim3 grid((n_nodes_of(net) + 127) / 128, net.n_datasets);
+    dim3 grid((n_work_of(net) + 127) / 128, net.n_datasets);
     k_moment_sums<<<grid, 128, 0, st>>>(net, ch, N, sums, psums);
 }
 
 void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const double *sums, const double *psums,
                         double *dev, double *pdev, cudaStream_t st)
 {
-    dim3 grid((n_nodes_of(net) + 127) / 128, net.n_datasets);
+    dim3 grid((n_work_of(net) + 127) / 128, net.n_datasets);
     k_moment_devs<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, dev, pdev);
 }
 
@@ -195,13 +196,13 @@ void launch_gelman_rubin(const DevNet &net, double N, const double *sums, const 
     // dataset == UINT32_MAX: all datasets, maxima only
     uint32_t d0 = dataset == UINT32_MAX ? 0 : dataset;
     uint32_t nd = dataset == UINT32_MAX ? net.n_datasets : 1;
-    dim3 grid((n_nodes_of(net) + 127) / 128, nd);
+    dim3 grid((n_work_of(net) + 127) / 128, nd);
     k_gelman_rubin<<<grid, 128, 0, st>>>(net, N, sums, dev, d0, nd, gr_out, (unsigned long long *) max_out);
 }
 
 void launch_node_moments(const DevNet &net, const DevChains &ch, uint32_t c, double N, double *mean, double *var, cudaStream_t st)
 {
-    k_node_moments<<<(n_nodes_of(net) + 127) / 128, 128, 0, st>>>(net, ch, c, N, mean, var);
+    k_node_moments<<<(n_work_of(net) + 127) / 128, 128, 0, st>>>(net, ch, c, N, mean, var);
 }
 
 }  // namespace gbn

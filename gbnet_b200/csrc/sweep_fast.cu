@@ -30,13 +30,14 @@
 // their children, duplicate (TF, target) edges.
 #include "kernels.cuh"
 #include "device_math.cuh"
+#include "topology.hpp"
 
 namespace gbn {
 
 namespace {
 
 constexpr int FX_NT = 512;           // X kernel: 16 warps = 16-TF speculative window
-constexpr int FS_NT = 256;           // S kernel: one thread per target of a tile (= TILE_TARGETS)
+constexpr int FS_NT = 256;           // S kernel: 8 warps = 8 groups of 32 targets per CTA
 constexpr int FT_NT = 128;           // T kernel
 
 struct SweepArgs {
@@ -214,12 +215,11 @@ __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, Swee
 }
 
 // ---------------------------------------------------------------------------------- S phase
-// One CTA per (tile of consecutive targets, chain).  The tile's slots are one contiguous range:
-// S bytes and the packed parent ids are staged in shared memory with coalesced loads; warps then
-// take GROUPS of 32 targets (tile-local descending in-degree order, so the lanes of a warp finish
-// together and the longest groups start first) from a shared counter, each lane walking its
-// target's edges in input order out of shared memory; finally the new S values and the counters go
-// back with one coalesced pass over the tile's slots.
+// One WARP per (group of 32 device targets, chain); lane = target.  Device targets are sorted by
+// in-degree and a group's slots are stored transposed (topology.hpp), so when the lanes visit their
+// j-th parent edge together every access below is one run of consecutive addresses: S bytes, packed
+// parent ids, and the read-modify-write of the {count S=0, count S=2} pairs.  No shared-memory
+// staging of the slots, no block-level barrier after the start, no write-back pass.
 //
 // Likelihood algebra.  With N_h = YNOISE[h][y], K = sum_h YPROB[h] N_h, zc = (1-z)^n, omz = 1 - zc
 // (HNodeORNOR.cpp:64,82,96 and HNode.cpp:40-46 expanded):
@@ -234,73 +234,65 @@ template <int MODE, bool STAGE_FX>
 __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t s_next;
-    const uint32_t nX = net.nX, E = net.E, nH = net.nH, D = net.stab_D;
+    const uint32_t nX = net.nX, E = net.E, Ep = net.Ep, nH = net.nH, D = net.stab_D;
     double *sTab = reinterpret_cast<double *>(smem_raw);                       // [7][D]
     double2 *sFX = reinterpret_cast<double2 *>(sTab + 7 * D);                   // [nX] if staged
-    uint32_t *sPar = reinterpret_cast<uint32_t *>(sFX + (STAGE_FX ? nX : 0));  // [tile_slots]
-    uint8_t *sS = reinterpret_cast<uint8_t *>(sPar + net.tile_slots);           // [tile_slots]
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t c = blockIdx.y;
     const uint32_t d = chain_dataset(net, c);
-    const uint32_t t0 = net.tile_trg0[blockIdx.x], t1 = net.tile_trg0[blockIdx.x + 1];
-    const uint32_t qb = net.trg_ptr[t0], nslot = net.trg_ptr[t1] - qb;
-    uint8_t *gS = ch.S + (size_t) c * E + qb;
     const double2 *gFX = ch.FXp + (size_t) c * nX;
-
-    if (tid == 0) s_next = 0;
-    if (MODE == 0) {
-        // the tile's counters are only touched by the final pass: start pulling their lines into L2 now
-        const char *cs = reinterpret_cast<const char *>(ch.cS + (size_t) c * E + qb);
-        for (uint32_t off = tid * 128u; off < nslot * 8u; off += FS_NT * 128u)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(cs + off));
-    }
-    for (uint32_t j = tid; j < nslot; j += FS_NT) { sS[j] = __ldcs(gS + j); sPar[j] = net.par_pack[qb + j]; }
     for (uint32_t j = tid; j < 7 * D; j += FS_NT) sTab[j] = net.stab[(size_t) d * 7 * D + j];
     if (STAGE_FX) for (uint32_t k = tid; k < nX; k += FS_NT) sFX[k] = gFX[k];
     __syncthreads();
 
+    const uint32_t g = blockIdx.x * (FS_NT / 32) + (tid >> 5);
+    if (g >= net.n_groups) return;
+    const uint32_t dt = 32 * g + lane;
+    const bool valid = dt < nH;
+    const uint32_t deg = valid ? net.deg[dt] : 0;
+    const uint32_t gb = net.gbase[g];
+    const uint32_t W = (net.gbase[g + 1] - gb) >> 5;                 // group width = largest in-degree
+    const uint32_t base = gb + lane;
+    uint8_t *gS = ch.S + (size_t) c * Ep;
     const uint32_t gchain = chain_global_id(net, c);
-    const uint32_t n_groups = (t1 - t0 + 31) / 32;
-    const double *inj_flat = (MODE == 0 && a.use_inj) ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + E) + nX : nullptr;
-    uint8_t *gStf = ch.Stf + (size_t) c * E;
-    for (;;) {
-        uint32_t g = 0;
-        if (lane == 0) g = atomicAdd(&s_next, 1u);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if (g >= n_groups) break;
-        const uint32_t ti = t0 + 32 * g + lane;
-        if (ti >= t1) continue;
-        const uint32_t i = net.trg_order[ti];
-        const uint32_t y = net.y[(size_t) d * nH + i];
-        const uint32_t cls = (y != 1) ? 0 : 1;                     // ZY for DE targets, ZN otherwise
-        const double z = cls ? net.z_n : net.z_y;
-        const double rz = 1. / z;
-        const double ca = net.ynoise[2][y] - net.ynoise[0][y];     // a
-        const double cb = net.ynoise[1][y] - net.ynoise[2][y];     // b
-        const double *c0t = sTab + y * D, *omzt = sTab + (3 + cls) * D;
-        const uint32_t q0 = net.trg_ptr[i], deg = net.trg_ptr[i + 1] - q0;
-        const uint32_t l0 = q0 - qb;                               // first local slot
+    const uint32_t y = valid ? net.y[(size_t) d * nH + dt] : 1u;
+    const uint32_t ref_i = valid ? net.ref_of_dt[dt] : 0u;
+    const uint32_t cls = (y != 1) ? 0 : 1;                          // ZY for DE targets, ZN otherwise
+    const double z = cls ? net.z_n : net.z_y;
+    const double rz = 1. / z;
+    const double ca = net.ynoise[2][y] - net.ynoise[0][y];          // a
+    const double cb = net.ynoise[1][y] - net.ynoise[2][y];          // b
+    const double *c0t = sTab + y * D, *omzt = sTab + (3 + cls) * D;
 
-        // products over the parents in append_parent order (HNodeORNOR.cpp:55-62, 72-81)
-        double P0 = 1., P2 = 1.;
-        uint32_t n = 0;
-        for (uint32_t j = 0; j < deg; j++) {
-            const uint32_t s = sS[l0 + j];
-            const uint32_t kk = sPar[l0 + j] & 0x3fffffffu;
-            const double f = (STAGE_FX ? sFX[kk].x : gFX[kk].x) * z;
-            n += (s != 1);
-            P0 *= (s == 0) ? f : 1.;
-            P2 *= (s == 2) ? f : 1.;
-        }
-        if (MODE == 0) {
-            u32x4 rnd = { 0, 0, 0, 0 };
-            for (uint32_t j = 0; j < deg; j++) {
-                const uint32_t q = q0 + j;
-                const uint32_t pk = sPar[l0 + j];
+    // products over the parents in append_parent order (HNodeORNOR.cpp:55-62, 72-81); pads hold S = 1
+    double P0 = 1., P2 = 1.;
+    uint32_t n = 0;
+    for (uint32_t j = 0; j < W; j++) {
+        const uint32_t q = base + 32 * j;
+        const uint32_t s = gS[q];
+        const uint32_t kk = net.par_pack[q] & 0x3fffffffu;
+        const double f = (STAGE_FX ? sFX[kk].x : gFX[kk].x) * z;
+        n += (s != 1);
+        P0 *= (s == 0) ? f : 1.;
+        P2 *= (s == 2) ? f : 1.;
+    }
+    if (MODE == 0) {
+        const double *inj_flat = a.use_inj ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + E) + nX : nullptr;
+        uint8_t *gStf = ch.Stf + (size_t) c * E;
+        uint2 *cS = ch.cS + (size_t) c * Ep;
+        u32x4 rnd = { 0, 0, 0, 0 };
+        // software pipeline: the loads of step j+1 are issued before step j is computed
+        uint32_t s_n = gS[base], pk_n = net.par_pack[base];
+        uint2 cs_n = W ? __ldcs(cS + base) : make_uint2(0, 0);
+        for (uint32_t j = 0; j < W; j++) {
+            const uint32_t q = base + 32 * j;
+            const uint32_t s = s_n, pk = pk_n;
+            uint2 cs = cs_n;
+            if (j + 1 < W) { s_n = gS[q + 32]; pk_n = net.par_pack[q + 32]; cs_n = __ldcs(cS + q + 32); }
+            if (!a.use_inj && (j & 3) == 0) rnd = keyed_s_block(net.seed, gchain, a.sweep, ref_i, j);
+            if (j < deg) {
                 const uint32_t kk = pk & 0x3fffffffu;
-                const uint32_t s = sS[l0 + j];
                 const double *sp = net.sprob[pk >> 30];
                 const double2 fx = STAGE_FX ? sFX[kk] : gFX[kk];
                 const double f = fx.x * z;
@@ -319,39 +311,25 @@ __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, S
                 double cum1 = cum0 + sp[1] * L1;
                 double cum2 = cum1 + sp[2] * L2;
                 if (!(cum2 > 0.)) { cum0 = 0. + sp[0]; cum1 = cum0 + sp[1]; cum2 = cum1 + sp[2]; }
-                double u;
-                if (a.use_inj) u = inj_flat[net.par_edge[q]];
-                else {
-                    if ((j & 3) == 0) rnd = keyed_s_block(net.seed, gchain, a.sweep, i, j);
-                    u = unit_from_word(pick_word(rnd, j & 3));
-                }
+                const double u = a.use_inj ? inj_flat[net.par_edge[q]] : unit_from_word(pick_word(rnd, j & 3));
                 const double dice = 0. * (1 - u) + cum2 * u;
                 const uint32_t ns = dice < cum0 ? 0u : (dice < cum1 ? 1u : (dice < cum2 ? 2u : s));
                 if (ns != s) {
-                    sS[l0 + j] = (uint8_t) ns;
+                    gS[q] = (uint8_t) ns;
                     gStf[net.tfpos_of_slot[q]] = (uint8_t) ns;
                     P0 = ns == 0 ? R0 * f : R0;
                     P2 = ns == 2 ? R2 * f : R2;
                     n = nR + (ns != 1);
                 }
+                cs.x += (ns == 0);                                  // Multinomial.cpp:101-105 as counts
+                cs.y += (ns == 2);
             }
+            __stcs(cS + q, cs);                                     // streamed: the product cache stays in L2
         }
-        ch.tc2[(size_t) c * nH + i] = make_double2(P0, P2);
-        ch.ny[(size_t) c * nH + i] = (uint16_t) (n | (y << 14));
     }
-    if (MODE == 0) {
-        __syncthreads();
-        // Multinomial.cpp:101-105 as counts: one coalesced pass over the tile's slots
-        uint2 *cS = ch.cS + (size_t) c * E + qb;
-#pragma unroll 8
-        for (uint32_t j = tid; j < nslot; j += FS_NT) {
-            const uint32_t v = sS[j];
-            __stcs(gS + j, (uint8_t) v);
-            uint2 cs = __ldcs(cS + j);                   // streamed: keep the product cache in L2 instead
-            cs.x += (v == 0);
-            cs.y += (v == 2);
-            __stcs(cS + j, cs);
-        }
+    if (valid) {
+        ch.tc2[(size_t) c * nH + dt] = make_double2(P0, P2);
+        ch.ny[(size_t) c * nH + dt] = (uint16_t) (n | (y << 14));
     }
 }
 
@@ -360,8 +338,8 @@ __global__ void k_fast_stf(DevNet net, DevChains ch)
 {
     const uint32_t c = blockIdx.y;
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= net.E) return;
-    ch.Stf[(size_t) c * net.E + net.tfpos_of_slot[q]] = ch.S[(size_t) c * net.E + q];
+    if (q >= net.Ep || net.par_edge[q] == 0xffffffffu) return;
+    ch.Stf[(size_t) c * net.E + net.tfpos_of_slot[q]] = ch.S[(size_t) c * net.Ep + q];
 }
 
 }  // namespace
@@ -372,18 +350,22 @@ static int check(cudaError_t e, const char **err)
     return 0;
 }
 
-// shared memory of the S kernel: FXp of the chain (when it fits), packed parents and S bytes of a tile
+// shared memory of the S kernel: the per-dataset tables and, when it fits, FXp of the chain
 static size_t s_smem_bytes(const DevNet &net, bool stage_fx)
 {
-    return sizeof(double) * 7 * (size_t) net.stab_D + (stage_fx ? sizeof(double2) * (size_t) net.nX : 0) + (size_t) net.tile_slots * 5 + 16;
+    return sizeof(double) * 7 * (size_t) net.stab_D + (stage_fx ? sizeof(double2) * (size_t) net.nX : 0) + 16;
 }
 
-static bool s_stage_fx(const DevNet &net) { return sizeof(double2) * (size_t) net.nX <= 32 * 1024; }
+static bool s_stage_fx(const DevNet &net)
+{
+    static const uint32_t want = env_u32("GBN_STAGE_FX", 1);      // 2 = off
+    return want != 2 && sizeof(double2) * (size_t) net.nX <= 48 * 1024;
+}
 
 bool fast_supported(const DevNet &net, const char **why)
 {
     if (net.nX >= (1u << 30)) { *why = "n_tf does not fit the packed parent id"; return false; }
-    if (s_smem_bytes(net, s_stage_fx(net)) > 200 * 1024) { *why = "in-degree too large for the S tile"; return false; }
+    if (s_smem_bytes(net, s_stage_fx(net)) > 200 * 1024) { *why = "in-degree too large for the S-phase tables"; return false; }
     if (net.Eu != net.E) { *why = "duplicate (TF, target) edges"; return false; }
     if (net.listen && !net.const_params) { *why = "T nodes listen to their children"; return false; }
     if (sizeof(double) * 7 * (size_t) net.stab_D + net.nX + 64 > 200 * 1024) { *why = "n_tf too large for the X window kernel"; return false; }
@@ -396,7 +378,8 @@ static int launch_s_t(const DevNet &net, const DevChains &ch, const SweepArgs &a
 {
     const size_t smem = s_smem_bytes(net, STAGE);
     if (check(cudaFuncSetAttribute(k_fast_s<MODE, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), err)) return -1;
-    k_fast_s<MODE, STAGE><<<dim3(net.n_tiles, ch.n_chains), FS_NT, smem, st>>>(net, ch, a);
+    const uint32_t gpb = FS_NT / 32;                                  // groups per block
+    k_fast_s<MODE, STAGE><<<dim3((net.n_groups + gpb - 1) / gpb, ch.n_chains), FS_NT, smem, st>>>(net, ch, a);
     return 0;
 }
 
@@ -411,7 +394,7 @@ int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st,
 {
     if (ch.n_chains == 0) return 0;
     SweepArgs a{ 0, 0, 0, 0 };
-    k_fast_stf<<<dim3((net.E + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
+    k_fast_stf<<<dim3((net.Ep + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
     k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, 0);
     if (launch_s(net, ch, a, 1, st, err)) return -1;
     if (check(cudaGetLastError(), err)) return -1;

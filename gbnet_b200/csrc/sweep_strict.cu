@@ -34,11 +34,11 @@ __global__ void __launch_bounds__(NT) k_sweep_strict(DevNet net, DevChains ch, u
     const uint32_t gchain = chain_global_id(net, c);
     uint8_t *gX = ch.X + (size_t) c * nX;
     double *gT = ch.T + (size_t) c * nX;
-    uint8_t *gS = ch.S + (size_t) c * E;
+    uint8_t *gS = ch.S + (size_t) c * net.Ep;
     uint32_t *cX1 = ch.cX1 + (size_t) c * nX;
     double *tMean = ch.tMean + (size_t) c * nX;
     double *tM2 = ch.tM2 + (size_t) c * nX;
-    uint2 *cS = ch.cS + (size_t) c * E;
+    uint2 *cS = ch.cS + (size_t) c * net.Ep;
     const uint8_t *gy = net.y + (size_t) d * nH;
     const double *yp = net.yprob + 3 * (size_t) d;
 
@@ -63,8 +63,9 @@ __global__ void __launch_bounds__(NT) k_sweep_strict(DevNet net, DevChains ch, u
                 const uint32_t y = gy[i];
                 const double z = (y != 1) ? net.z_y : net.z_n;
                 ParentScan p0, p1;
-                const uint32_t q1 = net.trg_ptr[i + 1];
-                for (uint32_t q = net.trg_ptr[i]; q < q1; q++) {
+                const uint32_t deg = net.deg[i];
+                uint32_t q = slot0(net, i);
+                for (uint32_t j = 0; j < deg; j++, q += 32) {
                     const uint32_t kk = net.par_tf[q];
                     const uint32_t s = gS[q];
                     const double t = sT[kk];
@@ -124,8 +125,9 @@ __global__ void __launch_bounds__(NT) k_sweep_strict(DevNet net, DevChains ch, u
                         const uint32_t y = gy[i];
                         const double z = (y != 1) ? net.z_y : net.z_n;
                         ParentScan p0, p1;
-                        const uint32_t q1 = net.trg_ptr[i + 1];
-                        for (uint32_t q = net.trg_ptr[i]; q < q1; q++) {
+                        const uint32_t deg = net.deg[i];
+                        uint32_t q = slot0(net, i);
+                        for (uint32_t j = 0; j < deg; j++, q += 32) {
                             const uint32_t kk = net.par_tf[q];
                             const uint32_t s = gS[q];
                             const uint32_t x = sX[kk];
@@ -158,21 +160,24 @@ __global__ void __launch_bounds__(NT) k_sweep_strict(DevNet net, DevChains ch, u
             const uint32_t y = gy[i];
             const double z = (y != 1) ? net.z_y : net.z_n;
             const double col[3] = { net.ynoise[0][y], net.ynoise[1][y], net.ynoise[2][y] };
-            const uint32_t q0 = net.trg_ptr[i], q1 = net.trg_ptr[i + 1];
-            for (uint32_t q = q0; q < q1; q++) {
+            const uint32_t q0 = slot0(net, i), deg = net.deg[i];
+            const uint32_t ref_i = net.ref_of_dt[i];
+            for (uint32_t j = 0; j < deg; j++) {
+                const uint32_t q = q0 + 32 * j;
                 const uint32_t cur = gS[q];
                 const uint32_t mi = net.mor_idx[q];
                 double llik[3];
 #pragma unroll
                 for (uint32_t v = 0; v < 3; v++) {
                     ParentScan ps;
-                    for (uint32_t qq = q0; qq < q1; qq++) {
+                    for (uint32_t jj = 0; jj < deg; jj++) {
+                        const uint32_t qq = q0 + 32 * jj;
                         const uint32_t kk = net.par_tf[qq];
-                        ps.add(sT[kk], sX[kk], qq == q ? v : (uint32_t) gS[qq], z);
+                        ps.add(sT[kk], sX[kk], jj == j ? v : (uint32_t) gS[qq], z);
                     }
                     llik[v] = (0. + log(net.sprob[mi][v])) + log(ps.likelihood(yp, col));
                 }
-                const double u = inj ? inj_flat[nX + net.par_edge[q]] : keyed_s(net.seed, gchain, sweep, i, q - q0);
+                const double u = inj ? inj_flat[nX + net.par_edge[q]] : keyed_s(net.seed, gchain, sweep, ref_i, j);
                 const uint32_t ns = multinomial_draw<3>(llik, net.sprob[mi], u, cur);
                 gS[q] = (uint8_t) ns;
                 { uint2 cs = cS[q]; cs.x += (ns == 0); cs.y += (ns == 2); cS[q] = cs; }

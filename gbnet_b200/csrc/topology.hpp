@@ -1,16 +1,28 @@
-// Host-side topology compiler: integer edge list + evidence -> CSR arrays and priors.
+// Host-side topology compiler: integer edge list + evidence -> device arrays and priors.
 //
 // Replaces GraphORNOR::build_structure (reference libgbnet/src/GraphORNOR.cpp:13-265), which
 // builds one heap object graph PER CHAIN (ModelORNOR.cpp:23-27).  Here the network is compiled
-// once into flat arrays shared by every chain and every dataset:
+// once into flat arrays shared by every chain and every dataset.
 //
-//   by-target CSR  trg_ptr / par_tf / par_edge / mor_idx : parents of each target in edge input
-//                  order, i.e. HNodeORNOR::append_parent order (GraphORNOR.cpp:237-263).  A
-//                  position in this CSR is called a SLOT; S-node state and counters are stored
-//                  in slot order on the device.
+// Orders.  The reference's orders are what the ABI speaks: TFs and targets in sorted-id order
+// (std::set<string>, GraphORNOR.cpp:31-42), S nodes in edge input order.  On the device, targets are
+// RE-LABELLED by descending in-degree ("device targets", dt) so that the 32 lanes of a warp own
+// targets with (almost) equal numbers of parents, and the slots of each GROUP of 32 consecutive
+// device targets are laid out transposed:
+//
+//     slot(dt, j) = gbase[dt / 32] + 32 * j + dt % 32,     j = 0 .. deg[dt]-1 in edge input order
+//                                                          (= HNodeORNOR::append_parent order,
+//                                                          GraphORNOR.cpp:237-263)
+//
+// so that when the lanes of a warp all visit their j-th parent, S bytes, packed parent ids and the
+// statistics counters are read and written as consecutive addresses.  A group is padded to the
+// in-degree of its first (largest) target; pad slots carry par_edge = UINT32_MAX, S = 1 (edge off)
+// and are never referenced by the by-TF lists.  The host permutes at the boundary (state get/set
+// through slot_of_edge, evidence through dt_of_ref, per-target outputs through ref_of_dt).
+//
 //   by-TF CSR      tf_ptr / tf_child / tf_slot : the UNIQUE targets of each TF in ascending
-//                  target order (HParentNode::children is a std::set, HParentNode.h:18) with the
-//                  slot of the (first) connecting edge.
+//                  REFERENCE target order (HParentNode::children is a std::set, HParentNode.h:18),
+//                  stored as device target ids, with the slot of the (first) connecting edge.
 //   per TF         Beta prior (a, b, mean, ln B) from the log out-degree (GraphORNOR.cpp:213-223)
 //   per dataset    observed state y per target, YPROB (GraphORNOR.cpp:113-134)
 #pragma once
@@ -18,6 +30,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -25,27 +38,33 @@
 
 namespace gbn {
 
-constexpr uint32_t TILE_TARGETS = 512;     // fast S kernel: 16 groups of 32 targets per tile
-constexpr uint32_t TILE_SLOTS = 8192;
+inline uint32_t env_u32(const char *name, uint32_t dflt)
+{
+    const char *v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    long x = std::strtol(v, nullptr, 10);
+    return x > 0 ? (uint32_t) x : dflt;
+}
 
 struct Topology {
     uint32_t nX = 0, nH = 0, E = 0, Eu = 0;
+    uint32_t Ep = 0;                                // padded slot count
+    uint32_t n_groups = 0;                          // ceil(nH / 32)
     uint32_t max_indeg = 0, max_outdeg = 0;
-    std::vector<uint32_t> tf_uid, trg_uid;          // sorted unique ids
-    std::vector<uint32_t> trg_ptr, par_tf, par_edge, slot_of_edge, slot_trg;
-    std::vector<uint8_t> mor_idx;                   // per slot, mor + 1
+    std::vector<uint32_t> tf_uid, trg_uid;          // sorted unique ids (reference order)
+    std::vector<uint32_t> dt_of_ref, ref_of_dt;     // reference target index <-> device target index
+    std::vector<uint32_t> deg;                      // [nH] in-degree per device target
+    std::vector<uint32_t> gbase;                    // [n_groups+1] first slot of each group
+    // per slot [Ep]
+    std::vector<uint32_t> par_tf, par_edge, slot_trg, tfpos_of_slot, par_pack;
+    std::vector<uint8_t> mor_idx;                   // mor + 1 (1 for pads)
+    std::vector<uint32_t> slot_of_edge;             // [E]
     std::vector<uint32_t> tf_ptr, tf_child, tf_slot;
-    std::vector<uint32_t> tfpos_of_slot;            // slot -> position in the by-TF CSR (UINT32_MAX for a duplicate edge)
-    // fast S phase: targets are cut into TILES of consecutive targets (<= TILE_TARGETS targets and
-    // <= tile_slots slots, so one tile's slots are one contiguous, coalescible range); inside a tile
-    // threads take targets in descending in-degree order (trg_order) so a warp's lanes finish together
-    std::vector<uint32_t> tile_trg0;                // [n_tiles+1] first target of each tile
-    std::vector<uint32_t> trg_order;                // [nH] tile-local order
-    std::vector<uint32_t> par_pack;                 // [E] slot -> par_tf | (mor+1) << 30
-    uint32_t tile_slots = 0;                        // slot capacity of a tile
     std::vector<uint32_t> n_h_child;                // edges per TF (GraphORNOR.cpp:206-211)
     std::vector<uint8_t> x_prior_active;            // per TF
     std::vector<double> t_a, t_b, t_mean, t_lnB;    // per TF
+
+    uint32_t slot(uint32_t dt, uint32_t j) const { return gbase[dt >> 5] + 32 * j + (dt & 31); }
 };
 
 inline uint32_t rank_of(const std::vector<uint32_t> &sorted, uint32_t v)
@@ -75,82 +94,91 @@ inline Topology compile_topology(uint32_t n_edge, const uint32_t *src, const uin
     tp.nH = (uint32_t) tp.trg_uid.size();
     const uint32_t nX = tp.nX, nH = tp.nH, E = tp.E;
 
-    std::vector<uint32_t> e_tf(E), e_trg(E);
-    tp.trg_ptr.assign(nH + 1, 0);
+    // reference ranks and in-degrees
+    std::vector<uint32_t> e_tf(E), e_ref(E), indeg_ref(nH, 0);
     tp.n_h_child.assign(nX, 0);
     for (uint32_t e = 0; e < E; e++) {
         e_tf[e] = rank_of(tp.tf_uid, src[e]);
-        e_trg[e] = rank_of(tp.trg_uid, trg[e]);
-        tp.trg_ptr[e_trg[e] + 1]++;
-        tp.n_h_child[e_tf[e]]++;
+        e_ref[e] = rank_of(tp.trg_uid, trg[e]);
+        indeg_ref[e_ref[e]]++;
+        tp.n_h_child[e_tf[e]]++;                                        // GraphORNOR.cpp:206-211
     }
-    for (uint32_t i = 0; i < nH; i++) {
-        tp.max_indeg = std::max(tp.max_indeg, tp.trg_ptr[i + 1]);
-        tp.trg_ptr[i + 1] += tp.trg_ptr[i];
+    // device target order: descending in-degree, ties in reference order
+    tp.ref_of_dt.resize(nH);
+    for (uint32_t i = 0; i < nH; i++) tp.ref_of_dt[i] = i;
+    if (env_u32("GBN_SORT_TARGETS", 1) != 2)
+        std::stable_sort(tp.ref_of_dt.begin(), tp.ref_of_dt.end(),
+                         [&](uint32_t a, uint32_t b) { return indeg_ref[a] > indeg_ref[b]; });
+    tp.dt_of_ref.resize(nH);
+    tp.deg.resize(nH);
+    for (uint32_t dt = 0; dt < nH; dt++) {
+        tp.dt_of_ref[tp.ref_of_dt[dt]] = dt;
+        tp.deg[dt] = indeg_ref[tp.ref_of_dt[dt]];
+        tp.max_indeg = std::max(tp.max_indeg, tp.deg[dt]);
     }
-    tp.par_tf.resize(E); tp.par_edge.resize(E); tp.slot_of_edge.resize(E);
-    tp.slot_trg.resize(E); tp.mor_idx.resize(E);
+    // groups of 32 device targets, padded to the widest member
+    tp.n_groups = (nH + 31) / 32;
+    tp.gbase.assign(tp.n_groups + 1, 0);
+    for (uint32_t g = 0; g < tp.n_groups; g++) {
+        uint32_t w = 0;
+        for (uint32_t dt = 32 * g; dt < std::min(nH, 32 * g + 32); dt++) w = std::max(w, tp.deg[dt]);
+        tp.gbase[g + 1] = tp.gbase[g] + 32 * w;
+    }
+    tp.Ep = tp.gbase[tp.n_groups];
+    const uint32_t Ep = tp.Ep;
+    tp.par_tf.assign(Ep, 0); tp.par_edge.assign(Ep, UINT32_MAX); tp.slot_trg.assign(Ep, 0);
+    tp.mor_idx.assign(Ep, 1); tp.tfpos_of_slot.assign(Ep, UINT32_MAX); tp.par_pack.assign(Ep, 1u << 30);   // pad: TF 0, mor+1 = 1, never drawn
+    tp.slot_of_edge.resize(E);
+    for (uint32_t g = 0; g < tp.n_groups; g++)                          // pads also know their lane's target
+        for (uint32_t q = tp.gbase[g]; q < tp.gbase[g + 1]; q++)
+            tp.slot_trg[q] = std::min(nH - 1, 32 * g + ((q - tp.gbase[g]) & 31));
     {
         std::vector<uint32_t> fill(nH, 0);
-        for (uint32_t e = 0; e < E; e++) {
-            uint32_t i = e_trg[e];
-            uint32_t q = tp.trg_ptr[i] + fill[i]++;
+        for (uint32_t e = 0; e < E; e++) {                              // edge input order = append_parent order
+            const uint32_t dt = tp.dt_of_ref[e_ref[e]];
+            const uint32_t q = tp.slot(dt, fill[dt]++);
             tp.par_tf[q] = e_tf[e];
             tp.par_edge[q] = e;
             tp.slot_of_edge[e] = q;
-            tp.slot_trg[q] = i;
+            tp.slot_trg[q] = dt;
             tp.mor_idx[q] = (uint8_t) (mor[e] + 1);
+            tp.par_pack[q] = e_tf[e] | ((uint32_t) (mor[e] + 1) << 30);
         }
     }
-    // unique children per TF, ascending target order
+    // unique children per TF, ascending REFERENCE target order
     tp.tf_ptr.assign(nX + 1, 0);
     {
         std::vector<int64_t> last(nX, -1);
-        for (uint32_t i = 0; i < nH; i++)
-            for (uint32_t q = tp.trg_ptr[i]; q < tp.trg_ptr[i + 1]; q++) {
-                uint32_t k = tp.par_tf[q];
-                if (last[k] != (int64_t) i) { last[k] = i; tp.tf_ptr[k + 1]++; }
+        for (uint32_t r = 0; r < nH; r++) {
+            const uint32_t dt = tp.dt_of_ref[r];
+            for (uint32_t j = 0; j < tp.deg[dt]; j++) {
+                uint32_t k = tp.par_tf[tp.slot(dt, j)];
+                if (last[k] != (int64_t) r) { last[k] = r; tp.tf_ptr[k + 1]++; }
             }
+        }
         for (uint32_t k = 0; k < nX; k++) {
             tp.max_outdeg = std::max(tp.max_outdeg, tp.tf_ptr[k + 1]);
             tp.tf_ptr[k + 1] += tp.tf_ptr[k];
         }
         tp.Eu = tp.tf_ptr[nX];
         tp.tf_child.resize(tp.Eu); tp.tf_slot.resize(tp.Eu);
-        tp.tfpos_of_slot.assign(E, UINT32_MAX);
         std::vector<uint32_t> pos(nX, 0);
         std::fill(last.begin(), last.end(), -1);
-        for (uint32_t i = 0; i < nH; i++)
-            for (uint32_t q = tp.trg_ptr[i]; q < tp.trg_ptr[i + 1]; q++) {
-                uint32_t k = tp.par_tf[q];
-                if (last[k] != (int64_t) i) {
-                    last[k] = i;
-                    uint32_t c = tp.tf_ptr[k] + pos[k]++;
-                    tp.tf_child[c] = i;
+        for (uint32_t r = 0; r < nH; r++) {
+            const uint32_t dt = tp.dt_of_ref[r];
+            for (uint32_t j = 0; j < tp.deg[dt]; j++) {
+                const uint32_t q = tp.slot(dt, j);
+                const uint32_t k = tp.par_tf[q];
+                if (last[k] != (int64_t) r) {
+                    last[k] = r;
+                    const uint32_t c = tp.tf_ptr[k] + pos[k]++;
+                    tp.tf_child[c] = dt;
                     tp.tf_slot[c] = q;
                     tp.tfpos_of_slot[q] = c;
                 }
             }
-    }
-    // tiles for the fast S phase
-    tp.tile_slots = std::max<uint32_t>(TILE_SLOTS, tp.max_indeg);
-    tp.tile_trg0.assign(1, 0);
-    {
-        uint32_t cnt = 0, slots = 0;
-        for (uint32_t i = 0; i < nH; i++) {
-            uint32_t d = tp.trg_ptr[i + 1] - tp.trg_ptr[i];
-            if (cnt == TILE_TARGETS || slots + d > tp.tile_slots) { tp.tile_trg0.push_back(i); cnt = 0; slots = 0; }
-            cnt++; slots += d;
         }
-        tp.tile_trg0.push_back(nH);
     }
-    tp.trg_order.resize(nH);
-    for (uint32_t i = 0; i < nH; i++) tp.trg_order[i] = i;
-    for (size_t t = 0; t + 1 < tp.tile_trg0.size(); t++)
-        std::stable_sort(tp.trg_order.begin() + tp.tile_trg0[t], tp.trg_order.begin() + tp.tile_trg0[t + 1],
-                         [&](uint32_t a, uint32_t b) { return tp.trg_ptr[a + 1] - tp.trg_ptr[a] > tp.trg_ptr[b + 1] - tp.trg_ptr[b]; });
-    tp.par_pack.resize(E);
-    for (uint32_t q = 0; q < E; q++) tp.par_pack[q] = tp.par_tf[q] | ((uint32_t) tp.mor_idx[q] << 30);
     tp.x_prior_active.assign(nX, 0);
     for (uint32_t i = 0; i < n_active; i++) {
         uint32_t k = rank_of(tp.tf_uid, active_tf[i]);
@@ -171,10 +199,10 @@ inline Topology compile_topology(uint32_t n_edge, const uint32_t *src, const uin
     return tp;
 }
 
-// Evidence of one dataset -> observed state per target and YPROB (GraphORNOR.cpp:108-134)
+// Evidence of one dataset -> observed state per DEVICE target and YPROB (GraphORNOR.cpp:108-134)
 inline void compile_evidence(const Topology &tp, uint32_t n_evid, const uint32_t *evid_trg,
                              const int32_t *evid_val, bool comp_yprob,
-                             uint8_t *y_out /* [nH] */, double yprob_out[3])
+                             uint8_t *y_out /* [nH], device target order */, double yprob_out[3])
 {
     yprob_out[0] = 0.05; yprob_out[1] = 0.90; yprob_out[2] = 0.05;      // GraphORNOR.h:45
     for (uint32_t i = 0; i < n_evid; i++)
@@ -194,7 +222,7 @@ inline void compile_evidence(const Topology &tp, uint32_t n_evid, const uint32_t
     for (uint32_t i = 0; i < tp.nH; i++) y_out[i] = 1;                 // 1 -> not DEG
     for (auto &kv : evidence) {
         uint32_t h = rank_of(tp.trg_uid, kv.first);
-        if (h != UINT32_MAX) y_out[h] = (uint8_t) (kv.second + 1);
+        if (h != UINT32_MAX) y_out[tp.dt_of_ref[h]] = (uint8_t) (kv.second + 1);
     }
 }
 
