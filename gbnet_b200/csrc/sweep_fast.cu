@@ -47,11 +47,34 @@ struct SweepArgs {
     uint32_t inj_row;                // sweep row inside the injection arrays
 };
 
+// m * 2^e -> mantissa in [0.5, 1) and the exponent moved into e (frexp).  Likelihood products are
+// positive normal numbers, so the exponent field is rewritten directly; zero / subnormal / inf / nan
+// take the library path.
 __device__ __forceinline__ void normalise(double &m, int &e)
 {
-    int ex;
-    m = frexp(m, &ex);
-    e += ex;
+    const int hi = __double2hiint(m);
+    const int ef = (hi >> 20) & 0x7ff;
+    if (ef != 0 && ef != 0x7ff) {
+        e += ef - 1022;
+        m = __hiloint2double((hi & 0x800fffff) | (1022 << 20), __double2loint(m));
+    } else {
+        int ex;
+        m = frexp(m, &ex);
+        e += ex;
+    }
+}
+
+// the two outcome likelihoods a * 2^ea and b * 2^eb (a, b in [0.25, 2)) brought to one scale.  Only
+// their ratio matters for the draw, except that the reference falls back to the prior when both
+// underflow (Multinomial.cpp:78-85) and rounds subnormals: near the bottom of the double range the
+// exact ldexp is used, elsewhere the smaller one is scaled by 2^(difference) with a bit pattern.
+__device__ __forceinline__ void common_scale(double a, int ea, double b, int eb, double &la, double &lb)
+{
+    const int emax = ea > eb ? ea : eb;
+    if (emax < -960) { la = ldexp(a, ea); lb = ldexp(b, eb); return; }
+    const int da = ea - emax, db = eb - emax;                       // one is 0, the other <= 0
+    la = da < -1000 ? 0. : a * __hiloint2double((1023 + da) << 20, 0);
+    lb = db < -1000 ? 0. : b * __hiloint2double((1023 + db) << 20, 0);
 }
 
 // the per-target likelihood from the cached products and the tables over n (see the S phase):
@@ -121,16 +144,22 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
             cbeg = net.tf_ptr[kw]; cend = net.tf_ptr[kw + 1];
             double mc = 1., mf = 1.;
             int ec = 0, ef = 0, cnt = 0;
-            // two children per lane and iteration: both cache entries are requested before either is used
-            for (uint32_t cc = cbeg + lane; cc < cend; cc += 64) {
+            // two children per lane and iteration; the child ids and S values of the NEXT iteration are
+            // requested before this iteration's cache entries are used (they do not depend on the state)
+            uint32_t cc = cbeg + lane;
+            uint32_t ia = 0, ib = 0, sa = 1, sb = 1;
+            if (cc < cend) { ia = net.tf_child[cc]; sa = __ldcs(gStf + cc); }
+            if (cc + 32 < cend) { ib = net.tf_child[cc + 32]; sb = __ldcs(gStf + cc + 32); }
+            for (; cc < cend; cc += 64) {
                 const bool two = cc + 32 < cend;
-                const uint32_t ia = net.tf_child[cc], ib = two ? net.tf_child[cc + 32] : ia;
-                const uint32_t sa = __ldcs(gStf + cc), sb = two ? (uint32_t) __ldcs(gStf + cc + 32) : 1u;
-                const double2 pa = tc2[ia], pb = tc2[ib];
-                const uint32_t na = gny[ia], nb = gny[ib];
+                const uint32_t ca_ = ia, cb_ = two ? ib : ia, sa_ = sa, sb_ = two ? sb : 1u;
+                const double2 pa = tc2[ca_], pb = tc2[cb_];
+                const uint32_t na = gny[ca_], nb = gny[cb_];
+                if (cc + 64 < cend) { ia = net.tf_child[cc + 64]; sa = __ldcs(gStf + cc + 64); }
+                if (cc + 96 < cend) { ib = net.tf_child[cc + 96]; sb = __ldcs(gStf + cc + 96); }
                 double Lca, Lfa, Lcb, Lfb;
-                child_likelihoods(net, sTab, D, pa, na, sa, fac, Lca, Lfa);
-                child_likelihoods(net, sTab, D, pb, nb, sb, fac, Lcb, Lfb);
+                child_likelihoods(net, sTab, D, pa, na, sa_, fac, Lca, Lfa);
+                child_likelihoods(net, sTab, D, pb, nb, sb_, fac, Lcb, Lfb);
                 mc *= Lca; mf *= Lfa;
                 if (two) { mc *= Lcb; mf *= Lfb; }
                 if (++cnt == 8) { normalise(mc, ec); normalise(mf, ef); cnt = 0; }
@@ -144,9 +173,11 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
                 ec += __shfl_xor_sync(0xffffffffu, ec, o);
                 ef += __shfl_xor_sync(0xffffffffu, ef, o);
             }
+            normalise(mc, ec);
+            normalise(mf, ef);
             const double *prob = net.xprob[net.x_prior_active[kw]];
-            const double lik_cur = ldexp(prob[xcur] * mc, ec);
-            const double lik_flip = ldexp(prob[1 - xcur] * mf, ef);
+            double lik_cur, lik_flip;
+            common_scale(prob[xcur] * mc, ec, prob[1 - xcur] * mf, ef, lik_cur, lik_flip);
             const double l0 = xcur ? lik_flip : lik_cur, l1 = xcur ? lik_cur : lik_flip;
             double cum0 = 0. + l0, cum1 = cum0 + l1;
             if (!(cum1 > 0.)) { cum0 = 0. + prob[0]; cum1 = cum0 + prob[1]; }     // Multinomial.cpp:78-85
@@ -157,9 +188,8 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
         }
         if (lane == 0) s_dec[warp] = dec;
         __syncthreads();
-        uint32_t first = NW;
-#pragma unroll
-        for (int w = NW - 1; w >= 0; w--) if (s_dec[w] & 2) first = (uint32_t) w;
+        const uint32_t flips = __ballot_sync(0xffffffffu, lane < NW && (s_dec[lane < NW ? lane : 0] & 2));
+        const uint32_t first = flips ? (uint32_t) __ffs(flips) - 1 : NW;
         const uint32_t ncommit = first < NW ? first + 1 : NW;
         if (warp < ncommit && kw < nX) {
             if (lane == 0) { sX[kw] = (uint8_t) (dec & 1); cX1[kw] += (uint32_t) (dec & 1); }
@@ -230,11 +260,11 @@ __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, Swee
 // without the edge) and differ only in which product takes the factor f and in n.
 // MODE 0: sweep (draw every S of the target, count, refresh the cache)
 // MODE 1: refresh only (rebuild the cache from X, T, S; no draws, no counts)
-template <int MODE, bool STAGE_FX>
+template <int MODE, bool STAGE_FX, bool INJ>
 __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t nX = net.nX, E = net.E, Ep = net.Ep, nH = net.nH, D = net.stab_D;
+    const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;
     double *sTab = reinterpret_cast<double *>(smem_raw);                       // [7][D]
     double2 *sFX = reinterpret_cast<double2 *>(sTab + 7 * D);                   // [nX] if staged
 
@@ -253,14 +283,12 @@ __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, S
     const uint32_t deg = valid ? net.deg[dt] : 0;
     const uint32_t gb = net.gbase[g];
     const uint32_t W = (net.gbase[g + 1] - gb) >> 5;                 // group width = largest in-degree
-    const uint32_t base = gb + lane;
-    uint8_t *gS = ch.S + (size_t) c * Ep;
-    const uint32_t gchain = chain_global_id(net, c);
+    const size_t base = (size_t) c * net.Ep + gb + lane;             // this lane's slot of step 0, in the chain arrays
+    uint8_t *pS = ch.S + base;
+    const uint32_t *pPar = net.par_pack + gb + lane;
     const uint32_t y = valid ? net.y[(size_t) d * nH + dt] : 1u;
-    const uint32_t ref_i = valid ? net.ref_of_dt[dt] : 0u;
     const uint32_t cls = (y != 1) ? 0 : 1;                          // ZY for DE targets, ZN otherwise
     const double z = cls ? net.z_n : net.z_y;
-    const double rz = 1. / z;
     const double ca = net.ynoise[2][y] - net.ynoise[0][y];          // a
     const double cb = net.ynoise[1][y] - net.ynoise[2][y];          // b
     const double *c0t = sTab + y * D, *omzt = sTab + (3 + cls) * D;
@@ -269,28 +297,29 @@ __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, S
     double P0 = 1., P2 = 1.;
     uint32_t n = 0;
     for (uint32_t j = 0; j < W; j++) {
-        const uint32_t q = base + 32 * j;
-        const uint32_t s = gS[q];
-        const uint32_t kk = net.par_pack[q] & 0x3fffffffu;
+        const uint32_t s = pS[32 * j];
+        const uint32_t kk = pPar[32 * j] & 0x3fffffffu;
         const double f = (STAGE_FX ? sFX[kk].x : gFX[kk].x) * z;
         n += (s != 1);
         P0 *= (s == 0) ? f : 1.;
         P2 *= (s == 2) ? f : 1.;
     }
     if (MODE == 0) {
-        const double *inj_flat = a.use_inj ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + E) + nX : nullptr;
-        uint8_t *gStf = ch.Stf + (size_t) c * E;
-        uint2 *cS = ch.cS + (size_t) c * Ep;
-        u32x4 rnd = { 0, 0, 0, 0 };
+        const double rz = 1. / z;
+        const uint32_t gchain = chain_global_id(net, c);
+        const uint32_t ref_i = valid ? net.ref_of_dt[dt] : 0u;
+        const uint32_t k0 = (uint32_t) net.seed, k1 = (uint32_t) (net.seed >> 32);
+        const double *inj_flat = INJ ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + net.E) + nX : nullptr;
+        const uint32_t *pEdge = net.par_edge + gb + lane;
+        uint2 *pC = ch.cS + base;
         // software pipeline: the loads of step j+1 are issued before step j is computed
-        uint32_t s_n = gS[base], pk_n = net.par_pack[base];
-        uint2 cs_n = W ? __ldcs(cS + base) : make_uint2(0, 0);
-        for (uint32_t j = 0; j < W; j++) {
-            const uint32_t q = base + 32 * j;
+        uint32_t s_n = pS[0], pk_n = pPar[0];
+        uint2 cs_n = __ldcs(pC);
+        // one step = this lane's j-th parent edge
+        auto step = [&](const uint32_t j, const uint32_t word) {
             const uint32_t s = s_n, pk = pk_n;
             uint2 cs = cs_n;
-            if (j + 1 < W) { s_n = gS[q + 32]; pk_n = net.par_pack[q + 32]; cs_n = __ldcs(cS + q + 32); }
-            if (!a.use_inj && (j & 3) == 0) rnd = keyed_s_block(net.seed, gchain, a.sweep, ref_i, j);
+            if (j + 1 < W) { s_n = pS[32 * (j + 1)]; pk_n = pPar[32 * (j + 1)]; cs_n = __ldcs(pC + 32 * (j + 1)); }
             if (j < deg) {
                 const uint32_t kk = pk & 0x3fffffffu;
                 const double *sp = net.sprob[pk >> 30];
@@ -306,17 +335,18 @@ __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, S
                 const double L0 = c01 + om1 * (B * f);              // S = 0: the factor joins pr0
                 const double L1 = c0t[nR] + omzt[nR] * B;           // S = 1: edge off
                 const double L2 = c01 + om1 * (R0 * (ca + w * f));  // S = 2: the factor joins pr2
-                // exp(log prior + log L) of Multinomial.cpp:66-75 as a product
-                double cum0 = 0. + sp[0] * L0;
+                // exp(log prior + log L) of Multinomial.cpp:66-75 as a product; the "0 +" and
+                // "0 * (1 - u)" terms of the reference's running sum / gsl_ran_flat add exact zeros
+                double cum0 = sp[0] * L0;
                 double cum1 = cum0 + sp[1] * L1;
                 double cum2 = cum1 + sp[2] * L2;
-                if (!(cum2 > 0.)) { cum0 = 0. + sp[0]; cum1 = cum0 + sp[1]; cum2 = cum1 + sp[2]; }
-                const double u = a.use_inj ? inj_flat[net.par_edge[q]] : unit_from_word(pick_word(rnd, j & 3));
-                const double dice = 0. * (1 - u) + cum2 * u;
+                if (!(cum2 > 0.)) { cum0 = sp[0]; cum1 = cum0 + sp[1]; cum2 = cum1 + sp[2]; }
+                const double u = INJ ? inj_flat[pEdge[32 * j]] : unit_from_word(word);
+                const double dice = cum2 * u;
                 const uint32_t ns = dice < cum0 ? 0u : (dice < cum1 ? 1u : (dice < cum2 ? 2u : s));
                 if (ns != s) {
-                    gS[q] = (uint8_t) ns;
-                    gStf[net.tfpos_of_slot[q]] = (uint8_t) ns;
+                    pS[32 * j] = (uint8_t) ns;
+                    ch.Stf[(size_t) c * net.E + net.tfpos_of_slot[gb + lane + 32 * j]] = (uint8_t) ns;
                     P0 = ns == 0 ? R0 * f : R0;
                     P2 = ns == 2 ? R2 * f : R2;
                     n = nR + (ns != 1);
@@ -324,7 +354,16 @@ __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, S
                 cs.x += (ns == 0);                                  // Multinomial.cpp:101-105 as counts
                 cs.y += (ns == 2);
             }
-            __stcs(cS + q, cs);                                     // streamed: the product cache stays in L2
+            __stcs(pC + 32 * j, cs);                                // streamed: the product cache stays in L2
+        };
+        for (uint32_t j0 = 0; j0 < W; j0 += 4) {
+            // one Philox block serves four consecutive parent edges of every lane's target
+            u32x4 rnd = { 0, 0, 0, 0 };
+            if (!INJ) rnd = philox4x32_10(ref_i, a.sweep, gchain, KIND_S | ((j0 >> 2) << 8), k0, k1);
+            step(j0, rnd.x);
+            if (j0 + 1 < W) step(j0 + 1, rnd.y);                     // W is warp-uniform
+            if (j0 + 2 < W) step(j0 + 2, rnd.z);
+            if (j0 + 3 < W) step(j0 + 3, rnd.w);
         }
     }
     if (valid) {
@@ -373,21 +412,22 @@ bool fast_supported(const DevNet &net, const char **why)
     return true;
 }
 
-template <int MODE, bool STAGE>
+template <int MODE, bool STAGE, bool INJ>
 static int launch_s_t(const DevNet &net, const DevChains &ch, const SweepArgs &a, cudaStream_t st, const char **err)
 {
     const size_t smem = s_smem_bytes(net, STAGE);
-    if (check(cudaFuncSetAttribute(k_fast_s<MODE, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), err)) return -1;
+    if (check(cudaFuncSetAttribute(k_fast_s<MODE, STAGE, INJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), err)) return -1;
     const uint32_t gpb = FS_NT / 32;                                  // groups per block
-    k_fast_s<MODE, STAGE><<<dim3((net.n_groups + gpb - 1) / gpb, ch.n_chains), FS_NT, smem, st>>>(net, ch, a);
+    k_fast_s<MODE, STAGE, INJ><<<dim3((net.n_groups + gpb - 1) / gpb, ch.n_chains), FS_NT, smem, st>>>(net, ch, a);
     return 0;
 }
 
 static int launch_s(const DevNet &net, const DevChains &ch, const SweepArgs &a, int mode, cudaStream_t st, const char **err)
 {
     const bool stage = s_stage_fx(net);
-    if (mode == 0) return stage ? launch_s_t<0, true>(net, ch, a, st, err) : launch_s_t<0, false>(net, ch, a, st, err);
-    return stage ? launch_s_t<1, true>(net, ch, a, st, err) : launch_s_t<1, false>(net, ch, a, st, err);
+    if (mode == 1) return stage ? launch_s_t<1, true, false>(net, ch, a, st, err) : launch_s_t<1, false, false>(net, ch, a, st, err);
+    if (a.use_inj) return stage ? launch_s_t<0, true, true>(net, ch, a, st, err) : launch_s_t<0, false, true>(net, ch, a, st, err);
+    return stage ? launch_s_t<0, true, false>(net, ch, a, st, err) : launch_s_t<0, false, false>(net, ch, a, st, err);
 }
 
 int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err)
