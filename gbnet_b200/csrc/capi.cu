@@ -111,8 +111,13 @@ struct gbn_model {
     bool moments_valid = false;
     // per-kernel timing (gbn_model_set_phase_timing)
     bool phase_timing = false;
-    std::vector<cudaEvent_t> phase_ev;
+    std::vector<cudaEvent_t> phase_ev;  // [group][3 n + 1]
     uint32_t phase_pending = 0;         // sweeps whose events are recorded but not yet read
+    uint32_t phase_groups = 1, phase_stride = 0;
+    // chain groups on separate streams (fast path): one group's X kernel overlaps another's S kernel
+    std::vector<cudaStream_t> gstream;
+    std::vector<cudaEvent_t> gdone;
+    cudaEvent_t gfork = nullptr;
     double phase_ms[3] = { 0., 0., 0. };
     uint64_t phase_launches = 0;        // sweeps accumulated in phase_ms
     // comm
@@ -303,17 +308,42 @@ int sample_n(gbn_model *m, uint32_t n)
     CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
     int launched;
     if (m->kernel == GBN_KERNEL_FAST) {
-        cudaEvent_t *pev = nullptr;
+        // chains are independent: split them into groups, one stream each, joined at the end
+        static const uint32_t want_groups = env_u32("GBN_STREAM_GROUPS", 2);
+        uint32_t G = want_groups;
+        if (G > m->n_chains) G = m->n_chains;
+        if (G < 1) G = 1;
+        while (m->gstream.size() < G) {
+            cudaStream_t s; cudaEvent_t e;
+            CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            m->gstream.push_back(s); m->gdone.push_back(e);
+        }
+        if (!m->gfork) CUDA_TRY(cudaEventCreateWithFlags(&m->gfork, cudaEventDisableTiming));
+        const uint32_t stride = 3 * n + 1;
         if (m->phase_timing) {
-            while (m->phase_ev.size() < (size_t) 3 * n + 1) {
+            while (m->phase_ev.size() < (size_t) G * stride) {
                 cudaEvent_t e;
                 CUDA_TRY(cudaEventCreate(&e));
                 m->phase_ev.push_back(e);
             }
-            pev = m->phase_ev.data();
-            m->phase_pending = n;
+            m->phase_pending = n; m->phase_groups = G; m->phase_stride = stride;
         }
-        launched = launch_sweep_fast(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err, pev);
+        CUDA_TRY(cudaEventRecord(m->gfork, m->stream));
+        launched = 0;
+        for (uint32_t g = 0; g < G; g++) {
+            const uint32_t c0 = (uint32_t) ((uint64_t) m->n_chains * g / G), c1 = (uint32_t) ((uint64_t) m->n_chains * (g + 1) / G);
+            cudaStream_t st = G == 1 ? m->stream : m->gstream[g];
+            if (G > 1) CUDA_TRY(cudaStreamWaitEvent(st, m->gfork, 0));
+            int l = launch_sweep_fast(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, st, &err,
+                                      m->phase_timing ? m->phase_ev.data() + (size_t) g * stride : nullptr, c0, c1 - c0);
+            if (l < 0) { launched = -1; break; }
+            launched += l;
+            if (G > 1) {
+                CUDA_TRY(cudaEventRecord(m->gdone[g], st));
+                CUDA_TRY(cudaStreamWaitEvent(m->stream, m->gdone[g], 0));
+            }
+        }
     } else
         launched = launch_sweep_strict(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err);
     if (launched < 0) return fail(GBN_ERR_CUDA, std::string("sweep launch: ") + err);
@@ -354,6 +384,9 @@ extern "C" void gbn_model_destroy(gbn_model *m)
     if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
     for (void *p : m->owned) if (p) cudaFree(p);
     for (cudaEvent_t e : m->phase_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : m->gdone) cudaEventDestroy(e);
+    for (cudaStream_t st : m->gstream) cudaStreamDestroy(st);
+    if (m->gfork) cudaEventDestroy(m->gfork);
     if (m->tev0) cudaEventDestroy(m->tev0);
     if (m->tev1) cudaEventDestroy(m->tev1);
     if (m->ev0) cudaEventDestroy(m->ev0);
@@ -521,13 +554,15 @@ extern "C" int gbn_model_trg_ids(const gbn_model *m, uint32_t *out)
 // after a stream synchronize: fold the recorded per-kernel events into phase_ms
 static int collect_phase_times(gbn_model *m)
 {
-    for (uint32_t sw = 0; sw < m->phase_pending; sw++)
-        for (int ph = 0; ph < 3; ph++) {
-            float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, m->phase_ev[3 * sw + ph], m->phase_ev[3 * sw + ph + 1]));
-            m->phase_ms[ph] += ms;
-        }
-    m->phase_launches += m->phase_pending;
+    for (uint32_t g = 0; g < m->phase_groups; g++)
+        for (uint32_t sw = 0; sw < m->phase_pending; sw++)
+            for (int ph = 0; ph < 3; ph++) {
+                float ms = 0.f;
+                const size_t o = (size_t) g * m->phase_stride + 3 * sw + ph;
+                CUDA_TRY(cudaEventElapsedTime(&ms, m->phase_ev[o], m->phase_ev[o + 1]));
+                m->phase_ms[ph] += ms;
+            }
+    m->phase_launches += (uint64_t) m->phase_pending * m->phase_groups;   // launches of each kernel
     m->phase_pending = 0;
     return 0;
 }

@@ -30,8 +30,11 @@ size_t strict_smem_bytes(const DevNet &net);
 // ---- sweep_fast.cu: the throughput path (cached per-target products, speculative X windows)
 // phase_ev: NULL, or 3 * n_sweeps + 1 events recorded before the X, T, S kernels of every sweep and after the
 // last kernel (per-kernel device times for the roofline report)
+// chain0 / nchains: the local chains this call sweeps (the model layer runs disjoint chain groups on
+// separate streams so that one group's X kernel overlaps another group's S kernel)
 int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
-                      uint32_t stat_n0, cudaStream_t st, const char **err, cudaEvent_t *phase_ev = nullptr);
+                      uint32_t stat_n0, cudaStream_t st, const char **err, cudaEvent_t *phase_ev = nullptr,
+                      uint32_t chain0 = 0, uint32_t nchains = UINT32_MAX);
 // rebuild Stf / FX / FXinv / tcache from X, T, S (after creation and set_state)
 int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
 bool fast_supported(const DevNet &net, const char **why);

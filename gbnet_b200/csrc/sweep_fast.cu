@@ -45,6 +45,7 @@ struct SweepArgs {
     uint32_t stat_n;                 // statistics count AFTER this sweep
     uint32_t use_inj;                // 1: injected draws, row inj_row
     uint32_t inj_row;                // sweep row inside the injection arrays
+    uint32_t chain0;                 // first local chain of this launch (chains are split over streams)
 };
 
 // m * 2^e -> mantissa in [0.5, 1) and the exponent moved into e (frexp).  Likelihood products are
@@ -105,7 +106,7 @@ __device__ __forceinline__ void child_likelihoods(const DevNet &net, const doubl
 }
 
 // ---------------------------------------------------------------------------------- X phase
-template <int NT>
+template <int NT, bool NY_SMEM>
 __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, SweepArgs a)
 {
     constexpr int NW = NT / 32;
@@ -113,9 +114,10 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
     __shared__ int s_dec[NW];
     const uint32_t nX = net.nX, E = net.E, nH = net.nH, D = net.stab_D;
     double *sTab = reinterpret_cast<double *>(smem_x);       // [7][D]
-    uint8_t *sX = reinterpret_cast<uint8_t *>(sTab + 7 * D); // [nX]
+    uint16_t *sNy = reinterpret_cast<uint16_t *>(sTab + 7 * D);              // [nH] if staged
+    uint8_t *sX = reinterpret_cast<uint8_t *>(sNy + (NY_SMEM ? ((nH + 7) & ~7u) : 0)); // [nX]
 
-    const uint32_t c = blockIdx.x;
+    const uint32_t c = blockIdx.x + a.chain0;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t d = chain_dataset(net, c);
     const uint32_t gchain = chain_global_id(net, c);
@@ -129,6 +131,18 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
 
     for (uint32_t k = tid; k < nX; k += NT) sX[k] = gX[k];
     for (uint32_t j = tid; j < 7 * D; j += NT) sTab[j] = net.stab[(size_t) d * 7 * D + j];
+    if (NY_SMEM) {
+        // (n, y) of every target of this chain: X flips do not change it, so one coalesced copy per
+        // sweep replaces one scattered 2-byte gather per child
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(gny);        // chain rows are 4-byte aligned when nH is even
+        if ((((size_t) c * nH) & 1) == 0) {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(sNy);
+            for (uint32_t j = tid; j < (nH >> 1); j += NT) dst[j] = src[j];
+            if ((nH & 1) && tid == 0) sNy[nH - 1] = gny[nH - 1];
+        } else {
+            for (uint32_t j = tid; j < nH; j += NT) sNy[j] = gny[j];
+        }
+    }
     __syncthreads();
 
     uint32_t k0 = 0;
@@ -154,7 +168,7 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
                 const bool two = cc + 32 < cend;
                 const uint32_t ca_ = ia, cb_ = two ? ib : ia, sa_ = sa, sb_ = two ? sb : 1u;
                 const double2 pa = tc2[ca_], pb = tc2[cb_];
-                const uint32_t na = gny[ca_], nb = gny[cb_];
+                const uint32_t na = NY_SMEM ? sNy[ca_] : gny[ca_], nb = NY_SMEM ? sNy[cb_] : gny[cb_];
                 if (cc + 64 < cend) { ia = net.tf_child[cc + 64]; sa = __ldcs(gStf + cc + 64); }
                 if (cc + 96 < cend) { ib = net.tf_child[cc + 96]; sb = __ldcs(gStf + cc + 96); }
                 double Lca, Lfa, Lcb, Lfb;
@@ -218,7 +232,7 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
 __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, SweepArgs a, int update_t)
 {
     const uint32_t nX = net.nX;
-    const uint32_t c = blockIdx.y;
+    const uint32_t c = blockIdx.y + a.chain0;
     const uint32_t k = blockIdx.x * FT_NT + threadIdx.x;
     if (k >= nX) return;
     const size_t o = (size_t) c * nX + k;
@@ -269,7 +283,7 @@ __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, S
     double2 *sFX = reinterpret_cast<double2 *>(sTab + 7 * D);                   // [nX] if staged
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
-    const uint32_t c = blockIdx.y;
+    const uint32_t c = blockIdx.y + a.chain0;
     const uint32_t d = chain_dataset(net, c);
     const double2 *gFX = ch.FXp + (size_t) c * nX;
     for (uint32_t j = tid; j < 7 * D; j += FS_NT) sTab[j] = net.stab[(size_t) d * 7 * D + j];
@@ -293,6 +307,11 @@ __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, S
     const double cb = net.ynoise[1][y] - net.ynoise[2][y];          // b
     const double *c0t = sTab + y * D, *omzt = sTab + (3 + cls) * D;
 
+    if (MODE == 0) {
+        // the counters are first touched by the second pass: start pulling their lines into L2 now
+        const uint2 *pc = ch.cS + base;
+        for (uint32_t j = 0; j < W; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + 32 * j));
+    }
     // products over the parents in append_parent order (HNodeORNOR.cpp:55-62, 72-81); pads hold S = 1
     double P0 = 1., P2 = 1.;
     uint32_t n = 0;
@@ -401,53 +420,68 @@ static bool s_stage_fx(const DevNet &net)
     return want != 2 && sizeof(double2) * (size_t) net.nX <= 48 * 1024;
 }
 
+// shared memory of the X kernel: tables, (n, y) of every target when it fits, X of the chain
+static bool x_ny_smem(const DevNet &net)
+{
+    static const uint32_t want = env_u32("GBN_NY_SMEM", 1);        // 2 = off
+    return want != 2 && 2 * (size_t) net.nH <= 80 * 1024;
+}
+
+static size_t x_smem_bytes(const DevNet &net, bool ny_smem)
+{
+    return sizeof(double) * 7 * (size_t) net.stab_D + (ny_smem ? 2 * (((size_t) net.nH + 7) & ~(size_t) 7) : 0) + net.nX + 16;
+}
+
 bool fast_supported(const DevNet &net, const char **why)
 {
     if (net.nX >= (1u << 30)) { *why = "n_tf does not fit the packed parent id"; return false; }
     if (s_smem_bytes(net, s_stage_fx(net)) > 200 * 1024) { *why = "in-degree too large for the S-phase tables"; return false; }
     if (net.Eu != net.E) { *why = "duplicate (TF, target) edges"; return false; }
     if (net.listen && !net.const_params) { *why = "T nodes listen to their children"; return false; }
-    if (sizeof(double) * 7 * (size_t) net.stab_D + net.nX + 64 > 200 * 1024) { *why = "n_tf too large for the X window kernel"; return false; }
+    if (x_smem_bytes(net, x_ny_smem(net)) + 64 > 200 * 1024) { *why = "n_tf too large for the X window kernel"; return false; }
     if (net.max_indeg >= (1u << 14)) { *why = "in-degree does not fit the packed (n, y) word"; return false; }
     return true;
 }
 
 template <int MODE, bool STAGE, bool INJ>
-static int launch_s_t(const DevNet &net, const DevChains &ch, const SweepArgs &a, cudaStream_t st, const char **err)
+static int launch_s_t(const DevNet &net, const DevChains &ch, const SweepArgs &a, uint32_t nchains, cudaStream_t st, const char **err)
 {
     const size_t smem = s_smem_bytes(net, STAGE);
     if (check(cudaFuncSetAttribute(k_fast_s<MODE, STAGE, INJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), err)) return -1;
     const uint32_t gpb = FS_NT / 32;                                  // groups per block
-    k_fast_s<MODE, STAGE, INJ><<<dim3((net.n_groups + gpb - 1) / gpb, ch.n_chains), FS_NT, smem, st>>>(net, ch, a);
+    k_fast_s<MODE, STAGE, INJ><<<dim3((net.n_groups + gpb - 1) / gpb, nchains), FS_NT, smem, st>>>(net, ch, a);
     return 0;
 }
 
-static int launch_s(const DevNet &net, const DevChains &ch, const SweepArgs &a, int mode, cudaStream_t st, const char **err)
+static int launch_s(const DevNet &net, const DevChains &ch, const SweepArgs &a, int mode, uint32_t nc, cudaStream_t st, const char **err)
 {
     const bool stage = s_stage_fx(net);
-    if (mode == 1) return stage ? launch_s_t<1, true, false>(net, ch, a, st, err) : launch_s_t<1, false, false>(net, ch, a, st, err);
-    if (a.use_inj) return stage ? launch_s_t<0, true, true>(net, ch, a, st, err) : launch_s_t<0, false, true>(net, ch, a, st, err);
-    return stage ? launch_s_t<0, true, false>(net, ch, a, st, err) : launch_s_t<0, false, false>(net, ch, a, st, err);
+    if (mode == 1) return stage ? launch_s_t<1, true, false>(net, ch, a, nc, st, err) : launch_s_t<1, false, false>(net, ch, a, nc, st, err);
+    if (a.use_inj) return stage ? launch_s_t<0, true, true>(net, ch, a, nc, st, err) : launch_s_t<0, false, true>(net, ch, a, nc, st, err);
+    return stage ? launch_s_t<0, true, false>(net, ch, a, nc, st, err) : launch_s_t<0, false, false>(net, ch, a, nc, st, err);
 }
 
 int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err)
 {
     if (ch.n_chains == 0) return 0;
-    SweepArgs a{ 0, 0, 0, 0 };
+    SweepArgs a{ 0, 0, 0, 0, 0 };
     k_fast_stf<<<dim3((net.Ep + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
     k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, 0);
-    if (launch_s(net, ch, a, 1, st, err)) return -1;
+    if (launch_s(net, ch, a, 1, ch.n_chains, st, err)) return -1;
     if (check(cudaGetLastError(), err)) return -1;
     return 3;
 }
 
 int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
-                      uint32_t stat_n0, cudaStream_t st, const char **err, cudaEvent_t *phase_ev)
+                      uint32_t stat_n0, cudaStream_t st, const char **err, cudaEvent_t *phase_ev,
+                      uint32_t chain0, uint32_t nchains)
 {
-    if (n_sweeps == 0 || ch.n_chains == 0) return 0;
-    const size_t smem_x = sizeof(double) * 7 * (size_t) net.stab_D + net.nX;
-    if (check(cudaFuncSetAttribute(k_fast_x<FX_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int) (smem_x > 48 * 1024 ? smem_x : 48 * 1024)), err)) return -1;
+    if (nchains == UINT32_MAX) nchains = ch.n_chains - chain0;
+    if (n_sweeps == 0 || nchains == 0) return 0;
+    const bool ny_smem = x_ny_smem(net);
+    const size_t smem_x = x_smem_bytes(net, ny_smem);
+    if (check(cudaFuncSetAttribute(ny_smem ? k_fast_x<FX_NT, true> : k_fast_x<FX_NT, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x), err)) return -1;
     int launches = 0;
     for (uint32_t sw = 0; sw < n_sweeps; sw++) {
         SweepArgs a;
@@ -455,12 +489,14 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         a.stat_n = stat_n0 + sw + 1;
         a.use_inj = (ch.inj_flat != nullptr && (ch.inj_pos + sw) < ch.inj_sweeps) ? 1 : 0;
         a.inj_row = ch.inj_pos + sw;
+        a.chain0 = chain0;
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw], st);
-        k_fast_x<FX_NT><<<ch.n_chains, FX_NT, smem_x, st>>>(net, ch, a);
+        if (ny_smem) k_fast_x<FX_NT, true><<<nchains, FX_NT, smem_x, st>>>(net, ch, a);
+        else k_fast_x<FX_NT, false><<<nchains, FX_NT, smem_x, st>>>(net, ch, a);
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
-        k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, net.const_params ? 0 : 1);
+        k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, nchains), FT_NT, 0, st>>>(net, ch, a, net.const_params ? 0 : 1);
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 2], st);
-        if (launch_s(net, ch, a, 0, st, err)) return -1;
+        if (launch_s(net, ch, a, 0, nchains, st, err)) return -1;
         launches += 3;
     }
     if (phase_ev) cudaEventRecord(phase_ev[3 * n_sweeps], st);
