@@ -96,6 +96,7 @@ SYMBOLS = {
     "gbn_model_sweep_count": (C.c_int, [_vp, _P(_u64)]),
     "gbn_model_timer_start": (C.c_int, [_vp]),
     "gbn_model_timer_stop": (C.c_int, [_vp, _P(_dbl)]),
+    "gbn_model_debug_counters": (C.c_int, [_vp, C.c_int, _P(_u64)]),
     "gbn_model_synchronize": (C.c_int, [_vp]),
 }
 

@@ -215,9 +215,9 @@ int upload_evidence(gbn_model *m, const gbn_evidence *ev)
         // tables of the fast S phase (sweep_fast.cu): per dataset, over n = number of parents with S != 1
         const uint32_t D = m->net.stab_D;
         const double ynoise[3][3] = { { 0.945, 0.050, 0.005 }, { 0.050, 0.900, 0.050 }, { 0.005, 0.050, 0.945 } };
-        std::vector<double> tab((size_t) m->n_datasets * 7 * D);
+        std::vector<double> tab((size_t) m->n_datasets * STAB_ROWS * D);
         for (uint32_t d = 0; d < m->n_datasets; d++) {
-            double *t = &tab[(size_t) d * 7 * D];
+            double *t = &tab[(size_t) d * STAB_ROWS * D];
             const double *yp = &m->h_yprob[(size_t) d * 3];
             for (int cls = 0; cls < 2; cls++) {
                 double z = cls ? m->net.z_n : m->net.z_y, v = 1.;
@@ -226,8 +226,12 @@ int upload_evidence(gbn_model *m, const gbn_evidence *ev)
             for (int y = 0; y < 3; y++) {
                 const int cls = (y != 1) ? 0 : 1;
                 const double K = yp[0] * ynoise[0][y] + yp[1] * ynoise[1][y] + yp[2] * ynoise[2][y];
-                for (uint32_t n = 0; n < D; n++)
-                    t[y * D + n] = t[(3 + cls) * D + n] * ynoise[0][y] + t[(5 + cls) * D + n] * K;
+                for (uint32_t n = 0; n < D; n++) {
+                    const double omz = t[(3 + cls) * D + n];
+                    t[y * D + n] = omz * ynoise[0][y] + t[(5 + cls) * D + n] * K;
+                    t[(7 + y) * D + n] = omz * (ynoise[2][y] - ynoise[0][y]);
+                    t[(10 + y) * D + n] = omz * (ynoise[1][y] - ynoise[2][y]);
+                }
             }
         }
         CUDA_TRY(cudaMemcpy(m->d_stab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
@@ -478,7 +482,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     if (int rc = dev_alloc(m, &m->d_y, (size_t) m->n_datasets * tp.nH)) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_yprob, (size_t) m->n_datasets * 3)) return bail(rc);
     n.stab_D = (tp.max_indeg + 2 + 1) & ~1u;     // even: the arrays behind the tables stay 16-byte aligned in shared memory
-    if (int rc = dev_alloc(m, &m->d_stab, (size_t) m->n_datasets * 7 * n.stab_D)) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_stab, (size_t) m->n_datasets * STAB_ROWS * n.stab_D)) return bail(rc);
     n.y = m->d_y; n.yprob = m->d_yprob; n.stab = m->d_stab;
     if (int rc = upload_evidence(m, ev)) return bail(rc);
 
@@ -951,6 +955,26 @@ extern "C" int gbn_model_timer_stop(gbn_model *m, double *ms)
     float f = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&f, m->tev0, m->tev1));
     *ms = f;
+    return 0;
+}
+
+// diagnostics of the speculative X windows: rounds, TFs committed, flips (since enabled)
+extern "C" int gbn_model_debug_counters(gbn_model *m, int enable, uint64_t out[4])
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (int rc = use_device(m)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (out) {
+        for (int i = 0; i < 4; i++) out[i] = 0;
+        if (m->ch.dbg) CUDA_TRY(cudaMemcpy(out, m->ch.dbg, 32, cudaMemcpyDeviceToHost));
+    }
+    if (enable && !m->ch.dbg) {
+        unsigned long long *p = nullptr;
+        if (int rc = dev_alloc(m, &p, 4)) return rc;
+        m->ch.dbg = p;
+    }
+    if (m->ch.dbg) CUDA_TRY(cudaMemset(m->ch.dbg, 0, 32));
+    if (!enable) m->ch.dbg = nullptr;
     return 0;
 }
 

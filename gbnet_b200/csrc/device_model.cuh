@@ -7,7 +7,7 @@
 //   statistics    cX1[c][nX] u32  (#sweeps with X=1; X=0 is N - cX1)
 //                 tMean[c][nX], tM2[c][nX] f64 (Welford, gsl_rstat order of operations)
 //                 cS[c][Ep] u32x2 in slot order: #sweeps with S=0 and with S=2 (S=1 is N - both)
-//   fast kernel   tc2[c][nH] {pr0, pr2} f64x2 and ny[c][nH] u16 (n | y << 14): the per-target product cache
+//   fast kernel   tc2[c][nH] {pr0, pr2} f64x2 and ny[c][nH] u16 (y * D + n): the per-target product cache
 //                 Stf[c][E] u8   copy of S in by-TF CSR order (coalesced reads in the X phase)
 //                 FXp[c][nX] f64x2   1 - t*x and its reciprocal
 // Integer counts replace the reference's gsl_rstat workspaces of 0/1 indicators
@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 
 namespace gbn {
+
+constexpr uint32_t STAB_ROWS = 13;
 
 struct DevNet {
     uint32_t nX, nH, E, Eu;
@@ -40,7 +42,8 @@ struct DevNet {
     const double *t_a, *t_b, *t_mean, *t_lnB;   // [nX]
     const uint8_t *y;             // [n_datasets][nH]
     const double *yprob;          // [n_datasets][3]
-    const double *stab;           // [n_datasets][7][stab_D] fast S phase tables over n: c0[y=0..2], omz[cls], zc[cls]
+    const double *stab;           // [n_datasets][STAB_ROWS][stab_D] fast-path tables over n: c0[y=0..2], omz[cls], zc[cls],
+                                  // A[y] = omz (N2 - N0), B[y] = omz (N1 - N2)
     uint32_t stab_D;              // max_indeg + 2 rounded up to even
     const double *zctab;          // [2][max_indeg+2]  (1-z)^n by repeated multiplication; row 0 = ZY, row 1 = ZN
     double xprob[2][2];           // [prior_active][v]   GraphORNOR.h:40-41
@@ -62,9 +65,10 @@ struct DevChains {
     uint2 *cS;                    // {count S=0, count S=2}
     // fast kernel only
     double2 *tc2;                 // [c][nH] {pr0, pr2}: products over the parents with S = 0 / S = 2
-    uint16_t *ny;                 // [c][nH] n | y << 14, n = number of parents with S != 1
+    uint16_t *ny;                 // [c][nH] y * stab_D + n, n = number of parents with S != 1
     uint8_t *Stf;
     double2 *FXp;                 // {1 - t*x, 1 / (1 - t*x)}
+    unsigned long long *dbg;      // [4] diagnostics: X-window rounds, TFs committed, flips, (unused)
     // injected draws (NULL = keyed Philox streams)
     const double *inj_flat;       // [chain][inj_sweeps][nX + E]  X then S in edge input order
     const double *inj_beta;       // [chain][inj_sweeps][nX]

@@ -78,30 +78,19 @@ __device__ __forceinline__ void common_scale(double a, int ea, double b, int eb,
     lb = db < -1000 ? 0. : b * __hiloint2double((1023 + db) << 20, 0);
 }
 
-// the per-target likelihood from the cached products and the tables over n (see the S phase):
-//   L = c0[n] + omz[n] * pr0 * (a + pr2 * b)
-struct TargetConst { const double *c0t, *omzt; double ca, cb; };
-
-__device__ __forceinline__ TargetConst target_const(const DevNet &net, const double *sTab, uint32_t D, uint32_t y)
+// X phase view of the per-target likelihood (see the S phase for the algebra): with idx = y * D + n,
+//   L = c0[idx] + pr0 * (A[idx] + pr2 * B[idx]),   A = omz * (N_2 - N_0),  B = omz * (N_1 - N_2)
+// (rows 0-2, 7-9, 10-12 of net.stab).  Likelihood of a child of X_k now (Lc) and with X_k flipped
+// (Lf): the flip multiplies the product that holds the edge's factor by fac.
+__device__ __forceinline__ void child_likelihoods(const double *xC0, const double *xA, const double *xB, double2 pr,
+                                                  uint32_t idx, uint32_t s, double fac, double &Lc, double &Lf)
 {
-    const uint32_t cls = (y != 1) ? 0 : 1;                         // ZY for DE targets, ZN otherwise
-    return TargetConst{ sTab + y * D, sTab + (3 + cls) * D,
-                        net.ynoise[2][y] - net.ynoise[0][y], net.ynoise[1][y] - net.ynoise[2][y] };
-}
-
-// likelihood of a child of X_k now (Lc) and with X_k flipped (Lf): the flip multiplies the product
-// that holds the edge's factor by fac
-__device__ __forceinline__ void child_likelihoods(const DevNet &net, const double *sTab, uint32_t D, double2 pr, uint32_t ny,
-                                                  uint32_t s, double fac, double &Lc, double &Lf)
-{
-    const uint32_t n = ny & 0x3fffu;
-    const TargetConst k = target_const(net, sTab, D, ny >> 14);
-    const double c0 = k.c0t[n], om = k.omzt[n];
-    const double w = pr.y * k.cb;
-    const double B = pr.x * (k.ca + w);
-    Lc = c0 + om * B;
-    const double f0 = c0 + om * (B * fac);                          // the edge feeds pr0
-    const double f2 = c0 + om * (pr.x * (k.ca + w * fac));          // the edge feeds pr2
+    const double c0 = xC0[idx], A = xA[idx], Bq = xB[idx];
+    const double w = pr.y * Bq;
+    const double u = pr.x * (A + w);
+    Lc = c0 + u;
+    const double f0 = c0 + fac * u;                                  // the edge feeds pr0
+    const double f2 = c0 + pr.x * (A + fac * w);                     // the edge feeds pr2
     Lf = s == 0 ? f0 : (s == 2 ? f2 : Lc);
 }
 
@@ -113,9 +102,13 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
     extern __shared__ __align__(16) unsigned char smem_x[];
     __shared__ int s_dec[NW];
     const uint32_t nX = net.nX, E = net.E, nH = net.nH, D = net.stab_D;
-    double *sTab = reinterpret_cast<double *>(smem_x);       // [7][D]
-    uint16_t *sNy = reinterpret_cast<uint16_t *>(sTab + 7 * D);              // [nH] if staged
-    uint8_t *sX = reinterpret_cast<uint8_t *>(sNy + (NY_SMEM ? ((nH + 7) & ~7u) : 0)); // [nX]
+    double *xC0 = reinterpret_cast<double *>(smem_x);        // [3][D] c0 by idx = y * D + n
+    double *xA = xC0 + 3 * D, *xB = xA + 3 * D;              // [3][D] each
+    uint32_t *sU = reinterpret_cast<uint32_t *>(xB + 3 * D); // [nX rounded up to 4] the sweep's X uniforms (Philox words)
+    double *sG = reinterpret_cast<double *>(sU + ((nX + 3) & ~3u));          // [nX] 1 - T
+    uint32_t *sPtr = reinterpret_cast<uint32_t *>(sG + nX);                  // [nX + 1 rounded up to 4] tf_ptr
+    uint16_t *sNy = reinterpret_cast<uint16_t *>(sPtr + ((nX + 4) & ~3u));   // [nH] if staged
+    uint8_t *sX = reinterpret_cast<uint8_t *>(sNy + (NY_SMEM ? ((nH + 7) & ~7u) : 0)); // [nX] value | prior class << 1
 
     const uint32_t c = blockIdx.x + a.chain0;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -129,8 +122,22 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
     uint32_t *cX1 = ch.cX1 + (size_t) c * nX;
     const double *inj_flat = a.use_inj ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + E) : nullptr;
 
-    for (uint32_t k = tid; k < nX; k += NT) sX[k] = gX[k];
-    for (uint32_t j = tid; j < 7 * D; j += NT) sTab[j] = net.stab[(size_t) d * 7 * D + j];
+    // everything a round needs per TF is staged once: a round must not wait on global memory for
+    // anything but the children's cache entries (a dependent global load costs ~1 us per round)
+    for (uint32_t k = tid; k < nX; k += NT) {
+        sX[k] = (uint8_t) (gX[k] | (net.x_prior_active[k] << 1));
+        sG[k] = 1. - gT[k];                       // (1 - t*x) at x = 1   (HNodeORNOR.cpp:59)
+    }
+    for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.tf_ptr[k];
+    {
+        const double *tab = net.stab + (size_t) d * STAB_ROWS * D;
+        for (uint32_t j = tid; j < 3 * D; j += NT) { xC0[j] = tab[j]; xA[j] = tab[7 * D + j]; xB[j] = tab[10 * D + j]; }
+    }
+    if (!a.use_inj)     // every X uniform of this chain and sweep: one Philox block per four TFs, computed once
+        for (uint32_t blk = tid; blk < (nX + 3) / 4; blk += NT) {
+            const u32x4 r = philox4x32_10(blk, a.sweep, gchain, KIND_X, (uint32_t) net.seed, (uint32_t) (net.seed >> 32));
+            sU[4 * blk] = r.x; sU[4 * blk + 1] = r.y; sU[4 * blk + 2] = r.z; sU[4 * blk + 3] = r.w;
+        }
     if (NY_SMEM) {
         // (n, y) of every target of this chain: X flips do not change it, so one coalesced copy per
         // sweep replaces one scattered 2-byte gather per child
@@ -152,31 +159,49 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
         double fac = 1.;
         uint32_t cbeg = 0, cend = 0;
         if (kw < nX) {
-            const uint32_t xcur = sX[kw];
-            const double g = 1. - gT[kw];         // (1 - t*x) at x = 1   (HNodeORNOR.cpp:59)
+            const uint32_t xcur = sX[kw] & 1u;
+            const double g = sG[kw];
             fac = xcur ? 1. / g : g;              // factor that turns the product into the flipped one
-            cbeg = net.tf_ptr[kw]; cend = net.tf_ptr[kw + 1];
+            cbeg = sPtr[kw]; cend = sPtr[kw + 1];
             double mc = 1., mf = 1.;
             int ec = 0, ef = 0, cnt = 0;
-            // two children per lane and iteration; the child ids and S values of the NEXT iteration are
-            // requested before this iteration's cache entries are used (they do not depend on the state)
+            // Two children per lane and iteration, software-pipelined with two explicit register sets
+            // (no rotating copies, which would wait on the loads): while iteration i is computed from
+            // set X, the cache entries of iteration i+1 are in flight into set Y and the child ids of
+            // iteration i+2 into X's id registers.  The pipeline lives inside one round, so every entry
+            // is read after the flips of all earlier (committed) windows.  s = 0xff marks "no child".
+            struct Ids { uint32_t i0, i1, s0, s1; };
+            struct Dat { double2 p0, p1; uint32_t n0, n1; };
+            auto load_ids = [&](uint32_t cc) -> Ids {
+                Ids r{ 0u, 0u, 0xffu, 0xffu };
+                if (cc < cend) { r.i0 = net.tf_child[cc]; r.s0 = __ldcs(gStf + cc); }
+                if (cc + 32 < cend) { r.i1 = net.tf_child[cc + 32]; r.s1 = __ldcs(gStf + cc + 32); }
+                return r;
+            };
+            auto gather = [&](const Ids &id) -> Dat {
+                return Dat{ tc2[id.i0], tc2[id.i1], NY_SMEM ? sNy[id.i0] : gny[id.i0], NY_SMEM ? sNy[id.i1] : gny[id.i1] };
+            };
             uint32_t cc = cbeg + lane;
-            uint32_t ia = 0, ib = 0, sa = 1, sb = 1;
-            if (cc < cend) { ia = net.tf_child[cc]; sa = __ldcs(gStf + cc); }
-            if (cc + 32 < cend) { ib = net.tf_child[cc + 32]; sb = __ldcs(gStf + cc + 32); }
-            for (; cc < cend; cc += 64) {
-                const bool two = cc + 32 < cend;
-                const uint32_t ca_ = ia, cb_ = two ? ib : ia, sa_ = sa, sb_ = two ? sb : 1u;
-                const double2 pa = tc2[ca_], pb = tc2[cb_];
-                const uint32_t na = NY_SMEM ? sNy[ca_] : gny[ca_], nb = NY_SMEM ? sNy[cb_] : gny[cb_];
-                if (cc + 64 < cend) { ia = net.tf_child[cc + 64]; sa = __ldcs(gStf + cc + 64); }
-                if (cc + 96 < cend) { ib = net.tf_child[cc + 96]; sb = __ldcs(gStf + cc + 96); }
-                double Lca, Lfa, Lcb, Lfb;
-                child_likelihoods(net, sTab, D, pa, na, sa_, fac, Lca, Lfa);
-                child_likelihoods(net, sTab, D, pb, nb, sb_, fac, Lcb, Lfb);
-                mc *= Lca; mf *= Lfa;
-                if (two) { mc *= Lcb; mf *= Lfb; }
+            auto step = [&](Ids &idX, Dat &dX, const Ids &idY, Dat &dY) {
+                dY = gather(idY);                                     // next iteration's entries
+                const uint32_t s0 = idX.s0, s1 = idX.s1;
+                idX = load_ids(cc + 128);                             // ids two iterations ahead
+                double Lc, Lf;
+                child_likelihoods(xC0, xA, xB, dX.p0, dX.n0, s0, fac, Lc, Lf);       // cc < cend: always a child
+                mc *= Lc; mf *= Lf;
+                if (s1 != 0xffu) {
+                    child_likelihoods(xC0, xA, xB, dX.p1, dX.n1, s1, fac, Lc, Lf);
+                    mc *= Lc; mf *= Lf;
+                }
                 if (++cnt == 8) { normalise(mc, ec); normalise(mf, ef); cnt = 0; }
+                cc += 64;
+            };
+            Ids idA = load_ids(cc), idB = load_ids(cc + 64);
+            Dat dA = gather(idA), dB;
+            while (cc < cend) {
+                step(idA, dA, idB, dB);
+                if (cc >= cend) break;
+                step(idB, dB, idA, dA);
             }
             normalise(mc, ec);
             normalise(mf, ef);
@@ -189,13 +214,13 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
             }
             normalise(mc, ec);
             normalise(mf, ef);
-            const double *prob = net.xprob[net.x_prior_active[kw]];
+            const double *prob = net.xprob[sX[kw] >> 1];
             double lik_cur, lik_flip;
             common_scale(prob[xcur] * mc, ec, prob[1 - xcur] * mf, ef, lik_cur, lik_flip);
             const double l0 = xcur ? lik_flip : lik_cur, l1 = xcur ? lik_cur : lik_flip;
             double cum0 = 0. + l0, cum1 = cum0 + l1;
             if (!(cum1 > 0.)) { cum0 = 0. + prob[0]; cum1 = cum0 + prob[1]; }     // Multinomial.cpp:78-85
-            const double u = a.use_inj ? inj_flat[kw] : keyed_u(net.seed, gchain, a.sweep, kw, KIND_X);
+            const double u = a.use_inj ? inj_flat[kw] : unit_from_word(sU[kw]);
             const double dice = 0. * (1 - u) + cum1 * u;
             const uint32_t nx = dice < cum0 ? 0u : (dice < cum1 ? 1u : xcur);
             dec = (int) nx | ((nx != xcur) ? 2 : 0);
@@ -206,7 +231,7 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
         const uint32_t first = flips ? (uint32_t) __ffs(flips) - 1 : NW;
         const uint32_t ncommit = first < NW ? first + 1 : NW;
         if (warp < ncommit && kw < nX) {
-            if (lane == 0) { sX[kw] = (uint8_t) (dec & 1); cX1[kw] += (uint32_t) (dec & 1); }
+            if (lane == 0) sX[kw] = (uint8_t) ((sX[kw] & 2u) | (dec & 1));
             if (dec & 2) {
                 // apply the flip of X_kw to the cached product of each child that depends on it
                 for (uint32_t cc = cbeg + lane; cc < cend; cc += 32) {
@@ -220,9 +245,15 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
             }
         }
         __syncthreads();
+        if (tid == 0 && ch.dbg) {
+            atomicAdd(ch.dbg + 0, 1ull);
+            atomicAdd(ch.dbg + 1, (unsigned long long) (k0 + ncommit <= nX ? ncommit : nX - k0));
+            atomicAdd(ch.dbg + 2, first < NW ? 1ull : 0ull);
+        }
         k0 += ncommit;
     }
-    for (uint32_t k = tid; k < nX; k += NT) gX[k] = sX[k];
+    // every TF was committed exactly once: write X back and count (Multinomial.cpp:101-105 as a count)
+    for (uint32_t k = tid; k < nX; k += NT) { const uint32_t x = sX[k] & 1u; gX[k] = (uint8_t) x; cX1[k] += x; }
 }
 
 // ---------------------------------------------------------------------------------- T phase
@@ -286,7 +317,7 @@ __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, S
     const uint32_t c = blockIdx.y + a.chain0;
     const uint32_t d = chain_dataset(net, c);
     const double2 *gFX = ch.FXp + (size_t) c * nX;
-    for (uint32_t j = tid; j < 7 * D; j += FS_NT) sTab[j] = net.stab[(size_t) d * 7 * D + j];
+    for (uint32_t j = tid; j < 7 * D; j += FS_NT) sTab[j] = net.stab[(size_t) d * STAB_ROWS * D + j];
     if (STAGE_FX) for (uint32_t k = tid; k < nX; k += FS_NT) sFX[k] = gFX[k];
     __syncthreads();
 
@@ -387,7 +418,7 @@ __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, S
     }
     if (valid) {
         ch.tc2[(size_t) c * nH + dt] = make_double2(P0, P2);
-        ch.ny[(size_t) c * nH + dt] = (uint16_t) (n | (y << 14));
+        ch.ny[(size_t) c * nH + dt] = (uint16_t) (y * D + n);          // index into the X phase tables
     }
 }
 
@@ -429,7 +460,9 @@ static bool x_ny_smem(const DevNet &net)
 
 static size_t x_smem_bytes(const DevNet &net, bool ny_smem)
 {
-    return sizeof(double) * 7 * (size_t) net.stab_D + (ny_smem ? 2 * (((size_t) net.nH + 7) & ~(size_t) 7) : 0) + net.nX + 16;
+    return sizeof(double) * 9 * (size_t) net.stab_D + 4 * (((size_t) net.nX + 3) & ~(size_t) 3)
+           + sizeof(double) * (size_t) net.nX + 4 * (((size_t) net.nX + 4) & ~(size_t) 3)
+           + (ny_smem ? 2 * (((size_t) net.nH + 7) & ~(size_t) 7) : 0) + net.nX + 16;
 }
 
 bool fast_supported(const DevNet &net, const char **why)
@@ -439,7 +472,7 @@ bool fast_supported(const DevNet &net, const char **why)
     if (net.Eu != net.E) { *why = "duplicate (TF, target) edges"; return false; }
     if (net.listen && !net.const_params) { *why = "T nodes listen to their children"; return false; }
     if (x_smem_bytes(net, x_ny_smem(net)) + 64 > 200 * 1024) { *why = "n_tf too large for the X window kernel"; return false; }
-    if (net.max_indeg >= (1u << 14)) { *why = "in-degree does not fit the packed (n, y) word"; return false; }
+    if (3 * (size_t) net.stab_D > 65535) { *why = "in-degree does not fit the 16-bit (y, n) table index"; return false; }
     return true;
 }
 

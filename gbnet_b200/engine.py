@@ -265,6 +265,11 @@ class Sampler:
         _capi.check(self._lib.gbn_model_timer_stop(self._h, C.byref(v)))
         return v.value
 
+    def debug_counters(self, enable=True):
+        out = (C.c_uint64 * 4)()
+        _capi.check(self._lib.gbn_model_debug_counters(self._h, int(bool(enable)), out))
+        return [int(v) for v in out]
+
     def synchronize(self):
         _capi.check(self._lib.gbn_model_synchronize(self._h))
 

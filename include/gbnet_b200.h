@@ -177,6 +177,9 @@ int gbn_model_sweep_count(const gbn_model *m, uint64_t *n);
 /* device time between two points chosen by the caller (CUDA events on the model's stream) */
 int gbn_model_timer_start(gbn_model *m);
 int gbn_model_timer_stop(gbn_model *m, double *ms);
+/* diagnostics of the fast X kernel's speculative windows since the last call: rounds, TFs committed,
+ * rounds that ended in a flip; enable != 0 switches counting on, 0 off */
+int gbn_model_debug_counters(gbn_model *m, int enable, uint64_t out[4]);
 int gbn_model_synchronize(gbn_model *m);
 
 #ifdef __cplusplus
