@@ -7,7 +7,7 @@
 //   statistics    cX1[c][nX] u32  (#sweeps with X=1; X=0 is N - cX1)
 //                 tMean[c][nX], tM2[c][nX] f64 (Welford, gsl_rstat order of operations)
 //                 cS[c][Ep] u32x2 in slot order: #sweeps with S=0 and with S=2 (S=1 is N - both)
-//   fast kernel   tc2[c][nH] {pr0, pr2} f64x2 and ny[c][nH] u16 (y * D + n): the per-target product cache
+//   fast kernel   tc2[c][nH] {beta, gamma} f64x2 and ny[c][nH] u16 (y * D + n): the per-target product cache
 //                 Stf[c][E] u8   copy of S in by-TF CSR order (coalesced reads in the X phase)
 //                 FXp[c][nX] f64x2   1 - t*x and its reciprocal
 // Integer counts replace the reference's gsl_rstat workspaces of 0/1 indicators
@@ -64,7 +64,7 @@ struct DevChains {
     double *tMean, *tM2;
     uint2 *cS;                    // {count S=0, count S=2}
     // fast kernel only
-    double2 *tc2;                 // [c][nH] {pr0, pr2}: products over the parents with S = 0 / S = 2
+    double2 *tc2;                 // [c][nH] {beta, gamma} = {pr0 omz (N2-N0), pr0 pr2 omz (N1-N2)}: L = c0[ny] + beta + gamma
     uint16_t *ny;                 // [c][nH] y * stab_D + n, n = number of parents with S != 1
     uint8_t *Stf;
     double2 *FXp;                 // {1 - t*x, 1 / (1 - t*x)}

@@ -78,19 +78,20 @@ __device__ __forceinline__ void common_scale(double a, int ea, double b, int eb,
     lb = db < -1000 ? 0. : b * __hiloint2double((1023 + db) << 20, 0);
 }
 
-// X phase view of the per-target likelihood (see the S phase for the algebra): with idx = y * D + n,
-//   L = c0[idx] + pr0 * (A[idx] + pr2 * B[idx]),   A = omz * (N_2 - N_0),  B = omz * (N_1 - N_2)
-// (rows 0-2, 7-9, 10-12 of net.stab).  Likelihood of a child of X_k now (Lc) and with X_k flipped
-// (Lf): the flip multiplies the product that holds the edge's factor by fac.
-__device__ __forceinline__ void child_likelihoods(const double *xC0, const double *xA, const double *xB, double2 pr,
-                                                  uint32_t idx, uint32_t s, double fac, double &Lc, double &Lf)
+// X phase view of the per-target likelihood (see the S phase for the algebra).  The S phase leaves,
+// per target and chain, the pair
+//     beta = pr0 * omz[n] * (N_2 - N_0),   gamma = pr0 * pr2 * omz[n] * (N_1 - N_2)
+// (tc2) and the table index idx = y * D + n (ny), so that L = c0[idx] + beta + gamma, an edge with
+// S = 0 scales both terms by its factor and an edge with S = 2 scales gamma only.  One 16-byte gather,
+// one 2-byte and one 8-byte shared-memory lookup per child.
+__device__ __forceinline__ void child_likelihoods(const double *xC0, double2 bg, uint32_t idx, uint32_t s, double fac,
+                                                  double &Lc, double &Lf)
 {
-    const double c0 = xC0[idx], A = xA[idx], Bq = xB[idx];
-    const double w = pr.y * Bq;
-    const double u = pr.x * (A + w);
-    Lc = c0 + u;
-    const double f0 = c0 + fac * u;                                  // the edge feeds pr0
-    const double f2 = c0 + pr.x * (A + fac * w);                     // the edge feeds pr2
+    const double c0 = xC0[idx];
+    const double sum = bg.x + bg.y;
+    Lc = c0 + sum;
+    const double f0 = c0 + fac * sum;                                // the edge feeds pr0
+    const double f2 = c0 + (bg.x + fac * bg.y);                      // the edge feeds pr2
     Lf = s == 0 ? f0 : (s == 2 ? f2 : Lc);
 }
 
@@ -103,8 +104,7 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
     __shared__ int s_dec[NW];
     const uint32_t nX = net.nX, E = net.E, nH = net.nH, D = net.stab_D;
     double *xC0 = reinterpret_cast<double *>(smem_x);        // [3][D] c0 by idx = y * D + n
-    double *xA = xC0 + 3 * D, *xB = xA + 3 * D;              // [3][D] each
-    uint32_t *sU = reinterpret_cast<uint32_t *>(xB + 3 * D); // [nX rounded up to 4] the sweep's X uniforms (Philox words)
+    uint32_t *sU = reinterpret_cast<uint32_t *>(xC0 + 3 * D + (D & 1)); // [nX rounded up to 4] the sweep's X uniforms (Philox words)
     double *sG = reinterpret_cast<double *>(sU + ((nX + 3) & ~3u));          // [nX] 1 - T
     uint32_t *sPtr = reinterpret_cast<uint32_t *>(sG + nX);                  // [nX + 1 rounded up to 4] tf_ptr
     uint16_t *sNy = reinterpret_cast<uint16_t *>(sPtr + ((nX + 4) & ~3u));   // [nH] if staged
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
     for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.tf_ptr[k];
     {
         const double *tab = net.stab + (size_t) d * STAB_ROWS * D;
-        for (uint32_t j = tid; j < 3 * D; j += NT) { xC0[j] = tab[j]; xA[j] = tab[7 * D + j]; xB[j] = tab[10 * D + j]; }
+        for (uint32_t j = tid; j < 3 * D; j += NT) xC0[j] = tab[j];
     }
     if (!a.use_inj)     // every X uniform of this chain and sweep: one Philox block per four TFs, computed once
         for (uint32_t blk = tid; blk < (nX + 3) / 4; blk += NT) {
@@ -187,10 +187,10 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
                 const uint32_t s0 = idX.s0, s1 = idX.s1;
                 idX = load_ids(cc + 128);                             // ids two iterations ahead
                 double Lc, Lf;
-                child_likelihoods(xC0, xA, xB, dX.p0, dX.n0, s0, fac, Lc, Lf);       // cc < cend: always a child
+                child_likelihoods(xC0, dX.p0, dX.n0, s0, fac, Lc, Lf);               // cc < cend: always a child
                 mc *= Lc; mf *= Lf;
                 if (s1 != 0xffu) {
-                    child_likelihoods(xC0, xA, xB, dX.p1, dX.n1, s1, fac, Lc, Lf);
+                    child_likelihoods(xC0, dX.p1, dX.n1, s1, fac, Lc, Lf);
                     mc *= Lc; mf *= Lf;
                 }
                 if (++cnt == 8) { normalise(mc, ec); normalise(mf, ef); cnt = 0; }
@@ -238,9 +238,10 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
                     const uint32_t s = gStf[cc];
                     if (s == 1) continue;
                     const uint32_t i = net.tf_child[cc];
-                    double2 pr = tc2[i];
-                    if (s == 0) pr.x *= fac; else pr.y *= fac;
-                    tc2[i] = pr;
+                    double2 bg = tc2[i];
+                    if (s == 0) bg.x *= fac;
+                    bg.y *= fac;
+                    tc2[i] = bg;
                 }
             }
         }
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, S
         }
     }
     if (valid) {
-        ch.tc2[(size_t) c * nH + dt] = make_double2(P0, P2);
+        ch.tc2[(size_t) c * nH + dt] = make_double2(P0 * (omzt[n] * ca), (P0 * P2) * (omzt[n] * cb));   // {beta, gamma}
         ch.ny[(size_t) c * nH + dt] = (uint16_t) (y * D + n);          // index into the X phase tables
     }
 }
@@ -460,7 +461,7 @@ static bool x_ny_smem(const DevNet &net)
 
 static size_t x_smem_bytes(const DevNet &net, bool ny_smem)
 {
-    return sizeof(double) * 9 * (size_t) net.stab_D + 4 * (((size_t) net.nX + 3) & ~(size_t) 3)
+    return sizeof(double) * (3 * (size_t) net.stab_D + 2) + 4 * (((size_t) net.nX + 3) & ~(size_t) 3)
            + sizeof(double) * (size_t) net.nX + 4 * (((size_t) net.nX + 4) & ~(size_t) 3)
            + (ny_smem ? 2 * (((size_t) net.nH + 7) & ~(size_t) 7) : 0) + net.nX + 16;
 }
