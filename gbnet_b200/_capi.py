@@ -91,6 +91,7 @@ SYMBOLS = {
     "gbn_philox_kat": (C.c_int, [C.c_int, _P(_u32), _P(_u32), _P(_u32)]),
     "gbn_model_last_device_ms": (C.c_int, [_vp, _P(_dbl)]),
     "gbn_model_set_phase_timing": (C.c_int, [_vp, C.c_int]),
+    "gbn_model_set_stream_groups": (C.c_int, [_vp, _u32]),
     "gbn_model_phase_ms": (C.c_int, [_vp, _P(_dbl), _P(_u64)]),
     "gbn_model_launch_count": (C.c_int, [_vp, _P(_u64)]),
     "gbn_model_sweep_count": (C.c_int, [_vp, _P(_u64)]),

@@ -55,6 +55,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         flags = list(NVCC_FLAGS)
         if VARIANT == "fma" and src == "sweep_fast.cu":
             flags[flags.index("-fmad=false")] = "-fmad=true"
+        if VARIANT.startswith("s") and VARIANT[1:].isdigit() and src == "sweep_fast.cu":
+            flags.append("-DGBN_S_MINB=" + VARIANT[1:])
         cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False

@@ -118,6 +118,7 @@ struct gbn_model {
     std::vector<cudaStream_t> gstream;
     std::vector<cudaEvent_t> gdone;
     cudaEvent_t gfork = nullptr;
+    uint32_t stream_groups = 0;         // 0 = default (GBN_STREAM_GROUPS or 4)
     double phase_ms[3] = { 0., 0., 0. };
     uint64_t phase_launches = 0;        // sweeps accumulated in phase_ms
     // comm
@@ -313,8 +314,8 @@ int sample_n(gbn_model *m, uint32_t n)
     int launched;
     if (m->kernel == GBN_KERNEL_FAST) {
         // chains are independent: split them into groups, one stream each, joined at the end
-        static const uint32_t want_groups = env_u32("GBN_STREAM_GROUPS", 2);
-        uint32_t G = want_groups;
+        static const uint32_t want_groups = env_u32("GBN_STREAM_GROUPS", 4);   // measured best on B200 (profiles/r1_summary.md)
+        uint32_t G = m->stream_groups ? m->stream_groups : want_groups;
         if (G > m->n_chains) G = m->n_chains;
         if (G < 1) G = 1;
         while (m->gstream.size() < G) {
@@ -590,6 +591,14 @@ extern "C" int gbn_model_set_phase_timing(gbn_model *m, int on)
     m->phase_ms[0] = m->phase_ms[1] = m->phase_ms[2] = 0.;
     m->phase_launches = 0;
     m->phase_pending = 0;
+    return 0;
+}
+
+extern "C" int gbn_model_set_stream_groups(gbn_model *m, uint32_t groups)
+{
+    if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (groups > 64) return fail(GBN_ERR_INVALID, "at most 64 stream groups");
+    m->stream_groups = groups;
     return 0;
 }
 

@@ -4,27 +4,31 @@
 // What changes against the reference's loop (GraphBase.cpp:22-27 -> Multinomial.cpp:56-108 ->
 // XNode.cpp:16-22 / SNode.cpp:15-21 -> HNode.cpp:33-53 -> HNodeORNOR.cpp:40-106):
 //
-//  * Per target and chain a 32-byte cache {pr0, pr2, zc, L} holds the two parent products, the
-//    (1-z)^n term and the current likelihood.  The reference rescans all parents of a target for
-//    each of the 3 latent states and each candidate value (15-21 x sum indeg^2 parent visits per
-//    sweep); here an X candidate costs one cache line and ~20 flops, an S candidate ~15 flops.
+//  * The reference rescans all parents of a target for each of the 3 latent states and each
+//    candidate value (15-21 x sum indeg^2 parent visits per sweep).  Here the target likelihood is
+//    written as  L = c0[y,n] + pr0 * omz[n] * (a_y + pr2 * b_y)  (pr0 / pr2 = products over the
+//    parents with S = 0 / S = 2, n = number of parents with S != 1; algebra at k_fast_s) and a
+//    16-byte per-(target, chain) cache {beta, gamma} + a 16-bit table index carry it from the S
+//    phase to the next X phase: an X candidate costs one gather and ~6 flops, an S candidate ~5.
 //  * X phase (k_fast_x, one CTA per chain): X updates are sequential in the reference and do not
-//    commute when TFs share a target.  Each warp of the CTA evaluates one TF of a WINDOW of
+//    commute when TFs share a target.  Each warp of the CTA evaluates one TF of a WINDOW of 16
 //    consecutive TFs against the same state; draws are taken for all of them; the window commits
 //    up to and including the first TF whose value changed, applies that flip to the cache, and the
 //    next window starts behind it.  A TF's conditional is only used if no earlier TF of its window
 //    flipped, i.e. exactly when it equals the conditional the sequential sweep would have seen, so
 //    the chain is the sequential chain, not an approximation of it.  X values rarely change
-//    (prior 0.01 / 0.99), so a 16-wide window advances ~14 TFs per round.
+//    (measured: 96 rounds per sweep for 1,500 TFs, 15.7 TFs committed per round).
 //  * The sum of child log-likelihoods becomes a product with explicit exponent tracking (no log,
-//    no exp per child); the underflow fallback of Multinomial.cpp:78-85 is kept: the scaled
-//    product underflows to zero where exp(sum log) does.
+//    no exp per child); the underflow fallback of Multinomial.cpp:78-85 is kept.
 //  * T phase (k_fast_t, thread per (chain, TF)): T nodes that do not listen to their children are
-//    mutually independent (TNode.cpp:19-22).  Also refreshes FX = 1 - t*x and 1/FX.
-//  * S phase (k_fast_s, thread per (chain, target)): S updates of different targets commute; a
-//    thread walks its target's edges in input order with leave-one-out products (multiply by the
-//    precomputed reciprocal factor), no transcendental: exp(log p + log L) = p * L.
-//    Targets are assigned to lanes in descending in-degree order so a warp's lanes finish together.
+//    mutually independent (TNode.cpp:19-22).  Also publishes FXp = {1 - t*x, 1 / (1 - t*x)}.
+//  * S phase (k_fast_s, one warp per (group of 32 targets, chain)): S updates of different targets
+//    commute; a lane walks its target's edges in input order with leave-one-out products
+//    (multiply by the precomputed reciprocal factor), no transcendental: exp(log p + log L) = p * L.
+//    Device targets are sorted by in-degree and slots are stored transposed (topology.hpp), so the
+//    lanes of a warp finish together and every S / parent-id / counter access is coalesced.
+//  * Chains are independent, so the model layer runs disjoint chain groups on separate streams
+//    (capi.cu): one group's latency-bound X kernel overlaps another group's S kernel.
 //
 // Not handled here (the model layer routes these to the strict kernel): T nodes that listen to
 // their children, duplicate (TF, target) edges.
@@ -306,8 +310,11 @@ __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, Swee
 // without the edge) and differ only in which product takes the factor f and in n.
 // MODE 0: sweep (draw every S of the target, count, refresh the cache)
 // MODE 1: refresh only (rebuild the cache from X, T, S; no draws, no counts)
+#ifndef GBN_S_MINB
+#define GBN_S_MINB 4          // 64 registers: 4 CTAs (32 warps) per SM measured best (profiles/r1_summary.md)
+#endif
 template <int MODE, bool STAGE_FX, bool INJ>
-__global__ void __launch_bounds__(FS_NT, 3) k_fast_s(DevNet net, DevChains ch, SweepArgs a)
+__global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevChains ch, SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;

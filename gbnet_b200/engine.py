@@ -240,6 +240,9 @@ class Sampler:
     def set_phase_timing(self, on=True):
         _capi.check(self._lib.gbn_model_set_phase_timing(self._h, int(bool(on))))
 
+    def set_stream_groups(self, groups=0):
+        _capi.check(self._lib.gbn_model_set_stream_groups(self._h, int(groups)))
+
     def phase_ms(self):
         """(ms in the X, T, S kernels, sweeps covered) since set_phase_timing(True)"""
         ms = (C.c_double * 3)()

@@ -170,6 +170,9 @@ int gbn_model_last_device_ms(const gbn_model *m, double *ms);
  * accumulated milliseconds per kernel and the number of sweeps they cover */
 int gbn_model_set_phase_timing(gbn_model *m, int on);
 int gbn_model_phase_ms(const gbn_model *m, double ms_out[3], uint64_t *sweeps);
+/* the fast path sweeps disjoint chain groups on separate streams so that one group's X kernel overlaps
+ * another group's S kernel; 0 restores the default (4), 1 serialises the kernels (per-kernel timing) */
+int gbn_model_set_stream_groups(gbn_model *m, uint32_t groups);
 /* number of kernels this library launched on behalf of the model since creation */
 int gbn_model_launch_count(const gbn_model *m, uint64_t *n);
 /* total sweeps drawn since creation (Philox counter word) */

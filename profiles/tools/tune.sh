@@ -4,5 +4,6 @@ run() { echo "== $*"; env "$@" python bench.py --steps 3 --warmup 2 --no-cpu-bas
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('%.3e' % d['value'], 'ms/step %.2f' % d['ms_per_step'], {k: round(v,3) for k,v in d['roofline']['kernel_ms_per_sweep'].items()})"; }
 run GBN_STREAM_GROUPS=1
-run GBN_STREAM_GROUPS=2
+run GBN_STREAM_GROUPS=1 GBN_LIB_VARIANT=s4
 run GBN_STREAM_GROUPS=4
+run GBN_STREAM_GROUPS=4 GBN_LIB_VARIANT=s4

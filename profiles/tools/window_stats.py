@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0,'/root/repo')
+import sys; import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import gbnet_b200, numpy as np
 from gbnet_b200 import synth
 net = synth.shape("C3"); hy = synth.cli_default_hyper()
