@@ -168,6 +168,21 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ native arm
+class _StdoutToStderr:
+    """NCCL prints its version banner on stdout when a communicator is created; the contract wants
+    exactly one JSON line there, so file descriptor 1 points at stderr while communicators are set up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def run_native(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -177,7 +192,9 @@ def run_native(args):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
 
     import gbnet_b200
     from gbnet_b200 import synth
@@ -193,9 +210,11 @@ def run_native(args):
     assert G.kernel() == gbnet_b200.KERNEL_FAST
     if world > 1:
         import torch
-        uid = [gbnet_b200.Sampler.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        G.attach_comm(rank, world, uid[0])
+        with _StdoutToStderr():
+            uid = [gbnet_b200.Sampler.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            G.attach_comm(rank, world, uid[0])
+            G.max_gelman_rubin()                   # first all-reduce (lazy NCCL connection set-up)
 
     def barrier():
         if world > 1:

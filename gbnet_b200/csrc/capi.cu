@@ -84,7 +84,7 @@ struct NcclApi {
     }
 };
 NcclApi g_nccl;
-constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+constexpr int NCCL_FLOAT64 = 8, NCCL_UINT64 = 5, NCCL_SUM = 0;
 }  // namespace
 
 // ------------------------------------------------------------------------------ model
@@ -107,6 +107,7 @@ struct gbn_model {
     uint8_t *d_y = nullptr; double *d_yprob = nullptr, *d_stab = nullptr;
     double *d_inj_flat = nullptr, *d_inj_beta = nullptr, *d_inj_exp = nullptr;
     double *d_sums = nullptr, *d_psums = nullptr, *d_dev = nullptr, *d_pdev = nullptr, *d_gr = nullptr, *d_max = nullptr;
+    unsigned long long *d_isums = nullptr;
     double *d_scratch = nullptr; size_t scratch_bytes = 0;
     bool moments_valid = false;
     // per-kernel timing (gbn_model_set_phase_timing)
@@ -263,10 +264,10 @@ int use_device(const gbn_model *m)
     return 0;
 }
 
-int allreduce(gbn_model *m, double *buf, size_t n, int op)
+int allreduce(gbn_model *m, void *buf, size_t n, int op, int dtype = NCCL_FLOAT64)
 {
     if (!m->comm || m->world <= 1) return 0;
-    int rc = g_nccl.AllReduce(buf, buf, n, NCCL_FLOAT64, op, m->comm, m->stream);
+    int rc = g_nccl.AllReduce(buf, buf, n, dtype, op, m->comm, m->stream);
     if (rc != 0) return fail(GBN_ERR_COMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
     return 0;
 }
@@ -277,13 +278,18 @@ int compute_moments(gbn_model *m)
     if (m->moments_valid) return 0;
     const size_t ns = (size_t) m->n_datasets * n_stats_of(m->net);
     const double N = (double) m->stat_n;
+    // counts of the discrete nodes overflow the exact integer path only beyond M * N^2 >= 2^63
+    if ((double) m->n_graphs * N * N >= 9.0e18) return fail(GBN_ERR_UNSUPPORTED, "chain length too large for the exact moment sums");
+    launch_count_sums(m->net, m->ch, N, m->d_isums, m->stream);
     launch_moment_sums(m->net, m->ch, N, m->d_sums, m->d_psums, m->stream);
+    if (int rc = allreduce(m, m->d_isums, 4 * ns, NCCL_SUM, NCCL_UINT64)) return rc;
     if (int rc = allreduce(m, m->d_sums, 2 * ns, NCCL_SUM)) return rc;
     if (int rc = allreduce(m, m->d_psums, ns, NCCL_SUM)) return rc;
     launch_moment_devs(m->net, m->ch, N, m->d_sums, m->d_psums, m->d_dev, m->d_pdev, m->stream);
     if (int rc = allreduce(m, m->d_dev, ns, NCCL_SUM)) return rc;
     if (int rc = allreduce(m, m->d_pdev, ns, NCCL_SUM)) return rc;
-    m->launches += 2;
+    launch_expand_counts(m->net, N, m->d_isums, m->d_sums, m->d_psums, m->d_dev, m->d_pdev, m->stream);
+    m->launches += m->net.const_params ? 2 : 4;
     CUDA_TRY(cudaGetLastError());
     m->moments_valid = true;
     return 0;
@@ -518,6 +524,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     if (int rc = dev_alloc(m, &m->d_psums, ns)) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_dev, ns)) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_pdev, ns)) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_isums, 4 * ns)) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_gr, (size_t) n_nodes_of(n))) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_max, (size_t) m->n_datasets)) return bail(rc);
 

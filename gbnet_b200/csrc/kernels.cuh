@@ -52,6 +52,11 @@ void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double
 //         pdev[d][stat] = sum over global chains >= 1 of (mean_k - pmu)^2, pmu = psums / (M - 1)
 void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const double *sums, const double *psums,
                         double *dev, double *pdev, cudaStream_t st);
+// discrete nodes: isums[d][stat] = { sum c, sum c^2, the same over global chains >= 1 } (u64, exact);
+// after the all-reduce, launch_expand_counts fills sums / psums / dev / pdev for those stats
+void launch_count_sums(const DevNet &net, const DevChains &ch, double N, unsigned long long *isums, cudaStream_t st);
+void launch_expand_counts(const DevNet &net, double N, const unsigned long long *isums, double *sums, double *psums,
+                          double *dev, double *pdev, cudaStream_t st);
 // finalize: Gelman-Rubin per node (random_nodes order) of dataset d, and its maximum
 void launch_gelman_rubin(const DevNet &net, double N, const double *sums, const double *dev,
                          uint32_t dataset, double *gr_out /* [n_nodes] or NULL */, double *max_out /* [n_datasets] */,

@@ -5,7 +5,9 @@
 // Per chain k and stat j the reference keeps mean_kj and variance_kj (RVNode.cpp:115-123).  For the
 // discrete nodes these follow exactly from the outcome counts: mean = c/N and
 // variance = sum (x - mean)^2 / (N-1) = c (N-c) / N / (N-1).  For T they are the Welford pair.
-// The cross-chain reduction is done in two passes so that it distributes over ranks:
+// The cross-chain reduction distributes over ranks.  Discrete nodes (X, S: all but nX of the
+// statistics) use exact integer sums of the counts in one pass (k_count_sums / k_expand_counts);
+// the continuous T nodes use two floating-point passes:
 //   pass 1  sum_k mean_kj, sum_k variance_kj                     (-> all-reduce, sum)
 //   pass 2  sum_k (mean_kj - mu_j)^2                             (-> all-reduce, sum)
 //   final   B = N * pass2 / (M-1), W = pass1.var / M, Vhat, R    (every rank, redundantly)
@@ -72,12 +74,12 @@ __device__ __forceinline__ void node_moments(const DevNet &net, const DevChains 
     }
 }
 
-__global__ void k_moment_sums(DevNet net, DevChains ch, double N, double *sums, double *psums)
+__global__ void k_moment_sums(DevNet net, DevChains ch, double N, double *sums, double *psums, uint32_t n0, uint32_t n1)
 {
     const uint32_t n_stats = n_stats_of(net);
     const uint32_t d = blockIdx.y;
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_work_of(net)) return;
+    const uint32_t n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n1) return;
     const NodeRef r = node_ref(net, n);
     double sm[3] = { 0., 0., 0. }, sv[3] = { 0., 0., 0. }, ps[3] = { 0., 0., 0. };
     for (uint32_t l = 0; l < net.n_graphs_local; l++) {
@@ -97,12 +99,12 @@ __global__ void k_moment_sums(DevNet net, DevChains ch, double N, double *sums, 
 }
 
 __global__ void k_moment_devs(DevNet net, DevChains ch, double N, const double *sums, const double *psums,
-                              double *dev, double *pdev)
+                              double *dev, double *pdev, uint32_t n0, uint32_t n1)
 {
     const uint32_t n_stats = n_stats_of(net);
     const uint32_t d = blockIdx.y;
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_work_of(net)) return;
+    const uint32_t n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n1) return;
     const NodeRef r = node_ref(net, n);
     const double M = (double) net.n_graphs;
     double mu[3], pmu[3], dv[3] = { 0., 0., 0. }, pd[3] = { 0., 0., 0. };
@@ -126,6 +128,76 @@ __global__ void k_moment_devs(DevNet net, DevChains ch, double N, const double *
         dev[o] = dv[j];
         pdev[o] = pd[j];
     }
+}
+
+// ---- discrete nodes: exact integer moments -------------------------------------------------------
+// For an outcome with per-chain counts c_k (k = 1..M chains, N sweeps): sum_k mean_k = S1 / N,
+// sum_k var_k = (N S1 - S2) / (N (N-1)), sum_k (mean_k - mu)^2 = (M S2 - S1^2) / (M N^2), with
+// S1 = sum c_k, S2 = sum c_k^2 - integers, so ONE pass over the counters and ONE all-reduce give the
+// between- and within-chain terms exactly (no second pass, no fp64 division per chain and slot).
+// isums[d][stat] = { S1, S2, P1, P2 }, P* restricted to GLOBAL chains >= 1 (posterior getters).
+__device__ __forceinline__ void acc_count(unsigned long long *a, unsigned long long c, bool post)
+{
+    a[0] += c; a[1] += c * c;
+    if (post) { a[2] += c; a[3] += c * c; }
+}
+
+__global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long N, unsigned long long *isums)
+{
+    const uint32_t n_stats = n_stats_of(net);
+    const uint32_t nT = net.const_params ? 0 : net.nX;
+    const uint32_t d = blockIdx.y;
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;          // X_k for w < nX, then slots
+    if (w >= net.nX + net.Ep) return;
+    unsigned long long acc[3][4] = { { 0 } };
+    uint32_t stat0, ns;
+    if (w < net.nX) {
+        stat0 = 2 * w; ns = 2;
+        for (uint32_t l = 0; l < net.n_graphs_local; l++) {
+            const unsigned long long c1 = ch.cX1[(size_t) (d * net.n_graphs_local + l) * net.nX + w];
+            const bool post = (net.chain_offset + l) >= 1;
+            acc_count(acc[0], N - c1, post);
+            acc_count(acc[1], c1, post);
+        }
+    } else {
+        const uint32_t q = w - net.nX;
+        const uint32_t e = net.par_edge[q];
+        if (e == 0xffffffffu) return;                                   // pad slot
+        stat0 = 2 * net.nX + nT + 3 * e; ns = 3;
+        for (uint32_t l = 0; l < net.n_graphs_local; l++) {
+            const uint2 cs = ch.cS[(size_t) (d * net.n_graphs_local + l) * net.Ep + q];
+            const bool post = (net.chain_offset + l) >= 1;
+            acc_count(acc[0], cs.x, post);
+            acc_count(acc[1], N - cs.x - cs.y, post);
+            acc_count(acc[2], cs.y, post);
+        }
+    }
+    for (uint32_t j = 0; j < ns; j++) {
+        unsigned long long *o = isums + 4 * ((size_t) d * n_stats + stat0 + j);
+        o[0] = acc[j][0]; o[1] = acc[j][1]; o[2] = acc[j][2]; o[3] = acc[j][3];
+    }
+}
+
+// globally reduced integer sums -> the same four quantities the float path produces
+__global__ void k_expand_counts(DevNet net, double Nd, const unsigned long long *isums,
+                                double *sums, double *psums, double *dev, double *pdev)
+{
+    const uint32_t n_stats = n_stats_of(net);
+    const uint32_t nT = net.const_params ? 0 : net.nX;
+    const uint32_t d = blockIdx.y;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_stats) return;
+    if (j >= 2 * net.nX && j < 2 * net.nX + nT) return;                 // T stats: float path
+    const size_t o = (size_t) d * n_stats + j;
+    const unsigned long long *a = isums + 4 * o;
+    const unsigned __int128 S1 = a[0], S2 = a[1], P1 = a[2], P2 = a[3];
+    const unsigned __int128 N = (unsigned __int128) (unsigned long long) Nd, M = net.n_graphs;
+    const double M_d = (double) net.n_graphs, n_d = M_d - 1.;
+    sums[2 * o] = (double) a[0] / Nd;
+    sums[2 * o + 1] = Nd > 1. ? (double) (N * S1 - S2) / (Nd * (Nd - 1.)) : 0.;
+    psums[o] = (double) a[2] / Nd;
+    dev[o] = (double) (M * S2 - S1 * S1) / (M_d * Nd * Nd);
+    pdev[o] = n_d >= 1. ? (double) ((M - 1) * P2 - P1 * P1) / (n_d * Nd * Nd) : 0.;
 }
 
 // ModelBase::get_gelman_rubin (ModelBase.cpp:72-92) from the globally reduced sums
@@ -179,15 +251,32 @@ __global__ void k_node_moments(DevNet net, DevChains ch, uint32_t c, double N, d
 
 void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double *sums, double *psums, cudaStream_t st)
 {
-    dim3 grid((n_work_of(net) + 127) / 128, net.n_datasets);
-    k_moment_sums<<<grid, 128, 0, st>>>(net, ch, N, sums, psums);
+    const uint32_t nT = net.const_params ? 0 : net.nX;                  // T nodes only: the rest is k_count_sums
+    if (nT == 0) return;
+    dim3 grid((nT + 127) / 128, net.n_datasets);
+    k_moment_sums<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, net.nX, net.nX + nT);
+}
+
+void launch_count_sums(const DevNet &net, const DevChains &ch, double N, unsigned long long *isums, cudaStream_t st)
+{
+    dim3 grid((net.nX + net.Ep + 127) / 128, net.n_datasets);
+    k_count_sums<<<grid, 128, 0, st>>>(net, ch, (unsigned long long) N, isums);
+}
+
+void launch_expand_counts(const DevNet &net, double N, const unsigned long long *isums, double *sums, double *psums,
+                          double *dev, double *pdev, cudaStream_t st)
+{
+    dim3 grid((n_stats_of(net) + 127) / 128, net.n_datasets);
+    k_expand_counts<<<grid, 128, 0, st>>>(net, N, isums, sums, psums, dev, pdev);
 }
 
 void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const double *sums, const double *psums,
                         double *dev, double *pdev, cudaStream_t st)
 {
-    dim3 grid((n_work_of(net) + 127) / 128, net.n_datasets);
-    k_moment_devs<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, dev, pdev);
+    const uint32_t nT = net.const_params ? 0 : net.nX;                  // T nodes only
+    if (nT == 0) return;
+    dim3 grid((nT + 127) / 128, net.n_datasets);
+    k_moment_devs<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, dev, pdev, net.nX, net.nX + nT);
 }
 
 void launch_gelman_rubin(const DevNet &net, double N, const double *sums, const double *dev,
