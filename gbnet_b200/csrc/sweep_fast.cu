@@ -30,8 +30,10 @@
 //  * Chains are independent, so the model layer runs disjoint chain groups on separate streams
 //    (capi.cu): one group's latency-bound X kernel overlaps another group's S kernel.
 //
-// Not handled here (the model layer routes these to the strict kernel): T nodes that listen to
-// their children, duplicate (TF, target) edges.
+//  * Listening T nodes (TNode.cpp:15-25): only ACTIVE TFs have a child-dependent blanket; they are
+//    walked sequentially per chain by k_fast_tl using the same cache, the rest stay parallel.
+//
+// Not handled here (the model layer routes these to the strict kernel): duplicate (TF, target) edges.
 #include "kernels.cuh"
 #include "device_math.cuh"
 #include "topology.hpp"
@@ -265,6 +267,9 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
 // Beta::sample (Beta.cpp:60-104) for T nodes that do not listen to their children: the blanket is
 // the Beta prior alone.  Also publishes FXp = {1 - t*x, 1 / (1 - t*x)} (HNodeORNOR.cpp:59) for
 // the S phase.
+// update_t: 0 = publish FXp only (refresh), 1 = update every T, 2 = update the T of inactive TFs only
+// (listening T nodes: an inactive TF's children do not depend on its T - the factor is (1 - t*0) z -
+// so its blanket is still the prior alone; the active ones are k_fast_tl's)
 __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, SweepArgs a, int update_t)
 {
     const uint32_t nX = net.nX;
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, Swee
     if (k >= nX) return;
     const size_t o = (size_t) c * nX + k;
     double t = ch.T[o];
+    if (update_t == 2 && ch.X[o] != 0) return;
     if (update_t) {
         const uint32_t gchain = chain_global_id(net, c);
         const double al = net.t_a[k], be = net.t_b[k], mean = net.t_mean[k], lnB = net.t_lnB[k];
@@ -292,6 +298,117 @@ __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, Swee
     }
     const double fx = 1. - t * (double) ch.X[o];
     ch.FXp[o] = make_double2(fx, 1. / fx);
+}
+
+// T nodes that LISTEN to their children (TNode.cpp:15-25; the pyx default), active TFs only: one CTA
+// per chain walks the chain's active TFs in index order (the reference's order; T updates of TFs
+// that share a target do not commute).  The blanket difference  sum_children log L(t') - log L(t)
+// comes from the product cache: the edge's factor (1 - t) z sits in beta and gamma (S = 0) or in
+// gamma only (S = 2), so L(t') = c0 + r (beta + gamma) resp. c0 + beta + r gamma with
+// r = (1 - t') / (1 - t); the product of the ratios is kept as mantissa x 2^e and one log is taken.
+constexpr int FTL_NT = 256;
+__global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, SweepArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_tl[];
+    __shared__ uint32_t s_count;
+    __shared__ double s_m[2][FTL_NT / 32];
+    __shared__ int s_e[2][FTL_NT / 32];
+    const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;
+    double *xC0 = reinterpret_cast<double *>(smem_tl);               // [3][D]
+    uint32_t *list = reinterpret_cast<uint32_t *>(xC0 + 3 * D);      // [nX] active TFs, ascending
+    const uint32_t c = blockIdx.x + a.chain0;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t d = chain_dataset(net, c);
+    const uint32_t gchain = chain_global_id(net, c);
+    const uint8_t *gX = ch.X + (size_t) c * nX;
+    const uint8_t *gStf = ch.Stf + (size_t) c * net.E;
+    double2 *tc2 = ch.tc2 + (size_t) c * nH;
+    const uint16_t *gny = ch.ny + (size_t) c * nH;
+
+    for (uint32_t j = tid; j < 3 * D; j += FTL_NT) xC0[j] = net.stab[(size_t) d * STAB_ROWS * D + j];
+    if (warp == 0) {
+        uint32_t count = 0;
+        for (uint32_t base = 0; base < nX; base += 32) {
+            const bool act = base + lane < nX && gX[base + lane] != 0;
+            const uint32_t mask = __ballot_sync(0xffffffffu, act);
+            if (act) list[count + __popc(mask & ((1u << lane) - 1))] = base + lane;
+            count += __popc(mask);
+        }
+        if (lane == 0) s_count = count;
+    }
+    __syncthreads();
+    const uint32_t count = s_count;
+    for (uint32_t idx = 0; idx < count; idx++) {
+        const uint32_t k = list[idx];
+        const size_t o = (size_t) c * nX + k;
+        const double al = net.t_a[k], be = net.t_b[k], mean = net.t_mean[k], lnB = net.t_lnB[k];
+        const size_t row = ((size_t) c * ch.inj_sweeps + a.inj_row) * nX + k;
+        const double prev = ch.T[o];
+        // every thread evaluates the same draw (uniform control flow, no broadcast needed)
+        const double draw = a.use_inj ? ch.inj_beta[row] : draw_beta(net.seed, gchain, a.sweep, k, al, be);
+        const double dx = draw - mean;
+        const double prop = prev + dx;
+        const double pdf_prev = beta_pdf(prev, al, be, lnB), pdf_prop = beta_pdf(prop, al, be, lnB);
+        const double r = (1. - prop) / (1. - prev);
+        const uint32_t cbeg = net.tf_ptr[k], cend = net.tf_ptr[k + 1];
+        double dll = 0.;
+        if (pdf_prop > 0.) {                        // out-of-range proposals are rejected before the children matter
+            double mo = 1., mn = 1.;
+            int eo = 0, en = 0, cnt = 0;
+            for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
+                const uint32_t s = gStf[cc];
+                if (s == 1) continue;
+                const uint32_t i = net.tf_child[cc];
+                const double2 bg = tc2[i];
+                const double c0 = xC0[gny[i]];
+                mo *= c0 + (bg.x + bg.y);
+                mn *= s == 0 ? c0 + r * (bg.x + bg.y) : c0 + (bg.x + r * bg.y);
+                if (++cnt == 8) { normalise(mo, eo); normalise(mn, en); cnt = 0; }
+            }
+            normalise(mo, eo);
+            normalise(mn, en);
+#pragma unroll
+            for (int w = 16; w > 0; w >>= 1) {
+                mo *= __shfl_xor_sync(0xffffffffu, mo, w);
+                mn *= __shfl_xor_sync(0xffffffffu, mn, w);
+                eo += __shfl_xor_sync(0xffffffffu, eo, w);
+                en += __shfl_xor_sync(0xffffffffu, en, w);
+            }
+            normalise(mo, eo);
+            normalise(mn, en);
+            if (lane == 0) { s_m[0][warp] = mo; s_m[1][warp] = mn; s_e[0][warp] = eo; s_e[1][warp] = en; }
+            __syncthreads();
+            mo = 1.; mn = 1.; eo = 0; en = 0;
+            for (int w = 0; w < FTL_NT / 32; w++) { mo *= s_m[0][w]; mn *= s_m[1][w]; eo += s_e[0][w]; en += s_e[1][w]; }
+            dll = log(mn / mo) + (double) (en - eo) * 0.69314718055994530942;
+            __syncthreads();                        // s_m / s_e free for the next TF
+        }
+        const double prev_ll = (0. + log(pdf_prev)) + 0.;
+        const double prop_ll = (0. + log(pdf_prop)) + dll;
+        const double t = mh_decide(prev, prop, prev_ll, prop_ll, mean, dx, al, be, lnB,
+                                   a.use_inj != 0, a.use_inj ? ch.inj_exp[row] : 0., net.seed, gchain, a.sweep, k);
+        if (t != prev) {
+            // accepted: move the edge factors of this TF inside the cached terms of its children
+            for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
+                const uint32_t s = gStf[cc];
+                if (s == 1) continue;
+                const uint32_t i = net.tf_child[cc];
+                double2 bg = tc2[i];
+                if (s == 0) bg.x *= r;
+                bg.y *= r;
+                tc2[i] = bg;
+            }
+        }
+        if (tid == 0) {
+            ch.T[o] = t;
+            double m = ch.tMean[o], m2 = ch.tM2[o];
+            welford_add(m, m2, t, (double) a.stat_n);
+            ch.tMean[o] = m; ch.tM2[o] = m2;
+            const double fx = 1. - t;
+            ch.FXp[o] = make_double2(fx, 1. / fx);
+        }
+        __syncthreads();                            // cache updates visible to the next active TF
+    }
 }
 
 // ---------------------------------------------------------------------------------- S phase
@@ -478,7 +595,6 @@ bool fast_supported(const DevNet &net, const char **why)
     if (net.nX >= (1u << 30)) { *why = "n_tf does not fit the packed parent id"; return false; }
     if (s_smem_bytes(net, s_stage_fx(net)) > 200 * 1024) { *why = "in-degree too large for the S-phase tables"; return false; }
     if (net.Eu != net.E) { *why = "duplicate (TF, target) edges"; return false; }
-    if (net.listen && !net.const_params) { *why = "T nodes listen to their children"; return false; }
     if (x_smem_bytes(net, x_ny_smem(net)) + 64 > 200 * 1024) { *why = "n_tf too large for the X window kernel"; return false; }
     if (3 * (size_t) net.stab_D > 65535) { *why = "in-degree does not fit the 16-bit (y, n) table index"; return false; }
     return true;
@@ -523,6 +639,10 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
     const size_t smem_x = x_smem_bytes(net, ny_smem);
     if (check(cudaFuncSetAttribute(ny_smem ? k_fast_x<FX_NT, true> : k_fast_x<FX_NT, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x), err)) return -1;
+    const size_t smem_tl = sizeof(double) * 3 * (size_t) net.stab_D + 4 * (size_t) net.nX + 16;
+    if (net.listen && !net.const_params &&
+        check(cudaFuncSetAttribute(k_fast_tl, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) (smem_tl > 48 * 1024 ? smem_tl : 48 * 1024)), err)) return -1;
     int launches = 0;
     for (uint32_t sw = 0; sw < n_sweeps; sw++) {
         SweepArgs a;
@@ -535,7 +655,12 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         if (ny_smem) k_fast_x<FX_NT, true><<<nchains, FX_NT, smem_x, st>>>(net, ch, a);
         else k_fast_x<FX_NT, false><<<nchains, FX_NT, smem_x, st>>>(net, ch, a);
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
-        k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, nchains), FT_NT, 0, st>>>(net, ch, a, net.const_params ? 0 : 1);
+        const bool tl = net.listen && !net.const_params;
+        k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, nchains), FT_NT, 0, st>>>(net, ch, a, net.const_params ? 0 : (tl ? 2 : 1));
+        if (tl) {
+            k_fast_tl<<<nchains, FTL_NT, smem_tl, st>>>(net, ch, a);
+            launches += 1;
+        }
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 2], st);
         if (launch_s(net, ch, a, 0, nchains, st, err)) return -1;
         launches += 3;

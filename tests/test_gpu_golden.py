@@ -21,8 +21,6 @@ def test_cuda_matches_reference_fixtures(path, kernel):
     import gbnet_b200
     g = np.load(path)
     pb = _problem_from_golden(g)
-    if kernel == 2 and pb.noise_listen_children and not pb.const_params:
-        pytest.skip("listening T nodes run on the strict kernel")
     G = sampler_from_problem(pb, kernel=kernel)
     G.set_state(0, g["state"])
     a, b = G.all_conditionals(0), g["conditionals"]

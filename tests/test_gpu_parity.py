@@ -146,10 +146,18 @@ def test_trajectory_variants_strict(case):
     _run_trajectory(pb, KERNEL_STRICT, 10, injected=True, chunks=(2,))
 
 
-@pytest.mark.parametrize("case", ["const", "yprob"])
+@pytest.mark.parametrize("case", ["const", "yprob", "listen", "pyx_defaults"])
 def test_trajectory_variants_fast(case):
     pb, _ = make_problem(NX=15, NY=100, AvgNTF=3.0, seed=34, **CASES[case])
     _run_trajectory(pb, KERNEL_FAST, 25, injected=False, chunks=(5,))
+    _run_trajectory(pb, KERNEL_FAST, 10, injected=True, chunks=(2,))
+
+
+def test_listening_t_fast_long():
+    """T nodes that listen to their children (the pyx default) on the fast path: 200 sweeps of the
+    oracle's chain, with several active TFs so the sequential part is exercised."""
+    pb, _ = make_problem(NX=40, NY=800, AvgNTF=3.0, seed=35, n_graphs=3, num_active_tfs=6, noise_listen_children=True)
+    _run_trajectory(pb, KERNEL_FAST, 200, injected=False, chunks=(50,))
 
 
 def test_fast_c1_shape_long():
@@ -172,7 +180,7 @@ def test_auto_kernel_selection_and_duplicates():
     pb, _ = make_problem(NX=10, NY=50, seed=13)
     assert sampler_from_problem(pb).kernel() == KERNEL_FAST
     pbl, _ = make_problem(NX=10, NY=50, seed=13, noise_listen_children=True)
-    assert sampler_from_problem(pbl).kernel() == KERNEL_STRICT
+    assert sampler_from_problem(pbl).kernel() == KERNEL_FAST
     # a duplicated (TF, target) edge with another sign: two S nodes, one child (HParentNode.h:18)
     pb.src = np.concatenate([pb.src, pb.src[:3]])
     pb.trg = np.concatenate([pb.trg, pb.trg[:3]])
