@@ -320,8 +320,11 @@ int sample_n(gbn_model *m, uint32_t n)
     int launched;
     if (m->kernel == GBN_KERNEL_FAST) {
         // chains are independent: split them into groups, one stream each, joined at the end
-        static const uint32_t want_groups = env_u32("GBN_STREAM_GROUPS", 4);   // measured best on B200 (profiles/r1_summary.md)
-        uint32_t G = m->stream_groups ? m->stream_groups : want_groups;
+        // measured on B200 (profiles/r1_summary.md): 4 groups for >= 192 chains; fewer chains are
+        // latency-bound and only pay for the extra launches
+        static const uint32_t env_groups = env_u32("GBN_STREAM_GROUPS", 0);
+        uint32_t G = m->stream_groups ? m->stream_groups
+                   : (env_groups ? env_groups : (m->n_chains >= 192 ? 4 : (m->n_chains >= 96 ? 2 : 1)));
         if (G > m->n_chains) G = m->n_chains;
         if (G < 1) G = 1;
         while (m->gstream.size() < G) {
