@@ -17,6 +17,45 @@ import pandas as pd
 from .model import ModelORNOR
 
 
+def get_tests(evid, rels):
+    """Per-TF enrichment / mode-of-regulation screen (reference gbnet/utils.py:10-68): Fisher's exact
+    test (alternative "greater") of DE among the TF's targets and of sign agreement, their Brown-style
+    combination rho (1 - log rho), target count and a signed score.  The reference calls
+    scipy.stats.fisher_exact once per TF and table; the one-sided p-value is the hypergeometric
+    survival function, evaluated here for all TFs at once."""
+    from scipy.stats import hypergeom
+
+    evid = evid.reset_index().set_index('uid')
+    tmp = rels.merge(evid.loc[:, ['val']], how='left', left_on='trguid', right_index=True)
+    all_degp = int((evid.val == 1).sum())
+    all_degn = int((evid.val == -1).sum())
+    all_ydeg = all_degp + all_degn
+    all_ndeg = int((evid.val == 0).sum())
+
+    def count(mask, name):
+        return tmp.loc[mask, ['srcuid', 'trguid']].groupby('srcuid').count()['trguid'].rename(name)
+
+    cols = [count(tmp.val != 0, 'trg_ydeg'), count(tmp.val == 0, 'trg_ndeg'),
+            count((tmp.type == 1) & (tmp.val == 1), 'morp_degp'), count((tmp.type == 1) & (tmp.val == -1), 'morp_degn'),
+            count((tmp.type == -1) & (tmp.val == 1), 'morn_degp'), count((tmp.type == -1) & (tmp.val == -1), 'morn_degn')]
+    df = pd.DataFrame(cols).T.fillna(0).astype(int)
+    df.index.name = 'srcuid'
+
+    def fisher_greater(a, b, c, d):
+        # table [[a, b], [c, d]]: P(X >= a), X ~ Hypergeom(total, a + b, a + c)
+        a, b, c, d = (np.asarray(v, np.int64) for v in (a, b, c, d))
+        return hypergeom.sf(a - 1, a + b + c + d, a + b, a + c)
+
+    df['enrichment'] = fisher_greater(df.trg_ydeg, all_ydeg - df.trg_ydeg, df.trg_ndeg, all_ndeg - df.trg_ndeg)
+    df['mor_binary'] = fisher_greater(df.morp_degp, df.morn_degp, df.morp_degn, df.morn_degn)
+    rho = df.enrichment * df.mor_binary
+    df['combined'] = rho.apply(lambda r: r * (1 - np.log(r)) if r > 0 else r)
+    df['trg_tot'] = df.trg_ndeg + df.trg_ydeg
+    df['score'] = (df.morp_degp + df.morn_degn - df.morp_degn - df.morn_degp) / df.trg_ydeg
+    df['gt_act'] = False
+    return df
+
+
 def get_model(ents, rels, evid,
               const_params=False, noise_listen_children=False, comp_yprob=False,
               t_focus=2., t_lmargin=2., t_hmargin=2., zn_focus=2., zn_lmargin=8., zn_hmargin=2.,
@@ -68,14 +107,13 @@ def sample_model(model, ents, tests, max_its=100, burn_its=10, verbosity=0):
 
 def frames_from_network(net):
     """ents / rels / evid / tests frames in the shape gbnet.tools.genData returns (tools.py:60-85)
-    for a gbnet_b200.synth.SynthNetwork; ``tests`` carries only the planted-TF flag."""
+    for a gbnet_b200.synth.SynthNetwork."""
     NX, NY = net.NX, net.NY
     ents = pd.DataFrame({"uid": np.arange(NX + NY), "name": [f"{i:04d}" for i in range(NX + NY)],
                          "type": ['Protein'] * NX + ['mRNA'] * NY})
     rels = pd.DataFrame({"srcuid": net.src.astype(np.int64), "trguid": net.trg.astype(np.int64),
                          "type": net.mor.astype(np.int64)})
     evid = pd.DataFrame({"uid": net.evid_trg.astype(np.int64), "val": net.evid_val.astype(np.int64)})
-    tests = pd.DataFrame(index=pd.Index(np.unique(net.src).astype(np.int64), name="srcuid"))
-    tests["trg_tot"] = np.bincount(net.src, minlength=NX)[tests.index.values]
-    tests["gt_act"] = tests.index.isin(net.gt_active.astype(np.int64))
+    tests = get_tests(evid, rels)
+    tests["gt_act"] = tests.index.isin(net.gt_active.astype(np.int64))                 # tools.py:84-85
     return ents, rels, evid, tests

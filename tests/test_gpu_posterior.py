@@ -57,3 +57,22 @@ def test_sample_model_protocol_through_pandas_api():
     assert gr[0][0] == "X" and len(gr[0]) == 3
     pm = model.get_posterior_means("S")
     assert pm[0][0] == "S" and "-->" in pm[0][1] and pm[0][2] in ("0", "1", "2")
+
+
+def test_cli_end_to_end(tmp_path):
+    """gbn-ornor-inference (reference gbnet/commands/ornor_inference.py): CSVs in, result CSV out."""
+    import pandas as pd
+    from gbnet_b200 import synth, utils
+    from gbnet_b200.commands import ornor_inference
+    net = synth.gen_network(NX=30, NY=900, AvgNTF=2.5, num_active_tfs=2, seed=21)
+    ents, rels, evid, tests = utils.frames_from_network(net)
+    for name, df in (("ents", ents), ("rels", rels), ("evid", evid)):
+        df.to_csv(tmp_path / f"{name}.csv", index=False)
+    out = tmp_path / "res.csv"
+    ornor_inference.main(["--ents", str(tmp_path / "ents.csv"), "--rels", str(tmp_path / "rels.csv"),
+                          "--evid", str(tmp_path / "evid.csv"), "--out", str(out), "--max_its", "60",
+                          "--n_graphs", "8", "--seed", "3"])
+    res = pd.read_csv(out)
+    assert {"X", "T", "enrichment", "mor_binary", "trg_tot", "symbol"} <= set(res.columns)
+    top = set(res.sort_values("X", ascending=False).head(2).iloc[:, 0])
+    assert top == set(int(v) for v in net.gt_active)

@@ -83,3 +83,25 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["impl"] == "reference" and line["unit"] == "edge-updates/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_get_tests_matches_fisher_exact():
+    """gbnet_b200.utils.get_tests against scipy.stats.fisher_exact, which the reference calls per TF
+    (gbnet/utils.py:36-52)."""
+    from scipy.stats import fisher_exact
+    from gbnet_b200 import utils
+    net = synth.gen_network(NX=25, NY=400, AvgNTF=3.0, num_active_tfs=3, seed=12)
+    ents, rels, evid, tests = utils.frames_from_network(net)
+    assert tests.gt_act.sum() == 3 and len(tests) == len(np.unique(net.src))
+    ev = evid.set_index("uid").val
+    all_ydeg, all_ndeg = int((ev != 0).sum()), int((ev == 0).sum())
+    for uid, row in tests.iterrows():
+        trg = rels.loc[rels.srcuid == uid]
+        val = ev.loc[trg.trguid].values
+        assert row.trg_ydeg == (val != 0).sum() and row.trg_ndeg == (val == 0).sum()
+        p = fisher_exact([[row.trg_ydeg, all_ydeg - row.trg_ydeg], [row.trg_ndeg, all_ndeg - row.trg_ndeg]],
+                         alternative="greater")[1]
+        assert abs(p - row.enrichment) < 1e-12
+        p = fisher_exact([[row.morp_degp, row.morn_degp], [row.morp_degn, row.morn_degn]], alternative="greater")[1]
+        assert abs(p - row.mor_binary) < 1e-12
+        assert row.trg_tot == len(trg)
