@@ -88,6 +88,9 @@ SYMBOLS = {
     "gbn_model_inject_draws": (C.c_int, [_vp, _u32, _P(_dbl), _P(_dbl), _P(_dbl)]),
     "gbn_model_export_draws": (C.c_int, [_vp, _u32, _u32, _u32, _P(_dbl), _P(_dbl), _P(_dbl)]),
     "gbn_model_node_moments": (C.c_int, [_vp, _u32, _P(_dbl), _P(_dbl)]),
+    "gbn_model_checkpoint_size": (C.c_int, [_vp, _P(C.c_size_t)]),
+    "gbn_model_checkpoint_save": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "gbn_model_checkpoint_load": (C.c_int, [_vp, _vp, C.c_size_t]),
     "gbn_philox_kat": (C.c_int, [C.c_int, _P(_u32), _P(_u32), _P(_u32)]),
     "gbn_model_last_device_ms": (C.c_int, [_vp, _P(_dbl)]),
     "gbn_model_set_phase_timing": (C.c_int, [_vp, C.c_int]),

@@ -932,6 +932,70 @@ extern "C" int gbn_philox_kat(int device, const uint32_t ctr[4], const uint32_t 
     return 0;
 }
 
+// ------------------------------------------------------------------------------ checkpoint / resume
+// The reference has no serialisation of chain state or statistics; this is the "next"
+// row of §8(f): everything a bit-exact continuation needs - X, T, S, the counters and Welford pairs,
+// the sweep / statistics counters - as one flat blob.  Layout: 4 x u64 header {magic, n_chains,
+// sweeps_total, stat_n} then the arrays in the order below.
+namespace {
+constexpr uint64_t CKPT_MAGIC = 0x67626e5f636b7031ull;      // "gbn_ckp1"
+struct CkptPart { void *ptr; size_t bytes; };
+std::vector<CkptPart> ckpt_parts(gbn_model *m)
+{
+    const size_t C = m->n_chains, nX = m->tp.nX, Ep = m->tp.Ep;
+    return { { m->ch.X, C * nX }, { m->ch.T, sizeof(double) * C * nX }, { m->ch.S, C * Ep },
+             { m->ch.cX1, sizeof(uint32_t) * C * nX }, { m->ch.tMean, sizeof(double) * C * nX },
+             { m->ch.tM2, sizeof(double) * C * nX }, { m->ch.cS, sizeof(uint2) * C * Ep } };
+}
+}  // namespace
+
+extern "C" int gbn_model_checkpoint_size(gbn_model *m, size_t *bytes)
+{
+    if (!m || !bytes) return fail(GBN_ERR_INVALID, "null argument");
+    size_t n = 4 * sizeof(uint64_t);
+    for (auto &p : ckpt_parts(m)) n += p.bytes;
+    *bytes = n;
+    return 0;
+}
+
+extern "C" int gbn_model_checkpoint_save(gbn_model *m, void *out, size_t bytes)
+{
+    if (!m || !out) return fail(GBN_ERR_INVALID, "null argument");
+    size_t need = 0;
+    gbn_model_checkpoint_size(m, &need);
+    if (bytes < need) return fail(GBN_ERR_INVALID, "checkpoint buffer too small");
+    if (int rc = use_device(m)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    uint64_t hdr[4] = { CKPT_MAGIC, m->n_chains, m->sweeps_total, m->stat_n };
+    std::memcpy(out, hdr, sizeof hdr);
+    char *o = (char *) out + sizeof hdr;
+    for (auto &p : ckpt_parts(m)) { CUDA_TRY(cudaMemcpy(o, p.ptr, p.bytes, cudaMemcpyDeviceToHost)); o += p.bytes; }
+    return 0;
+}
+
+extern "C" int gbn_model_checkpoint_load(gbn_model *m, const void *in, size_t bytes)
+{
+    if (!m || !in) return fail(GBN_ERR_INVALID, "null argument");
+    size_t need = 0;
+    gbn_model_checkpoint_size(m, &need);
+    uint64_t hdr[4];
+    if (bytes < sizeof hdr) return fail(GBN_ERR_INVALID, "checkpoint truncated");
+    std::memcpy(hdr, in, sizeof hdr);
+    if (hdr[0] != CKPT_MAGIC || hdr[1] != m->n_chains || bytes != need)
+        return fail(GBN_ERR_INVALID, "checkpoint does not belong to a model of this shape");
+    if (int rc = use_device(m)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    const char *i = (const char *) in + sizeof hdr;
+    for (auto &p : ckpt_parts(m)) { CUDA_TRY(cudaMemcpy(p.ptr, i, p.bytes, cudaMemcpyHostToDevice)); i += p.bytes; }
+    m->sweeps_total = hdr[2];
+    m->stat_n = (uint32_t) hdr[3];
+    m->moments_valid = false;
+    m->ch.inj_flat = m->ch.inj_beta = m->ch.inj_exp = nullptr; m->ch.inj_sweeps = m->ch.inj_pos = 0;
+    if (int rc = refresh_fast(m)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------ measurement
 extern "C" int gbn_model_last_device_ms(const gbn_model *m, double *ms)
 {

@@ -231,6 +231,24 @@ class Sampler:
         _capi.check(self._lib.gbn_model_node_moments(self._h, int(chain), _capi.dptr(mean), _capi.dptr(var)))
         return mean, var
 
+    # ---------------------------------------------------------------- checkpoint / signal
+    def checkpoint(self) -> bytes:
+        n = C.c_size_t()
+        _capi.check(self._lib.gbn_model_checkpoint_size(self._h, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _capi.check(self._lib.gbn_model_checkpoint_save(self._h, buf, n.value))
+        return buf.raw
+
+    def restore(self, blob: bytes):
+        buf = C.create_string_buffer(blob, len(blob))
+        _capi.check(self._lib.gbn_model_checkpoint_load(self._h, buf, len(blob)))
+
+    @staticmethod
+    def set_signal(signum: int):
+        """gbn::set_signal (ModelBase.cpp:211-214): a non-zero value stops sample() after the
+        current batch; sample() clears it (ModelBase.cpp:126)."""
+        _capi.load().gbn_set_signal(int(signum))
+
     # ---------------------------------------------------------------- measurement
     def last_device_ms(self):
         v = C.c_double()

@@ -17,7 +17,7 @@ from .engine import KERNEL_AUTO, Sampler
 
 def _rank(symbols):
     """symbol -> rank in byte-wise lexicographic order (std::set<std::string>)"""
-    order = sorted(set(symbols), key=lambda s: s.encode("utf8"))
+    order = sorted(set(symbols), key=lambda s: str(s).encode("utf8"))   # the reference requires str symbols (pyx:58)
     return {s: i for i, s in enumerate(order)}, order
 
 

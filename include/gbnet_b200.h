@@ -162,6 +162,13 @@ int gbn_model_node_moments(gbn_model *m, uint32_t chain, double *mean /* [n_stat
 /* Philox4x32-10 evaluated on the device (known-answer test hook) */
 int gbn_philox_kat(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
+/* ---- checkpoint / resume (absent from the reference) ----
+ * One flat blob with the chain states, statistics and sweep counters of every local chain; loading it
+ * into a model built from the same inputs continues the chains bit for bit. */
+int gbn_model_checkpoint_size(gbn_model *m, size_t *bytes);
+int gbn_model_checkpoint_save(gbn_model *m, void *out, size_t bytes);
+int gbn_model_checkpoint_load(gbn_model *m, const void *in, size_t bytes);
+
 /* ---- measurement ---- */
 /* device time (CUDA events on the model's stream) of the last sample_n / sample call, in ms */
 int gbn_model_last_device_ms(const gbn_model *m, double *ms);

@@ -327,3 +327,37 @@ def test_full_size_properties(shape):
         m = ~np.isnan(b)
         assert rel_err(a[m], b[m]).max() < LL_RTOL
     assert F.launch_count() > 0 and F.last_device_ms() > 0
+
+
+def test_checkpoint_resume_is_bit_exact():
+    pb, _ = make_problem(NX=15, NY=100, AvgNTF=3.0, seed=51, n_graphs=3)
+    A = sampler_from_problem(pb)
+    A.sample_n(17)
+    blob = A.checkpoint()
+    A.sample_n(13)
+    B = sampler_from_problem(pb)
+    B.restore(blob)
+    assert B.chain_length() == 17 and B.sweep_count() == 17
+    B.sample_n(13)
+    for c in range(3):
+        assert np.array_equal(A.get_state(c), B.get_state(c))
+        ma, va = A.node_moments(c)
+        mb, vb = B.node_moments(c)
+        assert np.array_equal(ma, mb) and np.array_equal(va, vb)
+    assert A.max_gelman_rubin() == B.max_gelman_rubin()
+    other, _ = make_problem(NX=15, NY=100, AvgNTF=3.0, seed=51, n_graphs=4)
+    with pytest.raises(gbnet_b200.GbnError):
+        sampler_from_problem(other).restore(blob)
+
+
+def test_signal_stops_sample_between_batches():
+    """ModelBase.cpp:121,126: the flag is polled between dN-batches and cleared afterwards."""
+    pb, _ = make_problem(NX=10, NY=50, seed=53)
+    G = sampler_from_problem(pb)
+    G.sample_n(30)                       # R-hat finite but > 1.1 is not guaranteed; use the signal on a fresh count
+    G.burn_stats()
+    gbnet_b200.Sampler.set_signal(2)
+    G.sample(3000, 30)
+    assert G.chain_length() == 0         # the loop condition is tested before the first batch
+    G.sample(60, 30)                     # the flag was cleared
+    assert G.chain_length() >= 30

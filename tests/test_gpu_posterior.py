@@ -66,6 +66,7 @@ def test_cli_end_to_end(tmp_path):
     from gbnet_b200.commands import ornor_inference
     net = synth.gen_network(NX=30, NY=900, AvgNTF=2.5, num_active_tfs=2, seed=21)
     ents, rels, evid, tests = utils.frames_from_network(net)
+    ents["name"] = "G" + ents["name"]              # gene symbols that survive a CSV round trip as strings
     for name, df in (("ents", ents), ("rels", rels), ("evid", evid)):
         df.to_csv(tmp_path / f"{name}.csv", index=False)
     out = tmp_path / "res.csv"
