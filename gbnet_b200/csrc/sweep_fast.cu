@@ -487,14 +487,9 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
         const double *inj_flat = INJ ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + net.E) + nX : nullptr;
         const uint32_t *pEdge = net.par_edge + gb + lane;
         uint2 *pC = ch.cS + base;
-        // software pipeline: the loads of step j+1 are issued before step j is computed
-        uint32_t s_n = pS[0], pk_n = pPar[0];
-        uint2 cs_n = __ldcs(pC);
-        // one step = this lane's j-th parent edge
-        auto step = [&](const uint32_t j, const uint32_t word) {
-            const uint32_t s = s_n, pk = pk_n;
-            uint2 cs = cs_n;
-            if (j + 1 < W) { s_n = pS[32 * (j + 1)]; pk_n = pPar[32 * (j + 1)]; cs_n = __ldcs(pC + 32 * (j + 1)); }
+        // one step = this lane's j-th parent edge; jj = position inside the current block of 4
+        auto step = [&](const uint32_t j, const uint32_t jj, const uint32_t s, const uint32_t pk, uint2 cs,
+                        const uint32_t word, uint8_t *bS, uint2 *bC) {
             if (j < deg) {
                 const uint32_t kk = pk & 0x3fffffffu;
                 const double *sp = net.sprob[pk >> 30];
@@ -520,7 +515,7 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                 const double dice = cum2 * u;
                 const uint32_t ns = dice < cum0 ? 0u : (dice < cum1 ? 1u : (dice < cum2 ? 2u : s));
                 if (ns != s) {
-                    pS[32 * j] = (uint8_t) ns;
+                    bS[32 * jj] = (uint8_t) ns;
                     ch.Stf[(size_t) c * net.E + net.tfpos_of_slot[gb + lane + 32 * j]] = (uint8_t) ns;
                     P0 = ns == 0 ? R0 * f : R0;
                     P2 = ns == 2 ? R2 * f : R2;
@@ -529,16 +524,27 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                 cs.x += (ns == 0);                                  // Multinomial.cpp:101-105 as counts
                 cs.y += (ns == 2);
             }
-            __stcs(pC + 32 * j, cs);                                // streamed: the product cache stays in L2
+            __stcs(bC + 32 * jj, cs);                               // streamed: the product cache stays in L2
         };
-        for (uint32_t j0 = 0; j0 < W; j0 += 4) {
-            // one Philox block serves four consecutive parent edges of every lane's target
+        // blocks of four steps: the block's S bytes, parent ids and counter pairs are requested together
+        // off three running pointers (immediate offsets), one Philox block serves the four edges of
+        // every lane's target, and the other warps of the SM cover the load latency
+        uint8_t *bS = pS;
+        const uint32_t *bP = pPar;
+        uint2 *bC = pC;
+        for (uint32_t j0 = 0; j0 < W; j0 += 4, bS += 128, bP += 128, bC += 128) {
+            const uint32_t nb = W - j0;                              // steps in this block (warp-uniform)
+            uint32_t s4[4], p4[4];
+            uint2 c4[4];
+#pragma unroll
+            for (int u4 = 0; u4 < 4; u4++)
+                if ((uint32_t) u4 < nb) { s4[u4] = bS[32 * u4]; p4[u4] = bP[32 * u4]; c4[u4] = __ldcs(bC + 32 * u4); }
             u32x4 rnd = { 0, 0, 0, 0 };
             if (!INJ) rnd = philox4x32_10(ref_i, a.sweep, gchain, KIND_S | ((j0 >> 2) << 8), k0, k1);
-            step(j0, rnd.x);
-            if (j0 + 1 < W) step(j0 + 1, rnd.y);                     // W is warp-uniform
-            if (j0 + 2 < W) step(j0 + 2, rnd.z);
-            if (j0 + 3 < W) step(j0 + 3, rnd.w);
+            step(j0, 0, s4[0], p4[0], c4[0], rnd.x, bS, bC);
+            if (nb > 1) step(j0 + 1, 1, s4[1], p4[1], c4[1], rnd.y, bS, bC);
+            if (nb > 2) step(j0 + 2, 2, s4[2], p4[2], c4[2], rnd.z, bS, bC);
+            if (nb > 3) step(j0 + 3, 3, s4[3], p4[3], c4[3], rnd.w, bS, bC);
         }
     }
     if (valid) {
