@@ -12,8 +12,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-# GBN_LIB_VARIANT=fma builds / loads a second library whose fast path is compiled with FMA contraction
-# (an experiment knob: the shipped default keeps -fmad=false everywhere)
+# GBN_LIB_VARIANT builds / loads a second library next to the shipped one: "chk" compiles bounds checks
+# into the fast kernels, "fma" allows FMA contraction there, "s3"/"s4" set the S kernel's CTAs per SM
+# (experiment knobs: the shipped default keeps -fmad=false everywhere)
 VARIANT = os.environ.get("GBN_LIB_VARIANT", "")
 LIB = os.path.join(HERE, "libgbnet_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 SOURCES = ["capi.cu", "eval_kernels.cu", "sweep_strict.cu", "sweep_fast.cu", "moments.cu"]
@@ -55,6 +56,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         flags = list(NVCC_FLAGS)
         if VARIANT == "fma" and src == "sweep_fast.cu":
             flags[flags.index("-fmad=false")] = "-fmad=true"
+        if VARIANT == "chk":
+            flags.append("-DGBN_BOUNDS")
         if VARIANT.startswith("s") and VARIANT[1:].isdigit() and src == "sweep_fast.cu":
             flags.append("-DGBN_S_MINB=" + VARIANT[1:])
         cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]

@@ -34,9 +34,18 @@
 //    walked sequentially per chain by k_fast_tl using the same cache, the rest stay parallel.
 //
 // Not handled here (the model layer routes these to the strict kernel): duplicate (TF, target) edges.
+#include <cstdio>
 #include "kernels.cuh"
 #include "device_math.cuh"
 #include "topology.hpp"
+
+// Bounds checks of every data-dependent index, compiled in by the "chk" build variant
+// (GBN_LIB_VARIANT=chk; compute-sanitizer is closed on this pool): a violation traps the kernel.
+#ifdef GBN_BOUNDS
+#define GBN_CHECK(cond) do { if (!(cond)) { printf("GBN_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define GBN_CHECK(cond) do { } while (0)
+#endif
 
 namespace gbn {
 
@@ -169,6 +178,7 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
             const double g = sG[kw];
             fac = xcur ? 1. / g : g;              // factor that turns the product into the flipped one
             cbeg = sPtr[kw]; cend = sPtr[kw + 1];
+            GBN_CHECK(cbeg <= cend && cend <= E);
             double mc = 1., mf = 1.;
             int ec = 0, ef = 0, cnt = 0;
             // Two children per lane and iteration, software-pipelined with two explicit register sets
@@ -185,6 +195,7 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
                 return r;
             };
             auto gather = [&](const Ids &id) -> Dat {
+                GBN_CHECK(id.i0 < nH && id.i1 < nH);
                 return Dat{ tc2[id.i0], tc2[id.i1], NY_SMEM ? sNy[id.i0] : gny[id.i0], NY_SMEM ? sNy[id.i1] : gny[id.i1] };
             };
             uint32_t cc = cbeg + lane;
@@ -193,6 +204,7 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
                 const uint32_t s0 = idX.s0, s1 = idX.s1;
                 idX = load_ids(cc + 128);                             // ids two iterations ahead
                 double Lc, Lf;
+                GBN_CHECK(s0 <= 2 && dX.n0 < 3 * D && (s1 == 0xffu || (s1 <= 2 && dX.n1 < 3 * D)));
                 child_likelihoods(xC0, dX.p0, dX.n0, s0, fac, Lc, Lf);               // cc < cend: always a child
                 mc *= Lc; mf *= Lf;
                 if (s1 != 0xffu) {
@@ -359,6 +371,7 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
                 const uint32_t s = gStf[cc];
                 if (s == 1) continue;
                 const uint32_t i = net.tf_child[cc];
+                GBN_CHECK(i < nH && gny[i] < 3 * D);
                 const double2 bg = tc2[i];
                 const double c0 = xC0[gny[i]];
                 mo *= c0 + (bg.x + bg.y);
@@ -474,6 +487,7 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
     for (uint32_t j = 0; j < W; j++) {
         const uint32_t s = pS[32 * j];
         const uint32_t kk = pPar[32 * j] & 0x3fffffffu;
+        GBN_CHECK(kk < nX && s <= 2 && gb + lane + 32 * j < net.Ep);
         const double f = (STAGE_FX ? sFX[kk].x : gFX[kk].x) * z;
         n += (s != 1);
         P0 *= (s == 0) ? f : 1.;
@@ -499,6 +513,7 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                 const double R0 = s == 0 ? P0 * finv : P0;          // products without this edge
                 const double R2 = s == 2 ? P2 * finv : P2;
                 const uint32_t nR = n - (s != 1);
+                GBN_CHECK(kk < nX && s <= 2 && (pk >> 30) <= 2 && nR + 1 < D && n <= deg);
                 const double w = R2 * cb;
                 const double B = R0 * (ca + w);
                 const double om1 = omzt[nR + 1], c01 = c0t[nR + 1];
@@ -516,6 +531,7 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                 const uint32_t ns = dice < cum0 ? 0u : (dice < cum1 ? 1u : (dice < cum2 ? 2u : s));
                 if (ns != s) {
                     bS[32 * jj] = (uint8_t) ns;
+                    GBN_CHECK(net.tfpos_of_slot[gb + lane + 32 * j] < net.E);
                     ch.Stf[(size_t) c * net.E + net.tfpos_of_slot[gb + lane + 32 * j]] = (uint8_t) ns;
                     P0 = ns == 0 ? R0 * f : R0;
                     P2 = ns == 2 ? R2 * f : R2;
@@ -547,6 +563,7 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
             if (nb > 3) step(j0 + 3, 3, s4[3], p4[3], c4[3], rnd.w, bS, bC);
         }
     }
+    GBN_CHECK(n + (y * D) < 3 * D && n <= deg);
     if (valid) {
         ch.tc2[(size_t) c * nH + dt] = make_double2(P0 * (omzt[n] * ca), (P0 * P2) * (omzt[n] * cb));   // {beta, gamma}
         ch.ny[(size_t) c * nH + dt] = (uint16_t) (y * D + n);          // index into the X phase tables
