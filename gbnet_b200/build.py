@@ -56,6 +56,10 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         flags = list(NVCC_FLAGS)
         if VARIANT == "fma" and src == "sweep_fast.cu":
             flags[flags.index("-fmad=false")] = "-fmad=true"
+        if VARIANT == "nt512" and src == "sweep_fast.cu":
+            flags += ["-DGBN_S_NT=512", "-DGBN_S_MINB=2"]
+        if VARIANT == "nt128" and src == "sweep_fast.cu":
+            flags += ["-DGBN_S_NT=128", "-DGBN_S_MINB=8"]
         if VARIANT == "chk":
             flags.append("-DGBN_BOUNDS")
         if VARIANT.startswith("s") and VARIANT[1:].isdigit() and src == "sweep_fast.cu":

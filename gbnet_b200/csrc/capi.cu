@@ -116,8 +116,8 @@ struct gbn_model {
     uint32_t phase_pending = 0;         // sweeps whose events are recorded but not yet read
     uint32_t phase_groups = 1, phase_stride = 0;
     // chain groups on separate streams (fast path): one group's X kernel overlaps another's S kernel
-    std::vector<cudaStream_t> gstream;
-    std::vector<cudaEvent_t> gdone;
+    std::vector<cudaStream_t> gstream, xstream;     // per group: T/S stream, high-priority X stream
+    std::vector<cudaEvent_t> gdone, gevx, gevs;
     cudaEvent_t gfork = nullptr;
     uint32_t stream_groups = 0;         // 0 = default (GBN_STREAM_GROUPS or 4)
     double phase_ms[3] = { 0., 0., 0. };
@@ -327,11 +327,18 @@ int sample_n(gbn_model *m, uint32_t n)
                    : (env_groups ? env_groups : (m->n_chains >= 192 ? 4 : (m->n_chains >= 96 ? 2 : 1)));
         if (G > m->n_chains) G = m->n_chains;
         if (G < 1) G = 1;
+        static const uint32_t prio_x = env_u32("GBN_PRIO_X", 1);        // 2 = off
         while (m->gstream.size() < G) {
-            cudaStream_t s; cudaEvent_t e;
-            CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            cudaStream_t s, sx; cudaEvent_t e, e1, e2;
+            int lo = 0, hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, lo));
+            CUDA_TRY(cudaStreamCreateWithPriority(&sx, cudaStreamNonBlocking, hi));
             CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            m->gstream.push_back(s); m->gdone.push_back(e);
+            CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            m->gstream.push_back(s); m->xstream.push_back(sx); m->gdone.push_back(e);
+            m->gevx.push_back(e1); m->gevs.push_back(e2);
         }
         if (!m->gfork) CUDA_TRY(cudaEventCreateWithFlags(&m->gfork, cudaEventDisableTiming));
         const uint32_t stride = 3 * n + 1;
@@ -348,9 +355,12 @@ int sample_n(gbn_model *m, uint32_t n)
         for (uint32_t g = 0; g < G; g++) {
             const uint32_t c0 = (uint32_t) ((uint64_t) m->n_chains * g / G), c1 = (uint32_t) ((uint64_t) m->n_chains * (g + 1) / G);
             cudaStream_t st = G == 1 ? m->stream : m->gstream[g];
+            const bool px = G > 1 && prio_x != 2 && !m->phase_timing;
             if (G > 1) CUDA_TRY(cudaStreamWaitEvent(st, m->gfork, 0));
+            if (px) CUDA_TRY(cudaStreamWaitEvent(m->xstream[g], m->gfork, 0));
             int l = launch_sweep_fast(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, st, &err,
-                                      m->phase_timing ? m->phase_ev.data() + (size_t) g * stride : nullptr, c0, c1 - c0);
+                                      m->phase_timing ? m->phase_ev.data() + (size_t) g * stride : nullptr, c0, c1 - c0,
+                                      px ? m->xstream[g] : nullptr, px ? m->gevx[g] : nullptr, px ? m->gevs[g] : nullptr);
             if (l < 0) { launched = -1; break; }
             launched += l;
             if (G > 1) {
@@ -400,6 +410,9 @@ extern "C" void gbn_model_destroy(gbn_model *m)
     for (cudaEvent_t e : m->phase_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : m->gdone) cudaEventDestroy(e);
     for (cudaStream_t st : m->gstream) cudaStreamDestroy(st);
+    for (cudaStream_t st : m->xstream) cudaStreamDestroy(st);
+    for (cudaEvent_t e : m->gevx) cudaEventDestroy(e);
+    for (cudaEvent_t e : m->gevs) cudaEventDestroy(e);
     if (m->gfork) cudaEventDestroy(m->gfork);
     if (m->tev0) cudaEventDestroy(m->tev0);
     if (m->tev1) cudaEventDestroy(m->tev1);

@@ -34,7 +34,8 @@ size_t strict_smem_bytes(const DevNet &net);
 // separate streams so that one group's X kernel overlaps another group's S kernel)
 int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
                       uint32_t stat_n0, cudaStream_t st, const char **err, cudaEvent_t *phase_ev = nullptr,
-                      uint32_t chain0 = 0, uint32_t nchains = UINT32_MAX);
+                      uint32_t chain0 = 0, uint32_t nchains = UINT32_MAX,
+                      cudaStream_t stx = nullptr, cudaEvent_t evx = nullptr, cudaEvent_t evs = nullptr);
 // rebuild Stf / FX / FXinv / tcache from X, T, S (after creation and set_state)
 int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
 bool fast_supported(const DevNet &net, const char **why);

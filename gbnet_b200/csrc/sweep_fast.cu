@@ -52,7 +52,10 @@ namespace gbn {
 namespace {
 
 constexpr int FX_NT = 512;           // X kernel: 16 warps = 16-TF speculative window
-constexpr int FS_NT = 256;           // S kernel: 8 warps = 8 groups of 32 targets per CTA
+#ifndef GBN_S_NT
+#define GBN_S_NT 256
+#endif
+constexpr int FS_NT = GBN_S_NT;      // S kernel: one warp = one group of 32 targets
 constexpr int FT_NT = 128;           // T kernel
 
 struct SweepArgs {
@@ -654,8 +657,9 @@ int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st,
 
 int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
                       uint32_t stat_n0, cudaStream_t st, const char **err, cudaEvent_t *phase_ev,
-                      uint32_t chain0, uint32_t nchains)
+                      uint32_t chain0, uint32_t nchains, cudaStream_t stx, cudaEvent_t evx, cudaEvent_t evs)
 {
+    if (stx == nullptr) stx = st;                      // X kernels on their own (high-priority) stream when given
     if (nchains == UINT32_MAX) nchains = ch.n_chains - chain0;
     if (n_sweeps == 0 || nchains == 0) return 0;
     const bool ny_smem = x_ny_smem(net);
@@ -675,8 +679,10 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         a.inj_row = ch.inj_pos + sw;
         a.chain0 = chain0;
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw], st);
-        if (ny_smem) k_fast_x<FX_NT, true><<<nchains, FX_NT, smem_x, st>>>(net, ch, a);
-        else k_fast_x<FX_NT, false><<<nchains, FX_NT, smem_x, st>>>(net, ch, a);
+        if (stx != st && sw > 0) cudaStreamWaitEvent(stx, evs, 0);      // this chain group's previous S phase
+        if (ny_smem) k_fast_x<FX_NT, true><<<nchains, FX_NT, smem_x, stx>>>(net, ch, a);
+        else k_fast_x<FX_NT, false><<<nchains, FX_NT, smem_x, stx>>>(net, ch, a);
+        if (stx != st) { cudaEventRecord(evx, stx); cudaStreamWaitEvent(st, evx, 0); }
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
         const bool tl = net.listen && !net.const_params;
         k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, nchains), FT_NT, 0, st>>>(net, ch, a, net.const_params ? 0 : (tl ? 2 : 1));
@@ -686,6 +692,7 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         }
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 2], st);
         if (launch_s(net, ch, a, 0, nchains, st, err)) return -1;
+        if (stx != st) cudaEventRecord(evs, st);
         launches += 3;
     }
     if (phase_ev) cudaEventRecord(phase_ev[3 * n_sweeps], st);
