@@ -76,10 +76,39 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"--- nvcc {src} ---\n{out}\n")
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
     subprocess.run(cmd, check=True)
     return LIB
 
 
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))
+
+
+# ---------------------------------------------------------------------------------- Cython binding
+PYX = os.path.join(HERE, "ModelORNOR.pyx")
+
+
+def cython_ext_path() -> str:
+    import sysconfig
+    return os.path.join(HERE, "ModelORNOR" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_cython(force: bool = False) -> str:
+    """gbnet_b200/ModelORNOR.pyx -> in-tree extension module linked against libgbnet_b200.so
+    (the reference compiles its .pyx together with libgbnet's sources, setup.py:19-23)."""
+    import sysconfig
+    out = cython_ext_path()
+    srcs = [PYX, os.path.join(HERE, "ModelORNOR.pxd"), os.path.join(HERE, "..", "include", "gbnet_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(f) <= os.path.getmtime(out) for f in srcs):
+        return out
+    import numpy
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cpp = os.path.join(objdir, "ModelORNOR.cpp")
+    subprocess.run([sys.executable, "-m", "cython", "--cplus", "-3", "-o", cpp, PYX], check=True)
+    inc = [sysconfig.get_paths()["include"], numpy.get_include(), os.path.join(HERE, "..", "include")]
+    cmd = ["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-w"] + ["-I" + i for i in inc] + \
+          [cpp, "-o", out, "-L" + HERE, "-lgbnet_b200", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return out

@@ -150,13 +150,6 @@ int dev_upload(gbn_model *m, T **out, const std::vector<T> &v)
     return 0;
 }
 
-double host_keyed_u(uint64_t seed, uint32_t chain, uint32_t sweep, uint32_t node, uint32_t kind)
-{
-    u32x4 r = philox4x32_10(node >> 2, sweep, chain, kind, (uint32_t) seed, (uint32_t) (seed >> 32));
-    uint32_t w = (node & 3) == 0 ? r.x : ((node & 3) == 1 ? r.y : ((node & 3) == 2 ? r.z : r.w));
-    return (double) w * (1.0 / 4294967296.0);
-}
-
 // initial chain state (GraphORNOR.cpp:57-73, 223-224, 246): X drawn from its prior by the
 // Multinomial ctor (Multinomial.cpp:42-49: inside the base-class ctor the blanket is prob[v]),
 // T at the prior mean, S at mor + 1.  The two cumulative likelihoods exp(log(prob[v])) are evaluated

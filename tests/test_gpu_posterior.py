@@ -77,3 +77,31 @@ def test_cli_end_to_end(tmp_path):
     assert {"X", "T", "enrichment", "mor_binary", "trg_tot", "symbol"} <= set(res.columns)
     top = set(res.sort_values("X", ascending=False).head(2).iloc[:, 0])
     assert top == set(int(v) for v in net.gt_active)
+
+
+def test_cython_binding_matches_ctypes_binding():
+    """gbnet_b200/ModelORNOR.pyx (the reference's Cython class re-pointed at the C ABI) and the ctypes
+    binding drive the same library: same chains, same results."""
+    import gbnet_b200
+    from gbnet_b200 import build, synth, utils
+    build.build_cython()
+    from gbnet_b200.ModelORNOR import PyModelORNOR
+    net = synth.gen_network(NX=20, NY=300, AvgNTF=2.5, num_active_tfs=2, seed=31)
+    ents, rels, evid, _ = utils.frames_from_network(net)
+    kw = dict(n_graphs=4, seed=9)
+    A = PyModelORNOR(ents, rels.copy(), evid, **kw)                  # pyx defaults: T listens to its children
+    B = gbnet_b200.ModelORNOR(ents, rels.copy(), evid, **kw)
+    assert A.kernel() == B.sampler.kernel() == gbnet_b200.KERNEL_FAST
+    A.sample(90, 30)
+    B.sample(90, 30)
+    assert A.get_max_gelman_rubin() == B.get_max_gelman_rubin()
+    assert A.get_gelman_rubin() == B.get_gelman_rubin()
+    for k in ("X", "T", "S", "Q"):
+        assert A.get_posterior_means(k) == B.get_posterior_means(k)
+        assert A.get_posterior_sdevs(k) == B.get_posterior_sdevs(k)
+    A.burn_stats()
+    assert A.get_max_gelman_rubin() == float("inf")
+    with pytest.raises(IndexError, match="MOR values"):          # std::out_of_range in the reference (GraphORNOR.cpp:40-41)
+        bad = rels.copy()
+        bad.loc[0, "type"] = 5
+        PyModelORNOR(ents, bad, evid)
