@@ -49,7 +49,7 @@ class Params(C.Structure):
 
 class Dims(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_tf", "n_trg", "n_edge", "n_nodes", "n_datasets", "n_graphs",
-                                          "n_graphs_local", "chain_offset", "n_stats")]
+                                          "n_graphs_local", "chain_offset", "n_stats", "simulation")]
 
 
 # every symbol include/gbnet_b200.h declares: name -> (restype, argtypes)

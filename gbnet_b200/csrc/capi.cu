@@ -110,6 +110,7 @@ struct gbn_model {
     unsigned long long *d_isums = nullptr;
     double *d_scratch = nullptr; size_t scratch_bytes = 0;
     bool moments_valid = false;
+    bool sim = false;                   // simulation mode (empty evidence)
     // per-kernel timing (gbn_model_set_phase_timing)
     bool phase_timing = false;
     std::vector<cudaEvent_t> phase_ev;  // [group][3 n + 1]
@@ -165,6 +166,10 @@ int init_chains(gbn_model *m)
     }
     launch_init_chains(m->net, m->ch, cum, m->stream);
     m->launches += 1;
+    if (m->sim) {       // H starts at 1 ("no deg"), Y copies it (GraphORNOR.cpp:94-96, YDataNode.cpp:20-25)
+        CUDA_TRY(cudaMemsetAsync(m->ch.H, 1, (size_t) m->n_chains * m->tp.nH, m->stream));
+        CUDA_TRY(cudaMemsetAsync(m->ch.Y, 1, (size_t) m->n_chains * m->tp.nH, m->stream));
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -176,6 +181,10 @@ int zero_stats(gbn_model *m)
     CUDA_TRY(cudaMemsetAsync(m->ch.tMean, 0, sizeof(double) * C * nX, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->ch.tM2, 0, sizeof(double) * C * nX, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->ch.cS, 0, sizeof(uint2) * C * E, m->stream));
+    if (m->sim) {
+        CUDA_TRY(cudaMemsetAsync(m->ch.cH, 0, sizeof(uint2) * C * m->tp.nH, m->stream));
+        CUDA_TRY(cudaMemsetAsync(m->ch.cY, 0, sizeof(uint2) * C * m->tp.nH, m->stream));
+    }
     m->stat_n = 0;
     m->moments_valid = false;
     return 0;
@@ -194,13 +203,14 @@ int refresh_fast(gbn_model *m)
 int upload_evidence(gbn_model *m, const gbn_evidence *ev)
 {
     const Topology &tp = m->tp;
-    if (!ev || ev->n_evid == 0 || ev->n_datasets == 0)
-        return fail(GBN_ERR_UNSUPPORTED, "empty evidence selects the reference's simulation mode (GraphORNOR.cpp:28), which is outside the sampling path");
-    if (ev->n_datasets != m->n_datasets) return fail(GBN_ERR_INVALID, "n_datasets differs from the model's");
+    const bool empty = !ev || ev->n_evid == 0 || ev->n_datasets == 0;
+    if (empty != m->sim) return fail(GBN_ERR_INVALID, "evidence cannot switch a model between inference and simulation mode");
+    if (!empty && ev->n_datasets != m->n_datasets) return fail(GBN_ERR_INVALID, "n_datasets differs from the model's");
     m->h_y.assign((size_t) m->n_datasets * tp.nH, 1);
     m->h_yprob.assign((size_t) m->n_datasets * 3, 0.);
+    if (empty) { m->h_yprob[0] = 0.05; m->h_yprob[1] = 0.90; m->h_yprob[2] = 0.05; }   // GraphORNOR.h:45
     try {
-        for (uint32_t d = 0; d < m->n_datasets; d++)
+        for (uint32_t d = 0; !empty && d < m->n_datasets; d++)
             compile_evidence(tp, ev->n_evid, ev->evid_trg, ev->evid_val + (size_t) d * ev->n_evid, m->p.comp_yprob != 0,
                              &m->h_y[(size_t) d * tp.nH], &m->h_yprob[(size_t) d * 3]);
     } catch (const std::exception &ex) {
@@ -311,7 +321,9 @@ int sample_n(gbn_model *m, uint32_t n)
     const char *err = nullptr;
     CUDA_TRY(cudaEventRecord(m->ev0, m->stream));
     int launched;
-    if (m->kernel == GBN_KERNEL_FAST) {
+    if (m->sim) {
+        launched = launch_sim_sweep(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err);
+    } else if (m->kernel == GBN_KERNEL_FAST) {
         // chains are independent: split them into groups, one stream each, joined at the end
         // measured on B200 (profiles/r1_summary.md): 4 groups for >= 192 chains; fewer chains are
         // latency-bound and only pay for the extra launches
@@ -420,8 +432,9 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     if (!netin || !p || !out) return fail(GBN_ERR_INVALID, "null argument");
     *out = nullptr;
     if (p->n_graphs == 0) return fail(GBN_ERR_INVALID, "n_graphs must be positive");
-    if (!ev || ev->n_evid == 0 || ev->n_datasets == 0)
-        return fail(GBN_ERR_UNSUPPORTED, "empty evidence selects the reference's simulation mode (GraphORNOR.cpp:28), which is outside the sampling path");
+    // empty evidence selects the reference's simulation mode (GraphORNOR.cpp:28)
+    const bool sim = !ev || ev->n_evid == 0 || ev->n_datasets == 0;
+    if (sim && ev && ev->n_datasets > 1) return fail(GBN_ERR_INVALID, "simulation mode takes no datasets");
     for (int r = 0; r < 3; r++)
         for (int v = 0; v < 3; v++)
             if (!(p->sprior[3 * r + v] >= 0.)) return fail(GBN_ERR_INVALID, "sprior entries must be non-negative");   // Multinomial.cpp:39
@@ -445,7 +458,8 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         return bail(fail(GBN_ERR_INVALID, ex.what()));
     }
     const Topology &tp = m->tp;
-    m->n_datasets = ev->n_datasets;
+    m->n_datasets = sim ? 1 : ev->n_datasets;
+    m->sim = sim;
     m->n_graphs = p->n_graphs;
     m->n_graphs_local = p->n_graphs_local ? p->n_graphs_local : p->n_graphs;
     m->chain_offset = p->chain_offset;
@@ -481,6 +495,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     n.z_y = p->z_alpha / (p->z_alpha + p->z_beta);                                    // GraphORNOR.cpp:155-164
     n.z_n = p->z0_alpha / (p->z0_alpha + p->z0_beta);
     n.n_datasets = m->n_datasets; n.n_graphs_local = m->n_graphs_local; n.chain_offset = m->chain_offset; n.n_graphs = m->n_graphs;
+    n.sim = sim ? 1 : 0;
     n.listen = p->noise_listen_children ? 1 : 0;
     n.const_params = p->const_params ? 1 : 0;
     n.seed = p->seed;
@@ -505,10 +520,11 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     // ---- kernel choice
     const char *why = nullptr;
     bool fast_ok = fast_supported(n, &why);
-    if (p->kernel == GBN_KERNEL_FAST && !fast_ok)
+    if (!sim && p->kernel == GBN_KERNEL_FAST && !fast_ok)
         return bail(fail(GBN_ERR_UNSUPPORTED, std::string("fast kernel unavailable: ") + why));
     m->kernel = (p->kernel == GBN_KERNEL_STRICT) ? GBN_KERNEL_STRICT : (fast_ok ? GBN_KERNEL_FAST : GBN_KERNEL_STRICT);
-    if (m->kernel == GBN_KERNEL_STRICT && strict_smem_bytes(n) > 227 * 1024)
+    if (sim) m->kernel = GBN_KERNEL_STRICT;          // simulation has its own kernels (sim_kernels.cu), reference arithmetic
+    if (!sim && m->kernel == GBN_KERNEL_STRICT && strict_smem_bytes(n) > 227 * 1024)
         return bail(fail(GBN_ERR_UNSUPPORTED, "strict kernel: n_tf too large for shared memory"));
 
     // ---- chains
@@ -522,6 +538,12 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     if (int rc = dev_alloc(m, &ch.tMean, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.tM2, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.cS, C * Ep)) return bail(rc);
+    if (sim) {
+        if (int rc = dev_alloc(m, &ch.H, C * nH)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.Y, C * nH)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.cH, C * nH)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.cY, C * nH)) return bail(rc);
+    }
     if (m->kernel == GBN_KERNEL_FAST) {
         if (int rc = dev_alloc(m, &ch.tc2, C * nH)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.ny, C * nH)) return bail(rc);
@@ -553,6 +575,7 @@ extern "C" int gbn_model_dims(const gbn_model *m, gbn_dims *out)
     out->n_datasets = m->n_datasets; out->n_graphs = m->n_graphs;
     out->n_graphs_local = m->n_graphs_local; out->chain_offset = m->chain_offset;
     out->n_stats = n_stats_of(m->net);
+    out->simulation = m->sim ? 1 : 0;
     return 0;
 }
 
@@ -697,9 +720,17 @@ static int posterior(gbn_model *m, uint32_t dataset, char kind, double *out, uin
 {
     if (!m || !n_out) return fail(GBN_ERR_INVALID, "null argument");
     if (dataset >= m->n_datasets) return fail(GBN_ERR_INVALID, "dataset out of range");
-    const uint32_t nX = m->tp.nX, E = m->tp.E, nT = m->net.const_params ? 0 : nX;
+    const uint32_t nX = m->tp.nX, nH = m->tp.nH, E = m->tp.E, nT = m->net.const_params ? 0 : nX;
     uint32_t off, cnt;
-    switch (kind) {
+    int hy = -1;                              // simulation mode: 0 = H, 1 = Y (interleaved per target)
+    if (m->sim) {
+        switch (kind) {                       // X and S are not random nodes there (GraphORNOR.cpp:58-63, 247-248)
+        case 'H': off = 0; cnt = 3 * nH; hy = 0; break;
+        case 'Y': off = 0; cnt = 3 * nH; hy = 1; break;
+        case 'T': off = 6 * nH; cnt = nT; break;
+        default: *n_out = 0; return 0;
+        }
+    } else switch (kind) {
     case 'X': off = 0; cnt = 2 * nX; break;
     case 'T': off = 2 * nX; cnt = nT; break;
     case 'S': off = 2 * nX + nT; cnt = 3 * E; break;
@@ -716,9 +747,12 @@ static int posterior(gbn_model *m, uint32_t dataset, char kind, double *out, uin
     }
     if (int rc = compute_moments(m)) return rc;
     const size_t base = (size_t) dataset * n_stats_of(m->net) + off;
-    std::vector<double> h(cnt);
-    CUDA_TRY(cudaMemcpyAsync(h.data(), (want_sd ? m->d_pdev : m->d_psums) + base, sizeof(double) * cnt, cudaMemcpyDeviceToHost, m->stream));
+    std::vector<double> h(hy >= 0 ? 2 * cnt : cnt);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), (want_sd ? m->d_pdev : m->d_psums) + base, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (hy >= 0)                              // pick H_i (or Y_i) out of H_0 Y_0 H_1 Y_1 ...
+        for (uint32_t i = 0; i < nH; i++)
+            for (uint32_t j = 0; j < 3; j++) h[3 * i + j] = h[6 * i + 3 * hy + j];
     const double n = M - 1.;
     for (uint32_t i = 0; i < cnt; i++) {
         if (want_sd) out[i] = n > 1. ? std::sqrt(h[i] / (n - 1.)) : 0.;
@@ -736,6 +770,7 @@ extern "C" int gbn_model_posterior_sdevs(gbn_model *m, uint32_t dataset, char ki
 extern "C" int gbn_model_print_stats(gbn_model *m)
 {
     if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (m->sim) return fail(GBN_ERR_UNSUPPORTED, "print_stats is not available in simulation mode");
     const char kinds[3] = { 'X', 'T', 'S' };
     const uint32_t per[3] = { 2, 1, 3 };
     for (int t = 0; t < 3; t++) {
@@ -763,6 +798,7 @@ extern "C" int gbn_model_set_evidence(gbn_model *m, const gbn_evidence *ev)
 {
     if (!m) return fail(GBN_ERR_INVALID, "null model");
     if (int rc = use_device(m)) return rc;
+    if (m->sim) return fail(GBN_ERR_UNSUPPORTED, "a simulation-mode model has no evidence to replace");
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     if (int rc = upload_evidence(m, ev)) return rc;
     m->sweeps_total = 0;
@@ -811,6 +847,16 @@ extern "C" int gbn_model_get_state(gbn_model *m, uint32_t chain, double *out)
     std::vector<uint8_t> X(nX), S(Ep);
     std::vector<double> T(nX);
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (m->sim) {           // random_nodes order of simulation mode: H_0 Y_0 H_1 Y_1 ... then T
+        const uint32_t nH = m->tp.nH;
+        std::vector<uint8_t> H(nH), Y(nH);
+        CUDA_TRY(cudaMemcpy(H.data(), m->ch.H + (size_t) chain * nH, nH, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(Y.data(), m->ch.Y + (size_t) chain * nH, nH, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(T.data(), m->ch.T + (size_t) chain * nX, sizeof(double) * nX, cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < nH; r++) { out[2 * r] = H[m->tp.dt_of_ref[r]]; out[2 * r + 1] = Y[m->tp.dt_of_ref[r]]; }
+        if (!m->net.const_params) for (uint32_t k = 0; k < nX; k++) out[2 * nH + k] = T[k];
+        return 0;
+    }
     CUDA_TRY(cudaMemcpy(X.data(), m->ch.X + (size_t) chain * nX, nX, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(T.data(), m->ch.T + (size_t) chain * nX, sizeof(double) * nX, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(S.data(), m->ch.S + (size_t) chain * Ep, Ep, cudaMemcpyDeviceToHost));
@@ -829,6 +875,23 @@ extern "C" int gbn_model_set_state(gbn_model *m, uint32_t chain, const double *i
     const uint32_t nX = m->tp.nX, E = m->tp.E, Ep = m->tp.Ep;
     std::vector<uint8_t> X(nX), S(Ep, 1);             // pad slots stay at 1 (edge off)
     std::vector<double> T(nX);
+    if (m->sim) {
+        const uint32_t nH = m->tp.nH;
+        std::vector<uint8_t> H(nH), Y(nH);
+        for (uint32_t r = 0; r < nH; r++) {
+            const double h = in[2 * r], y = in[2 * r + 1];
+            if ((h != 0. && h != 1. && h != 2.) || (y != 0. && y != 1. && y != 2.)) return fail(GBN_ERR_INVALID, "H / Y values must be 0, 1 or 2");
+            H[m->tp.dt_of_ref[r]] = (uint8_t) h; Y[m->tp.dt_of_ref[r]] = (uint8_t) y;
+        }
+        CUDA_TRY(cudaStreamSynchronize(m->stream));
+        CUDA_TRY(cudaMemcpy(m->ch.H + (size_t) chain * nH, H.data(), nH, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(m->ch.Y + (size_t) chain * nH, Y.data(), nH, cudaMemcpyHostToDevice));
+        if (!m->net.const_params) {
+            for (uint32_t k = 0; k < nX; k++) T[k] = in[2 * nH + k];
+            CUDA_TRY(cudaMemcpy(m->ch.T + (size_t) chain * nX, T.data(), sizeof(double) * nX, cudaMemcpyHostToDevice));
+        }
+        return 0;
+    }
     uint32_t o = 0;
     for (uint32_t k = 0; k < nX; k++) { double v = in[o++]; if (v != 0. && v != 1.) return fail(GBN_ERR_INVALID, "X values must be 0 or 1"); X[k] = (uint8_t) v; }
     if (!m->net.const_params) for (uint32_t k = 0; k < nX; k++) T[k] = in[o++];
@@ -849,7 +912,9 @@ static int eval_to_host(gbn_model *m, uint32_t chain, double *out, size_t n, int
     if (chain >= m->n_chains) return fail(GBN_ERR_INVALID, "chain out of range");
     if (int rc = use_device(m)) return rc;
     if (int rc = ensure_scratch(m, sizeof(double) * n)) return rc;
-    if (which == 0) launch_conditionals(m->net, m->ch, chain, m->d_scratch, m->stream);
+    if (m->sim && which != 0) return fail(GBN_ERR_UNSUPPORTED, "only eval_conditionals is available in simulation mode");
+    if (m->sim) launch_sim_conditionals(m->net, m->ch, chain, m->d_scratch, m->stream);
+    else if (which == 0) launch_conditionals(m->net, m->ch, chain, m->d_scratch, m->stream);
     else if (which == 1) launch_target_likelihoods(m->net, m->ch, chain, m->d_scratch, m->stream);
     else launch_joint_logprob(m->net, m->ch, chain, m->d_scratch, m->stream);
     m->launches += 1;
@@ -877,7 +942,8 @@ extern "C" int gbn_model_inject_draws(gbn_model *m, uint32_t n_sweeps, const dou
     if (n_sweeps == 0) return 0;
     if (!flat_u || !beta_v || !exp_v) return fail(GBN_ERR_INVALID, "null draw arrays");
     const size_t C = m->n_chains, nX = m->tp.nX, E = m->tp.E;
-    const size_t nf = C * n_sweeps * (nX + E), nb = C * n_sweeps * nX;
+    // per sweep: X then S in edge input order; in simulation mode H_0 Y_0 H_1 Y_1 ... (reference target order)
+    const size_t nf = C * n_sweeps * (m->sim ? 2 * (size_t) m->tp.nH : nX + E), nb = C * n_sweeps * nX;
     if (int rc = dev_alloc(m, &m->d_inj_flat, nf)) return rc;
     if (int rc = dev_alloc(m, &m->d_inj_beta, nb)) return rc;
     if (int rc = dev_alloc(m, &m->d_inj_exp, nb)) return rc;
@@ -895,10 +961,11 @@ extern "C" int gbn_model_export_draws(gbn_model *m, uint32_t chain, uint32_t swe
     if (chain >= m->n_chains) return fail(GBN_ERR_INVALID, "chain out of range");
     if (int rc = use_device(m)) return rc;
     const size_t nX = m->tp.nX, E = m->tp.E;
-    const size_t nf = (size_t) n * (nX + E), nb = (size_t) n * nX;
+    const size_t nf = (size_t) n * (m->sim ? 2 * (size_t) m->tp.nH : nX + E), nb = (size_t) n * nX;
     if (int rc = ensure_scratch(m, sizeof(double) * (nf + 2 * nb))) return rc;
     double *df = m->d_scratch, *db = df + nf, *de = db + nb;
-    launch_export_draws(m->net, chain_global_id(m->net, chain), sweep0, n, df, db, de, m->stream);
+    if (m->sim) launch_sim_export_draws(m->net, chain_global_id(m->net, chain), sweep0, n, df, db, de, m->stream);
+    else launch_export_draws(m->net, chain_global_id(m->net, chain), sweep0, n, df, db, de, m->stream);
     m->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(flat_u, df, sizeof(double) * nf, cudaMemcpyDeviceToHost, m->stream));
@@ -949,9 +1016,15 @@ struct CkptPart { void *ptr; size_t bytes; };
 std::vector<CkptPart> ckpt_parts(gbn_model *m)
 {
     const size_t C = m->n_chains, nX = m->tp.nX, Ep = m->tp.Ep;
-    return { { m->ch.X, C * nX }, { m->ch.T, sizeof(double) * C * nX }, { m->ch.S, C * Ep },
+    std::vector<CkptPart> parts = { { m->ch.X, C * nX }, { m->ch.T, sizeof(double) * C * nX }, { m->ch.S, C * Ep },
              { m->ch.cX1, sizeof(uint32_t) * C * nX }, { m->ch.tMean, sizeof(double) * C * nX },
              { m->ch.tM2, sizeof(double) * C * nX }, { m->ch.cS, sizeof(uint2) * C * Ep } };
+    if (m->sim) {
+        const size_t nH = m->tp.nH;
+        parts.push_back({ m->ch.H, C * nH }); parts.push_back({ m->ch.Y, C * nH });
+        parts.push_back({ m->ch.cH, sizeof(uint2) * C * nH }); parts.push_back({ m->ch.cY, sizeof(uint2) * C * nH });
+    }
+    return parts;
 }
 }  // namespace
 

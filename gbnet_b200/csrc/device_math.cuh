@@ -16,7 +16,7 @@ namespace gbn {
 //   key     = 64-bit model seed
 //   counter = (node group, sweep, global chain id, stream kind [| block << 8])
 // so any (chain, sweep, node) draw can be regenerated independently of every other.
-enum : uint32_t { KIND_X = 0, KIND_S = 1, KIND_TBETA = 2, KIND_TEXP = 3, KIND_INIT = 4 };
+enum : uint32_t { KIND_X = 0, KIND_S = 1, KIND_TBETA = 2, KIND_TEXP = 3, KIND_INIT = 4, KIND_H = 5, KIND_Y = 6 };
 
 struct u32x4 { uint32_t x, y, z, w; };
 
@@ -184,6 +184,13 @@ struct ParentScan {
         l += p1 * ynoise_col[1];
         l += p2 * ynoise_col[2];
         return l;
+    }
+    // HNodeORNOR::get_model_likelihood (HNodeORNOR.cpp:40-106) for h = 0, 1, 2
+    __device__ __forceinline__ void model_probs(const double *yprob, double p[3]) const
+    {
+        p[0] = (1. - pr0) * (1. - zc) + zc * yprob[0];
+        p[1] = pr1 * (1. - zc) + zc * yprob[1];
+        p[2] = (pr0 - pr2 * pr0) * (1. - zc) + zc * yprob[2];
     }
 };
 

@@ -52,6 +52,7 @@ struct DevNet {
     double z_y, z_n;              // ZY / ZN constants   GraphORNOR.cpp:155-164
     uint32_t n_datasets, n_graphs_local, chain_offset, n_graphs;
     int32_t listen, const_params;
+    int32_t sim;                  // simulation mode (empty evidence, GraphORNOR.cpp:28): X and S fixed, H and Y sampled
     uint64_t seed;
 };
 
@@ -68,6 +69,9 @@ struct DevChains {
     uint16_t *ny;                 // [c][nH] y * stab_D + n, n = number of parents with S != 1
     uint8_t *Stf;
     double2 *FXp;                 // {1 - t*x, 1 / (1 - t*x)}
+    // simulation mode only: latent / observed state per (chain, device target) and their outcome counts
+    uint8_t *H, *Y;
+    uint2 *cH, *cY;               // {count outcome 0, count outcome 2}
     unsigned long long *dbg;      // [4] diagnostics: X-window rounds, TFs committed, flips, (unused)
     // injected draws (NULL = keyed Philox streams)
     const double *inj_flat;       // [chain][inj_sweeps][nX + E]  X then S in edge input order

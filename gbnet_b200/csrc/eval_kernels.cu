@@ -158,7 +158,8 @@ __global__ void k_init_chains(DevNet net, DevChains ch, double c00, double c01, 
         const double c0 = act ? c10 : c00, c1 = act ? c11 : c01;
         const double u = keyed_u(net.seed, gchain, 0, j, KIND_INIT);
         const double dice = 0. * (1 - u) + c1 * u;
-        ch.X[(size_t) c * net.nX + j] = dice < c0 ? 0 : 1;
+        // simulation mode: X is a constant, 1 for the TFs of active_tf_set (GraphORNOR.cpp:58-63)
+        ch.X[(size_t) c * net.nX + j] = net.sim ? (act ? 1 : 0) : (dice < c0 ? 0 : 1);
         ch.T[(size_t) c * net.nX + j] = net.t_mean[j];
     }
     if (j < net.Ep) ch.S[(size_t) c * net.Ep + j] = net.mor_idx[j];     // pads: 1 = edge off

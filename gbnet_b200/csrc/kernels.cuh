@@ -40,6 +40,13 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
 int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
 bool fast_supported(const DevNet &net, const char **why);
 
+// ---- sim_kernels.cu: simulation mode (GraphORNOR.cpp:28,58-63,89-106): n_sweeps sweeps H, Y -> T
+int launch_sim_sweep(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
+                     uint32_t stat_n0, cudaStream_t st, const char **err);
+void launch_sim_conditionals(const DevNet &net, const DevChains &ch, uint32_t c, double *out, cudaStream_t st);
+void launch_sim_export_draws(const DevNet &net, uint32_t gchain, uint32_t sweep0, uint32_t n,
+                             double *flat_u, double *beta_v, double *exp_v, cudaStream_t st);
+
 // ---- moments.cu (K5): cross-chain moments -> Gelman-Rubin and posterior summaries
 struct MomentArgs {
     uint32_t n_stats;             // per dataset: 2 nX + nT + 3 E
@@ -67,9 +74,11 @@ void launch_node_moments(const DevNet &net, const DevChains &ch, uint32_t c, dou
 
 // stat index helpers shared by host and device: per dataset, stats are laid out
 //   X: 2 per TF (outcome 0, 1) | T: 1 per TF (absent if const_params) | S: 3 per edge in EDGE INPUT order
-__host__ __device__ inline uint32_t n_stats_of(const DevNet &n) { return 2 * n.nX + (n.const_params ? 0 : n.nX) + 3 * n.E; }
-__host__ __device__ inline uint32_t n_nodes_of(const DevNet &n) { return n.nX + (n.const_params ? 0 : n.nX) + n.E; }
+//   simulation mode: H_i, Y_i interleaved in reference target order (3 stats each) | T
+__host__ __device__ inline uint32_t n_t_of(const DevNet &n) { return n.const_params ? 0 : n.nX; }
+__host__ __device__ inline uint32_t n_stats_of(const DevNet &n) { return n.sim ? 6 * n.nH + n_t_of(n) : 2 * n.nX + n_t_of(n) + 3 * n.E; }
+__host__ __device__ inline uint32_t n_nodes_of(const DevNet &n) { return n.sim ? 2 * n.nH + n_t_of(n) : n.nX + n_t_of(n) + n.E; }
 // work items of the moment kernels: nodes in slot order, pad slots included (and skipped)
-__host__ __device__ inline uint32_t n_work_of(const DevNet &n) { return n.nX + (n.const_params ? 0 : n.nX) + n.Ep; }
+__host__ __device__ inline uint32_t n_work_of(const DevNet &n) { return n.sim ? 2 * n.nH + n_t_of(n) : n.nX + n_t_of(n) + n.Ep; }
 
 }  // namespace gbn

@@ -35,6 +35,15 @@ __device__ __forceinline__ NodeRef node_ref(const DevNet &net, uint32_t n)
 {
     const uint32_t nT = net.const_params ? 0 : net.nX;
     NodeRef r;
+    if (net.sim) {                                          // H_i | Y_i | T  (sim_kernels.cu)
+        if (n < 2 * net.nH) {
+            const uint32_t isY = n >= net.nH, dt = n - (isY ? net.nH : 0), ref = net.ref_of_dt[dt];
+            r.kind = 3 + isY; r.idx = dt; r.n_stats = 3; r.stat0 = 6 * ref + 3 * isY; r.node = 2 * ref + isY;
+        } else {
+            r.kind = 1; r.idx = n - 2 * net.nH; r.n_stats = 1; r.stat0 = 6 * net.nH + r.idx; r.node = n;
+        }
+        return r;
+    }
     if (n < net.nX) { r.kind = 0; r.idx = n; r.n_stats = 2; r.stat0 = 2 * n; r.node = n; }
     else if (n < net.nX + nT) { r.kind = 1; r.idx = n - net.nX; r.n_stats = 1; r.stat0 = 2 * net.nX + r.idx; r.node = n; }
     else {
@@ -65,7 +74,8 @@ __device__ __forceinline__ void node_moments(const DevNet &net, const DevChains 
         mean[0] = ch.tMean[(size_t) c * net.nX + r.idx];
         var[0] = N > 1. ? ch.tM2[(size_t) c * net.nX + r.idx] / (N - 1.) : 0.;
     } else {
-        const uint2 cs = ch.cS[(size_t) c * net.Ep + r.idx];
+        const uint2 cs = r.kind == 2 ? ch.cS[(size_t) c * net.Ep + r.idx]
+                       : (r.kind == 3 ? ch.cH : ch.cY)[(size_t) c * net.nH + r.idx];
         double c0 = (double) cs.x;
         double c2 = (double) cs.y;
         count_moment(c0, N, mean[0], var[0]);
@@ -148,10 +158,21 @@ __global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long N, uns
     const uint32_t nT = net.const_params ? 0 : net.nX;
     const uint32_t d = blockIdx.y;
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;          // X_k for w < nX, then slots
-    if (w >= net.nX + net.Ep) return;
+    if (w >= (net.sim ? 2 * net.nH : net.nX + net.Ep)) return;
     unsigned long long acc[3][4] = { { 0 } };
     uint32_t stat0, ns;
-    if (w < net.nX) {
+    if (net.sim) {                                                      // H_dt for w < nH, then Y_dt
+        const uint32_t isY = w >= net.nH, dt = w - (isY ? net.nH : 0);
+        stat0 = 6 * net.ref_of_dt[dt] + 3 * isY; ns = 3;
+        const uint2 *cnt = isY ? ch.cY : ch.cH;
+        for (uint32_t l = 0; l < net.n_graphs_local; l++) {
+            const uint2 cs = cnt[(size_t) (d * net.n_graphs_local + l) * net.nH + dt];
+            const bool post = (net.chain_offset + l) >= 1;
+            acc_count(acc[0], cs.x, post);
+            acc_count(acc[1], N - cs.x - cs.y, post);
+            acc_count(acc[2], cs.y, post);
+        }
+    } else if (w < net.nX) {
         stat0 = 2 * w; ns = 2;
         for (uint32_t l = 0; l < net.n_graphs_local; l++) {
             const unsigned long long c1 = ch.cX1[(size_t) (d * net.n_graphs_local + l) * net.nX + w];
@@ -187,7 +208,8 @@ __global__ void k_expand_counts(DevNet net, double Nd, const unsigned long long 
     const uint32_t d = blockIdx.y;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_stats) return;
-    if (j >= 2 * net.nX && j < 2 * net.nX + nT) return;                 // T stats: float path
+    const uint32_t t0 = net.sim ? 6 * net.nH : 2 * net.nX;
+    if (j >= t0 && j < t0 + nT) return;                                 // T stats: float path
     const size_t o = (size_t) d * n_stats + j;
     const unsigned long long *a = isums + 4 * o;
     const unsigned __int128 S1 = a[0], S2 = a[1], P1 = a[2], P2 = a[3];
@@ -254,12 +276,13 @@ void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double
     const uint32_t nT = net.const_params ? 0 : net.nX;                  // T nodes only: the rest is k_count_sums
     if (nT == 0) return;
     dim3 grid((nT + 127) / 128, net.n_datasets);
-    k_moment_sums<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, net.nX, net.nX + nT);
+    const uint32_t n0 = net.sim ? 2 * net.nH : net.nX;                  // first T work item
+    k_moment_sums<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, n0, n0 + nT);
 }
 
 void launch_count_sums(const DevNet &net, const DevChains &ch, double N, unsigned long long *isums, cudaStream_t st)
 {
-    dim3 grid((net.nX + net.Ep + 127) / 128, net.n_datasets);
+    dim3 grid(((net.sim ? 2 * net.nH : net.nX + net.Ep) + 127) / 128, net.n_datasets);
     k_count_sums<<<grid, 128, 0, st>>>(net, ch, (unsigned long long) N, isums);
 }
 
@@ -276,7 +299,8 @@ void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const 
     const uint32_t nT = net.const_params ? 0 : net.nX;                  // T nodes only
     if (nT == 0) return;
     dim3 grid((nT + 127) / 128, net.n_datasets);
-    k_moment_devs<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, dev, pdev, net.nX, net.nX + nT);
+    const uint32_t n0 = net.sim ? 2 * net.nH : net.nX;
+    k_moment_devs<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, dev, pdev, n0, n0 + nT);
 }
 
 void launch_gelman_rubin(const DevNet &net, double N, const double *sums, const double *dev,

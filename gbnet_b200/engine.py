@@ -99,6 +99,7 @@ class Sampler:
     def n_chains(self): return int(self.dims.n_datasets * self.dims.n_graphs_local)
     def n_datasets(self): return int(self.dims.n_datasets)
     def kernel(self): return int(self._lib.gbn_model_kernel(self._h))
+    def simulation(self): return bool(self.dims.simulation)
 
     def tf_ids(self):
         out = np.empty(self.n_tf(), np.uint32)
@@ -206,8 +207,9 @@ class Sampler:
         b = np.ascontiguousarray(beta_v, np.float64)
         e = np.ascontiguousarray(exp_v, np.float64)
         C_, nX, E = self.n_chains(), self.n_tf(), self.n_edges()
-        if f.ndim != 3 or f.shape[0] != C_ or f.shape[2] != nX + E:
-            raise ValueError("flat_u must be [n_chains, n_sweeps, n_tf + n_edge]")
+        per = 2 * self.n_targets() if self.simulation() else nX + E
+        if f.ndim != 3 or f.shape[0] != C_ or f.shape[2] != per:
+            raise ValueError("flat_u must be [n_chains, n_sweeps, n_tf + n_edge] (simulation mode: 2 n_targets)")
         n = f.shape[1]
         if b.shape != (C_, n, nX) or e.shape != (C_, n, nX):
             raise ValueError("beta_v / exp_v must be [n_chains, n_sweeps, n_tf]")
@@ -218,7 +220,7 @@ class Sampler:
 
     def export_draws(self, chain, sweep0, n):
         nX, E = self.n_tf(), self.n_edges()
-        f = np.empty((n, nX + E), np.float64)
+        f = np.empty((n, 2 * self.n_targets() if self.simulation() else nX + E), np.float64)
         b = np.empty((n, nX), np.float64)
         e = np.empty((n, nX), np.float64)
         _capi.check(self._lib.gbn_model_export_draws(self._h, int(chain), int(sweep0), int(n),

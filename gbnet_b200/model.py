@@ -111,6 +111,11 @@ class ModelORNOR:
 
     # ids exactly as RVNode builds them (RVNode.cpp:29-33; GraphORNOR.cpp:243): name + "_" + uid
     def _node_ids(self):
+        if self._sampler.simulation():          # evid=None: H and Y per target, then T (GraphORNOR.cpp:89-106)
+            ids = [[k, t] for t in self._trg_symbols for k in ("H", "Y")]
+            if not self._const_params:
+                ids += [["T", s] for s in self._tf_symbols]
+            return ids
         ids = [["X", s] for s in self._tf_symbols]
         if not self._const_params:
             ids += [["T", s] for s in self._tf_symbols]
@@ -140,7 +145,7 @@ class ModelORNOR:
         self._sampler.burn_stats()
 
     def _posterior(self, values, var_name):
-        per = {"X": 2, "T": 1, "S": 3}.get(var_name)
+        per = {"X": 2, "T": 1, "S": 3, "H": 3, "Y": 3}.get(var_name)
         if per is None:
             return []
         ids = [i for i in self._node_ids() if i[0] == var_name]

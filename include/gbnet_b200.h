@@ -85,7 +85,15 @@ const char *gbn_last_error(void);
 int gbn_abi_version(void);
 int gbn_device_count(void);
 
-/* new gbn::ModelORNOR(...)  (ModelORNOR.cpp:13-28 -> GraphORNOR::build_structure) */
+/* new gbn::ModelORNOR(...)  (ModelORNOR.cpp:13-28 -> GraphORNOR::build_structure)
+ *
+ * SIMULATION MODE.  As in the reference (GraphORNOR.cpp:28), EMPTY evidence (ev == NULL or n_evid == 0)
+ * builds a forward simulator instead of a sampler for inference: X is fixed (1 for the TFs of
+ * active_tf, 0 otherwise) and S is fixed at mor + 1; the random nodes, in sweep order, are
+ * H_0 Y_0 H_1 Y_1 ... (targets in sorted id order: latent and observed DE state, 3 outcomes each)
+ * followed by the T nodes.  n_nodes = 2 n_trg + nT, n_stats = 6 n_trg + nT; get/set_state,
+ * gelman_rubin, eval_conditionals and inject_draws (flat_u[chain][sweep][2 n_trg]) use that order;
+ * the posterior getters answer to 'H', 'Y' and 'T'. */
 int gbn_model_create(const gbn_network *net, const gbn_evidence *ev, const gbn_params *p, gbn_model **out);
 /* delete model (ModelORNOR.cpp:7-11) */
 void gbn_model_destroy(gbn_model *m);
@@ -95,6 +103,7 @@ typedef struct gbn_dims {
     uint32_t n_nodes;            /* random nodes per chain: nX + (const_params ? 0 : nX) + E */
     uint32_t n_datasets, n_graphs, n_graphs_local, chain_offset;
     uint32_t n_stats;            /* 2 nX + (const_params ? 0 : nX) + 3 E */
+    uint32_t simulation;         /* 1: built with empty evidence (simulation mode, see below) */
 } gbn_dims;
 int gbn_model_dims(const gbn_model *m, gbn_dims *out);
 /* the gbn_kernel_kind the model runs (GBN_KERNEL_AUTO resolved) */

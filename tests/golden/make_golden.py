@@ -102,5 +102,55 @@ def main():
         print(name, "->", path, os.path.getsize(path), "bytes; nodes", n_nodes)
 
 
+def main_sim():
+    """Simulation mode (empty evidence, GraphORNOR.cpp:28): the reference's forward simulator of H / Y."""
+    for name, listen in (("sim", False), ("sim_listen", True)):
+        net = synth.gen_network(NX=12, NY=70, AvgNTF=3.0, num_active_tfs=2, seed=104)
+        hy = dict(synth.cli_default_hyper(), noise_listen_children=listen)
+        pb = oracle.Problem(src=net.src, trg=net.trg, mor=net.mor, evid_trg=np.zeros(0, np.uint32),
+                            evid_val=np.zeros(0, np.int32), n_graphs=N_GRAPHS, seed=7, **hy)
+        pb.active_tf = net.gt_active
+        R = oracle.RefModel(pb)
+        n_nodes = R.n_nodes()
+        nX = int(np.unique(net.src).size)
+        nH = (n_nodes - nX) // 2
+        rng = np.random.default_rng(11)
+        out = dict(src=pb.src, trg=pb.trg, mor=pb.mor, evid_trg=pb.evid_trg, evid_val=pb.evid_val,
+                   active_tf=pb.active_tf, n_graphs=N_GRAPHS, hyper_keys=np.array(sorted(hy.keys())),
+                   hyper_vals=np.array([repr(hy[k]) for k in sorted(hy.keys())]))
+        st = R.get_state(0)
+        st[:2 * nH] = rng.integers(0, 3, 2 * nH)
+        st[2 * nH:] = rng.uniform(0.05, 0.95, nX)
+        R.set_state(0, st)
+        out["state"] = st
+        out["conditionals"] = R.all_conditionals(0)
+        init = np.stack([R.get_state(c) for c in (1, 1, 1)])            # fresh state (H = Y = 1, T at its prior mean)
+        flat = rng.random((N_GRAPHS, N_SWEEPS, 2 * nH))
+        beta = np.stack([[[rng.beta(*R.t_prior(2 * nH + k)) for k in range(nX)] for _ in range(N_SWEEPS)]
+                         for _ in range(N_GRAPHS)])
+        expo = rng.exponential(1.0, (N_GRAPHS, N_SWEEPS, nX))
+        for c in range(N_GRAPHS):
+            R.set_state(c, init[c])
+            R.inject(c, flat[c], beta[c], expo[c])
+        out["init"], out["flat_u"], out["beta_v"], out["exp_v"] = init, flat, beta, expo
+        states = []
+        for _ in range(N_SWEEPS // BLOCK):
+            R.sample_n(BLOCK)
+            states.append(np.stack([R.get_state(c) for c in range(N_GRAPHS)]))
+        out["states"] = np.stack(states)
+        nst = [R.node_info(n)[2] for n in range(n_nodes)]
+        out["node_kinds"] = np.array([R.node_info(n)[0] for n in range(n_nodes)])
+        out["node_means"] = np.array([[R.node_mean(c, n, s) for n in range(n_nodes) for s in range(nst[n])] for c in range(N_GRAPHS)])
+        out["node_vars"] = np.array([[R.node_variance(c, n, s) for n in range(n_nodes) for s in range(nst[n])] for c in range(N_GRAPHS)])
+        out["gelman_rubin"] = R.gelman_rubin()
+        for k in ("H", "Y", "T", "X", "S"):
+            out["post_mean_" + k] = R.posterior_means(k)
+            out["post_sd_" + k] = R.posterior_sdevs(k)
+        path = os.path.join(HERE, f"refsim_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(name, "->", path, os.path.getsize(path), "bytes; nodes", n_nodes)
+
+
 if __name__ == "__main__":
     main()
+    main_sim()

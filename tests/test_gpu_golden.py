@@ -57,3 +57,60 @@ def test_cuda_matches_reference_fixtures(path, kernel):
         if pm.size:
             assert np.abs(pm - g["post_mean_" + k]).max() < 1e-12
             assert np.abs(ps - g["post_sd_" + k]).max() < 1e-10
+
+
+SIM_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "refsim_*.npz")))
+
+
+@pytest.mark.parametrize("path", SIM_GOLDEN, ids=[os.path.basename(p) for p in SIM_GOLDEN])
+def test_simulation_mode_matches_reference_fixtures(path):
+    """Empty evidence = the reference's simulation mode (GraphORNOR.cpp:28): X and S fixed, H_i / Y_i
+    sampled forward, then T.  Fixtures come from the reference's own C++ under an injected stream."""
+    import oracle
+    g = np.load(path)
+    pb = _problem_from_golden(g)
+    G = sampler_from_problem(pb)
+    assert G.simulation() and G.n_nodes() == g["state"].size
+    nH = G.n_targets()
+    G.set_state(0, g["state"])
+    assert np.array_equal(G.get_state(0), g["state"])
+    a, b = G.all_conditionals(0), g["conditionals"]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = ~np.isnan(b)
+    assert rel_err(a[m], b[m]).max() < 1e-12
+    M = int(g["n_graphs"])
+    for c in range(M):
+        assert np.array_equal(sampler_from_problem(pb).get_state(c), g["init"][c])   # H = Y = 1, T at the prior mean
+        G.set_state(c, g["init"][c])
+    G.inject(g["flat_u"], g["beta_v"], g["exp_v"])
+    blocks = g["states"].shape[0]
+    per = g["flat_u"].shape[1] // blocks
+    for bidx in range(blocks):
+        G.sample_n(per)
+        for c in range(M):
+            st, ref = G.get_state(c), g["states"][bidx, c]
+            assert np.array_equal(st[:2 * nH], ref[:2 * nH]), (bidx, c)
+            assert np.abs(st[2 * nH:] - ref[2 * nH:]).max() < 1e-12
+    for c in range(M):
+        mean, var = G.node_moments(c)
+        assert np.abs(mean - g["node_means"][c]).max() < 1e-12
+        assert np.abs(var - g["node_vars"][c]).max() < 1e-12
+    gg, gr = G.gelman_rubin(), g["gelman_rubin"]
+    fin = np.isfinite(gr)
+    assert np.array_equal(np.isfinite(gg), fin) and rel_err(gg[fin], gr[fin]).max() < 1e-9
+    for k in ("H", "Y", "T", "X", "S"):
+        pm, ps = G.posterior_means(k), G.posterior_sdevs(k)
+        assert pm.shape == g["post_mean_" + k].shape
+        if pm.size:
+            assert np.abs(pm - g["post_mean_" + k]).max() < 1e-12
+            assert np.abs(ps - g["post_sd_" + k]).max() < 1e-10
+    # keyed streams: reproducible, and the planted TFs show up as DE calls on their targets
+    A, B = sampler_from_problem(pb), sampler_from_problem(pb)
+    A.sample_n(50)
+    B.sample_n(20)
+    blob = B.checkpoint()
+    C2 = sampler_from_problem(pb)
+    C2.restore(blob)
+    C2.sample_n(30)
+    assert np.array_equal(A.get_state(1), C2.get_state(1))
+    assert A.posterior_means("Y").reshape(nH, 3)[:, 1].min() < 0.5 < A.posterior_means("Y").reshape(nH, 3)[:, 1].max()

@@ -280,9 +280,13 @@ def test_errors():
     with pytest.raises(gbnet_b200.GbnError) as ei:
         sampler_from_problem(pb, mor=bad)
     assert "MOR values" in str(ei.value)
+    # empty evidence is not an error: it selects the reference's simulation mode (GraphORNOR.cpp:28)
+    sim = sampler_from_problem(pb, evid_trg=np.zeros(0, np.uint32), evid_val=np.zeros(0, np.int32))
+    assert sim.simulation() and sim.n_nodes() == 2 * sim.n_targets() + sim.n_tf()
     with pytest.raises(gbnet_b200.GbnError):
-        sampler_from_problem(pb, evid_trg=np.zeros(0, np.uint32), evid_val=np.zeros(0, np.int32))
+        sim.set_evidence(pb.evid_trg, pb.evid_val)
     G = sampler_from_problem(pb)
+    assert not G.simulation()
     with pytest.raises(gbnet_b200.GbnError):
         G.get_state(99)
     with pytest.raises(gbnet_b200.GbnError):

@@ -105,3 +105,31 @@ def test_cython_binding_matches_ctypes_binding():
         bad = rels.copy()
         bad.loc[0, "type"] = 5
         PyModelORNOR(ents, bad, evid)
+
+
+def test_simulation_mode_through_pandas_api():
+    """ModelORNOR(ents, rels, evid=None, active_tf_set_py=...) is the reference's data simulator
+    (pyx:54-55 -> GraphORNOR.cpp:28): targets of the planted TFs come out differentially expressed."""
+    import gbnet_b200
+    from gbnet_b200 import synth, utils
+    net = synth.gen_network(NX=20, NY=300, AvgNTF=2.5, num_active_tfs=2, seed=41)
+    ents, rels, _, _ = utils.frames_from_network(net)
+    active = {f"{int(k):04d}" for k in net.gt_active}
+    M = gbnet_b200.ModelORNOR(ents, rels, None, active, n_graphs=4, noise_listen_children=False,
+                              z_alpha=2000., z_beta=1., z0_alpha=200., z0_beta=1., seed=3)
+    assert M.sampler.simulation()
+    M.sample(300, 30)
+    ym = M.get_posterior_means("Y")
+    assert ym[0][0] == "Y" and ym[0][2] == "0" and len(ym) == 3 * M.sampler.n_targets()
+    assert M.get_posterior_means("X") == [] and len(M.get_posterior_means("H")) == len(ym)
+    gr = M.get_gelman_rubin()
+    assert [g[0] for g in gr[:4]] == ["H", "Y", "H", "Y"] and gr[-1][0] == "T"
+    # P(Y != unchanged) is high exactly for targets with an active parent
+    p_de = {sym: 0.0 for _, sym, _, _ in ym}
+    for _, sym, j, v in ym:
+        if j != "1":
+            p_de[sym] += v
+    has_active = set(f"{int(t):04d}" for t in net.trg[np.isin(net.src, net.gt_active)])
+    hit = np.mean([p_de[s] for s in has_active])
+    miss = np.mean([v for s, v in p_de.items() if s not in has_active])
+    assert hit > 0.3 and miss < 0.2 and hit > 3 * miss
