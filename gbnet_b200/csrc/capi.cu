@@ -499,17 +499,6 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     n.listen = p->noise_listen_children ? 1 : 0;
     n.const_params = p->const_params ? 1 : 0;
     n.seed = p->seed;
-    {
-        // (1-z)^n by repeated multiplication, the way zcompl_pn is built (HNodeORNOR.cpp:57,61)
-        std::vector<double> zct((size_t) 2 * (tp.max_indeg + 2));
-        for (int cls = 0; cls < 2; cls++) {
-            double z = cls ? n.z_n : n.z_y, v = 1.;
-            for (uint32_t j = 0; j < tp.max_indeg + 2; j++) { zct[(size_t) cls * (tp.max_indeg + 2) + j] = v; v *= (1. - z); }
-        }
-        double *d = nullptr;
-        if (int rc = dev_upload(m, &d, zct)) return bail(rc);
-        n.zctab = d;
-    }
     if (int rc = dev_alloc(m, &m->d_y, (size_t) m->n_datasets * tp.nH)) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_yprob, (size_t) m->n_datasets * 3)) return bail(rc);
     n.stab_D = (tp.max_indeg + 2 + 1) & ~1u;     // even: the arrays behind the tables stay 16-byte aligned in shared memory

@@ -247,23 +247,6 @@ __device__ __forceinline__ double target_likelihood(const DevNet &net, uint32_t 
     return ps.likelihood(yp, col);
 }
 
-// closed form used by the fast kernels: same expressions as ParentScan::likelihood with
-// pr1 = pr0 * pr2 (the reference multiplies the same factors interleaved in parent order,
-// HNodeORNOR.cpp:89-96; the two differ by rounding only)
-__device__ __forceinline__ double lik_from_products(double pr0, double pr2, double zc,
-                                                    const double yp[3], const double col[3])
-{
-    double omz = 1. - zc;
-    double p0 = (1. - pr0) * omz + zc * yp[0];
-    double p1 = (pr0 * pr2) * omz + zc * yp[1];
-    double p2 = (pr0 - pr2 * pr0) * omz + zc * yp[2];
-    double l = 0.;
-    l += p0 * col[0];
-    l += p1 * col[1];
-    l += p2 * col[2];
-    return l;
-}
-
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

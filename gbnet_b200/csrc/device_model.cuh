@@ -45,7 +45,6 @@ struct DevNet {
     const double *stab;           // [n_datasets][STAB_ROWS][stab_D] fast-path tables over n: c0[y=0..2], omz[cls], zc[cls],
                                   // A[y] = omz (N2 - N0), B[y] = omz (N1 - N2)
     uint32_t stab_D;              // max_indeg + 2 rounded up to even
-    const double *zctab;          // [2][max_indeg+2]  (1-z)^n by repeated multiplication; row 0 = ZY, row 1 = ZN
     double xprob[2][2];           // [prior_active][v]   GraphORNOR.h:40-41
     double sprob[3][3];           // [mor+1][v]          GraphORNOR.cpp:25
     double ynoise[3][3];          // [h][y]              GraphORNOR.h:46-48

@@ -48,11 +48,6 @@ void launch_sim_export_draws(const DevNet &net, uint32_t gchain, uint32_t sweep0
                              double *flat_u, double *beta_v, double *exp_v, cudaStream_t st);
 
 // ---- moments.cu (K5): cross-chain moments -> Gelman-Rubin and posterior summaries
-struct MomentArgs {
-    uint32_t n_stats;             // per dataset: 2 nX + nT + 3 E
-    uint32_t n_nodes;
-    double N;                     // chain length (sweeps since burn)
-};
 // pass 1: sums[d][stat][0] = sum_k mean_k, [1] = sum_k var_k over the LOCAL chains of dataset d;
 //         psums[d][stat] = sum of mean_k over local chains whose GLOBAL index is >= 1
 void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double *sums, double *psums, cudaStream_t st);
