@@ -7,6 +7,7 @@ gpurun snapshot.  -fmad=false: the reference's x86-64 build contains no FMA cont
 from __future__ import annotations
 
 import os
+import re
 import subprocess
 import sys
 
@@ -60,6 +61,11 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             flags += ["-DGBN_S_NT=512", "-DGBN_S_MINB=2"]
         if VARIANT == "nt128" and src == "sweep_fast.cu":
             flags += ["-DGBN_S_NT=128", "-DGBN_S_MINB=8"]
+        xv = re.fullmatch(r"xq(\d+)u(\d+)(?:n(\d+))?", VARIANT)
+        if xv and src == "sweep_fast.cu":
+            flags += ["-DGBN_XQ=" + xv.group(1), "-DGBN_XU=" + xv.group(2)]
+            if xv.group(3):
+                flags.append("-DGBN_X_NT=" + xv.group(3))
         if VARIANT == "chk":
             flags.append("-DGBN_BOUNDS")
         if VARIANT.startswith("s") and VARIANT[1:].isdigit() and src == "sweep_fast.cu":

@@ -358,7 +358,10 @@ int sample_n(gbn_model *m, uint32_t n)
         CUDA_TRY(cudaEventRecord(m->gfork, m->stream));
         launched = 0;
         for (uint32_t g = 0; g < G; g++) {
-            const uint32_t c0 = (uint32_t) ((uint64_t) m->n_chains * g / G), c1 = (uint32_t) ((uint64_t) m->n_chains * (g + 1) / G);
+            // group boundaries at whole bundles: the X kernel sweeps fast_x_bundle() chains per CTA
+            const uint32_t xq = fast_x_bundle();
+            const uint32_t c0 = (uint32_t) ((uint64_t) m->n_chains * g / G) / xq * xq;
+            const uint32_t c1 = g + 1 == G ? m->n_chains : (uint32_t) ((uint64_t) m->n_chains * (g + 1) / G) / xq * xq;
             cudaStream_t st = G == 1 ? m->stream : m->gstream[g];
             const bool px = G > 1 && prio_x != 2 && !m->phase_timing;
             if (G > 1) CUDA_TRY(cudaStreamWaitEvent(st, m->gfork, 0));
@@ -534,9 +537,11 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         if (int rc = dev_alloc(m, &ch.cY, C * nH)) return bail(rc);
     }
     if (m->kernel == GBN_KERNEL_FAST) {
-        if (int rc = dev_alloc(m, &ch.tc2, C * nH)) return bail(rc);
+        const size_t xq = fast_x_bundle();
+        if (int rc = dev_alloc(m, &ch.tc2, (C + xq - 1) / xq * xq * nH)) return bail(rc);    // interleaved by chain bundle
         if (int rc = dev_alloc(m, &ch.ny, C * nH)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.Stf, C * E)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.xU, C * ((nX + 3) & ~(size_t) 3))) return bail(rc);
         if (int rc = dev_alloc(m, &ch.FXp, C * nX)) return bail(rc);
     }
     const size_t ns = (size_t) m->n_datasets * n_stats_of(n);

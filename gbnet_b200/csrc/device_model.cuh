@@ -64,9 +64,10 @@ struct DevChains {
     double *tMean, *tM2;
     uint2 *cS;                    // {count S=0, count S=2}
     // fast kernel only
-    double2 *tc2;                 // [c][nH] {beta, gamma} = {pr0 omz (N2-N0), pr0 pr2 omz (N1-N2)}: L = c0[ny] + beta + gamma
+    double2 *tc2;                 // [c/XQ][nH][XQ] (interleaved by chain bundle) {beta, gamma} = {pr0 omz (N2-N0), pr0 pr2 omz (N1-N2)}: L = c0[ny] + beta + gamma
     uint16_t *ny;                 // [c][nH] y * stab_D + n, n = number of parents with S != 1
     uint8_t *Stf;
+    uint32_t *xU;                 // [c][nX rounded up to 4] Philox words of the current sweep's X draws (X kernel scratch)
     double2 *FXp;                 // {1 - t*x, 1 / (1 - t*x)}
     // simulation mode only: latent / observed state per (chain, device target) and their outcome counts
     uint8_t *H, *Y;

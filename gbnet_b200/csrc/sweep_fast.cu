@@ -51,7 +51,18 @@ namespace gbn {
 
 namespace {
 
-constexpr int FX_NT = 512;           // X kernel: 16 warps = 16-TF speculative window
+#ifndef GBN_X_NT
+#define GBN_X_NT 1024
+#endif
+constexpr int FX_NT = GBN_X_NT;      // X kernel: one warp per TF of the speculative window
+#ifndef GBN_XQ
+#define GBN_XQ 2
+#endif
+#ifndef GBN_XU
+#define GBN_XU 2
+#endif
+constexpr int XU = GBN_XU;           // X kernel: independent gathers per lane and pipeline stage
+constexpr int XQ = GBN_XQ;           // X kernel: chains per CTA = chains interleaved in the product cache (power of two)
 #ifndef GBN_S_NT
 #define GBN_S_NT 256
 #endif
@@ -114,120 +125,144 @@ __device__ __forceinline__ void child_likelihoods(const double *xC0, double2 bg,
 }
 
 // ---------------------------------------------------------------------------------- X phase
+// One CTA sweeps the X nodes of XQ chains (a "bundle": chains XQ p .. XQ p + XQ - 1).  The kernel is bound
+// by L1 wavefronts: a warp-wide gather costs one wavefront (~2 cycles) per distinct 128-byte line, and
+// the children of a TF are scattered over the product cache.  The cache is therefore interleaved by
+// bundle - tc2[bundle][target][XQ] - and a warp's lanes are (32 / XQ children) x (XQ chains): the XQ
+// lanes of one child read adjacent 16-byte entries of one line, which divides the wavefronts per
+// (child, chain) by XQ.  The chains of a bundle share the window position: a window commits up to the
+// first TF that changed in ANY of them (flips are rare, so the shorter commit costs little), and every
+// committed TF still saw exactly the state the sequential sweep of its own chain would have seen.
 template <int NT, bool NY_SMEM>
-__global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, SweepArgs a)
+__global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, SweepArgs a, uint32_t nchains)
 {
     constexpr int NW = NT / 32;
+    constexpr uint32_t Q = XQ, CPW = 32 / XQ, U = XU;                        // chains per CTA, children per warp and gather, gathers per lane and iteration
     extern __shared__ __align__(16) unsigned char smem_x[];
-    __shared__ int s_dec[NW];
+    __shared__ int s_dec[NW];                                                // OR over the bundle: bit 1 = some chain flipped
     const uint32_t nX = net.nX, E = net.E, nH = net.nH, D = net.stab_D;
-    double *xC0 = reinterpret_cast<double *>(smem_x);        // [3][D] c0 by idx = y * D + n
-    uint32_t *sU = reinterpret_cast<uint32_t *>(xC0 + 3 * D + (D & 1)); // [nX rounded up to 4] the sweep's X uniforms (Philox words)
-    double *sG = reinterpret_cast<double *>(sU + ((nX + 3) & ~3u));          // [nX] 1 - T
-    uint32_t *sPtr = reinterpret_cast<uint32_t *>(sG + nX);                  // [nX + 1 rounded up to 4] tf_ptr
-    uint16_t *sNy = reinterpret_cast<uint16_t *>(sPtr + ((nX + 4) & ~3u));   // [nH] if staged
-    uint8_t *sX = reinterpret_cast<uint8_t *>(sNy + (NY_SMEM ? ((nH + 7) & ~7u) : 0)); // [nX] value | prior class << 1
+    const uint32_t nXr = (nX + 3) & ~3u;
+    double *xC0all = reinterpret_cast<double *>(smem_x);                     // [Q][3][D] c0 by idx = y * D + n
+    uint32_t *sPtr = reinterpret_cast<uint32_t *>(xC0all + Q * 3 * D);       // [nX + 1 rounded up to 4] tf_ptr
+    uint8_t *sX = reinterpret_cast<uint8_t *>(sPtr + ((nX + 4) & ~3u));      // [Q][nX rounded up to 4] value | prior class << 1
+    uint16_t *sNy = reinterpret_cast<uint16_t *>(sX + Q * nXr);              // [nH][Q] table index of every target (NY_SMEM)
 
-    const uint32_t c = blockIdx.x + a.chain0;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t d = chain_dataset(net, c);
-    const uint32_t gchain = chain_global_id(net, c);
-    uint8_t *gX = ch.X + (size_t) c * nX;
-    const double *gT = ch.T + (size_t) c * nX;
-    const uint8_t *gStf = ch.Stf + (size_t) c * E;
-    double2 *tc2 = ch.tc2 + (size_t) c * nH;
-    const uint16_t *gny = ch.ny + (size_t) c * nH;
-    uint32_t *cX1 = ch.cX1 + (size_t) c * nX;
-    const double *inj_flat = a.use_inj ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + E) : nullptr;
+    const uint32_t h = lane % Q, cs = lane / Q;                              // this lane's chain and child slot
+    const uint32_t cbase = a.chain0 + Q * blockIdx.x;                        // a multiple of Q by construction
+    const uint32_t nvalid = min(Q, nchains - Q * blockIdx.x);                // a last, partial bundle recomputes its last chain
+    const uint32_t cmine = cbase + min(h, nvalid - 1);
+    double2 *tcb = ch.tc2 + (size_t) (cbase / Q) * nH * Q;                   // bundle base: entry (i, chain) at Q i + chain
 
     // everything a round needs per TF is staged once: a round must not wait on global memory for
     // anything but the children's cache entries (a dependent global load costs ~1 us per round)
-    for (uint32_t k = tid; k < nX; k += NT) {
-        sX[k] = (uint8_t) (gX[k] | (net.x_prior_active[k] << 1));
-        sG[k] = 1. - gT[k];                       // (1 - t*x) at x = 1   (HNodeORNOR.cpp:59)
+    for (uint32_t q = 0; q < Q; q++) {
+        const uint32_t c = cbase + min(q, nvalid - 1);
+        const uint32_t d = chain_dataset(net, c), gchain = chain_global_id(net, c);
+        const uint8_t *gX = ch.X + (size_t) c * nX;
+        for (uint32_t k = tid; k < nX; k += NT) sX[q * nX + k] = (uint8_t) (gX[k] | (net.x_prior_active[k] << 1));
+        const double *tab = net.stab + (size_t) d * STAB_ROWS * D;
+        for (uint32_t j = tid; j < 3 * D; j += NT) xC0all[q * 3 * D + j] = tab[j];
+        if (!a.use_inj) {   // every X uniform of this chain and sweep: one Philox block per four TFs, computed once
+            uint4 *gU = reinterpret_cast<uint4 *>(ch.xU + (size_t) c * nXr);
+            for (uint32_t blk = tid; blk < nXr / 4; blk += NT) {
+                const u32x4 r = philox4x32_10(blk, a.sweep, gchain, KIND_X, (uint32_t) net.seed, (uint32_t) (net.seed >> 32));
+                gU[blk] = make_uint4(r.x, r.y, r.z, r.w);
+            }
+        }
+        // (n, y) table index of every target: X flips do not change it, so one coalesced copy per sweep
+        // replaces a scattered 2-byte gather per child
+        if (NY_SMEM) {
+            const uint16_t *gny = ch.ny + (size_t) c * nH;
+            for (uint32_t i = tid; i < nH; i += NT) sNy[(size_t) i * Q + q] = gny[i];
+        }
     }
     for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.tf_ptr[k];
-    {
-        const double *tab = net.stab + (size_t) d * STAB_ROWS * D;
-        for (uint32_t j = tid; j < 3 * D; j += NT) xC0[j] = tab[j];
-    }
-    if (!a.use_inj)     // every X uniform of this chain and sweep: one Philox block per four TFs, computed once
-        for (uint32_t blk = tid; blk < (nX + 3) / 4; blk += NT) {
-            const u32x4 r = philox4x32_10(blk, a.sweep, gchain, KIND_X, (uint32_t) net.seed, (uint32_t) (net.seed >> 32));
-            sU[4 * blk] = r.x; sU[4 * blk + 1] = r.y; sU[4 * blk + 2] = r.z; sU[4 * blk + 3] = r.w;
-        }
-    if (NY_SMEM) {
-        // (n, y) of every target of this chain: X flips do not change it, so one coalesced copy per
-        // sweep replaces one scattered 2-byte gather per child
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(gny);        // chain rows are 4-byte aligned when nH is even
-        if ((((size_t) c * nH) & 1) == 0) {
-            uint32_t *dst = reinterpret_cast<uint32_t *>(sNy);
-            for (uint32_t j = tid; j < (nH >> 1); j += NT) dst[j] = src[j];
-            if ((nH & 1) && tid == 0) sNy[nH - 1] = gny[nH - 1];
-        } else {
-            for (uint32_t j = tid; j < nH; j += NT) sNy[j] = gny[j];
-        }
-    }
     __syncthreads();
+
+    const double *xC0 = xC0all + h * 3 * D;
+    const uint8_t *gStf = ch.Stf + (size_t) cmine * E;
+    const double *gT = ch.T + (size_t) cmine * nX;
+    const uint32_t *gU = ch.xU + (size_t) cmine * nXr;
+    const uint16_t *gNy = ch.ny + (size_t) cmine * nH;                       // networks too large for sNy gather it from here
+    const double *inj = a.use_inj ? ch.inj_flat + ((size_t) cmine * ch.inj_sweeps + a.inj_row) * (nX + E) : nullptr;
 
     uint32_t k0 = 0;
     while (k0 < nX) {
         const uint32_t kw = k0 + warp;
-        int dec = 0;                              // bit 0: drawn value, bit 1: value changed
+        int dec = 0;                              // bit 0: drawn value, bit 1: value changed (this lane's chain)
         double fac = 1.;
         uint32_t cbeg = 0, cend = 0;
         if (kw < nX) {
-            const uint32_t xcur = sX[kw] & 1u;
-            const double g = sG[kw];
+            const uint32_t xcur = sX[h * nX + kw] & 1u;
+            // per-TF scalars come from global memory (written by this CTA or an earlier kernel): the loads
+            // are issued with the first child ids and are off the critical path
+            const double g = 1. - gT[kw];         // (1 - t*x) at x = 1   (HNodeORNOR.cpp:59)
+            const uint32_t uword = a.use_inj ? 0u : gU[kw];
             fac = xcur ? 1. / g : g;              // factor that turns the product into the flipped one
             cbeg = sPtr[kw]; cend = sPtr[kw + 1];
             GBN_CHECK(cbeg <= cend && cend <= E);
             double mc = 1., mf = 1.;
             int ec = 0, ef = 0, cnt = 0;
-            // Two children per lane and iteration, software-pipelined with two explicit register sets
-            // (no rotating copies, which would wait on the loads): while iteration i is computed from
-            // set X, the cache entries of iteration i+1 are in flight into set Y and the child ids of
-            // iteration i+2 into X's id registers.  The pipeline lives inside one round, so every entry
-            // is read after the flips of all earlier (committed) windows.  s = 0xff marks "no child".
-            struct Ids { uint32_t i0, i1, s0, s1; };
-            struct Dat { double2 p0, p1; uint32_t n0, n1; };
+            // One (child, chain) per lane and iteration, software-pipelined with two explicit register sets
+            // (no rotating copies, which would wait on the loads): while iteration i is computed from set X,
+            // the cache entries of iteration i+1 are in flight into set Y and the child id / S value of
+            // iteration i+2 into X's id registers.  The pipeline lives inside one round, so every entry is
+            // read after the flips of all earlier (committed) windows.  s = 0xff marks "no child".
+            struct Ids { uint32_t i[U], s[U]; };
+            struct Dat { double2 p[U]; uint32_t ny[U]; };
             auto load_ids = [&](uint32_t cc) -> Ids {
-                Ids r{ 0u, 0u, 0xffu, 0xffu };
-                if (cc < cend) { r.i0 = net.tf_child[cc]; r.s0 = __ldcs(gStf + cc); }
-                if (cc + 32 < cend) { r.i1 = net.tf_child[cc + 32]; r.s1 = __ldcs(gStf + cc + 32); }
+                Ids r;
+#pragma unroll
+                for (uint32_t u = 0; u < U; u++) {
+                    const uint32_t c = cc + u * CPW;
+                    r.i[u] = 0u; r.s[u] = 0xffu;
+                    if (c < cend) { r.i[u] = net.tf_child[c]; r.s[u] = __ldcs(gStf + c); }
+                }
                 return r;
             };
             auto gather = [&](const Ids &id) -> Dat {
-                GBN_CHECK(id.i0 < nH && id.i1 < nH);
-                return Dat{ tc2[id.i0], tc2[id.i1], NY_SMEM ? sNy[id.i0] : gny[id.i0], NY_SMEM ? sNy[id.i1] : gny[id.i1] };
+                Dat r;
+#pragma unroll
+                for (uint32_t u = 0; u < U; u++) {
+                    GBN_CHECK(id.i[u] < nH);
+                    r.p[u] = tcb[(size_t) id.i[u] * Q + h];
+                    r.ny[u] = NY_SMEM ? sNy[(size_t) id.i[u] * Q + h] : gNy[id.i[u]];
+                }
+                return r;
             };
-            uint32_t cc = cbeg + lane;
+            uint32_t cc = cbeg + cs;
             auto step = [&](Ids &idX, Dat &dX, const Ids &idY, Dat &dY) {
                 dY = gather(idY);                                     // next iteration's entries
-                const uint32_t s0 = idX.s0, s1 = idX.s1;
-                idX = load_ids(cc + 128);                             // ids two iterations ahead
-                double Lc, Lf;
-                GBN_CHECK(s0 <= 2 && dX.n0 < 3 * D && (s1 == 0xffu || (s1 <= 2 && dX.n1 < 3 * D)));
-                child_likelihoods(xC0, dX.p0, dX.n0, s0, fac, Lc, Lf);               // cc < cend: always a child
-                mc *= Lc; mf *= Lf;
-                if (s1 != 0xffu) {
-                    child_likelihoods(xC0, dX.p1, dX.n1, s1, fac, Lc, Lf);
-                    mc *= Lc; mf *= Lf;
-                }
-                if (++cnt == 8) { normalise(mc, ec); normalise(mf, ef); cnt = 0; }
-                cc += 64;
+                uint32_t sv[U];
+#pragma unroll
+                for (uint32_t u = 0; u < U; u++) sv[u] = idX.s[u];
+                idX = load_ids(cc + 2 * U * CPW);                     // ids two iterations ahead
+#pragma unroll
+                for (uint32_t u = 0; u < U; u++)
+                    if (sv[u] != 0xffu) {
+                        double Lc, Lf;
+                        GBN_CHECK(sv[u] <= 2 && dX.ny[u] < 3 * D);
+                        child_likelihoods(xC0, dX.p[u], dX.ny[u], sv[u], fac, Lc, Lf);
+                        mc *= Lc; mf *= Lf;
+                    }
+                if ((cnt += U) >= 16) { normalise(mc, ec); normalise(mf, ef); cnt = 0; }
+                cc += U * CPW;
             };
-            Ids idA = load_ids(cc), idB = load_ids(cc + 64);
+            Ids idA = load_ids(cc), idB = load_ids(cc + U * CPW);
             Dat dA = gather(idA), dB;
-            while (cc < cend) {
+            const uint32_t cw = cbeg + U * CPW * ((cend - cbeg + U * CPW - 1) / (U * CPW));     // warp-uniform trip count
+            uint32_t cu = cbeg;
+            while (cu < cw) {
                 step(idA, dA, idB, dB);
-                if (cc >= cend) break;
+                if ((cu += U * CPW) >= cw) break;
                 step(idB, dB, idA, dA);
+                cu += U * CPW;
             }
             normalise(mc, ec);
             normalise(mf, ef);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+            for (int o = 16; o >= (int) Q; o >>= 1) {
                 mc *= __shfl_xor_sync(0xffffffffu, mc, o);
                 mf *= __shfl_xor_sync(0xffffffffu, mf, o);
                 ec += __shfl_xor_sync(0xffffffffu, ec, o);
@@ -235,34 +270,38 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
             }
             normalise(mc, ec);
             normalise(mf, ef);
-            const double *prob = net.xprob[sX[kw] >> 1];
+            const double *prob = net.xprob[sX[h * nX + kw] >> 1];
             double lik_cur, lik_flip;
             common_scale(prob[xcur] * mc, ec, prob[1 - xcur] * mf, ef, lik_cur, lik_flip);
             const double l0 = xcur ? lik_flip : lik_cur, l1 = xcur ? lik_cur : lik_flip;
             double cum0 = 0. + l0, cum1 = cum0 + l1;
             if (!(cum1 > 0.)) { cum0 = 0. + prob[0]; cum1 = cum0 + prob[1]; }     // Multinomial.cpp:78-85
-            const double u = a.use_inj ? inj_flat[kw] : unit_from_word(sU[kw]);
+            const double u = a.use_inj ? inj[kw] : unit_from_word(uword);
             const double dice = 0. * (1 - u) + cum1 * u;
             const uint32_t nx = dice < cum0 ? 0u : (dice < cum1 ? 1u : xcur);
-            dec = (int) nx | ((nx != xcur) ? 2 : 0);
+            dec = h < nvalid ? ((int) nx | ((nx != xcur) ? 2 : 0)) : 0;
         }
-        if (lane == 0) s_dec[warp] = dec;
+        const uint32_t flipped = __ballot_sync(0xffffffffu, (dec & 2) && cs == 0);    // bit q: chain q of the bundle flipped
+        if (lane == 0) s_dec[warp] = flipped ? 2 : 0;
         __syncthreads();
-        const uint32_t flips = __ballot_sync(0xffffffffu, lane < NW && (s_dec[lane < NW ? lane : 0] & 2));
+        const uint32_t flips = __ballot_sync(0xffffffffu, lane < NW && (s_dec[lane] & 2));
         const uint32_t first = flips ? (uint32_t) __ffs(flips) - 1 : NW;
         const uint32_t ncommit = first < NW ? first + 1 : NW;
         if (warp < ncommit && kw < nX) {
-            if (lane == 0) sX[kw] = (uint8_t) ((sX[kw] & 2u) | (dec & 1));
-            if (dec & 2) {
-                // apply the flip of X_kw to the cached product of each child that depends on it
+            if (cs == 0) sX[h * nX + kw] = (uint8_t) ((sX[h * nX + kw] & 2u) | (dec & 1));
+            for (uint32_t q = 0; q < Q; q++) {
+                if (!((flipped >> q) & 1u)) continue;
+                // apply the flip of X_kw in chain q to the cached terms of each child that depends on it
+                const double fq = __shfl_sync(0xffffffffu, fac, q);
+                const uint8_t *gS = ch.Stf + (size_t) (cbase + q) * E;
                 for (uint32_t cc = cbeg + lane; cc < cend; cc += 32) {
-                    const uint32_t s = gStf[cc];
+                    const uint32_t s = gS[cc];
                     if (s == 1) continue;
-                    const uint32_t i = net.tf_child[cc];
-                    double2 bg = tc2[i];
-                    if (s == 0) bg.x *= fac;
-                    bg.y *= fac;
-                    tc2[i] = bg;
+                    double2 *e = tcb + (size_t) net.tf_child[cc] * Q + q;
+                    double2 bg = *e;
+                    if (s == 0) bg.x *= fq;
+                    bg.y *= fq;
+                    *e = bg;
                 }
             }
         }
@@ -275,7 +314,11 @@ __global__ void __launch_bounds__(NT, 2) k_fast_x(DevNet net, DevChains ch, Swee
         k0 += ncommit;
     }
     // every TF was committed exactly once: write X back and count (Multinomial.cpp:101-105 as a count)
-    for (uint32_t k = tid; k < nX; k += NT) { const uint32_t x = sX[k] & 1u; gX[k] = (uint8_t) x; cX1[k] += x; }
+    for (uint32_t q = 0; q < nvalid; q++) {
+        uint8_t *gX = ch.X + (size_t) (cbase + q) * nX;
+        uint32_t *cX1 = ch.cX1 + (size_t) (cbase + q) * nX;
+        for (uint32_t k = tid; k < nX; k += NT) { const uint32_t x = sX[q * nX + k] & 1u; gX[k] = (uint8_t) x; cX1[k] += x; }
+    }
 }
 
 // ---------------------------------------------------------------------------------- T phase
@@ -337,7 +380,7 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
     const uint32_t gchain = chain_global_id(net, c);
     const uint8_t *gX = ch.X + (size_t) c * nX;
     const uint8_t *gStf = ch.Stf + (size_t) c * net.E;
-    double2 *tc2 = ch.tc2 + (size_t) c * nH;
+    double2 *tc2 = ch.tc2 + (size_t) (c / XQ) * nH * XQ + (c % XQ);      // bundle-interleaved: entry i at XQ i
     const uint16_t *gny = ch.ny + (size_t) c * nH;
 
     for (uint32_t j = tid; j < 3 * D; j += FTL_NT) xC0[j] = net.stab[(size_t) d * STAB_ROWS * D + j];
@@ -375,7 +418,7 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
                 if (s == 1) continue;
                 const uint32_t i = net.tf_child[cc];
                 GBN_CHECK(i < nH && gny[i] < 3 * D);
-                const double2 bg = tc2[i];
+                const double2 bg = tc2[XQ * (size_t) i];
                 const double c0 = xC0[gny[i]];
                 mo *= c0 + (bg.x + bg.y);
                 mn *= s == 0 ? c0 + r * (bg.x + bg.y) : c0 + (bg.x + r * bg.y);
@@ -409,10 +452,10 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
                 const uint32_t s = gStf[cc];
                 if (s == 1) continue;
                 const uint32_t i = net.tf_child[cc];
-                double2 bg = tc2[i];
+                double2 bg = tc2[XQ * (size_t) i];
                 if (s == 0) bg.x *= r;
                 bg.y *= r;
-                tc2[i] = bg;
+                tc2[XQ * (size_t) i] = bg;
             }
         }
         if (tid == 0) {
@@ -568,7 +611,8 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
     }
     GBN_CHECK(n + (y * D) < 3 * D && n <= deg);
     if (valid) {
-        ch.tc2[(size_t) c * nH + dt] = make_double2(P0 * (omzt[n] * ca), (P0 * P2) * (omzt[n] * cb));   // {beta, gamma}
+        ch.tc2[((size_t) (c / XQ) * nH + dt) * XQ + (c % XQ)] =
+            make_double2(P0 * (omzt[n] * ca), (P0 * P2) * (omzt[n] * cb));   // {beta, gamma}, interleaved by chain bundle
         ch.ny[(size_t) c * nH + dt] = (uint16_t) (y * D + n);          // index into the X phase tables
     }
 }
@@ -602,26 +646,28 @@ static bool s_stage_fx(const DevNet &net)
     return want != 2 && sizeof(double2) * (size_t) net.nX <= 48 * 1024;
 }
 
-// shared memory of the X kernel: tables, (n, y) of every target when it fits, X of the chain
-static bool x_ny_smem(const DevNet &net)
-{
-    static const uint32_t want = env_u32("GBN_NY_SMEM", 1);        // 2 = off
-    return want != 2 && 2 * (size_t) net.nH <= 80 * 1024;
-}
-
+// shared memory of the X kernel (XQ chains per CTA): tables, by-TF pointers, X and - when it fits - the
+// (n, y) index of every target
 static size_t x_smem_bytes(const DevNet &net, bool ny_smem)
 {
-    return sizeof(double) * (3 * (size_t) net.stab_D + 2) + 4 * (((size_t) net.nX + 3) & ~(size_t) 3)
-           + sizeof(double) * (size_t) net.nX + 4 * (((size_t) net.nX + 4) & ~(size_t) 3)
-           + (ny_smem ? 2 * (((size_t) net.nH + 7) & ~(size_t) 7) : 0) + net.nX + 16;
+    const size_t nX = net.nX, nXr = (nX + 3) & ~(size_t) 3, Q = XQ;
+    return sizeof(double) * Q * 3 * (size_t) net.stab_D + 4 * ((nX + 4) & ~(size_t) 3) + Q * nXr
+           + (ny_smem ? 2 * (size_t) net.nH * Q : 0) + 16;
 }
+static bool x_ny_smem(const DevNet &net)
+{
+    if (env_u32("GBN_X_NY", 1) == 2) return false;        // 2 = gather from global memory (tests of the large-network path)
+    return x_smem_bytes(net, true) + 256 <= 200 * 1024;
+}
+
+uint32_t fast_x_bundle() { return XQ; }
 
 bool fast_supported(const DevNet &net, const char **why)
 {
     if (net.nX >= (1u << 30)) { *why = "n_tf does not fit the packed parent id"; return false; }
     if (s_smem_bytes(net, s_stage_fx(net)) > 200 * 1024) { *why = "in-degree too large for the S-phase tables"; return false; }
     if (net.Eu != net.E) { *why = "duplicate (TF, target) edges"; return false; }
-    if (x_smem_bytes(net, x_ny_smem(net)) + 64 > 200 * 1024) { *why = "n_tf too large for the X window kernel"; return false; }
+    if (x_smem_bytes(net, false) + 256 > 200 * 1024) { *why = "n_tf too large for the X window kernel's shared memory"; return false; }
     if (3 * (size_t) net.stab_D > 65535) { *why = "in-degree does not fit the 16-bit (y, n) table index"; return false; }
     return true;
 }
@@ -664,6 +710,7 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
     if (n_sweeps == 0 || nchains == 0) return 0;
     const bool ny_smem = x_ny_smem(net);
     const size_t smem_x = x_smem_bytes(net, ny_smem);
+    if (chain0 % XQ) { *err = "chain groups must start at a multiple of the X kernel's bundle size"; return -1; }
     if (check(cudaFuncSetAttribute(ny_smem ? k_fast_x<FX_NT, true> : k_fast_x<FX_NT, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x), err)) return -1;
     const size_t smem_tl = sizeof(double) * 3 * (size_t) net.stab_D + 4 * (size_t) net.nX + 16;
@@ -680,8 +727,8 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         a.chain0 = chain0;
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw], st);
         if (stx != st && sw > 0) cudaStreamWaitEvent(stx, evs, 0);      // this chain group's previous S phase
-        if (ny_smem) k_fast_x<FX_NT, true><<<nchains, FX_NT, smem_x, stx>>>(net, ch, a);
-        else k_fast_x<FX_NT, false><<<nchains, FX_NT, smem_x, stx>>>(net, ch, a);
+        if (ny_smem) k_fast_x<FX_NT, true><<<(nchains + XQ - 1) / XQ, FX_NT, smem_x, stx>>>(net, ch, a, nchains);
+        else k_fast_x<FX_NT, false><<<(nchains + XQ - 1) / XQ, FX_NT, smem_x, stx>>>(net, ch, a, nchains);
         if (stx != st) { cudaEventRecord(evx, stx); cudaStreamWaitEvent(st, evx, 0); }
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
         const bool tl = net.listen && !net.const_params;

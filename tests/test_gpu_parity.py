@@ -153,6 +153,15 @@ def test_trajectory_variants_fast(case):
     _run_trajectory(pb, KERNEL_FAST, 10, injected=True, chunks=(2,))
 
 
+def test_fast_x_large_network_path(monkeypatch):
+    """Networks whose (n, y) index does not fit the X kernel's shared memory gather it from global
+    memory; forced here on a small problem (5 chains: a last, partial chain bundle as well)."""
+    monkeypatch.setenv("GBN_X_NY", "2")
+    pb, _ = make_problem(NX=30, NY=400, AvgNTF=3.0, seed=36, n_graphs=5)
+    _run_trajectory(pb, KERNEL_FAST, 60, injected=False, chunks=(20,))
+    _run_trajectory(pb, KERNEL_FAST, 10, injected=True, chunks=(5,))
+
+
 def test_listening_t_fast_long():
     """T nodes that listen to their children (the pyx default) on the fast path: 200 sweeps of the
     oracle's chain, with several active TFs so the sequential part is exercised."""
