@@ -10,6 +10,7 @@
 #include <cmath>
 #include <csignal>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <dlfcn.h>
 #include <limits>
@@ -794,12 +795,26 @@ extern "C" int gbn_model_set_evidence(gbn_model *m, const gbn_evidence *ev)
     if (int rc = use_device(m)) return rc;
     if (m->sim) return fail(GBN_ERR_UNSUPPORTED, "a simulation-mode model has no evidence to replace");
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    // GBN_TRACE=1: wall time of every stage on stderr (each stage is synchronised, so the total grows)
+    static const bool trace = env_u32("GBN_TRACE", 0) == 1;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(m->stream);
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[gbnet_b200] set_evidence %-16s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     if (int rc = upload_evidence(m, ev)) return rc;
+    lap("upload");
     m->sweeps_total = 0;
     m->ch.inj_flat = m->ch.inj_beta = m->ch.inj_exp = nullptr; m->ch.inj_sweeps = m->ch.inj_pos = 0;
     if (int rc = init_chains(m)) return rc;
+    lap("init_chains");
     if (int rc = zero_stats(m)) return rc;
+    lap("zero_stats");
     if (int rc = refresh_fast(m)) return rc;
+    lap("refresh_fast");
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     return 0;
 }

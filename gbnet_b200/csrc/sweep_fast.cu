@@ -617,13 +617,14 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
     }
 }
 
-// Stf from S (refresh only)
+// Stf from S (refresh only): one thread per position of the by-TF list, so the writes are consecutive
 __global__ void k_fast_stf(DevNet net, DevChains ch)
 {
     const uint32_t c = blockIdx.y;
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= net.Ep || net.par_edge[q] == 0xffffffffu) return;
-    ch.Stf[(size_t) c * net.E + net.tfpos_of_slot[q]] = ch.S[(size_t) c * net.Ep + q];
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= net.E) return;
+    GBN_CHECK(net.tf_slot[pos] < net.Ep);
+    ch.Stf[(size_t) c * net.E + pos] = ch.S[(size_t) c * net.Ep + net.tf_slot[pos]];
 }
 
 }  // namespace
@@ -694,7 +695,7 @@ int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st,
 {
     if (ch.n_chains == 0) return 0;
     SweepArgs a{ 0, 0, 0, 0, 0 };
-    k_fast_stf<<<dim3((net.Ep + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
+    k_fast_stf<<<dim3((net.E + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
     k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, 0);
     if (launch_s(net, ch, a, 1, ch.n_chains, st, err)) return -1;
     if (check(cudaGetLastError(), err)) return -1;

@@ -31,7 +31,6 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
-#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -52,6 +51,7 @@ struct Topology {
     uint32_t n_groups = 0;                          // ceil(nH / 32)
     uint32_t max_indeg = 0, max_outdeg = 0;
     std::vector<uint32_t> tf_uid, trg_uid;          // sorted unique ids (reference order)
+    std::vector<uint32_t> trg_lut;                  // id -> rank in trg_uid when the ids are dense enough (else empty)
     std::vector<uint32_t> dt_of_ref, ref_of_dt;     // reference target index <-> device target index
     std::vector<uint32_t> deg;                      // [nH] in-degree per device target
     std::vector<uint32_t> gbase;                    // [n_groups+1] first slot of each group
@@ -92,6 +92,10 @@ inline Topology compile_topology(uint32_t n_edge, const uint32_t *src, const uin
     }
     tp.nX = (uint32_t) tp.tf_uid.size();
     tp.nH = (uint32_t) tp.trg_uid.size();
+    if (!tp.trg_uid.empty() && (size_t) tp.trg_uid.back() < 16 * tp.trg_uid.size() + 4096) {
+        tp.trg_lut.assign((size_t) tp.trg_uid.back() + 1, UINT32_MAX);     // evidence is re-ranked on every set_evidence
+        for (uint32_t r = 0; r < tp.nH; r++) tp.trg_lut[tp.trg_uid[r]] = r;
+    }
     const uint32_t nX = tp.nX, nH = tp.nH, E = tp.E;
 
     // reference ranks and in-degrees
@@ -209,20 +213,27 @@ inline void compile_evidence(const Topology &tp, uint32_t n_evid, const uint32_t
         if (evid_val[i] < -1 || evid_val[i] > 1)
             throw std::out_of_range("evidence values can only be either -1, 0 or 1");
     // evidence_dict_t is a std::map filled with insert(): unique keys, first occurrence wins
-    // (reference gbnet/ModelORNOR.pyx:64-66)
-    std::map<uint32_t, int32_t> evidence;
-    for (uint32_t i = 0; i < n_evid; i++) evidence.insert({ evid_trg[i], evid_val[i] });
+    // (reference gbnet/ModelORNOR.pyx:64-66).  An open-addressing set of the keys gives the same
+    // result without the tree: this runs on the host inside every set_evidence call.
+    size_t cap = 16;
+    while (cap < 2 * (size_t) n_evid) cap <<= 1;
+    std::vector<uint32_t> first(cap, UINT32_MAX);                      // slot -> index of the key's first occurrence
+    unsigned int deg_counts[3] = { 0, 0, 0 };
+    for (uint32_t i = 0; i < tp.nH; i++) y_out[i] = 1;                 // 1 -> not DEG
+    for (uint32_t i = 0; i < n_evid; i++) {
+        const uint32_t key = evid_trg[i];
+        size_t hh = ((size_t) key * 0x9e3779b1u) & (cap - 1);
+        while (first[hh] != UINT32_MAX && evid_trg[first[hh]] != key) hh = (hh + 1) & (cap - 1);
+        if (first[hh] != UINT32_MAX) continue;                         // a repeated key: ignored
+        first[hh] = i;
+        deg_counts[evid_val[i] + 1] += 1;                              // keys outside the network count too
+        const uint32_t h = tp.trg_lut.empty() ? rank_of(tp.trg_uid, key) : (key < tp.trg_lut.size() ? tp.trg_lut[key] : UINT32_MAX);
+        if (h != UINT32_MAX) y_out[tp.dt_of_ref[h]] = (uint8_t) (evid_val[i] + 1);
+    }
     if (comp_yprob) {
-        unsigned int deg_counts[3] = { 0, 0, 0 };
-        for (auto &kv : evidence) deg_counts[kv.second + 1] += 1;
         yprob_out[0] = (double) deg_counts[0] / tp.nH;
         yprob_out[2] = (double) deg_counts[2] / tp.nH;
         yprob_out[1] = (double) 1. - yprob_out[0] - yprob_out[2];
-    }
-    for (uint32_t i = 0; i < tp.nH; i++) y_out[i] = 1;                 // 1 -> not DEG
-    for (auto &kv : evidence) {
-        uint32_t h = rank_of(tp.trg_uid, kv.first);
-        if (h != UINT32_MAX) y_out[tp.dt_of_ref[h]] = (uint8_t) (kv.second + 1);
     }
 }
 

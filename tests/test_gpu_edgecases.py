@@ -92,6 +92,20 @@ def test_evidence_quirks():
     pb2 = _problem([0, 1, 1], [5, 5, 6], [1, -1, 1], {5: 1, 6: -1, 70: 1}, comp_yprob=True)
     _run_trajectory(pb2, KERNEL_FAST, 20, injected=False, chunks=(20,))
     _run_trajectory(pb2, KERNEL_STRICT, 20, injected=False, chunks=(20,))
+    # sparse target ids (no dense id table on the host), repeated evidence keys (the first one wins) and
+    # replacing the evidence of a live model
+    big = 4_000_000_000
+    pb3 = _problem([0, 1, 1], [7, big, big - 9], [1, -1, 1], {7: 1, big: -1, 123456789: 1}, comp_yprob=True)
+    P3, G3 = _run_trajectory(pb3, KERNEL_FAST, 20, injected=False, chunks=(20,))
+    trg = np.array([big, 7, big, 99, big - 9], np.uint32)
+    val = np.array([1, -1, -1, 1, 0], np.int32)
+    G3.set_evidence(trg, val)
+    pb4 = _problem([0, 1, 1], [7, big, big - 9], [1, -1, 1], {big: 1, 7: -1, 99: 1, big - 9: 0}, comp_yprob=True)
+    P4 = oracle.PortModel(pb4)
+    G3.sample_n(15)
+    P4.sample_n(15)
+    for c in range(pb4.n_graphs):
+        _assert_state_equal(pb4, P4, G3.get_state(c), P4.get_state(c), f"replaced evidence, chain {c}")
 
 
 @pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not present")
