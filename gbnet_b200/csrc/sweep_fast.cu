@@ -494,14 +494,18 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;
-    double *sTab = reinterpret_cast<double *>(smem_raw);                       // [7][D]
-    double2 *sFX = reinterpret_cast<double2 *>(sTab + 7 * D);                   // [nX] if staged
+    double2 *sTab = reinterpret_cast<double2 *>(smem_raw);                      // [3][D] {c0[y][n], omz[class of y][n]}
+    double2 *sFX = sTab + 3 * D;                                                // [nX] if staged
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t c = blockIdx.y + a.chain0;
     const uint32_t d = chain_dataset(net, c);
     const double2 *gFX = ch.FXp + (size_t) c * nX;
-    for (uint32_t j = tid; j < 7 * D; j += FS_NT) sTab[j] = net.stab[(size_t) d * STAB_ROWS * D + j];
+    for (uint32_t j = tid; j < 3 * D; j += FS_NT) {
+        const double *tab = net.stab + (size_t) d * STAB_ROWS * D;
+        const uint32_t yy = j / D, nn = j - yy * D;
+        sTab[j] = make_double2(tab[j], tab[(3 + (yy != 1 ? 0 : 1)) * D + nn]);
+    }
     if (STAGE_FX) for (uint32_t k = tid; k < nX; k += FS_NT) sFX[k] = gFX[k];
     __syncthreads();
 
@@ -520,15 +524,17 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
     const double z = cls ? net.z_n : net.z_y;
     const double ca = net.ynoise[2][y] - net.ynoise[0][y];          // a
     const double cb = net.ynoise[1][y] - net.ynoise[2][y];          // b
-    const double *c0t = sTab + y * D, *omzt = sTab + (3 + cls) * D;
+    const double2 *cot = sTab + y * D;                              // {c0, omz} over n for this target's y
 
     if (MODE == 0) {
         // the counters are first touched by the second pass: start pulling their lines into L2 now
         const uint2 *pc = ch.cS + base;
         for (uint32_t j = 0; j < W; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + 32 * j));
     }
-    // products over the parents in append_parent order (HNodeORNOR.cpp:55-62, 72-81); pads hold S = 1
-    double P0 = 1., P2 = 1.;
+    // products over the parents in append_parent order (HNodeORNOR.cpp:55-62, 72-81); pads hold S = 1.
+    // The state carried along the edges is A = a pr0 and Bq = b pr0 pr2, so that
+    // L = c0[n] + omz[n] (A + Bq) and the a, b constants stay out of the edge loop.
+    double A = ca, Bq = cb;
     uint32_t n = 0;
     for (uint32_t j = 0; j < W; j++) {
         const uint32_t s = pS[32 * j];
@@ -536,8 +542,8 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
         GBN_CHECK(kk < nX && s <= 2 && gb + lane + 32 * j < net.Ep);
         const double f = (STAGE_FX ? sFX[kk].x : gFX[kk].x) * z;
         n += (s != 1);
-        P0 *= (s == 0) ? f : 1.;
-        P2 *= (s == 2) ? f : 1.;
+        A *= (s == 0) ? f : 1.;
+        Bq *= (s != 1) ? f : 1.;
     }
     if (MODE == 0) {
         const double rz = 1. / z;
@@ -556,16 +562,15 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                 const double2 fx = STAGE_FX ? sFX[kk] : gFX[kk];
                 const double f = fx.x * z;
                 const double finv = fx.y * rz;
-                const double R0 = s == 0 ? P0 * finv : P0;          // products without this edge
-                const double R2 = s == 2 ? P2 * finv : P2;
+                const double Ar = s == 0 ? A * finv : A;            // the state without this edge
+                const double Br = s != 1 ? Bq * finv : Bq;
                 const uint32_t nR = n - (s != 1);
                 GBN_CHECK(kk < nX && s <= 2 && (pk >> 30) <= 2 && nR + 1 < D && n <= deg);
-                const double w = R2 * cb;
-                const double B = R0 * (ca + w);
-                const double om1 = omzt[nR + 1], c01 = c0t[nR + 1];
-                const double L0 = c01 + om1 * (B * f);              // S = 0: the factor joins pr0
-                const double L1 = c0t[nR] + omzt[nR] * B;           // S = 1: edge off
-                const double L2 = c01 + om1 * (R0 * (ca + w * f));  // S = 2: the factor joins pr2
+                const double2 t0 = cot[nR], t1 = cot[nR + 1];
+                const double sum = Ar + Br;
+                const double L0 = t1.x + t1.y * (f * sum);          // S = 0: the factor joins pr0
+                const double L1 = t0.x + t0.y * sum;                // S = 1: edge off
+                const double L2 = t1.x + t1.y * (Ar + f * Br);      // S = 2: the factor joins pr2
                 // exp(log prior + log L) of Multinomial.cpp:66-75 as a product; the "0 +" and
                 // "0 * (1 - u)" terms of the reference's running sum / gsl_ran_flat add exact zeros
                 double cum0 = sp[0] * L0;
@@ -579,8 +584,8 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                     bS[32 * jj] = (uint8_t) ns;
                     GBN_CHECK(net.tfpos_of_slot[gb + lane + 32 * j] < net.E);
                     ch.Stf[(size_t) c * net.E + net.tfpos_of_slot[gb + lane + 32 * j]] = (uint8_t) ns;
-                    P0 = ns == 0 ? R0 * f : R0;
-                    P2 = ns == 2 ? R2 * f : R2;
+                    A = ns == 0 ? Ar * f : Ar;
+                    Bq = ns != 1 ? Br * f : Br;
                     n = nR + (ns != 1);
                 }
                 cs.x += (ns == 0);                                  // Multinomial.cpp:101-105 as counts
@@ -612,7 +617,7 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
     GBN_CHECK(n + (y * D) < 3 * D && n <= deg);
     if (valid) {
         ch.tc2[((size_t) (c / XQ) * nH + dt) * XQ + (c % XQ)] =
-            make_double2(P0 * (omzt[n] * ca), (P0 * P2) * (omzt[n] * cb));   // {beta, gamma}, interleaved by chain bundle
+            make_double2(cot[n].y * A, cot[n].y * Bq);                     // {beta, gamma}, interleaved by chain bundle
         ch.ny[(size_t) c * nH + dt] = (uint16_t) (y * D + n);          // index into the X phase tables
     }
 }
@@ -638,7 +643,7 @@ static int check(cudaError_t e, const char **err)
 // shared memory of the S kernel: the per-dataset tables and, when it fits, FXp of the chain
 static size_t s_smem_bytes(const DevNet &net, bool stage_fx)
 {
-    return sizeof(double) * 7 * (size_t) net.stab_D + (stage_fx ? sizeof(double2) * (size_t) net.nX : 0) + 16;
+    return sizeof(double2) * 3 * (size_t) net.stab_D + (stage_fx ? sizeof(double2) * (size_t) net.nX : 0) + 16;
 }
 
 static bool s_stage_fx(const DevNet &net)
