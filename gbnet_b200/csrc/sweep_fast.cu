@@ -80,6 +80,9 @@ struct SweepArgs {
 // m * 2^e -> mantissa in [0.5, 1) and the exponent moved into e (frexp).  Likelihood products are
 // positive normal numbers, so the exponent field is rewritten directly; zero / subnormal / inf / nan
 // take the library path.
+// out of line on purpose: inlined, the library path's instructions are issued (predicated off) by every call
+__device__ __noinline__ double frexp_rare(double m, int *ex) { return frexp(m, ex); }
+
 __device__ __forceinline__ void normalise(double &m, int &e)
 {
     const int hi = __double2hiint(m);
@@ -89,7 +92,7 @@ __device__ __forceinline__ void normalise(double &m, int &e)
         m = __hiloint2double((hi & 0x800fffff) | (1022 << 20), __double2loint(m));
     } else {
         int ex;
-        m = frexp(m, &ex);
+        m = frexp_rare(m, &ex);
         e += ex;
     }
 }

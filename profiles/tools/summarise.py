@@ -15,6 +15,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 OUT = os.path.join(ROOT, "profiles")
 GP = os.path.join(ROOT, "gpurun_out")
 
+
+
+def short_name(raw):
+    """k_fast_s<0 1 0>: kernel name with its template arguments, no commas (this is a CSV field)."""
+    m = re.search(r"(k_\w+)(<[^>]*>)?", raw)
+    if not m:
+        return raw.replace(",", " ")
+    targs = (m.group(2) or "").replace("(int)", "").replace("(bool)", "").replace(",", "")
+    return m.group(1) + targs
+
+
 rows = [r for r in csv.reader(open(os.path.join(GP, "r1_launches.csv"))) if r and not r[0].startswith("==")]
 hdr = rows[0]
 idx = {h: i for i, h in enumerate(hdr)}
@@ -22,7 +33,7 @@ agg = collections.OrderedDict()
 for r in rows[1:]:
     if len(r) < len(hdr):
         continue
-    name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "").replace("unnamed>::", "").strip()
+    name = short_name(r[idx["Kernel Name"]])
     v, u = float(r[idx["Metric Value"]]), r[idx["Metric Unit"]]
     ms = v / 1e6 if u.startswith("n") else (v / 1e3 if u.startswith("u") else v)
     a = agg.setdefault(name, [0, 0.0])
@@ -56,7 +67,7 @@ with open(os.path.join(OUT, "r1_kernels_ncu_full.csv"), "w") as f:
     f.write("kernel," + ",".join(f"{w} [{units[idx[w]]}]" if w in idx else w for w in want) + "," +
             ",".join(s.replace("smsp__average_warps_issue_stalled_", "stall_").replace("_per_issue_active.ratio", "") for s in stalls) + "\n")
     for r in rows[2:]:
-        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("unnamed>::", "").strip()
+        name = short_name(r[idx["Kernel Name"]])
         f.write(name + "," + ",".join(r[idx[w]].replace(",", "") if w in idx else "" for w in want) + "," +
                 ",".join(r[idx[s]] for s in stalls) + "\n")
         b = sum(float(r[idx[k]].replace(",", "")) * mult.get(units[idx[k]], 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
