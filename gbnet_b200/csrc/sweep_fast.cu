@@ -136,13 +136,16 @@ __device__ __forceinline__ void child_likelihoods(const double *xC0, double2 bg,
 // (child, chain) by XQ.  The chains of a bundle share the window position: a window commits up to the
 // first TF that changed in ANY of them (flips are rare, so the shorter commit costs little), and every
 // committed TF still saw exactly the state the sequential sweep of its own chain would have seen.
-template <int NT, bool NY_SMEM>
+// LPT lanes of a warp work on one TF (32: a warp per TF; 16 / 8: two / four TFs per warp, for networks whose
+// TFs have few targets - there the per-TF instruction overhead, issued by all warps at once, bounds a round).
+template <int NT, bool NY_SMEM, int LPT, int U>
 __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, SweepArgs a, uint32_t nchains)
 {
-    constexpr int NW = NT / 32;
-    constexpr uint32_t Q = XQ, CPW = 32 / XQ, U = XU;                        // chains per CTA, children per warp and gather, gathers per lane and iteration
+    constexpr int NW = NT / 32, NS = 32 / LPT, W = NW * NS;                  // warps, TFs per warp, TFs per window
+    constexpr uint32_t Q = XQ, CPW = LPT / XQ;                               // chains per CTA, children per TF and gather
+    static_assert(LPT >= 2 * XQ, "a TF needs at least two child slots");
     extern __shared__ __align__(16) unsigned char smem_x[];
-    __shared__ int s_dec[NW];                                                // OR over the bundle: bit 1 = some chain flipped
+    __shared__ uint32_t s_dec[W];                                            // per window position: chains of the bundle that flipped
     const uint32_t nX = net.nX, E = net.E, nH = net.nH, D = net.stab_D;
     const uint32_t nXr = (nX + 3) & ~3u;
     double *xC0all = reinterpret_cast<double *>(smem_x);                     // [Q][3][D] c0 by idx = y * D + n
@@ -151,14 +154,16 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     uint16_t *sNy = reinterpret_cast<uint16_t *>(sX + Q * nXr);              // [nH][Q] table index of every target (NY_SMEM)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t h = lane % Q, cs = lane / Q;                              // this lane's chain and child slot
+    const uint32_t sg = lane / LPT, sl = lane % LPT;                         // this lane's TF of the warp, lane within it
+    const uint32_t h = sl % Q, cs = sl / Q;                                  // this lane's chain and child slot
+    const uint32_t pos = warp * NS + sg;                                     // window position of this lane's TF
     const uint32_t cbase = a.chain0 + Q * blockIdx.x;                        // a multiple of Q by construction
     const uint32_t nvalid = min(Q, nchains - Q * blockIdx.x);                // a last, partial bundle recomputes its last chain
     const uint32_t cmine = cbase + min(h, nvalid - 1);
     double2 *tcb = ch.tc2 + (size_t) (cbase / Q) * nH * Q;                   // bundle base: entry (i, chain) at Q i + chain
 
     // everything a round needs per TF is staged once: a round must not wait on global memory for
-    // anything but the children's cache entries (a dependent global load costs ~1 us per round)
+    // anything but the children's ids and cache entries
     for (uint32_t q = 0; q < Q; q++) {
         const uint32_t c = cbase + min(q, nvalid - 1);
         const uint32_t d = chain_dataset(net, c), gchain = chain_global_id(net, c);
@@ -192,22 +197,24 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
 
     uint32_t k0 = 0;
     while (k0 < nX) {
-        const uint32_t kw = k0 + warp;
+        const uint32_t kw = k0 + pos;
+        const bool live = kw < nX;
         int dec = 0;                              // bit 0: drawn value, bit 1: value changed (this lane's chain)
         double fac = 1.;
         uint32_t cbeg = 0, cend = 0;
-        if (kw < nX) {
-            const uint32_t xcur = sX[h * nX + kw] & 1u;
+        if (NS > 1 || live) {                     // warp-uniform when a warp holds one TF; else dead TFs ride along empty
+            const uint32_t kr = live ? kw : 0u;
+            const uint32_t xcur = sX[h * nX + kr] & 1u;
             // per-TF scalars come from global memory (written by this CTA or an earlier kernel): the loads
             // are issued with the first child ids and are off the critical path
-            const double g = 1. - gT[kw];         // (1 - t*x) at x = 1   (HNodeORNOR.cpp:59)
-            const uint32_t uword = a.use_inj ? 0u : gU[kw];
+            const double g = 1. - gT[kr];         // (1 - t*x) at x = 1   (HNodeORNOR.cpp:59)
+            const uint32_t uword = a.use_inj ? 0u : gU[kr];
             fac = xcur ? 1. / g : g;              // factor that turns the product into the flipped one
-            cbeg = sPtr[kw]; cend = sPtr[kw + 1];
+            if (live) { cbeg = sPtr[kw]; cend = sPtr[kw + 1]; }
             GBN_CHECK(cbeg <= cend && cend <= E);
             double mc = 1., mf = 1.;
             int ec = 0, ef = 0, cnt = 0;
-            // One (child, chain) per lane and iteration, software-pipelined with two explicit register sets
+            // One (child, chain) per lane and gather, software-pipelined with two explicit register sets
             // (no rotating copies, which would wait on the loads): while iteration i is computed from set X,
             // the cache entries of iteration i+1 are in flight into set Y and the child id / S value of
             // iteration i+2 into X's id registers.  The pipeline lives inside one round, so every entry is
@@ -254,18 +261,18 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             };
             Ids idA = load_ids(cc), idB = load_ids(cc + U * CPW);
             Dat dA = gather(idA), dB;
-            const uint32_t cw = cbeg + U * CPW * ((cend - cbeg + U * CPW - 1) / (U * CPW));     // warp-uniform trip count
-            uint32_t cu = cbeg;
-            while (cu < cw) {
+            uint32_t trips = (cend - cbeg + U * CPW - 1) / (U * CPW);             // trip count, uniform over the warp
+            if (NS > 1) trips = __reduce_max_sync(0xffffffffu, trips);
+            while (trips > 0) {
                 step(idA, dA, idB, dB);
-                if ((cu += U * CPW) >= cw) break;
+                if (--trips == 0) break;
                 step(idB, dB, idA, dA);
-                cu += U * CPW;
+                --trips;
             }
             normalise(mc, ec);
             normalise(mf, ef);
 #pragma unroll
-            for (int o = 16; o >= (int) Q; o >>= 1) {
+            for (int o = LPT / 2; o >= (int) Q; o >>= 1) {
                 mc *= __shfl_xor_sync(0xffffffffu, mc, o);
                 mf *= __shfl_xor_sync(0xffffffffu, mf, o);
                 ec += __shfl_xor_sync(0xffffffffu, ec, o);
@@ -273,31 +280,38 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             }
             normalise(mc, ec);
             normalise(mf, ef);
-            const double *prob = net.xprob[sX[h * nX + kw] >> 1];
+            const double *prob = net.xprob[sX[h * nX + kr] >> 1];
             double lik_cur, lik_flip;
             common_scale(prob[xcur] * mc, ec, prob[1 - xcur] * mf, ef, lik_cur, lik_flip);
             const double l0 = xcur ? lik_flip : lik_cur, l1 = xcur ? lik_cur : lik_flip;
             double cum0 = 0. + l0, cum1 = cum0 + l1;
             if (!(cum1 > 0.)) { cum0 = 0. + prob[0]; cum1 = cum0 + prob[1]; }     // Multinomial.cpp:78-85
-            const double u = a.use_inj ? inj[kw] : unit_from_word(uword);
+            const double u = a.use_inj ? inj[kr] : unit_from_word(uword);
             const double dice = 0. * (1 - u) + cum1 * u;
             const uint32_t nx = dice < cum0 ? 0u : (dice < cum1 ? 1u : xcur);
-            dec = h < nvalid ? ((int) nx | ((nx != xcur) ? 2 : 0)) : 0;
+            dec = (live && h < nvalid) ? ((int) nx | ((nx != xcur) ? 2 : 0)) : 0;
         }
-        const uint32_t flipped = __ballot_sync(0xffffffffu, (dec & 2) && cs == 0);    // bit q: chain q of the bundle flipped
-        if (lane == 0) s_dec[warp] = flipped ? 2 : 0;
+        // bit q of a TF's word: chain q of the bundle flipped
+        const uint32_t fb = __ballot_sync(0xffffffffu, (dec & 2) && cs == 0);
+        const uint32_t flipped = (fb >> (sg * LPT)) & ((1u << Q) - 1u);
+        if (sl == 0) s_dec[pos] = flipped;
         __syncthreads();
-        const uint32_t flips = __ballot_sync(0xffffffffu, lane < NW && (s_dec[lane] & 2));
-        const uint32_t first = flips ? (uint32_t) __ffs(flips) - 1 : NW;
-        const uint32_t ncommit = first < NW ? first + 1 : NW;
-        if (warp < ncommit && kw < nX) {
-            if (cs == 0) sX[h * nX + kw] = (uint8_t) ((sX[h * nX + kw] & 2u) | (dec & 1));
+        uint32_t first = W;
+#pragma unroll
+        for (uint32_t w0 = 0; w0 < (uint32_t) W; w0 += 32) {
+            const uint32_t f = __ballot_sync(0xffffffffu, w0 + lane < (uint32_t) W && s_dec[(w0 + lane) % W] != 0);
+            if (f && first == (uint32_t) W) first = w0 + (uint32_t) __ffs(f) - 1;
+        }
+        const uint32_t ncommit = first < W ? first + 1 : W;
+        const bool mine = pos < ncommit && live;
+        if (mine && cs == 0) sX[h * nX + kw] = (uint8_t) ((sX[h * nX + kw] & 2u) | (dec & 1));
+        if (__any_sync(0xffffffffu, mine && flipped != 0)) {
+            // apply the flip of X_kw in chain q to the cached terms of each child that depends on it
             for (uint32_t q = 0; q < Q; q++) {
-                if (!((flipped >> q) & 1u)) continue;
-                // apply the flip of X_kw in chain q to the cached terms of each child that depends on it
-                const double fq = __shfl_sync(0xffffffffu, fac, q);
+                const double fq = __shfl_sync(0xffffffffu, fac, (lane & ~(uint32_t) (LPT - 1)) + q);
+                if (!(mine && ((flipped >> q) & 1u))) continue;
                 const uint8_t *gS = ch.Stf + (size_t) (cbase + q) * E;
-                for (uint32_t cc = cbeg + lane; cc < cend; cc += 32) {
+                for (uint32_t cc = cbeg + sl; cc < cend; cc += LPT) {
                     const uint32_t s = gS[cc];
                     if (s == 1) continue;
                     double2 *e = tcb + (size_t) net.tf_child[cc] * Q + q;
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
         if (tid == 0 && ch.dbg) {
             atomicAdd(ch.dbg + 0, 1ull);
             atomicAdd(ch.dbg + 1, (unsigned long long) (k0 + ncommit <= nX ? ncommit : nX - k0));
-            atomicAdd(ch.dbg + 2, first < NW ? 1ull : 0ull);
+            atomicAdd(ch.dbg + 2, first < W ? 1ull : 0ull);
         }
         k0 += ncommit;
     }
@@ -720,8 +734,17 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
     const bool ny_smem = x_ny_smem(net);
     const size_t smem_x = x_smem_bytes(net, ny_smem);
     if (chain0 % XQ) { *err = "chain groups must start at a multiple of the X kernel's bundle size"; return -1; }
-    if (check(cudaFuncSetAttribute(ny_smem ? k_fast_x<FX_NT, true> : k_fast_x<FX_NT, false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x), err)) return -1;
+    // Lanes per TF by the mean number of targets of a TF: a warp (and two gathers per lane and stage), half
+    // a warp, or a quarter in CTAs of 16 warps (two CTAs per SM when there are more bundles than SMs).
+    // Fewer lanes per TF = less per-TF instruction overhead, which bounds a round when TFs are small.
+    uint32_t lpt = env_u32("GBN_X_LPT", 0);                  // 8 / 16 / 32 force a path (tests)
+    if (lpt != 8 && lpt != 16 && lpt != 32) lpt = (uint64_t) net.E >= 48ull * net.nX ? 32 : ((uint64_t) net.E >= 20ull * net.nX ? 16 : 8);
+    void (*kx)(DevNet, DevChains, SweepArgs, uint32_t);
+    uint32_t x_nt = FX_NT;
+    if (lpt == 32) kx = ny_smem ? k_fast_x<FX_NT, true, 32, XU> : k_fast_x<FX_NT, false, 32, XU>;
+    else if (lpt == 16) kx = ny_smem ? k_fast_x<FX_NT, true, 16, 1> : k_fast_x<FX_NT, false, 16, 1>;
+    else { kx = ny_smem ? k_fast_x<FX_NT / 2, true, 8, 1> : k_fast_x<FX_NT / 2, false, 8, 1>; x_nt = FX_NT / 2; }
+    if (check(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x), err)) return -1;
     const size_t smem_tl = sizeof(double) * 3 * (size_t) net.stab_D + 4 * (size_t) net.nX + 16;
     if (net.listen && !net.const_params &&
         check(cudaFuncSetAttribute(k_fast_tl, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -736,8 +759,7 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         a.chain0 = chain0;
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw], st);
         if (stx != st && sw > 0) cudaStreamWaitEvent(stx, evs, 0);      // this chain group's previous S phase
-        if (ny_smem) k_fast_x<FX_NT, true><<<(nchains + XQ - 1) / XQ, FX_NT, smem_x, stx>>>(net, ch, a, nchains);
-        else k_fast_x<FX_NT, false><<<(nchains + XQ - 1) / XQ, FX_NT, smem_x, stx>>>(net, ch, a, nchains);
+        kx<<<(nchains + XQ - 1) / XQ, x_nt, smem_x, stx>>>(net, ch, a, nchains);
         if (stx != st) { cudaEventRecord(evx, stx); cudaStreamWaitEvent(st, evx, 0); }
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
         const bool tl = net.listen && !net.const_params;

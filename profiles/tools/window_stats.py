@@ -1,11 +1,26 @@
-import sys; import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-import gbnet_b200, numpy as np
+"""Speculative X windows: rounds per sweep, TFs committed per round and rounds ended by a flip, per
+chain bundle (the X kernel sweeps two chains per CTA).  python profiles/tools/window_stats.py [C2|C3]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import numpy as np
+
+import gbnet_b200
 from gbnet_b200 import synth
-net = synth.shape("C3"); hy = synth.cli_default_hyper()
-G = gbnet_b200.Sampler(net.src, net.trg, net.mor, net.evid_trg, net.evid_val, n_graphs=64, seed=1, **hy)
+
+shape = sys.argv[1] if len(sys.argv) > 1 else "C3"
+net = synth.shape(shape)
+hy = synth.cli_default_hyper()
+M = 64
+G = gbnet_b200.Sampler(net.src, net.trg, net.mor, net.evid_trg, net.evid_val, n_graphs=M, seed=1, **hy)
 G.debug_counters(True)
-for blk in range(4):
+bundles = M // 2
+for blk in range(6):
     G.sample_n(10)
     r, t, f, _ = G.debug_counters(True)
-    print("sweeps %d-%d: rounds/sweep/chain %.1f  TFs/round %.2f  flip rounds/sweep/chain %.1f" % (blk*10, blk*10+9, r/640, t/max(r,1), f/640))
-st = G.get_state(0); nX=G.n_tf(); print("X active", st[:nX].sum(), "S dist", np.bincount(st[2*nX:].astype(int)))
+    print("%s sweeps %d-%d: rounds/sweep/bundle %.1f  TFs/round %.2f  flip rounds/sweep/bundle %.1f"
+          % (shape, blk * 10, blk * 10 + 9, r / (10 * bundles), t / max(r, 1), f / (10 * bundles)))
+st = G.get_state(0)
+nX = G.n_tf()
+print("X active", st[:nX].sum(), "S dist", np.bincount(st[2 * nX:].astype(int)))

@@ -162,6 +162,16 @@ def test_fast_x_large_network_path(monkeypatch):
     _run_trajectory(pb, KERNEL_FAST, 10, injected=True, chunks=(5,))
 
 
+@pytest.mark.parametrize("lpt", ["8", "16", "32"])
+def test_fast_x_lanes_per_tf(monkeypatch, lpt):
+    """The X kernel gives a TF a whole warp, or a half / a quarter of one when TFs have few targets
+    (chosen by the mean out-degree); each forced here on a network with hubs and many small TFs."""
+    monkeypatch.setenv("GBN_X_LPT", lpt)
+    pb, _ = make_problem(NX=70, NY=300, AvgNTF=2.0, seed=37, n_graphs=3, num_active_tfs=4)
+    _run_trajectory(pb, KERNEL_FAST, 80, injected=False, chunks=(40,))
+    _run_trajectory(pb, KERNEL_FAST, 10, injected=True, chunks=(5,))
+
+
 def test_listening_t_fast_long():
     """T nodes that listen to their children (the pyx default) on the fast path: 200 sweeps of the
     oracle's chain, with several active TFs so the sequential part is exercised."""
