@@ -364,8 +364,10 @@ int sample_n(gbn_model *m, uint32_t n)
             const uint32_t c0 = (uint32_t) ((uint64_t) m->n_chains * g / G) / xq * xq;
             const uint32_t c1 = g + 1 == G ? m->n_chains : (uint32_t) ((uint64_t) m->n_chains * (g + 1) / G) / xq * xq;
             cudaStream_t st = G == 1 ? m->stream : m->gstream[g];
-            const bool px = G > 1 && prio_x != 2 && !m->phase_timing;
-            if (G > 1) CUDA_TRY(cudaStreamWaitEvent(st, m->gfork, 0));
+            // the X kernels get their own (high-priority) stream: they overlap the other groups' S kernels and,
+            // when the T nodes do not listen to their children, this group's own T draws
+            const bool px = (G > 1 || fast_t_beside_x(m->net)) && prio_x != 2 && !m->phase_timing;
+            if (G > 1 || px) CUDA_TRY(cudaStreamWaitEvent(st, m->gfork, 0));
             if (px) CUDA_TRY(cudaStreamWaitEvent(m->xstream[g], m->gfork, 0));
             int l = launch_sweep_fast(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, st, &err,
                                       m->phase_timing ? m->phase_ev.data() + (size_t) g * stride : nullptr, c0, c1 - c0,
@@ -377,6 +379,7 @@ int sample_n(gbn_model *m, uint32_t n)
                 CUDA_TRY(cudaStreamWaitEvent(m->stream, m->gdone[g], 0));
             }
         }
+        if (launched >= 0 && fast_t_beside_x(m->net) && (n & 1)) std::swap(m->ch.T, m->ch.T2);
     } else
         launched = launch_sweep_strict(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err);
     if (launched < 0) return fail(GBN_ERR_CUDA, std::string("sweep launch: ") + err);
@@ -526,6 +529,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     ch.n_chains = m->n_chains;
     if (int rc = dev_alloc(m, &ch.X, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.T, C * nX)) return bail(rc);
+    if (int rc = dev_alloc(m, &ch.T2, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.S, C * Ep)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.cX1, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.tMean, C * nX)) return bail(rc);

@@ -59,6 +59,7 @@ struct DevChains {
     uint32_t n_chains;            // local: n_datasets * n_graphs_local, dataset-major
     uint8_t *X;
     double *T;
+    double *T2;                   // fast kernel: alternate T buffer (the T draws of a sweep run beside its X phase)
     uint8_t *S;
     uint32_t *cX1;
     double *tMean, *tM2;

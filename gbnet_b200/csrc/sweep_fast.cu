@@ -37,6 +37,8 @@
 #include <cstdio>
 #include "kernels.cuh"
 #include "device_math.cuh"
+#include <utility>
+
 #include "topology.hpp"
 
 // Bounds checks of every data-dependent index, compiled in by the "chk" build variant
@@ -342,10 +344,12 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
 // Beta::sample (Beta.cpp:60-104) for T nodes that do not listen to their children: the blanket is
 // the Beta prior alone.  Also publishes FXp = {1 - t*x, 1 / (1 - t*x)} (HNodeORNOR.cpp:59) for
 // the S phase.
+// Tout: where the new values go (ch.T, or the alternate buffer when the draws run beside the X phase,
+// which still reads the old ones); publish: write FXp as well.
 // update_t: 0 = publish FXp only (refresh), 1 = update every T, 2 = update the T of inactive TFs only
 // (listening T nodes: an inactive TF's children do not depend on its T - the factor is (1 - t*0) z -
 // so its blanket is still the prior alone; the active ones are k_fast_tl's)
-__global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, SweepArgs a, int update_t)
+__global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, SweepArgs a, int update_t, double *Tout, int publish)
 {
     const uint32_t nX = net.nX;
     const uint32_t c = blockIdx.y + a.chain0;
@@ -366,12 +370,25 @@ __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, Swee
         const double prop_ll = (0. + log(beta_pdf(prop, al, be, lnB))) + 0.;
         t = mh_decide(prev, prop, prev_ll, prop_ll, mean, dx, al, be, lnB,
                       a.use_inj != 0, a.use_inj ? ch.inj_exp[row] : 0., net.seed, gchain, a.sweep, k);
-        ch.T[o] = t;
+        Tout[o] = t;
         double m = ch.tMean[o], m2 = ch.tM2[o];
         welford_add(m, m2, t, (double) a.stat_n);
         ch.tMean[o] = m; ch.tM2[o] = m2;
     }
-    const double fx = 1. - t * (double) ch.X[o];
+    if (publish) {
+        const double fx = 1. - t * (double) ch.X[o];
+        ch.FXp[o] = make_double2(fx, 1. / fx);
+    }
+}
+
+// FXp = {1 - t*x, 1 / (1 - t*x)} from T and the X the X phase just drew (HNodeORNOR.cpp:59): the
+// publishing half of k_fast_t when the T draws ran beside the X phase
+__global__ void __launch_bounds__(FT_NT) k_fast_fx(DevNet net, DevChains ch, SweepArgs a, const double *T)
+{
+    const uint32_t k = blockIdx.x * FT_NT + threadIdx.x;
+    if (k >= net.nX) return;
+    const size_t o = (size_t) (blockIdx.y + a.chain0) * net.nX + k;
+    const double fx = 1. - T[o] * (double) ch.X[o];
     ch.FXp[o] = make_double2(fx, 1. / fx);
 }
 
@@ -685,6 +702,10 @@ static bool x_ny_smem(const DevNet &net)
 
 uint32_t fast_x_bundle() { return XQ; }
 
+// the T draws of a sweep run beside its X phase (see launch_sweep_fast); the caller swaps ch.T / ch.T2 after
+// an odd number of sweeps
+bool fast_t_beside_x(const DevNet &net) { return !net.listen && !net.const_params && env_u32("GBN_T_BESIDE_X", 1) != 2; }
+
 bool fast_supported(const DevNet &net, const char **why)
 {
     if (net.nX >= (1u << 30)) { *why = "n_tf does not fit the packed parent id"; return false; }
@@ -718,7 +739,7 @@ int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st,
     if (ch.n_chains == 0) return 0;
     SweepArgs a{ 0, 0, 0, 0, 0 };
     k_fast_stf<<<dim3((net.E + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
-    k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, 0);
+    k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, 0, ch.T, 1);
     if (launch_s(net, ch, a, 1, ch.n_chains, st, err)) return -1;
     if (check(cudaGetLastError(), err)) return -1;
     return 3;
@@ -750,6 +771,13 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         check(cudaFuncSetAttribute(k_fast_tl, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int) (smem_tl > 48 * 1024 ? smem_tl : 48 * 1024)), err)) return -1;
     int launches = 0;
+    // T nodes that do not listen to their children are drawn from the prior alone: their update needs
+    // neither this sweep's X nor anything the X phase writes, so it runs beside the X kernel (on `st`,
+    // the X kernel on `stx`) into the alternate T buffer - the X phase still reads the previous values -
+    // and a small kernel publishes FXp once both are done.  The buffers swap roles every sweep.
+    const bool t_beside_x = fast_t_beside_x(net);
+    DevChains chl = ch;
+    const dim3 grid_t((net.nX + FT_NT - 1) / FT_NT, nchains);
     for (uint32_t sw = 0; sw < n_sweeps; sw++) {
         SweepArgs a;
         a.sweep = sweep0 + sw;
@@ -759,17 +787,27 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         a.chain0 = chain0;
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw], st);
         if (stx != st && sw > 0) cudaStreamWaitEvent(stx, evs, 0);      // this chain group's previous S phase
-        kx<<<(nchains + XQ - 1) / XQ, x_nt, smem_x, stx>>>(net, ch, a, nchains);
-        if (stx != st) { cudaEventRecord(evx, stx); cudaStreamWaitEvent(st, evx, 0); }
-        if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
-        const bool tl = net.listen && !net.const_params;
-        k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, nchains), FT_NT, 0, st>>>(net, ch, a, net.const_params ? 0 : (tl ? 2 : 1));
-        if (tl) {
-            k_fast_tl<<<nchains, FTL_NT, smem_tl, st>>>(net, ch, a);
+        kx<<<(nchains + XQ - 1) / XQ, x_nt, smem_x, stx>>>(net, chl, a, nchains);
+        if (stx != st) cudaEventRecord(evx, stx);
+        if (t_beside_x) {
+            if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
+            k_fast_t<<<grid_t, FT_NT, 0, st>>>(net, chl, a, 1, chl.T2, 0);
+            if (stx != st) cudaStreamWaitEvent(st, evx, 0);
+            k_fast_fx<<<grid_t, FT_NT, 0, st>>>(net, chl, a, chl.T2);
+            std::swap(chl.T, chl.T2);
             launches += 1;
+        } else {
+            if (stx != st) cudaStreamWaitEvent(st, evx, 0);
+            if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
+            const bool tl = net.listen && !net.const_params;
+            k_fast_t<<<grid_t, FT_NT, 0, st>>>(net, chl, a, net.const_params ? 0 : (tl ? 2 : 1), chl.T, 1);
+            if (tl) {
+                k_fast_tl<<<nchains, FTL_NT, smem_tl, st>>>(net, chl, a);
+                launches += 1;
+            }
         }
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 2], st);
-        if (launch_s(net, ch, a, 0, nchains, st, err)) return -1;
+        if (launch_s(net, chl, a, 0, nchains, st, err)) return -1;
         if (stx != st) cudaEventRecord(evs, st);
         launches += 3;
     }
