@@ -366,7 +366,7 @@ int sample_n(gbn_model *m, uint32_t n)
             cudaStream_t st = G == 1 ? m->stream : m->gstream[g];
             // the X kernels get their own (high-priority) stream: they overlap the other groups' S kernels and,
             // when the T nodes do not listen to their children, this group's own T draws
-            const bool px = (G > 1 || fast_t_beside_x(m->net)) && prio_x != 2 && !m->phase_timing;
+            const bool px = (G > 1 || fast_uses_x_stream(m->net)) && prio_x != 2 && !m->phase_timing;
             if (G > 1 || px) CUDA_TRY(cudaStreamWaitEvent(st, m->gfork, 0));
             if (px) CUDA_TRY(cudaStreamWaitEvent(m->xstream[g], m->gfork, 0));
             int l = launch_sweep_fast(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, st, &err,

@@ -430,77 +430,102 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
     }
     __syncthreads();
     const uint32_t count = s_count;
-    for (uint32_t idx = 0; idx < count; idx++) {
-        const uint32_t k = list[idx];
-        const size_t o = (size_t) c * nX + k;
-        const double al = net.t_a[k], be = net.t_b[k], mean = net.t_mean[k], lnB = net.t_lnB[k];
-        const size_t row = ((size_t) c * ch.inj_sweeps + a.inj_row) * nX + k;
-        const double prev = ch.T[o];
-        // every thread evaluates the same draw (uniform control flow, no broadcast needed)
-        const double draw = a.use_inj ? ch.inj_beta[row] : draw_beta(net.seed, gchain, a.sweep, k, al, be);
-        const double dx = draw - mean;
-        const double prop = prev + dx;
-        const double pdf_prev = beta_pdf(prev, al, be, lnB), pdf_prop = beta_pdf(prop, al, be, lnB);
-        const double r = (1. - prop) / (1. - prev);
-        const uint32_t cbeg = net.tf_ptr[k], cend = net.tf_ptr[k + 1];
-        double dll = 0.;
-        if (pdf_prop > 0.) {                        // out-of-range proposals are rejected before the children matter
-            double mo = 1., mn = 1.;
-            int eo = 0, en = 0, cnt = 0;
-            for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
-                const uint32_t s = gStf[cc];
-                if (s == 1) continue;
-                const uint32_t i = net.tf_child[cc];
-                GBN_CHECK(i < nH && gny[i] < 3 * D);
-                const double2 bg = tc2[XQ * (size_t) i];
-                const double c0 = xC0[gny[i]];
-                mo *= c0 + (bg.x + bg.y);
-                mn *= s == 0 ? c0 + r * (bg.x + bg.y) : c0 + (bg.x + r * bg.y);
-                if (++cnt == 8) { normalise(mo, eo); normalise(mn, en); cnt = 0; }
-            }
-            normalise(mo, eo);
-            normalise(mn, en);
+    // Everything of an update that does not depend on the children - the proposal, the prior densities,
+    // the proposal-density ratio, the exponential draw of the acceptance test - is computed for a batch of
+    // active TFs at once, one thread per TF; only the children's likelihood ratio, the decision and the
+    // cache update stay in the sequential walk.  (A TF's own T is not touched by the other TFs' updates.)
+    __shared__ double s_prop[FTL_NT], s_r[FTL_NT], s_prev_ll[FTL_NT], s_lpp[FTL_NT], s_logq[FTL_NT], s_expo[FTL_NT];
+    for (uint32_t b0 = 0; b0 < count; b0 += FTL_NT) {
+        const uint32_t nb = min(count - b0, (uint32_t) FTL_NT);
+        if (tid < nb) {
+            const uint32_t k = list[b0 + tid];
+            const size_t o = (size_t) c * nX + k;
+            const double al = net.t_a[k], be = net.t_b[k], mean = net.t_mean[k], lnB = net.t_lnB[k];
+            const size_t row = ((size_t) c * ch.inj_sweeps + a.inj_row) * nX + k;
+            const double prev = ch.T[o];
+            const double draw = a.use_inj ? ch.inj_beta[row] : draw_beta(net.seed, gchain, a.sweep, k, al, be);
+            const double dx = draw - mean;
+            const double prop = prev + dx;
+            const double pdf_prev = beta_pdf(prev, al, be, lnB), pdf_prop = beta_pdf(prop, al, be, lnB);
+            s_prop[tid] = prop;
+            s_r[tid] = (1. - prop) / (1. - prev);
+            s_prev_ll[tid] = (0. + log(pdf_prev)) + 0.;
+            s_lpp[tid] = 0. + log(pdf_prop);                // -inf for an out-of-range proposal
+            s_logq[tid] = log(beta_pdf(mean - dx, al, be, lnB) / beta_pdf(mean + dx, al, be, lnB));   // Beta.cpp:74-78
+            s_expo[tid] = a.use_inj ? ch.inj_exp[row] : draw_exp(net.seed, gchain, a.sweep, k);
+        }
+        __syncthreads();
+        for (uint32_t idx = 0; idx < nb; idx++) {
+            const uint32_t k = list[b0 + idx];
+            const size_t o = (size_t) c * nX + k;
+            const double prev = ch.T[o], prop = s_prop[idx], r = s_r[idx];
+            const uint32_t cbeg = net.tf_ptr[k], cend = net.tf_ptr[k + 1];
+            double dll = 0.;
+            if (s_lpp[idx] > -INFINITY) {               // out-of-range proposals are rejected before the children matter
+                double mo = 1., mn = 1.;
+                int eo = 0, en = 0, cnt = 0;
+                for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
+                    const uint32_t s = gStf[cc];
+                    if (s == 1) continue;
+                    const uint32_t i = net.tf_child[cc];
+                    GBN_CHECK(i < nH && gny[i] < 3 * D);
+                    const double2 bg = tc2[XQ * (size_t) i];
+                    const double c0 = xC0[gny[i]];
+                    mo *= c0 + (bg.x + bg.y);
+                    mn *= s == 0 ? c0 + r * (bg.x + bg.y) : c0 + (bg.x + r * bg.y);
+                    if (++cnt == 8) { normalise(mo, eo); normalise(mn, en); cnt = 0; }
+                }
+                normalise(mo, eo);
+                normalise(mn, en);
 #pragma unroll
-            for (int w = 16; w > 0; w >>= 1) {
-                mo *= __shfl_xor_sync(0xffffffffu, mo, w);
-                mn *= __shfl_xor_sync(0xffffffffu, mn, w);
-                eo += __shfl_xor_sync(0xffffffffu, eo, w);
-                en += __shfl_xor_sync(0xffffffffu, en, w);
+                for (int w = 16; w > 0; w >>= 1) {
+                    mo *= __shfl_xor_sync(0xffffffffu, mo, w);
+                    mn *= __shfl_xor_sync(0xffffffffu, mn, w);
+                    eo += __shfl_xor_sync(0xffffffffu, eo, w);
+                    en += __shfl_xor_sync(0xffffffffu, en, w);
+                }
+                normalise(mo, eo);
+                normalise(mn, en);
+                if (lane == 0) { s_m[0][warp] = mo; s_m[1][warp] = mn; s_e[0][warp] = eo; s_e[1][warp] = en; }
+                __syncthreads();
+                mo = 1.; mn = 1.; eo = 0; en = 0;
+                for (int w = 0; w < FTL_NT / 32; w++) { mo *= s_m[0][w]; mn *= s_m[1][w]; eo += s_e[0][w]; en += s_e[1][w]; }
+                dll = log(mn / mo) + (double) (en - eo) * 0.69314718055994530942;
+                __syncthreads();                        // s_m / s_e free for the next TF
             }
-            normalise(mo, eo);
-            normalise(mn, en);
-            if (lane == 0) { s_m[0][warp] = mo; s_m[1][warp] = mn; s_e[0][warp] = eo; s_e[1][warp] = en; }
-            __syncthreads();
-            mo = 1.; mn = 1.; eo = 0; en = 0;
-            for (int w = 0; w < FTL_NT / 32; w++) { mo *= s_m[0][w]; mn *= s_m[1][w]; eo += s_e[0][w]; en += s_e[1][w]; }
-            dll = log(mn / mo) + (double) (en - eo) * 0.69314718055994530942;
-            __syncthreads();                        // s_m / s_e free for the next TF
-        }
-        const double prev_ll = (0. + log(pdf_prev)) + 0.;
-        const double prop_ll = (0. + log(pdf_prop)) + dll;
-        const double t = mh_decide(prev, prop, prev_ll, prop_ll, mean, dx, al, be, lnB,
-                                   a.use_inj != 0, a.use_inj ? ch.inj_exp[row] : 0., net.seed, gchain, a.sweep, k);
-        if (t != prev) {
-            // accepted: move the edge factors of this TF inside the cached terms of its children
-            for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
-                const uint32_t s = gStf[cc];
-                if (s == 1) continue;
-                const uint32_t i = net.tf_child[cc];
-                double2 bg = tc2[XQ * (size_t) i];
-                if (s == 0) bg.x *= r;
-                bg.y *= r;
-                tc2[XQ * (size_t) i] = bg;
+            // Beta::metropolis_hastings_with_prior_proposal (Beta.cpp:60-91), as mh_decide with its pieces precomputed
+            const double prev_ll = s_prev_ll[idx];
+            const double prop_ll = s_lpp[idx] + dll;
+            double t = prev;
+            if (prop_ll > -INFINITY) {
+                t = prop;
+                if (prev_ll > -INFINITY) {
+                    const double logratio = prop_ll - prev_ll + s_logq[idx];
+                    if (!(logratio >= 0.) && !(logratio > -s_expo[idx])) t = prev;
+                }
             }
+            if (t != prev) {
+                // accepted: move the edge factors of this TF inside the cached terms of its children
+                for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
+                    const uint32_t s = gStf[cc];
+                    if (s == 1) continue;
+                    const uint32_t i = net.tf_child[cc];
+                    double2 bg = tc2[XQ * (size_t) i];
+                    if (s == 0) bg.x *= r;
+                    bg.y *= r;
+                    tc2[XQ * (size_t) i] = bg;
+                }
+            }
+            if (tid == 0) {
+                ch.T[o] = t;
+                double m = ch.tMean[o], m2 = ch.tM2[o];
+                welford_add(m, m2, t, (double) a.stat_n);
+                ch.tMean[o] = m; ch.tM2[o] = m2;
+                const double fx = 1. - t;
+                ch.FXp[o] = make_double2(fx, 1. / fx);
+            }
+            __syncthreads();                            // cache updates visible to the next active TF
         }
-        if (tid == 0) {
-            ch.T[o] = t;
-            double m = ch.tMean[o], m2 = ch.tM2[o];
-            welford_add(m, m2, t, (double) a.stat_n);
-            ch.tMean[o] = m; ch.tM2[o] = m2;
-            const double fx = 1. - t;
-            ch.FXp[o] = make_double2(fx, 1. / fx);
-        }
-        __syncthreads();                            // cache updates visible to the next active TF
     }
 }
 
@@ -706,6 +731,10 @@ uint32_t fast_x_bundle() { return XQ; }
 // an odd number of sweeps
 bool fast_t_beside_x(const DevNet &net) { return !net.listen && !net.const_params && env_u32("GBN_T_BESIDE_X", 1) != 2; }
 
+// a second stream per chain group pays off even for a single group: T work runs beside the X kernel
+// (non-listening T nodes) or the two T kernels run side by side (listening ones)
+bool fast_uses_x_stream(const DevNet &net) { return !net.const_params && env_u32("GBN_T_BESIDE_X", 1) != 2; }
+
 bool fast_supported(const DevNet &net, const char **why)
 {
     if (net.nX >= (1u << 30)) { *why = "n_tf does not fit the packed parent id"; return false; }
@@ -800,9 +829,13 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
             if (stx != st) cudaStreamWaitEvent(st, evx, 0);
             if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
             const bool tl = net.listen && !net.const_params;
-            k_fast_t<<<grid_t, FT_NT, 0, st>>>(net, chl, a, net.const_params ? 0 : (tl ? 2 : 1), chl.T, 1);
+            // listening T nodes: the inactive TFs (prior draws, parallel) and the active ones (sequential
+            // walk per chain) are disjoint, so the two kernels run side by side when there is an X stream
+            cudaStream_t stt = tl ? stx : st;
+            k_fast_t<<<grid_t, FT_NT, 0, stt>>>(net, chl, a, net.const_params ? 0 : (tl ? 2 : 1), chl.T, 1);
             if (tl) {
                 k_fast_tl<<<nchains, FTL_NT, smem_tl, st>>>(net, chl, a);
+                if (stt != st) { cudaEventRecord(evx, stt); cudaStreamWaitEvent(st, evx, 0); }
                 launches += 1;
             }
         }
