@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     static_assert(LPT >= 2 * XQ, "a TF needs at least two child slots");
     extern __shared__ __align__(16) unsigned char smem_x[];
     __shared__ uint32_t s_dec[W];                                            // per window position: chains of the bundle that flipped
+    __shared__ double s_fac[W * XQ];                                         // per window position and chain: the flip factor
     const uint32_t nX = net.nX, E = net.E, nH = net.nH, D = net.stab_D;
     const uint32_t nXr = (nX + 3) & ~3u;
     double *xC0all = reinterpret_cast<double *>(smem_x);                     // [Q][3][D] c0 by idx = y * D + n
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
         const uint32_t fb = __ballot_sync(0xffffffffu, (dec & 2) && cs == 0);
         const uint32_t flipped = (fb >> (sg * LPT)) & ((1u << Q) - 1u);
         if (sl == 0) s_dec[pos] = flipped;
+        if (cs == 0) s_fac[pos * Q + h] = fac;
         __syncthreads();
         uint32_t first = W;
 #pragma unroll
@@ -305,15 +307,18 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             if (f && first == (uint32_t) W) first = w0 + (uint32_t) __ffs(f) - 1;
         }
         const uint32_t ncommit = first < W ? first + 1 : W;
-        const bool mine = pos < ncommit && live;
-        if (mine && cs == 0) sX[h * nX + kw] = (uint8_t) ((sX[h * nX + kw] & 2u) | (dec & 1));
-        if (__any_sync(0xffffffffu, mine && flipped != 0)) {
-            // apply the flip of X_kw in chain q to the cached terms of each child that depends on it
+        if (pos < ncommit && live && cs == 0) sX[h * nX + kw] = (uint8_t) ((sX[h * nX + kw] & 2u) | (dec & 1));
+        if (first < (uint32_t) W) {
+            // The window ends at the one TF that flipped (in one or more chains of the bundle): apply the flip
+            // to the cached terms of each child that depends on it.  The whole CTA does this - every other
+            // warp would only wait at the barrier, and a hub's children walked by one warp cost tens of
+            // microseconds of dependent loads.
+            const uint32_t kf = k0 + first, fb0 = sPtr[kf], fe0 = sPtr[kf + 1], fmask = s_dec[first];
             for (uint32_t q = 0; q < Q; q++) {
-                const double fq = __shfl_sync(0xffffffffu, fac, (lane & ~(uint32_t) (LPT - 1)) + q);
-                if (!(mine && ((flipped >> q) & 1u))) continue;
+                if (!((fmask >> q) & 1u)) continue;
+                const double fq = s_fac[first * Q + q];
                 const uint8_t *gS = ch.Stf + (size_t) (cbase + q) * E;
-                for (uint32_t cc = cbeg + sl; cc < cend; cc += LPT) {
+                for (uint32_t cc = fb0 + tid; cc < fe0; cc += NT) {
                     const uint32_t s = gS[cc];
                     if (s == 1) continue;
                     double2 *e = tcb + (size_t) net.tf_child[cc] * Q + q;

@@ -1,5 +1,5 @@
 """Speculative X windows: rounds per sweep, TFs committed per round and rounds ended by a flip, per
-chain bundle (the X kernel sweeps two chains per CTA).  python profiles/tools/window_stats.py [C2|C3]"""
+chain bundle (the X kernel sweeps two chains per CTA).  python profiles/tools/window_stats.py [C2|C3] [listen]"""
 import os
 import sys
 
@@ -11,7 +11,9 @@ from gbnet_b200 import synth
 
 shape = sys.argv[1] if len(sys.argv) > 1 else "C3"
 net = synth.shape(shape)
-hy = synth.cli_default_hyper()
+hy = dict(synth.cli_default_hyper())
+if len(sys.argv) > 2:
+    hy["noise_listen_children"] = sys.argv[2] == "listen"
 M = 64
 G = gbnet_b200.Sampler(net.src, net.trg, net.mor, net.evid_trg, net.evid_val, n_graphs=M, seed=1, **hy)
 G.debug_counters(True)
