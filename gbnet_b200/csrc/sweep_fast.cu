@@ -138,8 +138,8 @@ __device__ __forceinline__ void child_likelihoods(const double *xC0, double2 bg,
 // (child, chain) by XQ.  The chains of a bundle share the window position: a window commits up to the
 // first TF that changed in ANY of them (flips are rare, so the shorter commit costs little), and every
 // committed TF still saw exactly the state the sequential sweep of its own chain would have seen.
-// LPT lanes of a warp work on one TF (32: a warp per TF; 16 / 8: two / four TFs per warp, for networks whose
-// TFs have few targets - there the per-TF instruction overhead, issued by all warps at once, bounds a round).
+// LPT lanes of a warp work on one TF (32: a warp per TF; 16 / 8: two / four TFs per warp - the per-TF
+// instruction overhead is issued by all warps at once, and a longer window means fewer rounds).
 template <int NT, bool NY_SMEM, int LPT, int U>
 __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, SweepArgs a, uint32_t nchains)
 {
@@ -789,14 +789,19 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
     const bool ny_smem = x_ny_smem(net);
     const size_t smem_x = x_smem_bytes(net, ny_smem);
     if (chain0 % XQ) { *err = "chain groups must start at a multiple of the X kernel's bundle size"; return -1; }
-    // Lanes per TF by the mean number of targets of a TF: a warp (and two gathers per lane and stage), half
-    // a warp, or a quarter in CTAs of 16 warps (two CTAs per SM when there are more bundles than SMs).
-    // Fewer lanes per TF = less per-TF instruction overhead, which bounds a round when TFs are small.
+    // Lanes per TF by the mean number of targets of a TF: half a warp (a 64-TF window; two gathers per lane and
+    // stage when TFs are large), or a quarter in CTAs of 16 warps (two CTAs per SM when there are more bundles
+    // than SMs).  Fewer lanes per TF = less per-TF instruction overhead and, with the longer window, fewer
+    // rounds: the fixed latency of a round grows when the S kernels of other chain groups load the memory
+    // system (C3, 4 chain groups: a warp per TF 7.43e10, half a warp 7.81e10 edge-updates/s at equal
+    // stand-alone kernel time).  A whole warp per TF is kept for GBN_X_LPT=32.
     uint32_t lpt = env_u32("GBN_X_LPT", 0);                  // 8 / 16 / 32 force a path (tests)
-    if (lpt != 8 && lpt != 16 && lpt != 32) lpt = (uint64_t) net.E >= 48ull * net.nX ? 32 : ((uint64_t) net.E >= 20ull * net.nX ? 16 : 8);
+    const bool big = (uint64_t) net.E >= 48ull * net.nX;
+    if (lpt != 8 && lpt != 16 && lpt != 32) lpt = (uint64_t) net.E >= 20ull * net.nX ? 16 : 8;
     void (*kx)(DevNet, DevChains, SweepArgs, uint32_t);
     uint32_t x_nt = FX_NT;
     if (lpt == 32) kx = ny_smem ? k_fast_x<FX_NT, true, 32, XU> : k_fast_x<FX_NT, false, 32, XU>;
+    else if (lpt == 16 && big) kx = ny_smem ? k_fast_x<FX_NT, true, 16, XU> : k_fast_x<FX_NT, false, 16, XU>;
     else if (lpt == 16) kx = ny_smem ? k_fast_x<FX_NT, true, 16, 1> : k_fast_x<FX_NT, false, 16, 1>;
     else { kx = ny_smem ? k_fast_x<FX_NT / 2, true, 8, 1> : k_fast_x<FX_NT / 2, false, 8, 1>; x_nt = FX_NT / 2; }
     if (check(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x), err)) return -1;
