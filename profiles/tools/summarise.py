@@ -71,7 +71,7 @@ with open(os.path.join(OUT, "r1_kernels_ncu_full.csv"), "w") as f:
         f.write(name + "," + ",".join(r[idx[w]].replace(",", "") if w in idx else "" for w in want) + "," +
                 ",".join(r[idx[s]] for s in stalls) + "\n")
         b = sum(float(r[idx[k]].replace(",", "")) * mult.get(units[idx[k]], 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        key = "k_fast_x" if "k_fast_x" in name else ("k_fast_s" if "k_fast_s" in name else "k_fast_t")
+        key = next((k for k in ("k_fast_x", "k_fast_s", "k_fast_fx", "k_fast_tl", "k_fast_t") if k in name), name)
         traffic[key] = b
 traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, kernels serialised "
                     "(GBN_STREAM_GROUPS=1), C3 x 256 chains; see profiles/r1_kernels_ncu_full.csv")
