@@ -191,11 +191,11 @@ int zero_stats(gbn_model *m)
     return 0;
 }
 
-int refresh_fast(gbn_model *m)
+int refresh_fast(gbn_model *m, bool after_init = false)
 {
     if (m->kernel != GBN_KERNEL_FAST) return 0;
     const char *err = nullptr;
-    int n = launch_fast_refresh(m->net, m->ch, m->stream, &err);
+    int n = launch_fast_refresh(m->net, m->ch, m->stream, &err, after_init);
     if (n < 0) return fail(GBN_ERR_CUDA, std::string("fast refresh: ") + err);
     m->launches += (uint64_t) n;
     return 0;
@@ -560,7 +560,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
 
     if (int rc = init_chains(m)) return bail(rc);
     if (int rc = zero_stats(m)) return bail(rc);
-    if (int rc = refresh_fast(m)) return bail(rc);
+    if (int rc = refresh_fast(m, true)) return bail(rc);
     if (cudaStreamSynchronize(m->stream) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "initialisation failed on the device"));
     *out = m;
     return 0;
@@ -817,7 +817,7 @@ extern "C" int gbn_model_set_evidence(gbn_model *m, const gbn_evidence *ev)
     lap("init_chains");
     if (int rc = zero_stats(m)) return rc;
     lap("zero_stats");
-    if (int rc = refresh_fast(m)) return rc;
+    if (int rc = refresh_fast(m, true)) return rc;
     lap("refresh_fast");
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     return 0;

@@ -40,7 +40,8 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
                       uint32_t chain0 = 0, uint32_t nchains = UINT32_MAX,
                       cudaStream_t stx = nullptr, cudaEvent_t evx = nullptr, cudaEvent_t evs = nullptr);
 // rebuild Stf / FX / FXinv / tcache from X, T, S (after creation and set_state)
-int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
+// stf_valid: the by-TF copy of S is already current (right after launch_init_chains)
+int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err, bool stf_valid = false);
 bool fast_supported(const DevNet &net, const char **why);
 
 // ---- sim_kernels.cu: simulation mode (GraphORNOR.cpp:28,58-63,89-106): n_sweeps sweeps H, Y -> T

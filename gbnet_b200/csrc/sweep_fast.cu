@@ -768,11 +768,11 @@ static int launch_s(const DevNet &net, const DevChains &ch, const SweepArgs &a, 
     return stage ? launch_s_t<0, true, false>(net, ch, a, nc, st, err) : launch_s_t<0, false, false>(net, ch, a, nc, st, err);
 }
 
-int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err)
+int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err, bool stf_valid)
 {
     if (ch.n_chains == 0) return 0;
     SweepArgs a{ 0, 0, 0, 0, 0 };
-    k_fast_stf<<<dim3((net.E + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
+    if (!stf_valid) k_fast_stf<<<dim3((net.E + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
     k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, 0, ch.T, 1);
     if (launch_s(net, ch, a, 1, ch.n_chains, st, err)) return -1;
     if (check(cudaGetLastError(), err)) return -1;
