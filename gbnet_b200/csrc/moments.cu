@@ -84,59 +84,68 @@ __device__ __forceinline__ void node_moments(const DevNet &net, const DevChains 
     }
 }
 
-__global__ void k_moment_sums(DevNet net, DevChains ch, double N, double *sums, double *psums, uint32_t n0, uint32_t n1)
+// T nodes (one statistic each; the discrete nodes go through k_count_sums).  A block is 32 nodes x MS_SL
+// chain slices: lane = node (consecutive addresses), each slice sums every MS_SL-th chain, and the slices
+// are added up in a fixed order, so the result does not depend on the launch.
+constexpr int MS_SL = 16;
+__global__ void __launch_bounds__(32 * MS_SL) k_moment_sums(DevNet net, DevChains ch, double N, double *sums, double *psums, uint32_t n0, uint32_t n1)
 {
+    __shared__ double s_part[3][MS_SL][32];
     const uint32_t n_stats = n_stats_of(net);
     const uint32_t d = blockIdx.y;
-    const uint32_t n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n1) return;
-    const NodeRef r = node_ref(net, n);
-    double sm[3] = { 0., 0., 0. }, sv[3] = { 0., 0., 0. }, ps[3] = { 0., 0., 0. };
-    for (uint32_t l = 0; l < net.n_graphs_local; l++) {
-        double mean[3], var[3];
-        node_moments(net, ch, d * net.n_graphs_local + l, r, N, mean, var);
-        const bool post = (net.chain_offset + l) >= 1;
-        for (uint32_t j = 0; j < r.n_stats; j++) {
-            sm[j] += mean[j]; sv[j] += var[j];
-            if (post) ps[j] += mean[j];
+    const uint32_t lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const uint32_t n = n0 + blockIdx.x * 32 + lane;
+    const bool live = n < n1;
+    const NodeRef r = node_ref(net, live ? n : n0);
+    double sm = 0., sv = 0., ps = 0.;
+    if (live)
+        for (uint32_t l = sl; l < net.n_graphs_local; l += MS_SL) {
+            double mean[3], var[3];
+            node_moments(net, ch, d * net.n_graphs_local + l, r, N, mean, var);
+            sm += mean[0]; sv += var[0];
+            if ((net.chain_offset + l) >= 1) ps += mean[0];
         }
-    }
-    for (uint32_t j = 0; j < r.n_stats; j++) {
-        size_t o = (size_t) d * n_stats + r.stat0 + j;
-        sums[2 * o] = sm[j]; sums[2 * o + 1] = sv[j];
-        psums[o] = ps[j];
+    s_part[0][sl][lane] = sm; s_part[1][sl][lane] = sv; s_part[2][sl][lane] = ps;
+    __syncthreads();
+    if (sl == 0 && live) {
+        sm = sv = ps = 0.;
+        for (int q = 0; q < MS_SL; q++) { sm += s_part[0][q][lane]; sv += s_part[1][q][lane]; ps += s_part[2][q][lane]; }
+        const size_t o = (size_t) d * n_stats + r.stat0;
+        sums[2 * o] = sm; sums[2 * o + 1] = sv;
+        psums[o] = ps;
     }
 }
 
-__global__ void k_moment_devs(DevNet net, DevChains ch, double N, const double *sums, const double *psums,
-                              double *dev, double *pdev, uint32_t n0, uint32_t n1)
+__global__ void __launch_bounds__(32 * MS_SL) k_moment_devs(DevNet net, DevChains ch, double N, const double *sums, const double *psums,
+                                                            double *dev, double *pdev, uint32_t n0, uint32_t n1)
 {
+    __shared__ double s_part[2][MS_SL][32];
     const uint32_t n_stats = n_stats_of(net);
     const uint32_t d = blockIdx.y;
-    const uint32_t n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n1) return;
-    const NodeRef r = node_ref(net, n);
+    const uint32_t lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const uint32_t n = n0 + blockIdx.x * 32 + lane;
+    const bool live = n < n1;
+    const NodeRef r = node_ref(net, live ? n : n0);
     const double M = (double) net.n_graphs;
-    double mu[3], pmu[3], dv[3] = { 0., 0., 0. }, pd[3] = { 0., 0., 0. };
-    for (uint32_t j = 0; j < r.n_stats; j++) {
-        size_t o = (size_t) d * n_stats + r.stat0 + j;
-        mu[j] = sums[2 * o] / M;
-        pmu[j] = M > 1. ? psums[o] / (M - 1.) : 0.;
-    }
-    for (uint32_t l = 0; l < net.n_graphs_local; l++) {
-        double mean[3], var[3];
-        node_moments(net, ch, d * net.n_graphs_local + l, r, N, mean, var);
-        const bool post = (net.chain_offset + l) >= 1;
-        for (uint32_t j = 0; j < r.n_stats; j++) {
-            double a = mean[j] - mu[j];
-            dv[j] += a * a;
-            if (post) { double b = mean[j] - pmu[j]; pd[j] += b * b; }
+    const size_t o = (size_t) d * n_stats + r.stat0;
+    const double mu = sums[2 * o] / M;
+    const double pmu = M > 1. ? psums[o] / (M - 1.) : 0.;
+    double dv = 0., pd = 0.;
+    if (live)
+        for (uint32_t l = sl; l < net.n_graphs_local; l += MS_SL) {
+            double mean[3], var[3];
+            node_moments(net, ch, d * net.n_graphs_local + l, r, N, mean, var);
+            const double a = mean[0] - mu;
+            dv += a * a;
+            if ((net.chain_offset + l) >= 1) { const double b = mean[0] - pmu; pd += b * b; }
         }
-    }
-    for (uint32_t j = 0; j < r.n_stats; j++) {
-        size_t o = (size_t) d * n_stats + r.stat0 + j;
-        dev[o] = dv[j];
-        pdev[o] = pd[j];
+    s_part[0][sl][lane] = dv; s_part[1][sl][lane] = pd;
+    __syncthreads();
+    if (sl == 0 && live) {
+        dv = pd = 0.;
+        for (int q = 0; q < MS_SL; q++) { dv += s_part[0][q][lane]; pd += s_part[1][q][lane]; }
+        dev[o] = dv;
+        pdev[o] = pd;
     }
 }
 
@@ -275,9 +284,9 @@ void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double
 {
     const uint32_t nT = net.const_params ? 0 : net.nX;                  // T nodes only: the rest is k_count_sums
     if (nT == 0) return;
-    dim3 grid((nT + 127) / 128, net.n_datasets);
+    dim3 grid((nT + 31) / 32, net.n_datasets);
     const uint32_t n0 = net.sim ? 2 * net.nH : net.nX;                  // first T work item
-    k_moment_sums<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, n0, n0 + nT);
+    k_moment_sums<<<grid, 32 * MS_SL, 0, st>>>(net, ch, N, sums, psums, n0, n0 + nT);
 }
 
 void launch_count_sums(const DevNet &net, const DevChains &ch, double N, unsigned long long *isums, cudaStream_t st)
@@ -298,9 +307,9 @@ void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const 
 {
     const uint32_t nT = net.const_params ? 0 : net.nX;                  // T nodes only
     if (nT == 0) return;
-    dim3 grid((nT + 127) / 128, net.n_datasets);
+    dim3 grid((nT + 31) / 32, net.n_datasets);
     const uint32_t n0 = net.sim ? 2 * net.nH : net.nX;
-    k_moment_devs<<<grid, 128, 0, st>>>(net, ch, N, sums, psums, dev, pdev, n0, n0 + nT);
+    k_moment_devs<<<grid, 32 * MS_SL, 0, st>>>(net, ch, N, sums, psums, dev, pdev, n0, n0 + nT);
 }
 
 void launch_gelman_rubin(const DevNet &net, double N, const double *sums, const double *dev,
