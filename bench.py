@@ -321,7 +321,7 @@ def run_native(args):
                     "kernel_share_of_step": {n: phase_ms[i] / serial_ms for i, n in enumerate(names)},
                     "serialised_ms_per_step": serial_ms / args.roofline_steps,
                     "whole_sweep": {"achieved": sweep_gbs, "frac": sweep_gbs / peak, "bytes_per_edge_update": b_edge,
-                                    "how": "value / n_gpus x B_edge in the timed region (kernels of 4 chain groups overlapped)"}}
+                                    "how": "value / n_gpus x B_edge in the timed region (kernels of the chain groups overlapped)"}}
 
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,

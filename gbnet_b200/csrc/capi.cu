@@ -325,12 +325,13 @@ int sample_n(gbn_model *m, uint32_t n)
     if (m->sim) {
         launched = launch_sim_sweep(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err);
     } else if (m->kernel == GBN_KERNEL_FAST) {
-        // chains are independent: split them into groups, one stream each, joined at the end
-        // measured on B200 (profiles/r1_summary.md): 4 groups for >= 192 chains; fewer chains are
+        // chains are independent: split them into groups, one stream pair each, joined at the end.
+        // Measured on B200 (profiles/r1_summary.md): 3 groups for >= 192 chains (2: -4 %, 4: -1 %; from 5
+        // groups on the streams exceed the default 8 hardware queues and serialise); fewer chains are
         // latency-bound and only pay for the extra launches
         static const uint32_t env_groups = env_u32("GBN_STREAM_GROUPS", 0);
         uint32_t G = m->stream_groups ? m->stream_groups
-                   : (env_groups ? env_groups : (m->n_chains >= 192 ? 4 : (m->n_chains >= 96 ? 2 : 1)));
+                   : (env_groups ? env_groups : (m->n_chains >= 192 ? 3 : (m->n_chains >= 96 ? 2 : 1)));
         if (G > m->n_chains) G = m->n_chains;
         if (G < 1) G = 1;
         static const uint32_t prio_x = env_u32("GBN_PRIO_X", 1);        // 2 = off
