@@ -632,14 +632,17 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                 GBN_CHECK(kk < nX && s <= 2 && (pk >> 30) <= 2 && nR + 1 < D && n <= deg);
                 const double2 t0 = cot[nR], t1 = cot[nR + 1];
                 const double sum = Ar + Br;
-                const double L0 = t1.x + t1.y * (f * sum);          // S = 0: the factor joins pr0
-                const double L1 = t0.x + t0.y * sum;                // S = 1: edge off
-                const double L2 = t1.x + t1.y * (Ar + f * Br);      // S = 2: the factor joins pr2
+                // the file is compiled without FMA contraction (the reference's x86-64 build has none); these
+                // seven are explicit: this algebra differs from the reference's by rounding anyway (DESIGN.md
+                // section 4.4), and the edge loop is bound by instruction issue
+                const double L0 = __fma_rn(t1.y, f * sum, t1.x);                   // S = 0: the factor joins pr0
+                const double L1 = __fma_rn(t0.y, sum, t0.x);                       // S = 1: edge off
+                const double L2 = __fma_rn(t1.y, __fma_rn(f, Br, Ar), t1.x);       // S = 2: the factor joins pr2
                 // exp(log prior + log L) of Multinomial.cpp:66-75 as a product; the "0 +" and
                 // "0 * (1 - u)" terms of the reference's running sum / gsl_ran_flat add exact zeros
                 double cum0 = sp[0] * L0;
-                double cum1 = cum0 + sp[1] * L1;
-                double cum2 = cum1 + sp[2] * L2;
+                double cum1 = __fma_rn(sp[1], L1, cum0);
+                double cum2 = __fma_rn(sp[2], L2, cum1);
                 if (!(cum2 > 0.)) { cum0 = sp[0]; cum1 = cum0 + sp[1]; cum2 = cum1 + sp[2]; }
                 const double u = INJ ? inj_flat[pEdge[32 * j]] : unit_from_word(word);
                 const double dice = cum2 * u;
