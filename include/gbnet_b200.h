@@ -27,7 +27,7 @@ typedef enum gbn_status {
     GBN_OK = 0,
     GBN_ERR_INVALID = -1,      /* std::invalid_argument / std::out_of_range in the reference */
     GBN_ERR_CUDA = -2,         /* no device, launch failure, out of memory */
-    GBN_ERR_UNSUPPORTED = -3,  /* e.g. simulation mode (empty evidence, GraphORNOR.cpp:28) */
+    GBN_ERR_UNSUPPORTED = -3,  /* a request the selected kernel / mode cannot serve (e.g. new evidence for a simulation-mode model) */
     GBN_ERR_COMM = -4          /* NCCL */
 } gbn_status;
 
