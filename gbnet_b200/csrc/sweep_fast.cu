@@ -10,25 +10,28 @@
 //    parents with S = 0 / S = 2, n = number of parents with S != 1; algebra at k_fast_s) and a
 //    16-byte per-(target, chain) cache {beta, gamma} + a 16-bit table index carry it from the S
 //    phase to the next X phase: an X candidate costs one gather and ~6 flops, an S candidate ~5.
-//  * X phase (k_fast_x, one CTA per chain): X updates are sequential in the reference and do not
-//    commute when TFs share a target.  Each warp of the CTA evaluates one TF of a WINDOW of 16
-//    consecutive TFs against the same state; draws are taken for all of them; the window commits
-//    up to and including the first TF whose value changed, applies that flip to the cache, and the
-//    next window starts behind it.  A TF's conditional is only used if no earlier TF of its window
-//    flipped, i.e. exactly when it equals the conditional the sequential sweep would have seen, so
-//    the chain is the sequential chain, not an approximation of it.  X values rarely change
-//    (measured: 96 rounds per sweep for 1,500 TFs, 15.7 TFs committed per round).
+//  * X phase (k_fast_x, one CTA per PAIR of chains): X updates are sequential in the reference and do
+//    not commute when TFs share a target.  Each half-warp (a quarter or a whole warp for other degree
+//    profiles) evaluates one TF of a WINDOW of 64 consecutive TFs against the same state; draws are
+//    taken for all of them; the window commits up to and including the first TF whose value changed
+//    (in either chain), applies that flip to the cache, and the next window starts behind it.  A TF's
+//    conditional is only used if no earlier TF of its window flipped, i.e. exactly when it equals the
+//    conditional the sequential sweep would have seen, so the chain is the sequential chain, not an
+//    approximation of it.  X values rarely change (measured at 1,500 TFs: 27 rounds per sweep, 5 of
+//    them ended by a flip).  The cache is interleaved by chain pair, so the lanes of one child read one line.
 //  * The sum of child log-likelihoods becomes a product with explicit exponent tracking (no log,
 //    no exp per child); the underflow fallback of Multinomial.cpp:78-85 is kept.
 //  * T phase (k_fast_t, thread per (chain, TF)): T nodes that do not listen to their children are
-//    mutually independent (TNode.cpp:19-22).  Also publishes FXp = {1 - t*x, 1 / (1 - t*x)}.
+//    mutually independent (TNode.cpp:19-22) and need nothing from the sweep's X phase, so they are drawn
+//    beside it into an alternate buffer; k_fast_fx then publishes FXp = {1 - t*x, 1 / (1 - t*x)}.
 //  * S phase (k_fast_s, one warp per (group of 32 targets, chain)): S updates of different targets
-//    commute; a lane walks its target's edges in input order with leave-one-out products
-//    (multiply by the precomputed reciprocal factor), no transcendental: exp(log p + log L) = p * L.
+//    commute; a lane walks its target's edges in input order with leave-one-out values of
+//    A = a pr0 and Bq = b pr0 pr2 (multiply by the precomputed reciprocal factor), no transcendental:
+//    exp(log p + log L) = p * L.
 //    Device targets are sorted by in-degree and slots are stored transposed (topology.hpp), so the
 //    lanes of a warp finish together and every S / parent-id / counter access is coalesced.
-//  * Chains are independent, so the model layer runs disjoint chain groups on separate streams
-//    (capi.cu): one group's latency-bound X kernel overlaps another group's S kernel.
+//  * Chains are independent, so the model layer runs disjoint chain groups on separate stream pairs
+//    (capi.cu): one group's latency-bound X kernel overlaps another group's S kernel and its own T draws.
 //
 //  * Listening T nodes (TNode.cpp:15-25): only ACTIVE TFs have a child-dependent blanket; they are
 //    walked sequentially per chain by k_fast_tl using the same cache, the rest stay parallel.
