@@ -52,6 +52,11 @@ class Dims(C.Structure):
                                           "n_graphs_local", "chain_offset", "n_stats", "simulation")]
 
 
+class TopologyDims(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("n_tf", "n_trg", "n_edge", "n_edge_unique", "n_slots", "n_groups",
+                                          "max_indeg", "max_outdeg")]
+
+
 # every symbol include/gbnet_b200.h declares: name -> (restype, argtypes)
 _P = C.POINTER
 _vp, _u32, _u64, _dbl = C.c_void_p, C.c_uint32, C.c_uint64, C.c_double
@@ -92,6 +97,8 @@ SYMBOLS = {
     "gbn_model_checkpoint_save": (C.c_int, [_vp, _vp, C.c_size_t]),
     "gbn_model_checkpoint_load": (C.c_int, [_vp, _vp, C.c_size_t]),
     "gbn_philox_kat": (C.c_int, [C.c_int, _P(_u32), _P(_u32), _P(_u32)]),
+    "gbn_topology_probe": (C.c_int, [_P(Network), _P(Evidence), C.c_int, _P(TopologyDims), _P(_u32), _P(_u32), _P(_u32),
+                                     _P(_u32), _P(_u32), _P(_u32), _P(_u32), _P(C.c_uint8), _P(_dbl)]),
     "gbn_model_last_device_ms": (C.c_int, [_vp, _P(_dbl)]),
     "gbn_model_set_phase_timing": (C.c_int, [_vp, C.c_int]),
     "gbn_model_set_stream_groups": (C.c_int, [_vp, _u32]),

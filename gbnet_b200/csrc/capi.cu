@@ -824,6 +824,39 @@ extern "C" int gbn_model_set_evidence(gbn_model *m, const gbn_evidence *ev)
     return 0;
 }
 
+// ------------------------------------------------------------------------------ host-side probe
+extern "C" int gbn_topology_probe(const gbn_network *netin, const gbn_evidence *ev, int comp_yprob, gbn_topology_dims *dims,
+                                  uint32_t *slot_of_edge, uint32_t *deg, uint32_t *ref_of_dt, uint32_t *gbase,
+                                  uint32_t *tf_ptr, uint32_t *tf_child, uint32_t *tf_slot, uint8_t *y, double yprob[3])
+{
+    if (!netin) return fail(GBN_ERR_INVALID, "null argument");
+    Topology tp;
+    try {
+        tp = compile_topology(netin->n_edge, netin->src, netin->trg, netin->mor, netin->n_active, netin->active_tf, 2., 2., 2.);
+    } catch (const std::exception &ex) {
+        return fail(GBN_ERR_INVALID, ex.what());
+    }
+    if (dims) {
+        dims->n_tf = tp.nX; dims->n_trg = tp.nH; dims->n_edge = tp.E; dims->n_edge_unique = tp.Eu;
+        dims->n_slots = tp.Ep; dims->n_groups = tp.n_groups; dims->max_indeg = tp.max_indeg; dims->max_outdeg = tp.max_outdeg;
+    }
+    auto put = [](uint32_t *dst, const std::vector<uint32_t> &v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), sizeof(uint32_t) * v.size()); };
+    put(slot_of_edge, tp.slot_of_edge); put(deg, tp.deg); put(ref_of_dt, tp.ref_of_dt); put(gbase, tp.gbase);
+    put(tf_ptr, tp.tf_ptr); put(tf_child, tp.tf_child); put(tf_slot, tp.tf_slot);
+    if (ev && ev->n_evid > 0 && ev->n_datasets > 0 && (y || yprob)) {
+        std::vector<uint8_t> yy(tp.nH);
+        double yp[3];
+        try {
+            compile_evidence(tp, ev->n_evid, ev->evid_trg, ev->evid_val, comp_yprob != 0, yy.data(), yp);
+        } catch (const std::exception &ex) {
+            return fail(GBN_ERR_INVALID, ex.what());
+        }
+        if (y) std::memcpy(y, yy.data(), tp.nH);
+        if (yprob) { yprob[0] = yp[0]; yprob[1] = yp[1]; yprob[2] = yp[2]; }
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------ multi-GPU
 extern "C" int gbn_comm_unique_id(void *id_out)
 {

@@ -171,6 +171,23 @@ int gbn_model_node_moments(gbn_model *m, uint32_t chain, double *mean /* [n_stat
 /* Philox4x32-10 evaluated on the device (known-answer test hook) */
 int gbn_philox_kat(int device, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
+/* ---- host-side topology compiler (test hook; needs no device) ----
+ * Compiles a network and one evidence set exactly as gbn_model_create / gbn_model_set_evidence do
+ * (GraphORNOR::build_structure, GraphORNOR.cpp:13-265: ranks, edge order, evidence map, YPROB counts)
+ * and copies the device layout out.  Call once with NULL arrays for the sizes; any array may be NULL. */
+typedef struct gbn_topology_dims {
+    uint32_t n_tf, n_trg, n_edge, n_edge_unique;
+    uint32_t n_slots;            /* padded (target, parent) slots, 32-target groups stored transposed */
+    uint32_t n_groups, max_indeg, max_outdeg;
+} gbn_topology_dims;
+int gbn_topology_probe(const gbn_network *net, const gbn_evidence *ev, int comp_yprob, gbn_topology_dims *dims,
+                       uint32_t *slot_of_edge /* [n_edge] */, uint32_t *deg /* [n_trg], device target order */,
+                       uint32_t *ref_of_dt /* [n_trg] device target -> rank of its id */,
+                       uint32_t *gbase /* [n_groups + 1] first slot of each group */,
+                       uint32_t *tf_ptr /* [n_tf + 1] */, uint32_t *tf_child /* [n_edge_unique] device targets */,
+                       uint32_t *tf_slot /* [n_edge_unique] */, uint8_t *y /* [n_trg] device target order: evidence + 1 */,
+                       double yprob[3]);
+
 /* ---- checkpoint / resume (absent from the reference) ----
  * One flat blob with the chain states, statistics and sweep counters of every local chain; loading it
  * into a model built from the same inputs continues the chains bit for bit. */
@@ -187,7 +204,7 @@ int gbn_model_last_device_ms(const gbn_model *m, double *ms);
 int gbn_model_set_phase_timing(gbn_model *m, int on);
 int gbn_model_phase_ms(const gbn_model *m, double ms_out[3], uint64_t *sweeps);
 /* the fast path sweeps disjoint chain groups on separate streams so that one group's X kernel overlaps
- * another group's S kernel; 0 restores the default (4), 1 serialises the kernels (per-kernel timing) */
+ * another group's S kernel; 0 restores the default (3 for >= 192 chains), 1 serialises the kernels (per-kernel timing) */
 int gbn_model_set_stream_groups(gbn_model *m, uint32_t groups);
 /* number of kernels this library launched on behalf of the model since creation */
 int gbn_model_launch_count(const gbn_model *m, uint64_t *n);

@@ -105,3 +105,112 @@ def test_get_tests_matches_fisher_exact():
         p = fisher_exact([[row.morp_degp, row.morn_degp], [row.morp_degn, row.morn_degn]], alternative="greater")[1]
         assert abs(p - row.mor_binary) < 1e-12
         assert row.trg_tot == len(trg)
+
+
+# ---- the C++ topology / evidence compiler behind gbn_model_create, through its host-only probe ----------
+
+def _probe(src, trg, mor, evid_trg=None, evid_val=None, comp_yprob=False):
+    import ctypes as C
+
+    from gbnet_b200 import _capi
+    lib = _capi.load()
+    src = np.ascontiguousarray(src, np.uint32); trg = np.ascontiguousarray(trg, np.uint32)
+    mor = np.ascontiguousarray(mor, np.int32)
+    u32p, i32p = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    net = _capi.Network(len(src), src.ctypes.data_as(u32p), trg.ctypes.data_as(u32p), mor.ctypes.data_as(i32p), 0, None)
+    ev = None
+    if evid_trg is not None:
+        et = np.ascontiguousarray(evid_trg, np.uint32); evv = np.ascontiguousarray(evid_val, np.int32)
+        ev = _capi.Evidence(1, len(et), et.ctypes.data_as(u32p), evv.ctypes.data_as(i32p))
+    d = _capi.TopologyDims()
+    evp = C.byref(ev) if ev is not None else None
+    _capi.check(lib.gbn_topology_probe(C.byref(net), evp, int(comp_yprob), C.byref(d), *([None] * 9)))
+    out = {k: np.zeros(n, np.uint32) for k, n in (("slot_of_edge", d.n_edge), ("deg", d.n_trg), ("ref_of_dt", d.n_trg),
+                                                  ("gbase", d.n_groups + 1), ("tf_ptr", d.n_tf + 1),
+                                                  ("tf_child", d.n_edge_unique), ("tf_slot", d.n_edge_unique))}
+    y = np.zeros(d.n_trg, np.uint8)
+    yprob = np.zeros(3)
+    _capi.check(lib.gbn_topology_probe(
+        C.byref(net), evp, int(comp_yprob), C.byref(d),
+        *[out[k].ctypes.data_as(u32p) for k in ("slot_of_edge", "deg", "ref_of_dt", "gbase", "tf_ptr", "tf_child", "tf_slot")],
+        y.ctypes.data_as(C.POINTER(C.c_uint8)), yprob.ctypes.data_as(C.POINTER(C.c_double))))
+    out.update(dims=d, y=y, yprob=yprob)
+    return out
+
+
+def test_topology_compiler_layout_invariants():
+    """Device layout of the network (csrc/topology.hpp): targets sorted by in-degree, 32-target groups stored
+    transposed and padded to the group's largest in-degree, the by-TF list in ascending reference order."""
+    rng = np.random.default_rng(5)
+    n_tf, n_trg = 37, 451
+    ids_tf = rng.choice(10_000, n_tf, replace=False) + 1_000_000        # sparse, unordered ids
+    ids_trg = rng.choice(10_000, n_trg, replace=False)
+    pairs = {(int(rng.integers(n_tf)), int(rng.integers(n_trg))) for _ in range(2500)}
+    pairs |= {(0, t) for t in range(n_trg)}                               # every target has a parent; TF 0 is a hub
+    pairs = sorted(pairs, key=lambda _: rng.random())
+    src = np.array([ids_tf[a] for a, _ in pairs]); trg = np.array([ids_trg[b] for _, b in pairs])
+    mor = rng.integers(-1, 2, len(pairs))
+    o = _probe(src, trg, mor)
+    d = o["dims"]
+    tf_sorted, trg_sorted = np.unique(src), np.unique(trg)
+    assert (d.n_tf, d.n_trg, d.n_edge, d.n_edge_unique) == (len(tf_sorted), n_trg, len(pairs), len(pairs))
+    indeg_ref = np.bincount(np.searchsorted(trg_sorted, trg), minlength=n_trg)
+    # device targets: a permutation of the reference ranks, in-degree non-increasing
+    assert sorted(o["ref_of_dt"].tolist()) == list(range(n_trg))
+    assert np.array_equal(o["deg"], indeg_ref[o["ref_of_dt"]]) and np.all(np.diff(o["deg"].astype(int)) <= 0)
+    assert d.max_indeg == indeg_ref.max() and d.n_groups == (n_trg + 31) // 32
+    # groups: 32 targets x (largest in-degree of the group) slots
+    widths = np.diff(o["gbase"].astype(np.int64)) // 32
+    for g in range(d.n_groups):
+        assert widths[g] == o["deg"][32 * g: 32 * g + 32].max()
+    assert o["gbase"][0] == 0 and o["gbase"][-1] == d.n_slots
+    # every edge has its own slot; slot -> (device target, parent position) is consistent with the edge
+    slots = o["slot_of_edge"].astype(np.int64)
+    assert len(set(slots.tolist())) == len(pairs) and slots.max() < d.n_slots
+    dt_of_ref = np.argsort(o["ref_of_dt"])
+    seen_j = {}
+    for e, q in enumerate(slots):
+        g = np.searchsorted(o["gbase"], q, side="right") - 1
+        lane, j = (q - o["gbase"][g]) % 32, (q - o["gbase"][g]) // 32
+        dt = 32 * g + lane
+        assert dt == dt_of_ref[np.searchsorted(trg_sorted, trg[e])] and j < o["deg"][dt]
+        assert seen_j.setdefault((dt, j), e) == e
+        # parents of a target keep the input order of its edges (append_parent order, GraphORNOR.cpp:226-244)
+    for dt in range(n_trg):
+        es = [e for e in range(len(pairs)) if dt_of_ref[np.searchsorted(trg_sorted, trg[e])] == dt]
+        js = [int((slots[e] - o["gbase"][dt // 32]) // 32) for e in es]
+        assert js == list(range(len(es)))
+    # by-TF list: the TF's targets (device ids) in ascending reference order, with the slots of those edges
+    assert o["tf_ptr"][0] == 0 and o["tf_ptr"][-1] == len(pairs)
+    for k, uid in enumerate(tf_sorted):
+        es = sorted(np.nonzero(src == uid)[0], key=lambda e: np.searchsorted(trg_sorted, trg[e]))
+        lo, hi = o["tf_ptr"][k], o["tf_ptr"][k + 1]
+        assert o["tf_child"][lo:hi].tolist() == [int(dt_of_ref[np.searchsorted(trg_sorted, trg[e])]) for e in es]
+        assert o["tf_slot"][lo:hi].tolist() == [int(slots[e]) for e in es]
+    assert d.max_outdeg == np.diff(o["tf_ptr"].astype(int)).max()
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_evidence_compiler_first_key_wins_and_yprob_counts(sparse):
+    """evidence_dict_t is a std::map filled with insert(): the first value of a repeated key stays
+    (ModelORNOR.pyx:64-66); keys outside the network are ignored for y but counted by comp_yprob
+    (GraphORNOR.cpp:113-125).  Dense ids use a lookup table, sparse ids a binary search."""
+    scale = 3_000_001 if sparse else 1
+    trg_ids = np.array([5, 9, 2, 7, 11]) * scale
+    src = np.array([100, 100, 101, 101, 102]); mor = np.array([1, -1, 0, 1, -1])
+    evid_trg = np.array([9, 2, 9, 400, 11, 2, 401]) * scale
+    evid_val = np.array([1, -1, -1, 1, 0, 1, -1])
+    o = _probe(src, trg_ids, mor, evid_trg, evid_val, comp_yprob=True)
+    dt_of_ref = np.argsort(o["ref_of_dt"])
+    want = {2: -1, 9: 1, 11: 0}                                           # first occurrences of keys in the network
+    for r, uid in enumerate(np.unique(trg_ids)):
+        assert o["y"][dt_of_ref[r]] == want.get(int(uid // scale), 0) + 1
+    # unique keys: 9 -> +1, 2 -> -1, 400 -> +1, 11 -> 0, 401 -> -1 over 5 targets
+    assert np.allclose(o["yprob"], [2 / 5, 1 - 2 / 5 - 2 / 5, 2 / 5])
+    o2 = _probe(src, trg_ids, mor, evid_trg, evid_val, comp_yprob=False)
+    assert np.allclose(o2["yprob"], [0.05, 0.90, 0.05]) and np.array_equal(o2["y"], o["y"])
+    from gbnet_b200 import GbnError
+    with pytest.raises(GbnError):
+        _probe(src, trg_ids, mor, evid_trg, np.array([1, -1, -1, 2, 0, 1, -1]))
+    with pytest.raises(GbnError):
+        _probe(src, trg_ids, np.array([1, -1, 0, 5, -1]))
