@@ -17,92 +17,127 @@ import pandas as pd
 from .model import ModelORNOR
 
 
-def get_tests(evid, rels):
-    """Per-TF enrichment / mode-of-regulation screen (reference gbnet/utils.py:10-68): Fisher's exact
-    test (alternative "greater") of DE among the TF's targets and of sign agreement, their Brown-style
-    combination rho (1 - log rho), target count and a signed score.  The reference calls
-    scipy.stats.fisher_exact once per TF and table; the one-sided p-value is the hypergeometric
-    survival function, evaluated here for all TFs at once."""
+# columns of the screen: (name, sign of the edge or None, predicate on the evidence value)
+_COUNT_COLUMNS = (("trg_ydeg", None, lambda v: v != 0), ("trg_ndeg", None, lambda v: v == 0),
+                  ("morp_degp", 1, lambda v: v == 1), ("morp_degn", 1, lambda v: v == -1),
+                  ("morn_degp", -1, lambda v: v == 1), ("morn_degn", -1, lambda v: v == -1))
+
+
+def _fisher_greater(a, b, c, d):
+    """One-sided ("greater") Fisher p-value of the table [[a, b], [c, d]] for whole columns at once:
+    P(X >= a) with X ~ Hypergeom(a + b + c + d, a + b, a + c)."""
     from scipy.stats import hypergeom
-
-    evid = evid.reset_index().set_index('uid')
-    tmp = rels.merge(evid.loc[:, ['val']], how='left', left_on='trguid', right_index=True)
-    all_degp = int((evid.val == 1).sum())
-    all_degn = int((evid.val == -1).sum())
-    all_ydeg = all_degp + all_degn
-    all_ndeg = int((evid.val == 0).sum())
-
-    def count(mask, name):
-        return tmp.loc[mask, ['srcuid', 'trguid']].groupby('srcuid').count()['trguid'].rename(name)
-
-    cols = [count(tmp.val != 0, 'trg_ydeg'), count(tmp.val == 0, 'trg_ndeg'),
-            count((tmp.type == 1) & (tmp.val == 1), 'morp_degp'), count((tmp.type == 1) & (tmp.val == -1), 'morp_degn'),
-            count((tmp.type == -1) & (tmp.val == 1), 'morn_degp'), count((tmp.type == -1) & (tmp.val == -1), 'morn_degn')]
-    df = pd.DataFrame(cols).T.fillna(0).astype(int)
-    df.index.name = 'srcuid'
-
-    def fisher_greater(a, b, c, d):
-        # table [[a, b], [c, d]]: P(X >= a), X ~ Hypergeom(total, a + b, a + c)
-        a, b, c, d = (np.asarray(v, np.int64) for v in (a, b, c, d))
-        return hypergeom.sf(a - 1, a + b + c + d, a + b, a + c)
-
-    df['enrichment'] = fisher_greater(df.trg_ydeg, all_ydeg - df.trg_ydeg, df.trg_ndeg, all_ndeg - df.trg_ndeg)
-    df['mor_binary'] = fisher_greater(df.morp_degp, df.morn_degp, df.morp_degn, df.morn_degn)
-    rho = df.enrichment * df.mor_binary
-    df['combined'] = rho.apply(lambda r: r * (1 - np.log(r)) if r > 0 else r)
-    df['trg_tot'] = df.trg_ndeg + df.trg_ydeg
-    df['score'] = (df.morp_degp + df.morn_degn - df.morp_degn - df.morn_degp) / df.trg_ydeg
-    df['gt_act'] = False
-    return df
+    a, b, c, d = (np.asarray(v, np.int64) for v in (a, b, c, d))
+    return hypergeom.sf(a - 1, a + b + c + d, a + b, a + c)
 
 
-def get_model(ents, rels, evid,
-              const_params=False, noise_listen_children=False, comp_yprob=False,
-              t_focus=2., t_lmargin=2., t_hmargin=2., zn_focus=2., zn_lmargin=8., zn_hmargin=2.,
-              z_alpha=198, z_beta=2, z0_alpha=198, z0_beta=2, t_alpha=2, t_beta=2,
-              s_leniency=0.1, n_graphs=3, **extra):
-    assert s_leniency <= 0.5
-    sprior = [[1.0 - s_leniency, 0.9 * s_leniency, 0.1 * s_leniency],
-              [0.5 * s_leniency, 1.0 - s_leniency, 0.5 * s_leniency],
-              [0.1 * s_leniency, 0.9 * s_leniency, 1.0 - s_leniency]]
-    return ModelORNOR(ents, rels, evid,
-                      n_graphs=n_graphs, sprior=sprior,
-                      z_alpha=z_alpha, z_beta=z_beta, z0_alpha=z0_alpha, z0_beta=z0_beta, t_alpha=t_alpha, t_beta=t_beta,
-                      t_focus=t_focus, t_lmargin=t_lmargin, t_hmargin=t_hmargin, zn_focus=zn_focus,
-                      zn_lmargin=zn_lmargin, zn_hmargin=zn_hmargin,
-                      noise_listen_children=noise_listen_children, comp_yprob=comp_yprob, const_params=const_params,
-                      **extra)
+def get_tests(evid, rels):
+    """Per-TF enrichment / mode-of-regulation screen, the table reference gbnet/utils.py:10-68 builds:
+    for every source of ``rels`` the number of its targets that are / are not differentially expressed
+    and the 2x2 counts of edge sign against DE sign; Fisher's exact test ("greater") of DE enrichment and
+    of sign agreement; their product rho combined as rho (1 - log rho); the target total and a signed
+    score.  The reference calls scipy.stats.fisher_exact per TF and table; the p-value is the
+    hypergeometric survival function, evaluated here for all TFs at once (checked against fisher_exact
+    in tests/test_host_logic.py)."""
+    values = evid.reset_index().set_index("uid")["val"]
+    # left join on the target: NaN where the target has no evidence
+    edges = rels.merge(values.to_frame(), how="left", left_on="trguid", right_index=True)
+    n_de = int((values != 0).sum())
+    n_not_de = int((values == 0).sum())
+
+    counts = {}
+    for name, sign, pred in _COUNT_COLUMNS:
+        keep = pred(edges["val"]) & edges["val"].notna() if name == "trg_ndeg" else pred(edges["val"])
+        if sign is not None:
+            keep &= edges["type"] == sign
+        counts[name] = edges.loc[keep].groupby("srcuid")["trguid"].count()
+    # the reference's "val != 0" also keeps targets without evidence (NaN != 0): same here
+    table = pd.DataFrame(counts).fillna(0).astype(int)
+    table = table[[c[0] for c in _COUNT_COLUMNS]]
+    table.index.name = "srcuid"
+
+    table["enrichment"] = _fisher_greater(table.trg_ydeg, n_de - table.trg_ydeg, table.trg_ndeg, n_not_de - table.trg_ndeg)
+    table["mor_binary"] = _fisher_greater(table.morp_degp, table.morn_degp, table.morp_degn, table.morn_degn)
+    rho = (table.enrichment * table.mor_binary).to_numpy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        table["combined"] = np.where(rho > 0, rho * (1 - np.log(np.where(rho > 0, rho, 1.))), rho)
+    table["trg_tot"] = table.trg_ndeg + table.trg_ydeg
+    agree = table.morp_degp + table.morn_degn
+    disagree = table.morp_degn + table.morn_degp
+    table["score"] = (agree - disagree) / table.trg_ydeg
+    table["gt_act"] = False
+    return table
 
 
-def run_protocol(model, max_its=100, burn_its=10, verbosity=0):
-    """The sampling schedule of sample_model (utils.py:93-135); returns (iterations, max R-hat)."""
-    it = 0
+def s_prior_from_leniency(s_leniency):
+    """The 3x3 prior of the edge mode S given the annotated sign (rows: sign -1, 0, +1; columns: S = 0, 1, 2)
+    that reference gbnet/utils.py:78-81 derives from one leniency number."""
+    if not s_leniency <= 0.5:
+        raise AssertionError("s_leniency must not exceed 0.5")
+    keep, l = 1.0 - s_leniency, s_leniency
+    return [[keep, 0.9 * l, 0.1 * l],
+            [0.5 * l, keep, 0.5 * l],
+            [0.1 * l, 0.9 * l, keep]]
+
+
+_MODEL_DEFAULTS = dict(const_params=False, noise_listen_children=False, comp_yprob=False,
+                       t_focus=2., t_lmargin=2., t_hmargin=2., zn_focus=2., zn_lmargin=8., zn_hmargin=2.,
+                       z_alpha=198, z_beta=2, z0_alpha=198, z0_beta=2, t_alpha=2, t_beta=2, n_graphs=3)
+
+
+def get_model(ents, rels, evid, s_leniency=0.1, **options):
+    """A ``ModelORNOR`` with the defaults of reference gbnet/utils.py:70-87 (which differ from the class's own:
+    z priors 198 / 2, non-listening T nodes); ``s_leniency`` becomes the S prior.  Further keywords
+    (``seed``, ``device`` ...) go to the model unchanged."""
+    settings = dict(_MODEL_DEFAULTS)
+    settings.update(options)
+    return ModelORNOR(ents, rels, evid, sprior=s_prior_from_leniency(s_leniency), **settings)
+
+
+def run_protocol(model, max_its=100, burn_its=10, verbosity=0, batch=20):
+    """The sampling schedule of the reference's sample_model (utils.py:93-135), which defines "time to
+    R-hat < 1.1": ``burn_its`` batches, statistics dropped, then batches until the largest Gelman-Rubin
+    statistic is at most 1.1 or ``max_its`` batches (burn-in included) have run.
+    Returns (batches run, last max R-hat)."""
+    def log(tag, value):
+        if verbosity >= 1:
+            print(f"[{datetime.now()}] {tag}mgr={value: 10.4f}", flush=True)
+
+    done = 0
     for _ in range(burn_its):
-        it += 1
-        model.sample(20)
+        model.sample(batch)
+        done += 1
         if verbosity >= 1:
-            print(f"[{datetime.now()}] burn-in mgr={model.get_max_gelman_rubin(): 10.4f}", flush=True)
+            log("burn-in ", model.get_max_gelman_rubin())
     model.burn_stats()
-    mgr = float('inf')
-    while mgr > 1.1:
-        it += 1
-        model.sample(20)
-        mgr = model.get_max_gelman_rubin()
-        if verbosity >= 1:
-            print(f"[{datetime.now()}] mgr={mgr: 10.4f}", flush=True)
-        if it >= max_its:
+    rhat = float("inf")
+    while rhat > 1.1:
+        model.sample(batch)
+        done += 1
+        rhat = model.get_max_gelman_rubin()
+        log("", rhat)
+        if done >= max_its:
             break
-    return it, mgr
+    return done, rhat
+
+
+def _posterior_column(model, var_name, keep_idx, column):
+    """Series ``column`` indexed by symbol from a posterior-mean getter (tuples id, symbol, outcome, value)."""
+    rows = [(sym, val) for _, sym, idx, val in model.get_posterior_means(var_name) if idx == keep_idx]
+    return pd.Series(dict(rows), name=column, dtype=float).rename_axis("symbol")
 
 
 def sample_model(model, ents, tests, max_its=100, burn_its=10, verbosity=0):
-    it, _ = run_protocol(model, max_its=max_its, burn_its=burn_its, verbosity=verbosity)
-    print(f"Completed {it} iterations.")
-    X = pd.DataFrame([dict(symbol=symbol, X=val) for _, symbol, idx, val in model.get_posterior_means('X') if idx == '1']).set_index('symbol')
-    T = pd.DataFrame([dict(symbol=symbol, T=val) for _, symbol, idx, val in model.get_posterior_means('T') if idx == '0']).set_index('symbol')
-    df = X.merge(T, left_index=True, right_index=True)
-    df['uid'] = ents.loc[ents.type == 'Protein'].set_index('name').loc[df.index.values, 'uid']
-    return tests.merge(df.reset_index().set_index('uid'), left_index=True, right_index=True).sort_values('X', ascending=False)
+    """Run the protocol and return the reference's result table (utils.py:137-144): the screen ``tests``
+    joined with the posterior mean of X = 1 and of T per TF, most active TF first."""
+    done, _ = run_protocol(model, max_its=max_its, burn_its=burn_its, verbosity=verbosity)
+    print(f"Completed {done} iterations.")
+    post = pd.concat([_posterior_column(model, "X", "1", "X"), _posterior_column(model, "T", "0", "T")],
+                     axis=1, join="inner")
+    proteins = ents.loc[ents.type == "Protein"].set_index("name")["uid"]
+    post["uid"] = proteins.loc[post.index.values].to_numpy()
+    by_uid = post.reset_index().set_index("uid")
+    return tests.join(by_uid, how="inner").sort_values("X", ascending=False)
 
 
 def frames_from_network(net):
