@@ -112,6 +112,9 @@ struct gbn_model {
     double *d_scratch = nullptr; size_t scratch_bytes = 0;
     bool moments_valid = false;
     bool sim = false;                   // simulation mode (empty evidence)
+    // fast kernel: the sweep works on packed views of S and counts into per-batch 8-bit counters
+    bool s_bytes_valid = true;          // ch.S (bytes) agrees with ch.Sw (2-bit words)
+    uint32_t pending = 0;               // sweeps counted in ch.dC and not yet folded into ch.cS
     // per-kernel timing (gbn_model_set_phase_timing)
     bool phase_timing = false;
     std::vector<cudaEvent_t> phase_ev;  // [group][3 n + 1]
@@ -182,6 +185,8 @@ int zero_stats(gbn_model *m)
     CUDA_TRY(cudaMemsetAsync(m->ch.tMean, 0, sizeof(double) * C * nX, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->ch.tM2, 0, sizeof(double) * C * nX, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->ch.cS, 0, sizeof(uint2) * C * E, m->stream));
+    if (m->ch.dC) CUDA_TRY(cudaMemsetAsync(m->ch.dC, 0, sizeof(uint2) * C * m->tp.nD, m->stream));
+    m->pending = 0;
     if (m->sim) {
         CUDA_TRY(cudaMemsetAsync(m->ch.cH, 0, sizeof(uint2) * C * m->tp.nH, m->stream));
         CUDA_TRY(cudaMemsetAsync(m->ch.cY, 0, sizeof(uint2) * C * m->tp.nH, m->stream));
@@ -191,13 +196,39 @@ int zero_stats(gbn_model *m)
     return 0;
 }
 
-int refresh_fast(gbn_model *m, bool after_init = false)
+// the fast kernel's packed views and caches from X, T and the byte view of S
+int refresh_fast(gbn_model *m)
 {
     if (m->kernel != GBN_KERNEL_FAST) return 0;
     const char *err = nullptr;
-    int n = launch_fast_refresh(m->net, m->ch, m->stream, &err, after_init);
+    int n = launch_fast_refresh(m->net, m->ch, m->stream, &err);
     if (n < 0) return fail(GBN_ERR_CUDA, std::string("fast refresh: ") + err);
     m->launches += (uint64_t) n;
+    m->s_bytes_valid = true;
+    return 0;
+}
+
+// before anything reads ch.S: the fast sweep keeps S as 2-bit words
+int ensure_s_bytes(gbn_model *m)
+{
+    if (m->kernel != GBN_KERNEL_FAST || m->s_bytes_valid) return 0;
+    const char *err = nullptr;
+    int n = launch_fast_unpack(m->net, m->ch, m->stream, &err);
+    if (n < 0) return fail(GBN_ERR_CUDA, std::string("fast unpack: ") + err);
+    m->launches += (uint64_t) n;
+    m->s_bytes_valid = true;
+    return 0;
+}
+
+// before anything reads ch.cS: the fast sweep counts S outcomes into per-batch 8-bit counters
+int fold_counts(gbn_model *m)
+{
+    if (m->kernel != GBN_KERNEL_FAST || m->pending == 0) return 0;
+    const char *err = nullptr;
+    int n = launch_fast_fold(m->net, m->ch, m->stream, &err);
+    if (n < 0) return fail(GBN_ERR_CUDA, std::string("fast fold: ") + err);
+    m->launches += (uint64_t) n;
+    m->pending = 0;
     return 0;
 }
 
@@ -284,6 +315,7 @@ int compute_moments(gbn_model *m)
     const double N = (double) m->stat_n;
     // counts of the discrete nodes overflow the exact integer path only beyond M * N^2 >= 2^63
     if ((double) m->n_graphs * N * N >= 9.0e18) return fail(GBN_ERR_UNSUPPORTED, "chain length too large for the exact moment sums");
+    if (int rc = fold_counts(m)) return rc;
     launch_count_sums(m->net, m->ch, N, m->d_isums, m->stream);
     launch_moment_sums(m->net, m->ch, N, m->d_sums, m->d_psums, m->stream);
     if (int rc = allreduce(m, m->d_isums, 4 * ns, NCCL_SUM, NCCL_UINT64)) return rc;
@@ -315,6 +347,71 @@ int max_gelman_rubin(gbn_model *m, double *out)
     return 0;
 }
 
+// n sweeps of every chain on the fast path (n <= FAST_MAX_PENDING - pending): the chains are independent, so
+// they are split into groups, one stream pair each, joined at the end.
+// Measured on B200 (profiles/r1_summary.md): 3 groups for >= 192 chains (2: -4 %, 4: -1 %; from 5
+// groups on the streams exceed the default 8 hardware queues and serialise); fewer chains are
+// latency-bound and only pay for the extra launches
+int fast_batch(gbn_model *m, uint32_t n, uint32_t sweep0, uint32_t stat0, const char **err)
+{
+    static const uint32_t env_groups = env_u32("GBN_STREAM_GROUPS", 0);
+    uint32_t G = m->stream_groups ? m->stream_groups
+               : (env_groups ? env_groups : (m->n_chains >= 192 ? 3 : (m->n_chains >= 96 ? 2 : 1)));
+    const uint32_t xq = fast_x_bundle();
+    G = std::min(G, (m->n_chains + xq - 1) / xq);       // no empty groups (boundaries fall on whole bundles)
+    if (G < 1) G = 1;
+    static const uint32_t prio_x = env_u32("GBN_PRIO_X", 1);        // 2 = off
+    while (m->gstream.size() < G) {
+        cudaStream_t s, sx; cudaEvent_t e, e1, e2;
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, lo));
+        CUDA_TRY(cudaStreamCreateWithPriority(&sx, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        m->gstream.push_back(s); m->xstream.push_back(sx); m->gdone.push_back(e);
+        m->gevx.push_back(e1); m->gevs.push_back(e2);
+    }
+    if (!m->gfork) CUDA_TRY(cudaEventCreateWithFlags(&m->gfork, cudaEventDisableTiming));
+    const uint32_t stride = 3 * n + 1;
+    if (m->phase_timing) {
+        while (m->phase_ev.size() < (size_t) G * stride) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            m->phase_ev.push_back(e);
+        }
+        m->phase_pending = n; m->phase_groups = G; m->phase_stride = stride;
+    }
+    CUDA_TRY(cudaEventRecord(m->gfork, m->stream));
+    int launched = 0;
+    for (uint32_t g = 0; g < G; g++) {
+        // group boundaries at whole bundles: the X kernel sweeps fast_x_bundle() chains per CTA
+        const uint32_t nb = (m->n_chains + xq - 1) / xq;                 // bundles
+        const uint32_t c0 = (uint32_t) ((uint64_t) nb * g / G) * xq;
+        const uint32_t c1 = g + 1 == G ? m->n_chains : (uint32_t) ((uint64_t) nb * (g + 1) / G) * xq;
+        cudaStream_t st = G == 1 ? m->stream : m->gstream[g];
+        // the X kernels get their own (high-priority) stream: they overlap the other groups' S kernels and,
+        // when the T nodes do not listen to their children, this group's own T draws
+        const bool px = (G > 1 || fast_uses_x_stream(m->net)) && prio_x != 2 && !m->phase_timing;
+        if (G > 1 || px) CUDA_TRY(cudaStreamWaitEvent(st, m->gfork, 0));
+        if (px) CUDA_TRY(cudaStreamWaitEvent(m->xstream[g], m->gfork, 0));
+        int l = launch_sweep_fast(m->net, m->ch, n, sweep0, stat0, st, err,
+                                  m->phase_timing ? m->phase_ev.data() + (size_t) g * stride : nullptr, c0, c1 - c0,
+                                  px ? m->xstream[g] : nullptr, px ? m->gevx[g] : nullptr, px ? m->gevs[g] : nullptr);
+        if (l < 0) return -1;
+        launched += l;
+        if (G > 1) {
+            CUDA_TRY(cudaEventRecord(m->gdone[g], st));
+            CUDA_TRY(cudaStreamWaitEvent(m->stream, m->gdone[g], 0));
+        }
+    }
+    if (fast_t_beside_x(m->net) && (n & 1)) std::swap(m->ch.T, m->ch.T2);
+    m->pending += n;
+    m->s_bytes_valid = false;
+    return launched;
+}
+
 int sample_n(gbn_model *m, uint32_t n)
 {
     if (n == 0) return 0;
@@ -325,62 +422,20 @@ int sample_n(gbn_model *m, uint32_t n)
     if (m->sim) {
         launched = launch_sim_sweep(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err);
     } else if (m->kernel == GBN_KERNEL_FAST) {
-        // chains are independent: split them into groups, one stream pair each, joined at the end.
-        // Measured on B200 (profiles/r1_summary.md): 3 groups for >= 192 chains (2: -4 %, 4: -1 %; from 5
-        // groups on the streams exceed the default 8 hardware queues and serialise); fewer chains are
-        // latency-bound and only pay for the extra launches
-        static const uint32_t env_groups = env_u32("GBN_STREAM_GROUPS", 0);
-        uint32_t G = m->stream_groups ? m->stream_groups
-                   : (env_groups ? env_groups : (m->n_chains >= 192 ? 3 : (m->n_chains >= 96 ? 2 : 1)));
-        if (G > m->n_chains) G = m->n_chains;
-        if (G < 1) G = 1;
-        static const uint32_t prio_x = env_u32("GBN_PRIO_X", 1);        // 2 = off
-        while (m->gstream.size() < G) {
-            cudaStream_t s, sx; cudaEvent_t e, e1, e2;
-            int lo = 0, hi = 0;
-            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            CUDA_TRY(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, lo));
-            CUDA_TRY(cudaStreamCreateWithPriority(&sx, cudaStreamNonBlocking, hi));
-            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
-            m->gstream.push_back(s); m->xstream.push_back(sx); m->gdone.push_back(e);
-            m->gevx.push_back(e1); m->gevs.push_back(e2);
-        }
-        if (!m->gfork) CUDA_TRY(cudaEventCreateWithFlags(&m->gfork, cudaEventDisableTiming));
-        const uint32_t stride = 3 * n + 1;
-        if (m->phase_timing) {
-            while (m->phase_ev.size() < (size_t) G * stride) {
-                cudaEvent_t e;
-                CUDA_TRY(cudaEventCreate(&e));
-                m->phase_ev.push_back(e);
-            }
-            m->phase_pending = n; m->phase_groups = G; m->phase_stride = stride;
-        }
-        CUDA_TRY(cudaEventRecord(m->gfork, m->stream));
+        // the S nodes count into 8-bit per-batch counters: fold them into the totals before one could overflow
         launched = 0;
-        for (uint32_t g = 0; g < G; g++) {
-            // group boundaries at whole bundles: the X kernel sweeps fast_x_bundle() chains per CTA
-            const uint32_t xq = fast_x_bundle();
-            const uint32_t c0 = (uint32_t) ((uint64_t) m->n_chains * g / G) / xq * xq;
-            const uint32_t c1 = g + 1 == G ? m->n_chains : (uint32_t) ((uint64_t) m->n_chains * (g + 1) / G) / xq * xq;
-            cudaStream_t st = G == 1 ? m->stream : m->gstream[g];
-            // the X kernels get their own (high-priority) stream: they overlap the other groups' S kernels and,
-            // when the T nodes do not listen to their children, this group's own T draws
-            const bool px = (G > 1 || fast_uses_x_stream(m->net)) && prio_x != 2 && !m->phase_timing;
-            if (G > 1 || px) CUDA_TRY(cudaStreamWaitEvent(st, m->gfork, 0));
-            if (px) CUDA_TRY(cudaStreamWaitEvent(m->xstream[g], m->gfork, 0));
-            int l = launch_sweep_fast(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, st, &err,
-                                      m->phase_timing ? m->phase_ev.data() + (size_t) g * stride : nullptr, c0, c1 - c0,
-                                      px ? m->xstream[g] : nullptr, px ? m->gevx[g] : nullptr, px ? m->gevs[g] : nullptr);
+        for (uint32_t done = 0; done < n; ) {
+            if (m->pending + std::min(n - done, FAST_MAX_PENDING) > FAST_MAX_PENDING)
+                if (int rc = fold_counts(m)) return rc;
+            const uint32_t chunk = std::min(n - done, FAST_MAX_PENDING - m->pending);
+            g_error.clear();
+            int l = fast_batch(m, chunk, (uint32_t) m->sweeps_total + done, m->stat_n + done, &err);
             if (l < 0) { launched = -1; break; }
             launched += l;
-            if (G > 1) {
-                CUDA_TRY(cudaEventRecord(m->gdone[g], st));
-                CUDA_TRY(cudaStreamWaitEvent(m->stream, m->gdone[g], 0));
-            }
+            done += chunk;
+            if (m->ch.inj_flat && done < n) m->ch.inj_pos += chunk;   // the last chunk's rows are consumed below
         }
-        if (launched >= 0 && fast_t_beside_x(m->net) && (n & 1)) std::swap(m->ch.T, m->ch.T2);
+        if (launched < 0 && !err) return (int) GBN_ERR_CUDA;        // a CUDA_TRY inside fast_batch set the message
     } else
         launched = launch_sweep_strict(m->net, m->ch, n, (uint32_t) m->sweeps_total, m->stat_n, m->stream, &err);
     if (launched < 0) return fail(GBN_ERR_CUDA, std::string("sweep launch: ") + err);
@@ -390,7 +445,7 @@ int sample_n(gbn_model *m, uint32_t n)
     m->stat_n += n;
     m->moments_valid = false;
     if (m->ch.inj_flat) {
-        m->ch.inj_pos += n;
+        m->ch.inj_pos += (m->kernel == GBN_KERNEL_FAST && !m->sim) ? (n - 1) % FAST_MAX_PENDING + 1 : n;
         if (m->ch.inj_pos >= m->ch.inj_sweeps) { m->ch.inj_flat = m->ch.inj_beta = m->ch.inj_exp = nullptr; m->ch.inj_sweeps = m->ch.inj_pos = 0; }
     }
     return 0;
@@ -491,6 +546,10 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         UP(slot_of_edge, tp.slot_of_edge, u32) UP(slot_trg, tp.slot_trg, u32) UP(mor_idx, tp.mor_idx, u8)
         UP(tf_ptr, tp.tf_ptr, u32) UP(tf_child, tp.tf_child, u32) UP(tf_slot, tp.tf_slot, u32)
         UP(tfpos_of_slot, tp.tfpos_of_slot, u32) UP(par_pack, tp.par_pack, u32)
+        UP(sbase, tp.sbase, u32) UP(dbase, tp.dbase, u32) UP(sw_grp, tp.sw_grp, u32) UP(dblk_grp, tp.dblk_grp, u32)
+        UP(mor2, tp.mor2, u32)
+        { uint16_t *u16 = nullptr; if (int rc = dev_upload(m, &u16, tp.par16)) return bail(rc); n.par16 = reinterpret_cast<const uint2 *>(u16); }
+        n.nSw = tp.nSw; n.nD = tp.nD;
         UP(x_prior_active, tp.x_prior_active, u8)
         UP(t_a, tp.t_a, f64) UP(t_b, tp.t_b, f64) UP(t_mean, tp.t_mean, f64) UP(t_lnB, tp.t_lnB, f64)
 #undef UP
@@ -544,9 +603,13 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     }
     if (m->kernel == GBN_KERNEL_FAST) {
         const size_t xq = fast_x_bundle();
-        if (int rc = dev_alloc(m, &ch.tc2, (C + xq - 1) / xq * xq * nH)) return bail(rc);    // interleaved by chain bundle
+        const size_t n_tc2 = (C + xq - 1) / xq * xq * (nH + 1);                              // interleaved by chain bundle;
+        if (int rc = dev_alloc(m, &ch.tc2, n_tc2)) return bail(rc);                          // entry nH of a bundle stays {0, 0}
+        if (cudaMemset(ch.tc2, 0, sizeof(double2) * n_tc2) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "cudaMemset failed"));
         if (int rc = dev_alloc(m, &ch.ny, C * nH)) return bail(rc);
-        if (int rc = dev_alloc(m, &ch.Stf, C * E)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.Sw, C * tp.nSw)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.dC, C * tp.nD)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.Stfp, C * ((E + 15) / 16))) return bail(rc);
         if (int rc = dev_alloc(m, &ch.xU, C * ((nX + 3) & ~(size_t) 3))) return bail(rc);
         if (int rc = dev_alloc(m, &ch.FXp, C * nX)) return bail(rc);
     }
@@ -561,7 +624,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
 
     if (int rc = init_chains(m)) return bail(rc);
     if (int rc = zero_stats(m)) return bail(rc);
-    if (int rc = refresh_fast(m, true)) return bail(rc);
+    if (int rc = refresh_fast(m)) return bail(rc);
     if (cudaStreamSynchronize(m->stream) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "initialisation failed on the device"));
     *out = m;
     return 0;
@@ -818,7 +881,7 @@ extern "C" int gbn_model_set_evidence(gbn_model *m, const gbn_evidence *ev)
     lap("init_chains");
     if (int rc = zero_stats(m)) return rc;
     lap("zero_stats");
-    if (int rc = refresh_fast(m, true)) return rc;
+    if (int rc = refresh_fast(m)) return rc;
     lap("refresh_fast");
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     return 0;
@@ -893,6 +956,7 @@ extern "C" int gbn_model_get_state(gbn_model *m, uint32_t chain, double *out)
     const uint32_t nX = m->tp.nX, E = m->tp.E, Ep = m->tp.Ep;
     std::vector<uint8_t> X(nX), S(Ep);
     std::vector<double> T(nX);
+    if (int rc = ensure_s_bytes(m)) return rc;
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     if (m->sim) {           // random_nodes order of simulation mode: H_0 Y_0 H_1 Y_1 ... then T
         const uint32_t nH = m->tp.nH;
@@ -939,6 +1003,7 @@ extern "C" int gbn_model_set_state(gbn_model *m, uint32_t chain, const double *i
         }
         return 0;
     }
+    if (int rc = ensure_s_bytes(m)) return rc;          // the refresh below re-packs every chain from the byte view
     uint32_t o = 0;
     for (uint32_t k = 0; k < nX; k++) { double v = in[o++]; if (v != 0. && v != 1.) return fail(GBN_ERR_INVALID, "X values must be 0 or 1"); X[k] = (uint8_t) v; }
     if (!m->net.const_params) for (uint32_t k = 0; k < nX; k++) T[k] = in[o++];
@@ -959,6 +1024,7 @@ static int eval_to_host(gbn_model *m, uint32_t chain, double *out, size_t n, int
     if (chain >= m->n_chains) return fail(GBN_ERR_INVALID, "chain out of range");
     if (int rc = use_device(m)) return rc;
     if (int rc = ensure_scratch(m, sizeof(double) * n)) return rc;
+    if (int rc = ensure_s_bytes(m)) return rc;
     if (m->sim && which != 0) return fail(GBN_ERR_UNSUPPORTED, "only eval_conditionals is available in simulation mode");
     if (m->sim) launch_sim_conditionals(m->net, m->ch, chain, m->d_scratch, m->stream);
     else if (which == 0) launch_conditionals(m->net, m->ch, chain, m->d_scratch, m->stream);
@@ -1030,6 +1096,7 @@ extern "C" int gbn_model_node_moments(gbn_model *m, uint32_t chain, double *mean
     const size_t ns = n_stats_of(m->net);
     if (int rc = ensure_scratch(m, sizeof(double) * 2 * ns)) return rc;
     if (m->stat_n == 0) { for (size_t i = 0; i < ns; i++) { mean[i] = 0.; variance[i] = 0.; } return 0; }
+    if (int rc = fold_counts(m)) return rc;
     launch_node_moments(m->net, m->ch, chain, (double) m->stat_n, m->d_scratch, m->d_scratch + ns, m->stream);
     m->launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -1091,6 +1158,8 @@ extern "C" int gbn_model_checkpoint_save(gbn_model *m, void *out, size_t bytes)
     gbn_model_checkpoint_size(m, &need);
     if (bytes < need) return fail(GBN_ERR_INVALID, "checkpoint buffer too small");
     if (int rc = use_device(m)) return rc;
+    if (int rc = ensure_s_bytes(m)) return rc;
+    if (int rc = fold_counts(m)) return rc;
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     uint64_t hdr[4] = { CKPT_MAGIC, m->n_chains, m->sweeps_total, m->stat_n };
     std::memcpy(out, hdr, sizeof hdr);
@@ -1116,6 +1185,8 @@ extern "C" int gbn_model_checkpoint_load(gbn_model *m, const void *in, size_t by
     m->sweeps_total = hdr[2];
     m->stat_n = (uint32_t) hdr[3];
     m->moments_valid = false;
+    if (m->ch.dC) CUDA_TRY(cudaMemsetAsync(m->ch.dC, 0, sizeof(uint2) * (size_t) m->n_chains * m->tp.nD, m->stream));
+    m->pending = 0;
     m->ch.inj_flat = m->ch.inj_beta = m->ch.inj_exp = nullptr; m->ch.inj_sweeps = m->ch.inj_pos = 0;
     if (int rc = refresh_fast(m)) return rc;
     CUDA_TRY(cudaStreamSynchronize(m->stream));

@@ -8,7 +8,9 @@
 //                 tMean[c][nX], tM2[c][nX] f64 (Welford, gsl_rstat order of operations)
 //                 cS[c][Ep] u32x2 in slot order: #sweeps with S=0 and with S=2 (S=1 is N - both)
 //   fast kernel   tc2[c][nH] {beta, gamma} f64x2 and ny[c][nH] u16 (y * D + n): the per-target product cache
-//                 Stf[c][E] u8   copy of S in by-TF CSR order (coalesced reads in the X phase)
+//                 Sw[c][nSw] u32 S as 2-bit codes in slot order (the fast sweep's master copy of S)
+//                 dC[c][nD] u8x8 per-batch outcome counts of four steps, folded into cS on demand
+//                 Stfp[c][E/16] u32 copy of S in by-TF CSR order, 2-bit codes (coalesced reads in the X phase)
 //                 FXp[c][nX] f64x2   1 - t*x and its reciprocal
 // Integer counts replace the reference's gsl_rstat workspaces of 0/1 indicators
 // (Multinomial.cpp:101-105): mean = c/N, variance = N/(N-1) p (1-p).
@@ -38,6 +40,14 @@ struct DevNet {
     const uint32_t *tf_slot;      // [Eu]
     const uint32_t *tfpos_of_slot;// [Ep]  slot -> position in the by-TF CSR (fast kernel; needs Eu == E)
     const uint32_t *par_pack;     // [Ep]  slot -> par_tf | (mor+1) << 30 (TF 0, mor+1 = 1 for pads)
+    // packed views for the fast S kernel (topology.hpp): 16 steps per 2-bit word, 4 steps per block
+    const uint32_t *sbase;        // [n_groups+1] first S word of each group
+    const uint32_t *dbase;        // [n_groups+1] first 4-step block of each group
+    const uint32_t *sw_grp;       // [nSw / 32]  group of every row of 32 S words
+    const uint32_t *dblk_grp;     // [nD / 32]   group of every row of 32 blocks
+    const uint32_t *mor2;         // [nSw] prior row per step (3 = pad)
+    const uint2 *par16;           // [nD]  four 16-bit parent TFs per block
+    uint32_t nSw, nD;
     const uint8_t *x_prior_active;// [nX]
     const double *t_a, *t_b, *t_mean, *t_lnB;   // [nX]
     const uint8_t *y;             // [n_datasets][nH]
@@ -65,9 +75,13 @@ struct DevChains {
     double *tMean, *tM2;
     uint2 *cS;                    // {count S=0, count S=2}
     // fast kernel only
-    double2 *tc2;                 // [c/XQ][nH][XQ] (interleaved by chain bundle) {beta, gamma} = {pr0 omz (N2-N0), pr0 pr2 omz (N1-N2)}: L = c0[ny] + beta + gamma
+    double2 *tc2;                 // [c/XQ][nH + 1][XQ] (interleaved by chain bundle; entry nH is a dummy {0, 0} for idle lanes) {beta, gamma} = {pr0 omz (N2-N0), pr0 pr2 omz (N1-N2)}: L = c0[ny] + beta + gamma
     uint16_t *ny;                 // [c][nH] y * stab_D + n, n = number of parents with S != 1
-    uint8_t *Stf;
+    uint32_t *Sw;                 // [c][nSw] S as 2-bit codes, 16 steps per word: what the fast sweep reads and writes
+                                  // (ch.S is refreshed from it on demand, capi.cu)
+    uint2 *dC;                    // [c][nD] per-batch counts {S=0, S=2} of four steps as 4 x u8 each, folded into cS
+                                  // before anything reads the statistics (and before a byte could overflow)
+    uint32_t *Stfp;               // [c][ceil(E / 16)] copy of S in by-TF CSR order, 2-bit codes (coalesced reads in the X phase)
     uint32_t *xU;                 // [c][nX rounded up to 4] Philox words of the current sweep's X draws (X kernel scratch)
     double2 *FXp;                 // {1 - t*x, 1 / (1 - t*x)}
     // simulation mode only: latent / observed state per (chain, device target) and their outcome counts

@@ -163,8 +163,6 @@ __global__ void k_init_chains(DevNet net, DevChains ch, double c00, double c01, 
         ch.T[(size_t) c * net.nX + j] = net.t_mean[j];
     }
     if (j < net.Ep) ch.S[(size_t) c * net.Ep + j] = net.mor_idx[j];     // pads: 1 = edge off
-    // fast kernel: the by-TF copy of S, straight from the per-network table (no pass over the chain's S)
-    if (ch.Stf && net.tf_slot && j < net.E) ch.Stf[(size_t) c * net.E + j] = net.mor_idx[net.tf_slot[j]];
 }
 
 }  // namespace

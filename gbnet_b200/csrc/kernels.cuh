@@ -39,9 +39,15 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
                       uint32_t stat_n0, cudaStream_t st, const char **err, cudaEvent_t *phase_ev = nullptr,
                       uint32_t chain0 = 0, uint32_t nchains = UINT32_MAX,
                       cudaStream_t stx = nullptr, cudaEvent_t evx = nullptr, cudaEvent_t evs = nullptr);
-// rebuild Stf / FX / FXinv / tcache from X, T, S (after creation and set_state)
-// stf_valid: the by-TF copy of S is already current (right after launch_init_chains)
-int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err, bool stf_valid = false);
+// rebuild the packed S words, the by-TF copy, FXp and the product cache from X, T and the BYTE view of S
+// (after creation, set_state, checkpoint load)
+int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
+// the byte view of S (ch.S) from the packed words a fast sweep leaves behind
+int launch_fast_unpack(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
+// the S nodes' per-batch 8-bit outcome counts (ch.dC) added to the 32-bit totals (ch.cS); at most
+// FAST_MAX_PENDING sweeps may be drawn between two folds
+int launch_fast_fold(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
+constexpr uint32_t FAST_MAX_PENDING = 255;
 bool fast_supported(const DevNet &net, const char **why);
 
 // ---- sim_kernels.cu: simulation mode (GraphORNOR.cpp:28,58-63,89-106): n_sweeps sweeps H, Y -> T

@@ -80,7 +80,45 @@ struct SweepArgs {
     uint32_t use_inj;                // 1: injected draws, row inj_row
     uint32_t inj_row;                // sweep row inside the injection arrays
     uint32_t chain0;                 // first local chain of this launch (chains are split over streams)
+    uint32_t rk0[10], rk1[10];       // Philox round keys (seed words bumped by the Weyl constants): as kernel
+                                     // parameters they are constant-bank operands of the round's XOR
 };
+
+static SweepArgs sweep_args(const DevNet &net)
+{
+    SweepArgs a{};
+    uint32_t k0 = (uint32_t) net.seed, k1 = (uint32_t) (net.seed >> 32);
+    for (int r = 0; r < 10; r++) { a.rk0[r] = k0; a.rk1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return a;
+}
+
+// philox4x32_10 (device_math.cuh) with the key schedule taken from the kernel parameters
+__device__ __forceinline__ u32x4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const SweepArgs &a)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ a.rk0[r];
+        const uint32_t n2 = hi0 ^ c3 ^ a.rk1[r];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return u32x4{ c0, c1, c2, c3 };
+}
+
+// a *= f / n += k under a predicate, as ONE predicated instruction: the compiler turns `if (p) a *= f;` into a
+// multiply and two selects (three instructions for one), and the S kernel's edge loop is bound by issue
+__device__ __forceinline__ void mul_if(double &a, double f, bool p)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mul.rn.f64 %0, %0, %1;\n\t}" : "+d"(a) : "d"(f), "r"((int) p));
+}
+__device__ __forceinline__ void add_if(uint32_t &a, uint32_t k, bool p)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q add.u32 %0, %0, %1;\n\t}" : "+r"(a) : "r"(k), "r"((int) p));
+}
+
+// 2-bit S code at position pos of a packed array (16 codes per word)
+__device__ __forceinline__ uint32_t code_at(const uint32_t *w, uint32_t pos) { return (w[pos >> 4] >> (2 * (pos & 15))) & 3u; }
 
 // m * 2^e -> mantissa in [0.5, 1) and the exponent moved into e (frexp).  Likelihood products are
 // positive normal numbers, so the exponent field is rewritten directly; zero / subnormal / inf / nan
@@ -115,34 +153,23 @@ __device__ __forceinline__ void common_scale(double a, int ea, double b, int eb,
     lb = db < -1000 ? 0. : b * __hiloint2double((1023 + db) << 20, 0);
 }
 
-// X phase view of the per-target likelihood (see the S phase for the algebra).  The S phase leaves,
-// per target and chain, the pair
-//     beta = pr0 * omz[n] * (N_2 - N_0),   gamma = pr0 * pr2 * omz[n] * (N_1 - N_2)
-// (tc2) and the table index idx = y * D + n (ny), so that L = c0[idx] + beta + gamma, an edge with
-// S = 0 scales both terms by its factor and an edge with S = 2 scales gamma only.  One 16-byte gather,
-// one 2-byte and one 8-byte shared-memory lookup per child.
-__device__ __forceinline__ void child_likelihoods(const double *xC0, double2 bg, uint32_t idx, uint32_t s, double fac,
-                                                  double &Lc, double &Lf)
-{
-    const double c0 = xC0[idx];
-    const double sum = bg.x + bg.y;
-    Lc = c0 + sum;
-    const double f0 = c0 + fac * sum;                                // the edge feeds pr0
-    const double f2 = c0 + (bg.x + fac * bg.y);                      // the edge feeds pr2
-    Lf = s == 0 ? f0 : (s == 2 ? f2 : Lc);
-}
-
 // ---------------------------------------------------------------------------------- X phase
 // One CTA sweeps the X nodes of XQ chains (a "bundle": chains XQ p .. XQ p + XQ - 1).  The kernel is bound
-// by L1 wavefronts: a warp-wide gather costs one wavefront (~2 cycles) per distinct 128-byte line, and
-// the children of a TF are scattered over the product cache.  The cache is therefore interleaved by
-// bundle - tc2[bundle][target][XQ] - and a warp's lanes are (32 / XQ children) x (XQ chains): the XQ
-// lanes of one child read adjacent 16-byte entries of one line, which divides the wavefronts per
+// by L1 wavefronts and instruction issue: a warp-wide gather costs one wavefront (~2 cycles) per distinct
+// 128-byte line, and the children of a TF are scattered over the product cache.  The cache is therefore
+// interleaved by bundle - tc2[bundle][target][XQ] - and a warp's lanes are (32 / XQ children) x (XQ chains):
+// the XQ lanes of one child read adjacent 16-byte entries of one line, which divides the wavefronts per
 // (child, chain) by XQ.  The chains of a bundle share the window position: a window commits up to the
 // first TF that changed in ANY of them (flips are rare, so the shorter commit costs little), and every
 // committed TF still saw exactly the state the sequential sweep of its own chain would have seen.
 // LPT lanes of a warp work on one TF (32: a warp per TF; 16 / 8: two / four TFs per warp - the per-TF
 // instruction overhead is issued by all warps at once, and a longer window means fewer rounds).
+//
+// The child loop is written for instruction count (round 1: ~80 instructions per (child, chain), round 2:
+// see profiles/r2_sass_mix.txt): U children per lane and trip with the ids / S words of the NEXT trip
+// requested before the current trip's cache entries are used; idle lanes of a last trip read a dummy
+// target (entry nH: {0, 0}, table value 1) instead of branching; the flip multipliers {m_beta, m_gamma} of
+// an edge by S code come from a 3-entry shared-memory row per (TF, chain) instead of selects.
 template <int NT, bool NY_SMEM, int LPT, int U>
 __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, SweepArgs a, uint32_t nchains)
 {
@@ -151,13 +178,13 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     static_assert(LPT >= 2 * XQ, "a TF needs at least two child slots");
     extern __shared__ __align__(16) unsigned char smem_x[];
     __shared__ uint32_t s_dec[W];                                            // per window position: chains of the bundle that flipped
-    __shared__ double s_fac[W * XQ];                                         // per window position and chain: the flip factor
-    const uint32_t nX = net.nX, E = net.E, nH = net.nH, D = net.stab_D;
-    const uint32_t nXr = (nX + 3) & ~3u;
-    double *xC0all = reinterpret_cast<double *>(smem_x);                     // [Q][3][D] c0 by idx = y * D + n
-    uint32_t *sPtr = reinterpret_cast<uint32_t *>(xC0all + Q * 3 * D);       // [nX + 1 rounded up to 4] tf_ptr
+    const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;
+    const uint32_t nXr = (nX + 3) & ~3u, C0N = 3 * D + 2, nStfW = (net.E + 15) >> 4;
+    double2 *sMul = reinterpret_cast<double2 *>(smem_x);                     // [W][Q][4] flip multipliers by S code
+    double *xC0all = reinterpret_cast<double *>(sMul + W * Q * 4);           // [Q][C0N] c0 by idx = y * D + n; [3 D] = 1 (dummy)
+    uint32_t *sPtr = reinterpret_cast<uint32_t *>(xC0all + Q * C0N);         // [nX + 1 rounded up to 4] tf_ptr
     uint8_t *sX = reinterpret_cast<uint8_t *>(sPtr + ((nX + 4) & ~3u));      // [Q][nX rounded up to 4] value | prior class << 1
-    uint16_t *sNy = reinterpret_cast<uint16_t *>(sX + Q * nXr);              // [nH][Q] table index of every target (NY_SMEM)
+    uint16_t *sNy = reinterpret_cast<uint16_t *>(sX + Q * nXr);              // [nH + 1][Q] table index of every target (NY_SMEM)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sg = lane / LPT, sl = lane % LPT;                         // this lane's TF of the warp, lane within it
@@ -166,7 +193,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     const uint32_t cbase = a.chain0 + Q * blockIdx.x;                        // a multiple of Q by construction
     const uint32_t nvalid = min(Q, nchains - Q * blockIdx.x);                // a last, partial bundle recomputes its last chain
     const uint32_t cmine = cbase + min(h, nvalid - 1);
-    double2 *tcb = ch.tc2 + (size_t) (cbase / Q) * nH * Q;                   // bundle base: entry (i, chain) at Q i + chain
+    double2 *tcb = ch.tc2 + (size_t) (cbase / Q) * (nH + 1) * Q;             // bundle base: entry (i, chain) at Q i + chain
 
     // everything a round needs per TF is staged once: a round must not wait on global memory for
     // anything but the children's ids and cache entries
@@ -176,11 +203,11 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
         const uint8_t *gX = ch.X + (size_t) c * nX;
         for (uint32_t k = tid; k < nX; k += NT) sX[q * nX + k] = (uint8_t) (gX[k] | (net.x_prior_active[k] << 1));
         const double *tab = net.stab + (size_t) d * STAB_ROWS * D;
-        for (uint32_t j = tid; j < 3 * D; j += NT) xC0all[q * 3 * D + j] = tab[j];
+        for (uint32_t j = tid; j < C0N; j += NT) xC0all[q * C0N + j] = j < 3 * D ? tab[j] : 1.;
         if (!a.use_inj) {   // every X uniform of this chain and sweep: one Philox block per four TFs, computed once
             uint4 *gU = reinterpret_cast<uint4 *>(ch.xU + (size_t) c * nXr);
             for (uint32_t blk = tid; blk < nXr / 4; blk += NT) {
-                const u32x4 r = philox4x32_10(blk, a.sweep, gchain, KIND_X, (uint32_t) net.seed, (uint32_t) (net.seed >> 32));
+                const u32x4 r = philox_rk(blk, a.sweep, gchain, KIND_X, a);
                 gU[blk] = make_uint4(r.x, r.y, r.z, r.w);
             }
         }
@@ -189,25 +216,25 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
         if (NY_SMEM) {
             const uint16_t *gny = ch.ny + (size_t) c * nH;
             for (uint32_t i = tid; i < nH; i += NT) sNy[(size_t) i * Q + q] = gny[i];
+            if (tid == 0) sNy[(size_t) nH * Q + q] = (uint16_t) (3 * D);
         }
     }
     for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.tf_ptr[k];
     __syncthreads();
 
-    const double *xC0 = xC0all + h * 3 * D;
-    const uint8_t *gStf = ch.Stf + (size_t) cmine * E;
+    const double *xC0 = xC0all + h * C0N;
+    const uint32_t *gStf = ch.Stfp + (size_t) cmine * nStfW;
     const double *gT = ch.T + (size_t) cmine * nX;
     const uint32_t *gU = ch.xU + (size_t) cmine * nXr;
     const uint16_t *gNy = ch.ny + (size_t) cmine * nH;                       // networks too large for sNy gather it from here
-    const double *inj = a.use_inj ? ch.inj_flat + ((size_t) cmine * ch.inj_sweeps + a.inj_row) * (nX + E) : nullptr;
+    const double *inj = a.use_inj ? ch.inj_flat + ((size_t) cmine * ch.inj_sweeps + a.inj_row) * (nX + net.E) : nullptr;
+    double2 *mul = sMul + (pos * Q + h) * 4;
 
     uint32_t k0 = 0;
     while (k0 < nX) {
         const uint32_t kw = k0 + pos;
         const bool live = kw < nX;
         int dec = 0;                              // bit 0: drawn value, bit 1: value changed (this lane's chain)
-        double fac = 1.;
-        uint32_t cbeg = 0, cend = 0;
         if (NS > 1 || live) {                     // warp-uniform when a warp holds one TF; else dead TFs ride along empty
             const uint32_t kr = live ? kw : 0u;
             const uint32_t xcur = sX[h * nX + kr] & 1u;
@@ -215,65 +242,58 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             // are issued with the first child ids and are off the critical path
             const double g = 1. - gT[kr];         // (1 - t*x) at x = 1   (HNodeORNOR.cpp:59)
             const uint32_t uword = a.use_inj ? 0u : gU[kr];
-            fac = xcur ? 1. / g : g;              // factor that turns the product into the flipped one
+            uint32_t cbeg = 0, cend = 0;
             if (live) { cbeg = sPtr[kw]; cend = sPtr[kw + 1]; }
-            GBN_CHECK(cbeg <= cend && cend <= E);
+            GBN_CHECK(cbeg <= cend && cend <= net.E);
+            // One (child, chain) per lane and gather.  The ids and S words of the next trip are requested
+            // before this trip's entries are used; the pipeline lives inside one round, so every entry is
+            // read after the flips of all earlier (committed) windows.
+            uint32_t cc = cbeg + cs;
+            uint32_t id[U], sw[U];
+            auto load_ids = [&](uint32_t c0) {
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t c = c0 + u * CPW;
+                    const bool ok = c < cend;
+                    id[u] = nH; sw[u] = 0x55555555u;                         // idle lane: the dummy target, edge off
+                    if (ok) { id[u] = net.tf_child[c]; sw[u] = __ldg(gStf + (c >> 4)); }
+                }
+            };
+            load_ids(cc);
+            uint32_t trips = (cend - cbeg + U * CPW - 1) / (U * CPW);        // trip count, uniform over the warp
+            if (NS > 1) trips = __reduce_max_sync(0xffffffffu, trips);
+            // factor that turns the product into the flipped one; by S code of the edge it scales
+            // {beta, gamma} (S = 0), nothing (S = 1) or gamma only (S = 2)
+            double fac = g;
+            if (xcur) fac = 1. / g;
+            if (cs == 0) {
+                mul[0] = make_double2(fac, fac); mul[1] = make_double2(1., 1.); mul[2] = make_double2(1., fac);
+            }
+            __syncwarp();
             double mc = 1., mf = 1.;
             int ec = 0, ef = 0, cnt = 0;
-            // One (child, chain) per lane and gather, software-pipelined with two explicit register sets
-            // (no rotating copies, which would wait on the loads): while iteration i is computed from set X,
-            // the cache entries of iteration i+1 are in flight into set Y and the child id / S value of
-            // iteration i+2 into X's id registers.  The pipeline lives inside one round, so every entry is
-            // read after the flips of all earlier (committed) windows.  s = 0xff marks "no child".
-            struct Ids { uint32_t i[U], s[U]; };
-            struct Dat { double2 p[U]; uint32_t ny[U]; };
-            auto load_ids = [&](uint32_t cc) -> Ids {
-                Ids r;
+            for (; trips > 0; trips--) {
+                double2 bg[U];
+                uint32_t nyv[U], sh[U];
 #pragma unroll
-                for (uint32_t u = 0; u < U; u++) {
-                    const uint32_t c = cc + u * CPW;
-                    r.i[u] = 0u; r.s[u] = 0xffu;
-                    if (c < cend) { r.i[u] = net.tf_child[c]; r.s[u] = __ldcs(gStf + c); }
+                for (int u = 0; u < U; u++) {
+                    GBN_CHECK(id[u] <= nH);
+                    bg[u] = tcb[(size_t) id[u] * Q + h];
+                    nyv[u] = NY_SMEM ? sNy[(size_t) id[u] * Q + h] : (id[u] == nH ? 3 * D : gNy[id[u]]);
+                    sh[u] = (sw[u] >> (2 * ((cc + u * CPW) & 15))) & 3u;
                 }
-                return r;
-            };
-            auto gather = [&](const Ids &id) -> Dat {
-                Dat r;
-#pragma unroll
-                for (uint32_t u = 0; u < U; u++) {
-                    GBN_CHECK(id.i[u] < nH);
-                    r.p[u] = tcb[(size_t) id.i[u] * Q + h];
-                    r.ny[u] = NY_SMEM ? sNy[(size_t) id.i[u] * Q + h] : gNy[id.i[u]];
-                }
-                return r;
-            };
-            uint32_t cc = cbeg + cs;
-            auto step = [&](Ids &idX, Dat &dX, const Ids &idY, Dat &dY) {
-                dY = gather(idY);                                     // next iteration's entries
-                uint32_t sv[U];
-#pragma unroll
-                for (uint32_t u = 0; u < U; u++) sv[u] = idX.s[u];
-                idX = load_ids(cc + 2 * U * CPW);                     // ids two iterations ahead
-#pragma unroll
-                for (uint32_t u = 0; u < U; u++)
-                    if (sv[u] != 0xffu) {
-                        double Lc, Lf;
-                        GBN_CHECK(sv[u] <= 2 && dX.ny[u] < 3 * D);
-                        child_likelihoods(xC0, dX.p[u], dX.ny[u], sv[u], fac, Lc, Lf);
-                        mc *= Lc; mf *= Lf;
-                    }
-                if ((cnt += U) >= 16) { normalise(mc, ec); normalise(mf, ef); cnt = 0; }
                 cc += U * CPW;
-            };
-            Ids idA = load_ids(cc), idB = load_ids(cc + U * CPW);
-            Dat dA = gather(idA), dB;
-            uint32_t trips = (cend - cbeg + U * CPW - 1) / (U * CPW);             // trip count, uniform over the warp
-            if (NS > 1) trips = __reduce_max_sync(0xffffffffu, trips);
-            while (trips > 0) {
-                step(idA, dA, idB, dB);
-                if (--trips == 0) break;
-                step(idB, dB, idA, dA);
-                --trips;
+                load_ids(cc);                                                 // next trip
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    GBN_CHECK(nyv[u] <= 3 * D);
+                    const double2 m = mul[sh[u]];
+                    const double c0 = xC0[nyv[u]];
+                    const double Lc = c0 + (bg[u].x + bg[u].y);
+                    const double Lf = c0 + __fma_rn(m.x, bg[u].x, m.y * bg[u].y);
+                    mc *= Lc; mf *= Lf;
+                }
+                if ((cnt += U) >= 16) { normalise(mc, ec); normalise(mf, ef); cnt = 0; }
             }
             normalise(mc, ec);
             normalise(mf, ef);
@@ -301,7 +321,6 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
         const uint32_t fb = __ballot_sync(0xffffffffu, (dec & 2) && cs == 0);
         const uint32_t flipped = (fb >> (sg * LPT)) & ((1u << Q) - 1u);
         if (sl == 0) s_dec[pos] = flipped;
-        if (cs == 0) s_fac[pos * Q + h] = fac;
         __syncthreads();
         uint32_t first = W;
 #pragma unroll
@@ -319,12 +338,12 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             const uint32_t kf = k0 + first, fb0 = sPtr[kf], fe0 = sPtr[kf + 1], fmask = s_dec[first];
             for (uint32_t q = 0; q < Q; q++) {
                 if (!((fmask >> q) & 1u)) continue;
-                const double fq = s_fac[first * Q + q];
-                const uint8_t *gS = ch.Stf + (size_t) (cbase + q) * E;
-                for (uint32_t cc = fb0 + tid; cc < fe0; cc += NT) {
-                    const uint32_t s = gS[cc];
+                const double fq = sMul[(first * Q + q) * 4].x;
+                const uint32_t *gS = ch.Stfp + (size_t) (cbase + q) * nStfW;
+                for (uint32_t c2 = fb0 + tid; c2 < fe0; c2 += NT) {
+                    const uint32_t s = code_at(gS, c2);
                     if (s == 1) continue;
-                    double2 *e = tcb + (size_t) net.tf_child[cc] * Q + q;
+                    double2 *e = tcb + (size_t) net.tf_child[c2] * Q + q;
                     double2 bg = *e;
                     if (s == 0) bg.x *= fq;
                     bg.y *= fq;
@@ -421,8 +440,8 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
     const uint32_t d = chain_dataset(net, c);
     const uint32_t gchain = chain_global_id(net, c);
     const uint8_t *gX = ch.X + (size_t) c * nX;
-    const uint8_t *gStf = ch.Stf + (size_t) c * net.E;
-    double2 *tc2 = ch.tc2 + (size_t) (c / XQ) * nH * XQ + (c % XQ);      // bundle-interleaved: entry i at XQ i
+    const uint32_t *gStf = ch.Stfp + (size_t) c * ((net.E + 15) >> 4);
+    double2 *tc2 = ch.tc2 + (size_t) (c / XQ) * (nH + 1) * XQ + (c % XQ);    // bundle-interleaved: entry i at XQ i
     const uint16_t *gny = ch.ny + (size_t) c * nH;
 
     for (uint32_t j = tid; j < 3 * D; j += FTL_NT) xC0[j] = net.stab[(size_t) d * STAB_ROWS * D + j];
@@ -473,7 +492,7 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
                 double mo = 1., mn = 1.;
                 int eo = 0, en = 0, cnt = 0;
                 for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
-                    const uint32_t s = gStf[cc];
+                    const uint32_t s = code_at(gStf, cc);
                     if (s == 1) continue;
                     const uint32_t i = net.tf_child[cc];
                     GBN_CHECK(i < nH && gny[i] < 3 * D);
@@ -515,7 +534,7 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
             if (t != prev) {
                 // accepted: move the edge factors of this TF inside the cached terms of its children
                 for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
-                    const uint32_t s = gStf[cc];
+                    const uint32_t s = code_at(gStf, cc);
                     if (s == 1) continue;
                     const uint32_t i = net.tf_child[cc];
                     double2 bg = tc2[XQ * (size_t) i];
@@ -539,22 +558,32 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
 
 // ---------------------------------------------------------------------------------- S phase
 // One WARP per (group of 32 device targets, chain); lane = target.  Device targets are sorted by
-// in-degree and a group's slots are stored transposed (topology.hpp), so when the lanes visit their
-// j-th parent edge together every access below is one run of consecutive addresses: S bytes, packed
-// parent ids, and the read-modify-write of the {count S=0, count S=2} pairs.  No shared-memory
+// in-degree and a group's steps are stored transposed (topology.hpp), so when the lanes visit their
+// j-th parent edge together every access below is one run of consecutive addresses.  No shared-memory
 // staging of the slots, no block-level barrier after the start, no write-back pass.
+//
+// Packed views (round 2).  A lane reads the S codes of 16 consecutive steps as ONE
+// 32-bit word (2 bits per code) and keeps them in a register for both passes, the prior rows of those
+// steps as one more (static) word, the parent TFs of four steps as 4 x 16 bits, and counts outcomes in a
+// per-batch pair of 4 x 8-bit words per four steps (dC) that the model layer folds into the 32-bit totals
+// before anything reads them.  Per edge and sweep the kernel moves ~5 bytes (round 1: 17) and issues ~1/4
+// of the round-1 load / store instructions.
 //
 // Likelihood algebra.  With N_h = YNOISE[h][y], K = sum_h YPROB[h] N_h, zc = (1-z)^n, omz = 1 - zc
 // (HNodeORNOR.cpp:64,82,96 and HNode.cpp:40-46 expanded):
 //     L(pr0, pr2, n) = c0[n] + omz[n] * pr0 * (a + pr2 * b),
 //     c0[n] = omz[n] N_0 + zc[n] K,   a = N_2 - N_0,   b = N_1 - N_2.
 // c0 / omz / zc are per-dataset tables over n (net.stab, built on the host with zc by repeated
-// multiplication as in the reference).  The three candidates of one edge share R0, R2 (the products
-// without the edge) and differ only in which product takes the factor f and in n.
+// multiplication as in the reference).  The state carried along a target's edges is A = a pr0,
+// Bq = b pr0 pr2 and n.  At an edge the factor f = (1 - t x) z is first taken OUT of the state (multiply by
+// the reciprocal from FXp), the three candidates are evaluated from the state without the edge, the draw is
+// taken, and the factor of the drawn code is put back in - predicated multiplies, no selects, no branch.
+// Pad steps carry S = 1 and the prior row {0, 1, 0}: they draw 1 again and count nothing, so the loop does
+// not test for them.
 // MODE 0: sweep (draw every S of the target, count, refresh the cache)
 // MODE 1: refresh only (rebuild the cache from X, T, S; no draws, no counts)
 #ifndef GBN_S_MINB
-#define GBN_S_MINB 4          // 64 registers: 4 CTAs (32 warps) per SM measured best (profiles/r1_summary.md)
+#define GBN_S_MINB 4          // 64 registers: 4 CTAs (32 warps) per SM measured best in round 1 (profiles/r1_summary.md)
 #endif
 template <int MODE, bool STAGE_FX, bool INJ>
 __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevChains ch, SweepArgs a)
@@ -562,7 +591,8 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;
     double2 *sTab = reinterpret_cast<double2 *>(smem_raw);                      // [3][D] {c0[y][n], omz[class of y][n]}
-    double2 *sFX = sTab + 3 * D;                                                // [nX] if staged
+    double *sSp = reinterpret_cast<double *>(sTab + 3 * D);                     // [4][4] prior rows by code; row 3 = pad {0, 1, 0}
+    double2 *sFX = reinterpret_cast<double2 *>(sSp + 16);                       // [nX] if staged
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t c = blockIdx.y + a.chain0;
@@ -573,133 +603,226 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
         const uint32_t yy = j / D, nn = j - yy * D;
         sTab[j] = make_double2(tab[j], tab[(3 + (yy != 1 ? 0 : 1)) * D + nn]);
     }
+    if (tid < 16) {
+        const uint32_t r = tid >> 2, v = tid & 3;
+        sSp[tid] = r < 3 ? (v < 3 ? net.sprob[r][v] : 0.) : (v == 1 ? 1. : 0.);
+    }
     if (STAGE_FX) for (uint32_t k = tid; k < nX; k += FS_NT) sFX[k] = gFX[k];
     __syncthreads();
+    const double2 *fxp = STAGE_FX ? sFX : gFX;
 
     const uint32_t g = blockIdx.x * (FS_NT / 32) + (tid >> 5);
     if (g >= net.n_groups) return;
     const uint32_t dt = 32 * g + lane;
     const bool valid = dt < nH;
-    const uint32_t deg = valid ? net.deg[dt] : 0;
     const uint32_t gb = net.gbase[g];
     const uint32_t W = (net.gbase[g + 1] - gb) >> 5;                 // group width = largest in-degree
-    const size_t base = (size_t) c * net.Ep + gb + lane;             // this lane's slot of step 0, in the chain arrays
-    uint8_t *pS = ch.S + base;
-    const uint32_t *pPar = net.par_pack + gb + lane;
     const uint32_t y = valid ? net.y[(size_t) d * nH + dt] : 1u;
     const uint32_t cls = (y != 1) ? 0 : 1;                          // ZY for DE targets, ZN otherwise
     const double z = cls ? net.z_n : net.z_y;
     const double ca = net.ynoise[2][y] - net.ynoise[0][y];          // a
     const double cb = net.ynoise[1][y] - net.ynoise[2][y];          // b
     const double2 *cot = sTab + y * D;                              // {c0, omz} over n for this target's y
+    uint32_t *pSw = ch.Sw + (size_t) c * net.nSw + net.sbase[g] + lane;
+    const uint2 *pPar = net.par16 + net.dbase[g] + lane;
+    const uint32_t W4 = (W + 3) >> 2;                                // 4-step blocks (the last may hold pads)
 
     if (MODE == 0) {
         // the counters are first touched by the second pass: start pulling their lines into L2 now
-        const uint2 *pc = ch.cS + base;
-        for (uint32_t j = 0; j < W; j++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + 32 * j));
+        const uint2 *pc = ch.dC + (size_t) c * net.nD + net.dbase[g] + lane;
+        for (uint32_t b = 0; b < W4; b++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + 32 * b));
     }
-    // products over the parents in append_parent order (HNodeORNOR.cpp:55-62, 72-81); pads hold S = 1.
-    // The state carried along the edges is A = a pr0 and Bq = b pr0 pr2, so that
-    // L = c0[n] + omz[n] (A + Bq) and the a, b constants stay out of the edge loop.
+    // products over the parents in append_parent order (HNodeORNOR.cpp:55-62, 72-81): A = a pr0, Bq = b pr0 pr2
+    // so that L = c0[n] + omz[n] (A + Bq) and the a, b constants stay out of the edge loop; pads hold S = 1
     double A = ca, Bq = cb;
     uint32_t n = 0;
-    for (uint32_t j = 0; j < W; j++) {
-        const uint32_t s = pS[32 * j];
-        const uint32_t kk = pPar[32 * j] & 0x3fffffffu;
-        GBN_CHECK(kk < nX && s <= 2 && gb + lane + 32 * j < net.Ep);
-        const double f = (STAGE_FX ? sFX[kk].x : gFX[kk].x) * z;
-        n += (s != 1);
-        A *= (s == 0) ? f : 1.;
-        Bq *= (s != 1) ? f : 1.;
+    for (uint32_t b0 = 0; b0 < W4; b0 += 4) {
+        uint32_t sw = pSw[8 * b0];                                   // word b0 / 4 of this lane: 32 * (b0 / 4)
+        GBN_CHECK(net.sbase[g] + lane + 8 * b0 < net.nSw);
+        { const uint32_t x = sw ^ 0x55555555u; n += __popc((x | (x >> 1)) & 0x55555555u); }   // codes != 1
+        const uint32_t nb = min(4u, W4 - b0);
+        for (uint32_t b = 0; b < nb; b++) {
+            const uint2 pw = pPar[32 * (b0 + b)];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t s = sw & 3u;
+                sw >>= 2;
+                const uint32_t kk = (u & 1) ? ((u < 2 ? pw.x : pw.y) >> 16) : ((u < 2 ? pw.x : pw.y) & 0xffffu);
+                GBN_CHECK(kk < nX && s <= 2);
+                const double f = fxp[kk].x * z;
+                mul_if(A, f, s == 0);
+                mul_if(Bq, f, s != 1);
+            }
+        }
     }
     if (MODE == 0) {
         const double rz = 1. / z;
         const uint32_t gchain = chain_global_id(net, c);
         const uint32_t ref_i = valid ? net.ref_of_dt[dt] : 0u;
-        const uint32_t k0 = (uint32_t) net.seed, k1 = (uint32_t) (net.seed >> 32);
         const double *inj_flat = INJ ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + net.E) + nX : nullptr;
         const uint32_t *pEdge = net.par_edge + gb + lane;
-        uint2 *pC = ch.cS + base;
-        // one step = this lane's j-th parent edge; jj = position inside the current block of 4
-        auto step = [&](const uint32_t j, const uint32_t jj, const uint32_t s, const uint32_t pk, uint2 cs,
-                        const uint32_t word, uint8_t *bS, uint2 *bC) {
-            if (j < deg) {
-                const uint32_t kk = pk & 0x3fffffffu;
-                const double *sp = net.sprob[pk >> 30];
-                const double2 fx = STAGE_FX ? sFX[kk] : gFX[kk];
-                const double f = fx.x * z;
-                const double finv = fx.y * rz;
-                const double Ar = s == 0 ? A * finv : A;            // the state without this edge
-                const double Br = s != 1 ? Bq * finv : Bq;
-                const uint32_t nR = n - (s != 1);
-                GBN_CHECK(kk < nX && s <= 2 && (pk >> 30) <= 2 && nR + 1 < D && n <= deg);
-                const double2 t0 = cot[nR], t1 = cot[nR + 1];
-                const double sum = Ar + Br;
-                // the file is compiled without FMA contraction (the reference's x86-64 build has none); these
-                // seven are explicit: this algebra differs from the reference's by rounding anyway (DESIGN.md
-                // section 4.4), and the edge loop is bound by instruction issue
-                const double L0 = __fma_rn(t1.y, f * sum, t1.x);                   // S = 0: the factor joins pr0
-                const double L1 = __fma_rn(t0.y, sum, t0.x);                       // S = 1: edge off
-                const double L2 = __fma_rn(t1.y, __fma_rn(f, Br, Ar), t1.x);       // S = 2: the factor joins pr2
-                // exp(log prior + log L) of Multinomial.cpp:66-75 as a product; the "0 +" and
-                // "0 * (1 - u)" terms of the reference's running sum / gsl_ran_flat add exact zeros
-                double cum0 = sp[0] * L0;
-                double cum1 = __fma_rn(sp[1], L1, cum0);
-                double cum2 = __fma_rn(sp[2], L2, cum1);
-                if (!(cum2 > 0.)) { cum0 = sp[0]; cum1 = cum0 + sp[1]; cum2 = cum1 + sp[2]; }
-                const double u = INJ ? inj_flat[pEdge[32 * j]] : unit_from_word(word);
-                const double dice = cum2 * u;
-                const uint32_t ns = dice < cum0 ? 0u : (dice < cum1 ? 1u : (dice < cum2 ? 2u : s));
-                if (ns != s) {
-                    bS[32 * jj] = (uint8_t) ns;
-                    GBN_CHECK(net.tfpos_of_slot[gb + lane + 32 * j] < net.E);
-                    ch.Stf[(size_t) c * net.E + net.tfpos_of_slot[gb + lane + 32 * j]] = (uint8_t) ns;
-                    A = ns == 0 ? Ar * f : Ar;
-                    Bq = ns != 1 ? Br * f : Br;
-                    n = nR + (ns != 1);
-                }
-                cs.x += (ns == 0);                                  // Multinomial.cpp:101-105 as counts
-                cs.y += (ns == 2);
-            }
-            __stcs(bC + 32 * jj, cs);                               // streamed: the product cache stays in L2
-        };
-        // blocks of four steps: the block's S bytes, parent ids and counter pairs are requested together
-        // off three running pointers (immediate offsets), one Philox block serves the four edges of
-        // every lane's target, and the other warps of the SM cover the load latency
-        uint8_t *bS = pS;
-        const uint32_t *bP = pPar;
-        uint2 *bC = pC;
-        for (uint32_t j0 = 0; j0 < W; j0 += 4, bS += 128, bP += 128, bC += 128) {
-            const uint32_t nb = W - j0;                              // steps in this block (warp-uniform)
-            uint32_t s4[4], p4[4];
-            uint2 c4[4];
+        const uint32_t *pMor = net.mor2 + net.sbase[g] + lane;
+        uint2 *pC = ch.dC + (size_t) c * net.nD + net.dbase[g] + lane;
+        uint32_t *gStfp = ch.Stfp + (size_t) c * ((net.E + 15) >> 4);
+        for (uint32_t b0 = 0; b0 < W4; b0 += 4) {                    // one S word = up to four 4-step blocks
+            const uint32_t sw0 = pSw[8 * b0];
+            uint32_t sw = sw0, mw = pMor[8 * b0], chg = 0;
+            const uint32_t nb = min(4u, W4 - b0);
+            for (uint32_t b = 0; b < nb; b++) {
+                const uint32_t j0 = 4 * (b0 + b);
+                const uint2 pw = pPar[32 * (b0 + b)];
+                uint2 cw = __ldcs(pC + 32 * (b0 + b));
+                u32x4 rnd = { 0, 0, 0, 0 };
+                if (!INJ) rnd = philox_rk(ref_i, a.sweep, gchain, KIND_S | ((b0 + b) << 8), a);
+                uint32_t chg4 = 0;
 #pragma unroll
-            for (int u4 = 0; u4 < 4; u4++)
-                if ((uint32_t) u4 < nb) { s4[u4] = bS[32 * u4]; p4[u4] = bP[32 * u4]; c4[u4] = __ldcs(bC + 32 * u4); }
-            u32x4 rnd = { 0, 0, 0, 0 };
-            if (!INJ) rnd = philox4x32_10(ref_i, a.sweep, gchain, KIND_S | ((j0 >> 2) << 8), k0, k1);
-            step(j0, 0, s4[0], p4[0], c4[0], rnd.x, bS, bC);
-            if (nb > 1) step(j0 + 1, 1, s4[1], p4[1], c4[1], rnd.y, bS, bC);
-            if (nb > 2) step(j0 + 2, 2, s4[2], p4[2], c4[2], rnd.z, bS, bC);
-            if (nb > 3) step(j0 + 3, 3, s4[3], p4[3], c4[3], rnd.w, bS, bC);
+                for (int u = 0; u < 4; u++) {
+                    if (j0 + u < W) {                                // warp-uniform
+                        const uint32_t s = (sw >> (2 * u)) & 3u, r = (mw >> (2 * u)) & 3u;
+                        const uint32_t kk = (u & 1) ? ((u < 2 ? pw.x : pw.y) >> 16) : ((u < 2 ? pw.x : pw.y) & 0xffffu);
+                        GBN_CHECK(kk < nX && s <= 2 && n + 1 < D);
+                        const double2 fx = fxp[kk];
+                        const double f = fx.x * z, finv = fx.y * rz;
+                        // the state without this edge
+                        const double Af = A * finv, Bf = Bq * finv;
+                        const double Ar = s == 0 ? Af : A, Br = s != 1 ? Bf : Bq;
+                        const uint32_t nR = n - (s != 1);
+                        const double2 t0 = cot[nR], t1 = cot[nR + 1];
+                        const double2 sp01 = *reinterpret_cast<const double2 *>(sSp + 4 * r);
+                        const double sp2 = sSp[4 * r + 2];
+                        const double sum = Ar + Br;
+                        // the file is compiled without FMA contraction (the reference's x86-64 build has none); these
+                        // are explicit: this algebra differs from the reference's by rounding anyway (DESIGN.md
+                        // section 4.4), and the edge loop is bound by instruction issue
+                        const double L0 = __fma_rn(t1.y, f * sum, t1.x);                   // S = 0: the factor joins pr0
+                        const double L1 = __fma_rn(t0.y, sum, t0.x);                       // S = 1: edge off
+                        const double L2 = __fma_rn(t1.y, __fma_rn(f, Br, Ar), t1.x);       // S = 2: the factor joins pr2
+                        // exp(log prior + log L) of Multinomial.cpp:66-75 as a product; the "0 +" and
+                        // "0 * (1 - u)" terms of the reference's running sum / gsl_ran_flat add exact zeros
+                        double cum0 = sp01.x * L0;
+                        double cum1 = __fma_rn(sp01.y, L1, cum0);
+                        double cum2 = __fma_rn(sp2, L2, cum1);
+                        if (!(cum2 > 0.)) {                                                // Multinomial.cpp:78-85
+                            // (L >= c0[n] > 0: only an all-zero or NaN prior row gets here.  Counted, so that the
+                            // block stays a branch instead of six predicated instructions in the loop)
+                            if (ch.dbg) atomicAdd(ch.dbg + 3, 1ull);
+                            cum0 = sp01.x; cum1 = cum0 + sp01.y; cum2 = cum1 + sp2;
+                        }
+                        const uint32_t word = u == 0 ? rnd.x : (u == 1 ? rnd.y : (u == 2 ? rnd.z : rnd.w));
+                        double uu = unit_from_word(word);
+                        if (INJ) { const uint32_t e = pEdge[32 * (j0 + u)]; uu = e != 0xffffffffu ? inj_flat[e] : 0.5; }
+                        const double dice = cum2 * uu;
+                        // first v with dice < cum[v] (Multinomial.cpp:92-99); dice < cum[2] always holds (u < 1)
+                        // (a 32-bit uniform; an injected double can round up to cum[2]: the value is then kept)
+                        const bool q0 = dice < cum0, q1 = dice < cum1;
+                        uint32_t ns = q0 ? 0u : (q1 ? 1u : 2u);
+                        if (INJ && !(dice < cum2)) ns = s;
+                        add_if(cw.x, 1u << (8 * u), ns == 0);                              // Multinomial.cpp:101-105 as counts
+                        add_if(cw.y, 1u << (8 * u), ns == 2);
+                        const uint32_t x = s ^ ns;
+                        if (x) {
+                            chg4 |= x << (2 * u);
+                            A = ns == 0 ? Ar * f : Ar;
+                            Bq = ns != 1 ? Br * f : Br;
+                            n = nR + (ns != 1);
+                            const uint32_t tp = net.tfpos_of_slot[gb + lane + 32 * (j0 + u)];
+                            GBN_CHECK(tp < net.E);
+                            atomicXor(gStfp + (tp >> 4), x << (2 * (tp & 15)));
+                        }
+                    }
+                }
+                __stcs(pC + 32 * (b0 + b), cw);                      // streamed: the product cache stays in L2
+                chg |= chg4 << (8 * b);
+                sw >>= 8; mw >>= 8;
+            }
+            if (chg) pSw[8 * b0] = sw0 ^ chg;
         }
     }
-    GBN_CHECK(n + (y * D) < 3 * D && n <= deg);
+    GBN_CHECK(n + (y * D) < 3 * D);
     if (valid) {
-        ch.tc2[((size_t) (c / XQ) * nH + dt) * XQ + (c % XQ)] =
-            make_double2(cot[n].y * A, cot[n].y * Bq);                     // {beta, gamma}, interleaved by chain bundle
+        ch.tc2[((size_t) (c / XQ) * (nH + 1) + dt) * XQ + (c % XQ)] =
+            make_double2(cot[n].y * A, cot[n].y * Bq);                 // {beta, gamma}, interleaved by chain bundle
         ch.ny[(size_t) c * nH + dt] = (uint16_t) (y * D + n);          // index into the X phase tables
     }
 }
 
-// Stf from S (refresh only): one thread per position of the by-TF list, so the writes are consecutive
+// ---- conversions between the byte view of S (ch.S: parity hooks, state get / set, checkpoints, strict kernel)
+// and the packed views the fast sweep works on
+// S bytes -> 2-bit words (after creation, set_state, checkpoint load)
+__global__ void k_pack_s(DevNet net, DevChains ch)
+{
+    const uint32_t c = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= net.nSw) return;
+    const uint32_t row = i >> 5, lane = i & 31, g = net.sw_grp[row];
+    const uint32_t jw = row - (net.sbase[g] >> 5), gb = net.gbase[g], W = (net.gbase[g + 1] - gb) >> 5;
+    const uint8_t *S = ch.S + (size_t) c * net.Ep + gb + lane;
+    uint32_t w = 0;
+    for (uint32_t u = 0; u < 16; u++) {
+        const uint32_t j = 16 * jw + u;
+        const uint32_t code = j < W ? S[32 * j] : 1u;
+        GBN_CHECK(code <= 2);
+        w |= code << (2 * u);
+    }
+    ch.Sw[(size_t) c * net.nSw + i] = w;
+}
+
+// 2-bit words -> S bytes (before anything reads ch.S after a fast sweep)
+__global__ void k_unpack_s(DevNet net, DevChains ch)
+{
+    const uint32_t c = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= net.nSw) return;
+    const uint32_t row = i >> 5, lane = i & 31, g = net.sw_grp[row];
+    const uint32_t jw = row - (net.sbase[g] >> 5), gb = net.gbase[g], W = (net.gbase[g + 1] - gb) >> 5;
+    uint8_t *S = ch.S + (size_t) c * net.Ep + gb + lane;
+    const uint32_t w = ch.Sw[(size_t) c * net.nSw + i];
+    for (uint32_t u = 0; u < 16; u++) {
+        const uint32_t j = 16 * jw + u;
+        if (j < W) S[32 * j] = (uint8_t) ((w >> (2 * u)) & 3u);
+    }
+}
+
+// per-batch 8-bit counts -> 32-bit totals (Multinomial.cpp:101-105 as counts); dC is left at zero
+__global__ void k_fold_counts(DevNet net, DevChains ch)
+{
+    const uint32_t c = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= net.nD) return;
+    uint2 *pd = ch.dC + (size_t) c * net.nD + i;
+    const uint2 dv = *pd;
+    if ((dv.x | dv.y) == 0) return;
+    const uint32_t row = i >> 5, lane = i & 31, g = net.dblk_grp[row];
+    const uint32_t jb = row - (net.dbase[g] >> 5), gb = net.gbase[g], W = (net.gbase[g + 1] - gb) >> 5;
+    uint2 *cS = ch.cS + (size_t) c * net.Ep + gb + lane;
+#pragma unroll
+    for (uint32_t u = 0; u < 4; u++) {
+        const uint32_t j = 4 * jb + u;
+        const uint32_t d0 = (dv.x >> (8 * u)) & 0xffu, d2 = (dv.y >> (8 * u)) & 0xffu;
+        if (j < W && (d0 | d2)) {
+            uint2 t = cS[32 * j];
+            t.x += d0; t.y += d2;
+            cS[32 * j] = t;
+        }
+    }
+    *pd = make_uint2(0u, 0u);
+}
+
+// Stfp from S (refresh only): one thread per word of the by-TF list
 __global__ void k_fast_stf(DevNet net, DevChains ch)
 {
     const uint32_t c = blockIdx.y;
-    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= net.E) return;
-    GBN_CHECK(net.tf_slot[pos] < net.Ep);
-    ch.Stf[(size_t) c * net.E + pos] = ch.S[(size_t) c * net.Ep + net.tf_slot[pos]];
+    const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nStfW = (net.E + 15) >> 4;
+    if (wi >= nStfW) return;
+    uint32_t w = 0;
+    for (uint32_t u = 0; u < 16; u++) {
+        const uint32_t pos = 16 * wi + u;
+        uint32_t code = 1u;
+        if (pos < net.E) { GBN_CHECK(net.tf_slot[pos] < net.Ep); code = ch.S[(size_t) c * net.Ep + net.tf_slot[pos]]; }
+        w |= code << (2 * u);
+    }
+    ch.Stfp[(size_t) c * nStfW + wi] = w;
 }
 
 }  // namespace
@@ -710,10 +833,10 @@ static int check(cudaError_t e, const char **err)
     return 0;
 }
 
-// shared memory of the S kernel: the per-dataset tables and, when it fits, FXp of the chain
+// shared memory of the S kernel: the per-dataset tables, the prior rows and, when it fits, FXp of the chain
 static size_t s_smem_bytes(const DevNet &net, bool stage_fx)
 {
-    return sizeof(double2) * 3 * (size_t) net.stab_D + (stage_fx ? sizeof(double2) * (size_t) net.nX : 0) + 16;
+    return sizeof(double2) * 3 * (size_t) net.stab_D + 16 * sizeof(double) + (stage_fx ? sizeof(double2) * (size_t) net.nX : 0) + 16;
 }
 
 static bool s_stage_fx(const DevNet &net)
@@ -722,13 +845,13 @@ static bool s_stage_fx(const DevNet &net)
     return want != 2 && sizeof(double2) * (size_t) net.nX <= 48 * 1024;
 }
 
-// shared memory of the X kernel (XQ chains per CTA): tables, by-TF pointers, X and - when it fits - the
-// (n, y) index of every target
+// shared memory of the X kernel (XQ chains per CTA): flip multipliers of a window, tables, by-TF pointers, X and
+// - when it fits - the (n, y) index of every target
 static size_t x_smem_bytes(const DevNet &net, bool ny_smem)
 {
     const size_t nX = net.nX, nXr = (nX + 3) & ~(size_t) 3, Q = XQ;
-    return sizeof(double) * Q * 3 * (size_t) net.stab_D + 4 * ((nX + 4) & ~(size_t) 3) + Q * nXr
-           + (ny_smem ? 2 * (size_t) net.nH * Q : 0) + 16;
+    return sizeof(double2) * 64 * Q * 4 + sizeof(double) * Q * (3 * (size_t) net.stab_D + 2) + 4 * ((nX + 4) & ~(size_t) 3) + Q * nXr
+           + (ny_smem ? 2 * ((size_t) net.nH + 1) * Q : 0) + 16;
 }
 static bool x_ny_smem(const DevNet &net)
 {
@@ -748,11 +871,11 @@ bool fast_uses_x_stream(const DevNet &net) { return !net.const_params && env_u32
 
 bool fast_supported(const DevNet &net, const char **why)
 {
-    if (net.nX >= (1u << 30)) { *why = "n_tf does not fit the packed parent id"; return false; }
+    if (net.nX > 65535) { *why = "n_tf does not fit the 16-bit parent id"; return false; }
     if (s_smem_bytes(net, s_stage_fx(net)) > 200 * 1024) { *why = "in-degree too large for the S-phase tables"; return false; }
     if (net.Eu != net.E) { *why = "duplicate (TF, target) edges"; return false; }
     if (x_smem_bytes(net, false) + 256 > 200 * 1024) { *why = "n_tf too large for the X window kernel's shared memory"; return false; }
-    if (3 * (size_t) net.stab_D > 65535) { *why = "in-degree does not fit the 16-bit (y, n) table index"; return false; }
+    if (3 * (size_t) net.stab_D + 1 > 65535) { *why = "in-degree does not fit the 16-bit (y, n) table index"; return false; }
     return true;
 }
 
@@ -774,15 +897,34 @@ static int launch_s(const DevNet &net, const DevChains &ch, const SweepArgs &a, 
     return stage ? launch_s_t<0, true, false>(net, ch, a, nc, st, err) : launch_s_t<0, false, false>(net, ch, a, nc, st, err);
 }
 
-int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err, bool stf_valid)
+int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err)
 {
     if (ch.n_chains == 0) return 0;
-    SweepArgs a{ 0, 0, 0, 0, 0 };
-    if (!stf_valid) k_fast_stf<<<dim3((net.E + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
+    SweepArgs a = sweep_args(net);
+    k_pack_s<<<dim3((net.nSw + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
+    k_fast_stf<<<dim3(((net.E + 15) / 16 + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
     k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, 0, ch.T, 1);
     if (launch_s(net, ch, a, 1, ch.n_chains, st, err)) return -1;
     if (check(cudaGetLastError(), err)) return -1;
-    return 3;
+    return 4;
+}
+
+// ch.S (bytes) from the packed words the fast sweep keeps current
+int launch_fast_unpack(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err)
+{
+    if (ch.n_chains == 0) return 0;
+    k_unpack_s<<<dim3((net.nSw + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
+    if (check(cudaGetLastError(), err)) return -1;
+    return 1;
+}
+
+// per-batch 8-bit outcome counts of the S nodes -> the 32-bit totals in ch.cS
+int launch_fast_fold(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err)
+{
+    if (ch.n_chains == 0) return 0;
+    k_fold_counts<<<dim3((net.nD + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
+    if (check(cudaGetLastError(), err)) return -1;
+    return 1;
 }
 
 int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
@@ -824,7 +966,7 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
     DevChains chl = ch;
     const dim3 grid_t((net.nX + FT_NT - 1) / FT_NT, nchains);
     for (uint32_t sw = 0; sw < n_sweeps; sw++) {
-        SweepArgs a;
+        SweepArgs a = sweep_args(net);
         a.sweep = sweep0 + sw;
         a.stat_n = stat_n0 + sw + 1;
         a.use_inj = (ch.inj_flat != nullptr && (ch.inj_pos + sw) < ch.inj_sweeps) ? 1 : 0;

@@ -63,6 +63,16 @@ struct Topology {
     std::vector<uint32_t> n_h_child;                // edges per TF (GraphORNOR.cpp:206-211)
     std::vector<uint8_t> x_prior_active;            // per TF
     std::vector<double> t_a, t_b, t_mean, t_lnB;    // per TF
+    // packed views of the same slots for the fast S kernel (sweep_fast.cu): a lane's steps j = 0 .. W-1 are
+    // grouped into words of 16 steps (2-bit S codes / prior rows) and blocks of 4 steps (16-bit parent ids,
+    // 8-bit per-batch counter pairs):
+    //     S word      sbase[g] + 32 * (j / 16) + lane,  code at bits 2 (j % 16)
+    //     block       dbase[g] + 32 * (j / 4) + lane,   entry j % 4
+    std::vector<uint32_t> sbase, dbase;             // [n_groups+1]
+    std::vector<uint32_t> sw_grp, dblk_grp;         // group of every row of 32 words / 32 blocks
+    std::vector<uint32_t> mor2;                     // [nSw] prior row per step, 3 = pad (row {0, 1, 0}: never moves)
+    std::vector<uint16_t> par16;                    // [4 nD] parent TF per step (0 for pads)
+    uint32_t nSw = 0, nD = 0;
 
     uint32_t slot(uint32_t dt, uint32_t j) const { return gbase[dt >> 5] + 32 * j + (dt & 31); }
 };
@@ -183,6 +193,28 @@ inline Topology compile_topology(uint32_t n_edge, const uint32_t *src, const uin
             }
         }
     }
+    // packed views (fast S kernel)
+    tp.sbase.assign(tp.n_groups + 1, 0); tp.dbase.assign(tp.n_groups + 1, 0);
+    for (uint32_t g = 0; g < tp.n_groups; g++) {
+        const uint32_t w = (tp.gbase[g + 1] - tp.gbase[g]) >> 5;
+        tp.sbase[g + 1] = tp.sbase[g] + 32 * ((w + 15) / 16);
+        tp.dbase[g + 1] = tp.dbase[g] + 32 * ((w + 3) / 4);
+        for (uint32_t r = 0; r < (w + 15) / 16; r++) tp.sw_grp.push_back(g);
+        for (uint32_t r = 0; r < (w + 3) / 4; r++) tp.dblk_grp.push_back(g);
+    }
+    tp.nSw = tp.sbase[tp.n_groups]; tp.nD = tp.dbase[tp.n_groups];
+    tp.mor2.assign(tp.nSw, 0xffffffffu);
+    tp.par16.assign(4 * (size_t) tp.nD, 0);
+    if (nX <= 65536)
+        for (uint32_t dt = 0; dt < nH; dt++) {
+            const uint32_t g = dt >> 5, lane = dt & 31;
+            for (uint32_t j = 0; j < tp.deg[dt]; j++) {
+                const uint32_t q = tp.slot(dt, j);
+                uint32_t &mw = tp.mor2[tp.sbase[g] + 32 * (j / 16) + lane];
+                mw = (mw & ~(3u << (2 * (j % 16)))) | ((uint32_t) tp.mor_idx[q] << (2 * (j % 16)));
+                tp.par16[4 * (size_t) (tp.dbase[g] + 32 * (j / 4) + lane) + (j % 4)] = (uint16_t) tp.par_tf[q];
+            }
+        }
     tp.x_prior_active.assign(nX, 0);
     for (uint32_t i = 0; i < n_active; i++) {
         uint32_t k = rank_of(tp.tf_uid, active_tf[i]);

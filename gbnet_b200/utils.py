@@ -28,7 +28,12 @@ def _fisher_greater(a, b, c, d):
     P(X >= a) with X ~ Hypergeom(a + b + c + d, a + b, a + c)."""
     from scipy.stats import hypergeom
     a, b, c, d = (np.asarray(v, np.int64) for v in (a, b, c, d))
-    return hypergeom.sf(a - 1, a + b + c + d, a + b, a + c)
+    total = a + b + c + d
+    # an all-zero table (a TF none of whose signed edges reaches a DE target) has p = 1 in fisher_exact;
+    # the survival function of an empty population is NaN
+    with np.errstate(invalid="ignore"):
+        p = hypergeom.sf(a - 1, np.maximum(total, 1), a + b, a + c)
+    return np.where(total == 0, 1.0, p)
 
 
 def get_tests(evid, rels):

@@ -107,6 +107,26 @@ def test_get_tests_matches_fisher_exact():
         assert row.trg_tot == len(trg)
 
 
+def test_get_tests_empty_tables_give_p_one():
+    """A TF whose 2x2 table is all zeros (no DE target behind a signed edge, or only edges of type 0) gets
+    p = 1 from fisher_exact (reference gbnet/utils.py:36-52), not NaN."""
+    import pandas as pd
+    from scipy.stats import fisher_exact
+    from gbnet_b200 import utils
+    # TF 0: signed edges to DE targets; TF 1: all of its targets are non-DE; TF 2: edges of type 0 only
+    rels = pd.DataFrame({"srcuid": [0, 0, 0, 1, 1, 2, 2], "trguid": [10, 11, 12, 12, 13, 10, 11],
+                         "type": [1, -1, 1, 1, -1, 0, 0]})
+    evid = pd.DataFrame({"uid": [10, 11, 12, 13], "val": [1, -1, 0, 0]})
+    tests = utils.get_tests(evid, rels)
+    assert not tests[["enrichment", "mor_binary", "combined"]].isna().any().any()
+    for uid in (1, 2):
+        row = tests.loc[uid]
+        assert (row.morp_degp, row.morn_degp, row.morp_degn, row.morn_degn) == (0, 0, 0, 0)
+        assert row.mor_binary == 1.0 == fisher_exact([[0, 0], [0, 0]], alternative="greater")[1]
+    rho = tests.loc[1].enrichment * 1.0
+    assert abs(tests.loc[1].combined - rho * (1 - np.log(rho))) < 1e-15
+
+
 # ---- the C++ topology / evidence compiler behind gbn_model_create, through its host-only probe ----------
 
 def _probe(src, trg, mor, evid_trg=None, evid_val=None, comp_yprob=False):
