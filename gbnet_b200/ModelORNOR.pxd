@@ -50,6 +50,7 @@ cdef extern from "gbnet_b200.h":
         uint32_t n_graphs_local
         uint32_t chain_offset
         uint32_t n_stats
+        uint32_t simulation
     void gbn_params_default(gbn_params *p)
     const char *gbn_last_error()
     int gbn_model_create(const gbn_network *net, const gbn_evidence *ev, const gbn_params *p, gbn_model **out)

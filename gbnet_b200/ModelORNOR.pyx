@@ -17,7 +17,7 @@ from libc.string cimport memset
 
 cdef class PyModelORNOR:
     cdef gbn_model *h
-    cdef object _tf_symbols, _edges, _const_params
+    cdef object _tf_symbols, _trg_symbols, _edges, _const_params, _simulation
 
     def __cinit__(self, ents, rels, evid=None, set active_tf_set_py=set(),
                   sprior=None, z_alpha=25., z_beta=25., z0_alpha=None, z0_beta=None, t_alpha=2., t_beta=2.,
@@ -31,6 +31,7 @@ cdef class PyModelORNOR:
         m = marshal_frames(ents, rels, evid, active_tf_set_py)
         sprior_py = check_sprior(sprior)
         self._tf_symbols, self._edges, self._const_params = m["tf_symbols"], m["edges"], bool(const_params)
+        self._trg_symbols, self._simulation = m["trg_symbols"], False
 
         cdef uint32_t[::1] src = np.ascontiguousarray(m["src"], np.uint32)
         cdef uint32_t[::1] trg = np.ascontiguousarray(m["trg"], np.uint32)
@@ -70,12 +71,20 @@ cdef class PyModelORNOR:
             msg = gbn_last_error().decode()
             # the reference's ctor is `except +`: out_of_range -> IndexError, invalid_argument -> ValueError
             raise {-1: ValueError, -3: NotImplementedError}.get(rc, RuntimeError)(msg)
+        cdef gbn_dims dims
+        self._check(gbn_model_dims(self.h, &dims))
+        self._simulation = dims.simulation != 0
 
     cdef _check(self, int rc):
         if rc != 0:
             raise RuntimeError(gbn_last_error().decode())
 
     def _node_ids(self):
+        if self._simulation:          # evid=None: H and Y per target, then T (GraphORNOR.cpp:89-106)
+            ids = [[k, t] for t in self._trg_symbols for k in ("H", "Y")]
+            if not self._const_params:
+                ids += [["T", s] for s in self._tf_symbols]
+            return ids
         ids = [["X", s] for s in self._tf_symbols]
         if not self._const_params:
             ids += [["T", s] for s in self._tf_symbols]
@@ -114,7 +123,7 @@ cdef class PyModelORNOR:
         self._check(gbn_model_burn_stats(self.h))
 
     cdef _posterior(self, var_name, bint want_sd):
-        per = {"X": 2, "T": 1, "S": 3}.get(var_name)
+        per = {"X": 2, "T": 1, "S": 3, "H": 3, "Y": 3}.get(var_name)
         if per is None:
             return []
         cdef uint32_t n = 0

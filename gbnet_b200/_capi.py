@@ -126,7 +126,9 @@ def load():
     path = _build.LIB
     try:
         _build.build_native()
-    except Exception as exc:  # no nvcc here (GPU box with a prebuilt .so), or a compile error
+    except _build.CompileError:
+        raise                 # the sources do not compile: never fall back to a stale library
+    except Exception as exc:  # no nvcc here (a box with only the prebuilt .so)
         if not os.path.exists(path):
             raise ImportError(f"libgbnet_b200.so is missing and could not be built ({exc}); "
                               "gbnet_b200 has no CPU fallback") from exc

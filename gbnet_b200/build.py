@@ -19,10 +19,14 @@ CSRC = os.path.join(HERE, "csrc")
 VARIANT = os.environ.get("GBN_LIB_VARIANT", "")
 LIB = os.path.join(HERE, "libgbnet_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 SOURCES = ["capi.cu", "eval_kernels.cu", "sweep_strict.cu", "sweep_fast.cu", "sim_kernels.cu", "moments.cu"]
-HEADERS = ["device_math.cuh", "device_model.cuh", "kernels.cuh", "topology.hpp",
+HEADERS = ["device_math.cuh", "device_model.cuh", "kernels.cuh", "topology.hpp", "fast_common.cuh",
            os.path.join("..", "..", "include", "gbnet_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
+
+
+class CompileError(RuntimeError):
+    """nvcc ran and rejected the sources (as opposed to: nvcc is not installed here)."""
 
 
 def _stale() -> bool:
@@ -81,7 +85,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         elif verbose or out.strip():
             sys.stderr.write(f"--- nvcc {src} ---\n{out}\n")
     if failed:
-        raise RuntimeError("nvcc failed")
+        raise CompileError("nvcc failed")
     cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"]
     subprocess.run(cmd, check=True)
     return LIB

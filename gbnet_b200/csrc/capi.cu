@@ -50,6 +50,24 @@ static void sigint_handler(int signum) { g_signal = signum; }
 extern "C" void gbn_set_signal(int signum) { g_signal = signum; }
 extern "C" void gbn_install_sigint_handler(void) { std::signal(SIGINT, sigint_handler); }
 
+// The reference installs its SIGINT handler in the ModelBase ctor (ModelBase.cpp:40) and keeps it for the
+// life of the process, which takes KeyboardInterrupt away from Python.  Here the handler is installed for
+// the duration of a sampling call only: Ctrl-C stops the loop after the current batch (the reference's poll
+// point, ModelBase.cpp:121), the previous handler is put back, and the signal is raised again for it - so
+// the caller's own handler (Python: KeyboardInterrupt) still runs once the call has returned.
+namespace {
+struct SigintScope {
+    void (*prev)(int);
+    SigintScope() : prev(std::signal(SIGINT, sigint_handler)) {}
+    ~SigintScope()
+    {
+        std::signal(SIGINT, prev == SIG_ERR ? SIG_DFL : prev);
+        if (g_signal == SIGINT && prev != SIG_ERR && prev != SIG_IGN && prev != SIG_DFL && prev != sigint_handler) std::raise(SIGINT);
+        g_signal = 0;                  // clearSignal(), ModelBase.cpp:126
+    }
+};
+}  // namespace
+
 extern "C" int gbn_device_count(void)
 {
     int n = 0;
@@ -108,6 +126,7 @@ struct gbn_model {
     uint8_t *d_y = nullptr; double *d_yprob = nullptr, *d_stab = nullptr;
     double *d_inj_flat = nullptr, *d_inj_beta = nullptr, *d_inj_exp = nullptr;
     double *d_sums = nullptr, *d_psums = nullptr, *d_dev = nullptr, *d_pdev = nullptr, *d_gr = nullptr, *d_max = nullptr;
+    double *d_tsum = nullptr, *d_tdev = nullptr;      // T nodes: the two small buffers that cross the ranks
     unsigned long long *d_isums = nullptr;
     double *d_scratch = nullptr; size_t scratch_bytes = 0;
     bool moments_valid = false;
@@ -259,6 +278,8 @@ int upload_evidence(gbn_model *m, const gbn_evidence *ev)
             for (int cls = 0; cls < 2; cls++) {
                 double z = cls ? m->net.z_n : m->net.z_y, v = 1.;
                 for (uint32_t n = 0; n < D; n++) { t[(5 + cls) * D + n] = v; t[(3 + cls) * D + n] = 1. - v; v *= (1. - z); }
+                v = 1.;
+                for (uint32_t n = 0; n < D; n++) { t[(13 + cls) * D + n] = v; v *= z; }     // z^n: the factor product of n inactive parents
             }
             for (int y = 0; y < 3; y++) {
                 const int cls = (y != 1) ? 0 : 1;
@@ -311,20 +332,19 @@ int allreduce(gbn_model *m, void *buf, size_t n, int op, int dtype = NCCL_FLOAT6
 int compute_moments(gbn_model *m)
 {
     if (m->moments_valid) return 0;
-    const size_t ns = (size_t) m->n_datasets * n_stats_of(m->net);
     const double N = (double) m->stat_n;
     // counts of the discrete nodes overflow the exact integer path only beyond M * N^2 >= 2^63
     if ((double) m->n_graphs * N * N >= 9.0e18) return fail(GBN_ERR_UNSUPPORTED, "chain length too large for the exact moment sums");
     if (int rc = fold_counts(m)) return rc;
-    launch_count_sums(m->net, m->ch, N, m->d_isums, m->stream);
-    launch_moment_sums(m->net, m->ch, N, m->d_sums, m->d_psums, m->stream);
-    if (int rc = allreduce(m, m->d_isums, 4 * ns, NCCL_SUM, NCCL_UINT64)) return rc;
-    if (int rc = allreduce(m, m->d_sums, 2 * ns, NCCL_SUM)) return rc;
-    if (int rc = allreduce(m, m->d_psums, ns, NCCL_SUM)) return rc;
-    launch_moment_devs(m->net, m->ch, N, m->d_sums, m->d_psums, m->d_dev, m->d_pdev, m->stream);
-    if (int rc = allreduce(m, m->d_dev, ns, NCCL_SUM)) return rc;
-    if (int rc = allreduce(m, m->d_pdev, ns, NCCL_SUM)) return rc;
-    launch_expand_counts(m->net, N, m->d_isums, m->d_sums, m->d_psums, m->d_dev, m->d_pdev, m->stream);
+    // one u64 all-reduce of the stored counts' sums, two small fp64 ones for the T nodes (3 nX, then 2 nX)
+    const size_t nt = (size_t) m->n_datasets * n_t_of(m->net);
+    launch_count_sums(m->net, m->ch, m->d_isums, m->stream);
+    launch_moment_sums(m->net, m->ch, N, m->d_tsum, m->stream);
+    if (int rc = allreduce(m, m->d_isums, (size_t) m->n_datasets * moment_isum_words(m->net), NCCL_SUM, NCCL_UINT64)) return rc;
+    if (nt) if (int rc = allreduce(m, m->d_tsum, 3 * nt, NCCL_SUM)) return rc;
+    launch_moment_devs(m->net, m->ch, N, m->d_tsum, m->d_tdev, m->stream);
+    if (nt) if (int rc = allreduce(m, m->d_tdev, 2 * nt, NCCL_SUM)) return rc;
+    launch_expand_counts(m->net, N, m->d_isums, m->d_tsum, m->d_tdev, m->d_sums, m->d_psums, m->d_dev, m->d_pdev, m->stream);
     m->launches += m->net.const_params ? 2 : 4;
     CUDA_TRY(cudaGetLastError());
     m->moments_valid = true;
@@ -547,7 +567,8 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         UP(tf_ptr, tp.tf_ptr, u32) UP(tf_child, tp.tf_child, u32) UP(tf_slot, tp.tf_slot, u32)
         UP(tfpos_of_slot, tp.tfpos_of_slot, u32) UP(par_pack, tp.par_pack, u32)
         UP(sbase, tp.sbase, u32) UP(dbase, tp.dbase, u32) UP(sw_grp, tp.sw_grp, u32) UP(dblk_grp, tp.dblk_grp, u32)
-        UP(mor2, tp.mor2, u32)
+        UP(mor2, tp.mor2, u32) UP(tf_abit, tp.tf_abit, u32)
+        { uint32_t *t4 = nullptr; if (int rc = dev_upload(m, &t4, tp.tfpos4)) return bail(rc); n.tfpos4 = reinterpret_cast<const uint4 *>(t4); }
         { uint16_t *u16 = nullptr; if (int rc = dev_upload(m, &u16, tp.par16)) return bail(rc); n.par16 = reinterpret_cast<const uint2 *>(u16); }
         n.nSw = tp.nSw; n.nD = tp.nD;
         UP(x_prior_active, tp.x_prior_active, u8)
@@ -559,6 +580,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     std::memcpy(n.xprob, xprob, sizeof xprob);
     std::memcpy(n.ynoise, ynoise, sizeof ynoise);
     std::memcpy(n.sprob, p->sprior, sizeof(double) * 9);                              // GraphORNOR.cpp:25
+    n.sprob[3][0] = 0.; n.sprob[3][1] = 1.; n.sprob[3][2] = 0.;                       // pad steps of the fast S kernel: never move
     n.z_y = p->z_alpha / (p->z_alpha + p->z_beta);                                    // GraphORNOR.cpp:155-164
     n.z_n = p->z0_alpha / (p->z0_alpha + p->z0_beta);
     n.n_datasets = m->n_datasets; n.n_graphs_local = m->n_graphs_local; n.chain_offset = m->chain_offset; n.n_graphs = m->n_graphs;
@@ -608,6 +630,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         if (cudaMemset(ch.tc2, 0, sizeof(double2) * n_tc2) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "cudaMemset failed"));
         if (int rc = dev_alloc(m, &ch.ny, C * nH)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.Sw, C * tp.nSw)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.Aw, C * tp.nSw)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.dC, C * tp.nD)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.Stfp, C * ((E + 15) / 16))) return bail(rc);
         if (int rc = dev_alloc(m, &ch.xU, C * ((nX + 3) & ~(size_t) 3))) return bail(rc);
@@ -618,7 +641,9 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     if (int rc = dev_alloc(m, &m->d_psums, ns)) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_dev, ns)) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_pdev, ns)) return bail(rc);
-    if (int rc = dev_alloc(m, &m->d_isums, 4 * ns)) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_isums, (size_t) m->n_datasets * moment_isum_words(n))) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_tsum, 3 * (size_t) m->n_datasets * n_t_of(n))) return bail(rc);
+    if (int rc = dev_alloc(m, &m->d_tdev, 2 * (size_t) m->n_datasets * n_t_of(n))) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_gr, (size_t) n_nodes_of(n))) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_max, (size_t) m->n_datasets)) return bail(rc);
 
@@ -677,6 +702,7 @@ static int collect_phase_times(gbn_model *m)
 extern "C" int gbn_model_sample_n(gbn_model *m, uint32_t n)
 {
     if (!m) return fail(GBN_ERR_INVALID, "null model");
+    if (n == 0) { m->last_ms = 0.; return 0; }
     if (int rc = use_device(m)) return rc;
     if (int rc = sample_n(m, n)) return rc;
     CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -718,6 +744,10 @@ extern "C" int gbn_model_sample(gbn_model *m, uint32_t N, uint32_t dN)
 {
     if (!m) return fail(GBN_ERR_INVALID, "null model");
     if (int rc = use_device(m)) return rc;
+    m->last_ms = 0.;
+    if (N == 0) return 0;
+    if (dN == 0) return fail(GBN_ERR_INVALID, "deltaN must be positive (the reference's loop would never end)");
+    SigintScope sigint;
     double total_ms = 0.;
     uint32_t n;
     double gr = std::numeric_limits<double>::infinity();
@@ -731,9 +761,8 @@ extern "C" int gbn_model_sample(gbn_model *m, uint32_t N, uint32_t dN)
         dN = std::min(dN, N - n);
         n += dN;
         if (int rc = max_gelman_rubin(m, &gr)) return rc;
-        if (dN == 0) break;        // the reference would spin forever on dN = 0; stop instead
+        if (dN == 0) break;        // N - n reached 0: the for-condition ends the loop
     }
-    g_signal = 0;                  // clearSignal(), ModelBase.cpp:126
     m->last_ms = total_ms;
     return 0;
 }

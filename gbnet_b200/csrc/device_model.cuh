@@ -21,7 +21,7 @@
 
 namespace gbn {
 
-constexpr uint32_t STAB_ROWS = 13;
+constexpr uint32_t STAB_ROWS = 15;
 
 struct DevNet {
     uint32_t nX, nH, E, Eu;
@@ -47,16 +47,18 @@ struct DevNet {
     const uint32_t *dblk_grp;     // [nD / 32]   group of every row of 32 blocks
     const uint32_t *mor2;         // [nSw] prior row per step (3 = pad)
     const uint2 *par16;           // [nD]  four 16-bit parent TFs per block
+    const uint4 *tfpos4;          // [nD]  by-TF CSR position of the block's four steps (UINT32_MAX for pads)
+    const uint32_t *tf_abit;      // [Eu]  by-TF position -> 16 * (S word of the edge) + step inside the word
     uint32_t nSw, nD;
     const uint8_t *x_prior_active;// [nX]
     const double *t_a, *t_b, *t_mean, *t_lnB;   // [nX]
     const uint8_t *y;             // [n_datasets][nH]
     const double *yprob;          // [n_datasets][3]
     const double *stab;           // [n_datasets][STAB_ROWS][stab_D] fast-path tables over n: c0[y=0..2], omz[cls], zc[cls],
-                                  // A[y] = omz (N2 - N0), B[y] = omz (N1 - N2)
+                                  // A[y] = omz (N2 - N0), B[y] = omz (N1 - N2), z^n[cls]
     uint32_t stab_D;              // max_indeg + 2 rounded up to even
     double xprob[2][2];           // [prior_active][v]   GraphORNOR.h:40-41
-    double sprob[3][3];           // [mor+1][v]          GraphORNOR.cpp:25
+    double sprob[4][3];           // [mor+1][v]          GraphORNOR.cpp:25; row 3 = {0, 1, 0}: pad steps of the fast S kernel
     double ynoise[3][3];          // [h][y]              GraphORNOR.h:46-48
     double z_y, z_n;              // ZY / ZN constants   GraphORNOR.cpp:155-164
     uint32_t n_datasets, n_graphs_local, chain_offset, n_graphs;
@@ -79,6 +81,8 @@ struct DevChains {
     uint16_t *ny;                 // [c][nH] y * stab_D + n, n = number of parents with S != 1
     uint32_t *Sw;                 // [c][nSw] S as 2-bit codes, 16 steps per word: what the fast sweep reads and writes
                                   // (ch.S is refreshed from it on demand, capi.cu)
+    uint32_t *Aw;                 // [c][nSw] bit u of a word: the parent TF of step u of the matching S word is active (X = 1);
+                                  // kept current by the X kernel's flip patch, so the S kernel looks a TF's factor up only then
     uint2 *dC;                    // [c][nD] per-batch counts {S=0, S=2} of four steps as 4 x u8 each, folded into cS
                                   // before anything reads the statistics (and before a byte could overflow)
     uint32_t *Stfp;               // [c][ceil(E / 16)] copy of S in by-TF CSR order, 2-bit codes (coalesced reads in the X phase)

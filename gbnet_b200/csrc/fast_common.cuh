@@ -1,0 +1,100 @@
+// Helpers shared by the fast-path kernels (sweep_fast.cu: networks of any size, state in HBM; sweep_small.cu:
+// networks that fit one SM's shared memory, one persistent CTA per chain).
+#pragma once
+
+#include <cstdio>
+#include <cstdint>
+
+#include "device_model.cuh"
+#include "device_math.cuh"
+
+// Bounds checks of every data-dependent index, compiled in by the "chk" build variant
+// (GBN_LIB_VARIANT=chk; compute-sanitizer is closed on this pool): a violation traps the kernel.
+#ifdef GBN_BOUNDS
+#define GBN_CHECK(cond) do { if (!(cond)) { printf("GBN_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define GBN_CHECK(cond) do { } while (0)
+#endif
+
+namespace gbn {
+
+namespace {
+
+struct SweepArgs {
+    uint32_t sweep;                  // absolute sweep index (Philox counter word)
+    uint32_t stat_n;                 // statistics count AFTER this sweep
+    uint32_t use_inj;                // 1: injected draws, row inj_row
+    uint32_t inj_row;                // sweep row inside the injection arrays
+    uint32_t chain0;                 // first local chain of this launch (chains are split over streams)
+    uint32_t rk0[10], rk1[10];       // Philox round keys (seed words bumped by the Weyl constants): as kernel
+                                     // parameters they are constant-bank operands of the round's XOR
+};
+
+inline SweepArgs sweep_args(const DevNet &net)
+{
+    SweepArgs a{};
+    uint32_t k0 = (uint32_t) net.seed, k1 = (uint32_t) (net.seed >> 32);
+    for (int r = 0; r < 10; r++) { a.rk0[r] = k0; a.rk1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return a;
+}
+
+// philox4x32_10 (device_math.cuh) with the key schedule taken from the kernel parameters
+__device__ __forceinline__ u32x4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const SweepArgs &a)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ a.rk0[r];
+        const uint32_t n2 = hi0 ^ c3 ^ a.rk1[r];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    return u32x4{ c0, c1, c2, c3 };
+}
+
+// n += k under a predicate as ONE predicated instruction (the compiler's own choice for `if (p) n += k;` is an
+// add and a select; for a double multiply it insists on the select, so there is no mul_if)
+__device__ __forceinline__ void add_if(uint32_t &a, uint32_t k, bool p)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q add.u32 %0, %0, %1;\n\t}" : "+r"(a) : "r"(k), "r"((int) p));
+}
+
+// 2-bit S code at position pos of a packed array (16 codes per word)
+__device__ __forceinline__ uint32_t code_at(const uint32_t *w, uint32_t pos) { return (w[pos >> 4] >> (2 * (pos & 15))) & 3u; }
+
+// m * 2^e -> mantissa in [0.5, 1) and the exponent moved into e (frexp).  Likelihood products are
+// positive normal numbers, so the exponent field is rewritten directly; zero / subnormal / inf / nan
+// take the library path.
+// out of line on purpose: inlined, the library path's instructions are issued (predicated off) by every call
+__device__ __noinline__ double frexp_rare(double m, int *ex) { return frexp(m, ex); }
+
+__device__ __forceinline__ void normalise(double &m, int &e)
+{
+    const int hi = __double2hiint(m);
+    const int ef = (hi >> 20) & 0x7ff;
+    if (ef != 0 && ef != 0x7ff) {
+        e += ef - 1022;
+        m = __hiloint2double((hi & 0x800fffff) | (1022 << 20), __double2loint(m));
+    } else {
+        int ex;
+        m = frexp_rare(m, &ex);
+        e += ex;
+    }
+}
+
+// the two outcome likelihoods a * 2^ea and b * 2^eb (a, b in [0.25, 2)) brought to one scale.  Only
+// their ratio matters for the draw, except that the reference falls back to the prior when both
+// underflow (Multinomial.cpp:78-85) and rounds subnormals: near the bottom of the double range the
+// exact ldexp is used, elsewhere the smaller one is scaled by 2^(difference) with a bit pattern.
+__device__ __forceinline__ void common_scale(double a, int ea, double b, int eb, double &la, double &lb)
+{
+    const int emax = ea > eb ? ea : eb;
+    if (emax < -960) { la = ldexp(a, ea); lb = ldexp(b, eb); return; }
+    const int da = ea - emax, db = eb - emax;                       // one is 0, the other <= 0
+    la = da < -1000 ? 0. : a * __hiloint2double((1023 + da) << 20, 0);
+    lb = db < -1000 ? 0. : b * __hiloint2double((1023 + db) << 20, 0);
+}
+
+}  // namespace
+
+}  // namespace gbn

@@ -58,18 +58,16 @@ void launch_sim_export_draws(const DevNet &net, uint32_t gchain, uint32_t sweep0
                              double *flat_u, double *beta_v, double *exp_v, cudaStream_t st);
 
 // ---- moments.cu (K5): cross-chain moments -> Gelman-Rubin and posterior summaries
-// pass 1: sums[d][stat][0] = sum_k mean_k, [1] = sum_k var_k over the LOCAL chains of dataset d;
-//         psums[d][stat] = sum of mean_k over local chains whose GLOBAL index is >= 1
-void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double *sums, double *psums, cudaStream_t st);
-// pass 2: dev[d][stat] = sum_k (mean_k - mu)^2 with mu = sums[..][0] / M ;
-//         pdev[d][stat] = sum over global chains >= 1 of (mean_k - pmu)^2, pmu = psums / (M - 1)
-void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const double *sums, const double *psums,
-                        double *dev, double *pdev, cudaStream_t st);
-// discrete nodes: isums[d][stat] = { sum c, sum c^2, the same over global chains >= 1 } (u64, exact);
-// after the all-reduce, launch_expand_counts fills sums / psums / dev / pdev for those stats
-void launch_count_sums(const DevNet &net, const DevChains &ch, double N, unsigned long long *isums, cudaStream_t st);
-void launch_expand_counts(const DevNet &net, double N, const unsigned long long *isums, double *sums, double *psums,
-                          double *dev, double *pdev, cudaStream_t st);
+// T nodes, pass 1: tsum[d][k] = { sum_k mean_k, sum_k var_k, sum of mean_k over local chains whose GLOBAL index is >= 1 }
+void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double *tsum, cudaStream_t st);
+// T nodes, pass 2: tdev[d][k] = { sum_k (mean_k - mu)^2, sum over global chains >= 1 of (mean_k - pmu)^2 }
+void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const double *tsum, double *tdev, cudaStream_t st);
+// discrete nodes: exact u64 sums of the STORED counts (layout in moments.cu; moment_isum_words() words per dataset);
+// after the all-reduces, launch_expand_counts fills sums / psums / dev / pdev of every statistic
+size_t moment_isum_words(const DevNet &net);
+void launch_count_sums(const DevNet &net, const DevChains &ch, unsigned long long *isums, cudaStream_t st);
+void launch_expand_counts(const DevNet &net, double N, const unsigned long long *isums, const double *tsum, const double *tdev,
+                          double *sums, double *psums, double *dev, double *pdev, cudaStream_t st);
 // finalize: Gelman-Rubin per node (random_nodes order) of dataset d, and its maximum
 void launch_gelman_rubin(const DevNet &net, double N, const double *sums, const double *dev,
                          uint32_t dataset, double *gr_out /* [n_nodes] or NULL */, double *max_out /* [n_datasets] */,

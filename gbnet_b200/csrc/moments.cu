@@ -6,8 +6,8 @@
 // discrete nodes these follow exactly from the outcome counts: mean = c/N and
 // variance = sum (x - mean)^2 / (N-1) = c (N-c) / N / (N-1).  For T they are the Welford pair.
 // The cross-chain reduction distributes over ranks.  Discrete nodes (X, S: all but nX of the
-// statistics) use exact integer sums of the counts in one pass (k_count_sums / k_expand_counts);
-// the continuous T nodes use two floating-point passes:
+// statistics) use exact integer sums of the counts in one pass (k_count_sums / k_expand_counts: one
+// u64 all-reduce); the continuous T nodes use two floating-point passes over 3 nX and 2 nX doubles:
 //   pass 1  sum_k mean_kj, sum_k variance_kj                     (-> all-reduce, sum)
 //   pass 2  sum_k (mean_kj - mu_j)^2                             (-> all-reduce, sum)
 //   final   B = N * pass2 / (M-1), W = pass1.var / M, Vhat, R    (every rank, redundantly)
@@ -88,10 +88,10 @@ __device__ __forceinline__ void node_moments(const DevNet &net, const DevChains 
 // chain slices: lane = node (consecutive addresses), each slice sums every MS_SL-th chain, and the slices
 // are added up in a fixed order, so the result does not depend on the launch.
 constexpr int MS_SL = 16;
-__global__ void __launch_bounds__(32 * MS_SL) k_moment_sums(DevNet net, DevChains ch, double N, double *sums, double *psums, uint32_t n0, uint32_t n1)
+// tsum[d][k] = { sum_k mean, sum_k var, sum of mean over local chains whose GLOBAL index is >= 1 }
+__global__ void __launch_bounds__(32 * MS_SL) k_moment_sums(DevNet net, DevChains ch, double N, double *tsum, uint32_t n0, uint32_t n1)
 {
     __shared__ double s_part[3][MS_SL][32];
-    const uint32_t n_stats = n_stats_of(net);
     const uint32_t d = blockIdx.y;
     const uint32_t lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const uint32_t n = n0 + blockIdx.x * 32 + lane;
@@ -110,26 +110,25 @@ __global__ void __launch_bounds__(32 * MS_SL) k_moment_sums(DevNet net, DevChain
     if (sl == 0 && live) {
         sm = sv = ps = 0.;
         for (int q = 0; q < MS_SL; q++) { sm += s_part[0][q][lane]; sv += s_part[1][q][lane]; ps += s_part[2][q][lane]; }
-        const size_t o = (size_t) d * n_stats + r.stat0;
-        sums[2 * o] = sm; sums[2 * o + 1] = sv;
-        psums[o] = ps;
+        double *o = tsum + 3 * ((size_t) d * (n1 - n0) + (n - n0));
+        o[0] = sm; o[1] = sv; o[2] = ps;
     }
 }
 
-__global__ void __launch_bounds__(32 * MS_SL) k_moment_devs(DevNet net, DevChains ch, double N, const double *sums, const double *psums,
-                                                            double *dev, double *pdev, uint32_t n0, uint32_t n1)
+// tdev[d][k] = { sum_k (mean_k - mu)^2, the same over global chains >= 1 around their own mean }
+__global__ void __launch_bounds__(32 * MS_SL) k_moment_devs(DevNet net, DevChains ch, double N, const double *tsum, double *tdev,
+                                                            uint32_t n0, uint32_t n1)
 {
     __shared__ double s_part[2][MS_SL][32];
-    const uint32_t n_stats = n_stats_of(net);
     const uint32_t d = blockIdx.y;
     const uint32_t lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const uint32_t n = n0 + blockIdx.x * 32 + lane;
     const bool live = n < n1;
     const NodeRef r = node_ref(net, live ? n : n0);
     const double M = (double) net.n_graphs;
-    const size_t o = (size_t) d * n_stats + r.stat0;
-    const double mu = sums[2 * o] / M;
-    const double pmu = M > 1. ? psums[o] / (M - 1.) : 0.;
+    const size_t o = (size_t) d * (n1 - n0) + ((live ? n : n0) - n0);
+    const double mu = tsum[3 * o] / M;
+    const double pmu = M > 1. ? tsum[3 * o + 2] / (M - 1.) : 0.;
     double dv = 0., pd = 0.;
     if (live)
         for (uint32_t l = sl; l < net.n_graphs_local; l += MS_SL) {
@@ -144,8 +143,8 @@ __global__ void __launch_bounds__(32 * MS_SL) k_moment_devs(DevNet net, DevChain
     if (sl == 0 && live) {
         dv = pd = 0.;
         for (int q = 0; q < MS_SL; q++) { dv += s_part[0][q][lane]; pd += s_part[1][q][lane]; }
-        dev[o] = dv;
-        pdev[o] = pd;
+        tdev[2 * o] = dv;
+        tdev[2 * o + 1] = pd;
     }
 }
 
@@ -154,79 +153,95 @@ __global__ void __launch_bounds__(32 * MS_SL) k_moment_devs(DevNet net, DevChain
 // sum_k var_k = (N S1 - S2) / (N (N-1)), sum_k (mean_k - mu)^2 = (M S2 - S1^2) / (M N^2), with
 // S1 = sum c_k, S2 = sum c_k^2 - integers, so ONE pass over the counters and ONE all-reduce give the
 // between- and within-chain terms exactly (no second pass, no fp64 division per chain and slot).
-// isums[d][stat] = { S1, S2, P1, P2 }, P* restricted to GLOBAL chains >= 1 (posterior getters).
-__device__ __forceinline__ void acc_count(unsigned long long *a, unsigned long long c, bool post)
-{
-    a[0] += c; a[1] += c * c;
-    if (post) { a[2] += c; a[3] += c * c; }
-}
+//
+// What crosses the ranks (the one exchange step of the path) is kept to what the
+// STORED counters determine: an X node stores the count of outcome 1, an S (H, Y) node the counts a, b of
+// outcomes 0 and 2; the complementary outcome follows from c = N - (stored).  Per dataset:
+//     X_k :  { S1, S2, z }                      S1 = sum c, S2 = sum c^2 over the local chains
+//     S_e :  { A1, A2, B1, B2, AB, z }          AB = sum a b (the cross term the complement's S2 needs)
+// z carries the counts of GLOBAL chain 0 (zero on every rank but the one that owns it; a | b << 32 for S):
+// the posterior getters skip that chain (ModelBase.cpp:172,197), and "all chains minus chain 0" replaces a
+// second set of sums.  C3: 6 x 301,038 + 3 x 1,500 u64 = 14.5 MB per check (round 1: 28.9 MB + 36 MB of doubles).
+constexpr uint32_t IS_X = 3, IS_S = 6;
+__host__ __device__ inline size_t isum_words(const DevNet &n) { return n.sim ? (size_t) IS_S * 2 * n.nH : (size_t) IS_X * n.nX + (size_t) IS_S * n.E; }
 
-__global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long N, unsigned long long *isums)
+__global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long *isums)
 {
-    const uint32_t n_stats = n_stats_of(net);
-    const uint32_t nT = net.const_params ? 0 : net.nX;
     const uint32_t d = blockIdx.y;
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;          // X_k for w < nX, then slots
     if (w >= (net.sim ? 2 * net.nH : net.nX + net.Ep)) return;
-    unsigned long long acc[3][4] = { { 0 } };
-    uint32_t stat0, ns;
-    if (net.sim) {                                                      // H_dt for w < nH, then Y_dt
-        const uint32_t isY = w >= net.nH, dt = w - (isY ? net.nH : 0);
-        stat0 = 6 * net.ref_of_dt[dt] + 3 * isY; ns = 3;
-        const uint2 *cnt = isY ? ch.cY : ch.cH;
-        for (uint32_t l = 0; l < net.n_graphs_local; l++) {
-            const uint2 cs = cnt[(size_t) (d * net.n_graphs_local + l) * net.nH + dt];
-            const bool post = (net.chain_offset + l) >= 1;
-            acc_count(acc[0], cs.x, post);
-            acc_count(acc[1], N - cs.x - cs.y, post);
-            acc_count(acc[2], cs.y, post);
-        }
-    } else if (w < net.nX) {
-        stat0 = 2 * w; ns = 2;
+    unsigned long long *out = isums + (size_t) d * isum_words(net);
+    if (!net.sim && w < net.nX) {
+        unsigned long long s1 = 0, s2 = 0, z = 0;
         for (uint32_t l = 0; l < net.n_graphs_local; l++) {
             const unsigned long long c1 = ch.cX1[(size_t) (d * net.n_graphs_local + l) * net.nX + w];
-            const bool post = (net.chain_offset + l) >= 1;
-            acc_count(acc[0], N - c1, post);
-            acc_count(acc[1], c1, post);
+            s1 += c1; s2 += c1 * c1;
+            if (net.chain_offset + l == 0) z = c1;
         }
+        out[IS_X * w] = s1; out[IS_X * w + 1] = s2; out[IS_X * w + 2] = z;
+        return;
+    }
+    const uint2 *cnt;
+    size_t stride, idx, o;
+    if (net.sim) {                                                      // H_dt for w < nH, then Y_dt
+        const uint32_t isY = w >= net.nH, dt = w - (isY ? net.nH : 0);
+        cnt = isY ? ch.cY : ch.cH; stride = net.nH; idx = dt;
+        o = (size_t) IS_S * (2 * net.ref_of_dt[dt] + isY);
     } else {
-        const uint32_t q = w - net.nX;
-        const uint32_t e = net.par_edge[q];
+        const uint32_t q = w - net.nX, e = net.par_edge[q];
         if (e == 0xffffffffu) return;                                   // pad slot
-        stat0 = 2 * net.nX + nT + 3 * e; ns = 3;
-        for (uint32_t l = 0; l < net.n_graphs_local; l++) {
-            const uint2 cs = ch.cS[(size_t) (d * net.n_graphs_local + l) * net.Ep + q];
-            const bool post = (net.chain_offset + l) >= 1;
-            acc_count(acc[0], cs.x, post);
-            acc_count(acc[1], N - cs.x - cs.y, post);
-            acc_count(acc[2], cs.y, post);
-        }
+        cnt = ch.cS; stride = net.Ep; idx = q;
+        o = (size_t) IS_X * net.nX + (size_t) IS_S * e;
     }
-    for (uint32_t j = 0; j < ns; j++) {
-        unsigned long long *o = isums + 4 * ((size_t) d * n_stats + stat0 + j);
-        o[0] = acc[j][0]; o[1] = acc[j][1]; o[2] = acc[j][2]; o[3] = acc[j][3];
+    unsigned long long a1 = 0, a2 = 0, b1 = 0, b2 = 0, ab = 0, z = 0;
+    for (uint32_t l = 0; l < net.n_graphs_local; l++) {
+        const uint2 cs = cnt[(size_t) (d * net.n_graphs_local + l) * stride + idx];
+        const unsigned long long a = cs.x, b = cs.y;
+        a1 += a; a2 += a * a; b1 += b; b2 += b * b; ab += a * b;
+        if (net.chain_offset + l == 0) z = a | (b << 32);
     }
+    out[o] = a1; out[o + 1] = a2; out[o + 2] = b1; out[o + 3] = b2; out[o + 4] = ab; out[o + 5] = z;
 }
 
-// globally reduced integer sums -> the same four quantities the float path produces
-__global__ void k_expand_counts(DevNet net, double Nd, const unsigned long long *isums,
+// globally reduced sums -> per statistic: sums = {sum mean, sum var}, psums = sum of means over chains >= 1,
+// dev / pdev = sums of squared deviations of the chain means (all chains / chains >= 1)
+__global__ void k_expand_counts(DevNet net, double Nd, const unsigned long long *isums, const double *tsum, const double *tdev,
                                 double *sums, double *psums, double *dev, double *pdev)
 {
+    typedef unsigned __int128 u128;
     const uint32_t n_stats = n_stats_of(net);
     const uint32_t nT = net.const_params ? 0 : net.nX;
     const uint32_t d = blockIdx.y;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_stats) return;
-    const uint32_t t0 = net.sim ? 6 * net.nH : 2 * net.nX;
-    if (j >= t0 && j < t0 + nT) return;                                 // T stats: float path
     const size_t o = (size_t) d * n_stats + j;
-    const unsigned long long *a = isums + 4 * o;
-    const unsigned __int128 S1 = a[0], S2 = a[1], P1 = a[2], P2 = a[3];
-    const unsigned __int128 N = (unsigned __int128) (unsigned long long) Nd, M = net.n_graphs;
+    const uint32_t t0 = net.sim ? 6 * net.nH : 2 * net.nX;
+    if (j >= t0 && j < t0 + nT) {                                       // T statistics: the two floating-point passes
+        const size_t q = (size_t) d * nT + (j - t0);
+        sums[2 * o] = tsum[3 * q]; sums[2 * o + 1] = tsum[3 * q + 1]; psums[o] = tsum[3 * q + 2];
+        dev[o] = tdev[2 * q]; pdev[o] = tdev[2 * q + 1];
+        return;
+    }
+    const unsigned long long *in = isums + (size_t) d * isum_words(net);
+    const u128 N = (u128) (unsigned long long) Nd, M = net.n_graphs;
+    u128 S1, S2, c0;                                                    // over all chains; c0 = the count in global chain 0
+    if (!net.sim && j < 2 * net.nX) {
+        const unsigned long long *a = in + (size_t) IS_X * (j >> 1);
+        S1 = a[0]; S2 = a[1]; c0 = a[2];
+        if ((j & 1) == 0) { S2 = M * N * N - 2 * N * S1 + S2; S1 = M * N - S1; c0 = N - c0; }       // outcome 0: c = N - c1
+    } else {
+        const uint32_t js = net.sim ? j : j - 2 * net.nX - nT, node = js / 3, v = js - 3 * node;
+        const unsigned long long *a = in + (net.sim ? 0 : (size_t) IS_X * net.nX) + (size_t) IS_S * node;
+        const u128 A1 = a[0], A2 = a[1], B1 = a[2], B2 = a[3], AB = a[4], za = a[5] & 0xffffffffull, zb = a[5] >> 32;
+        if (v == 0) { S1 = A1; S2 = A2; c0 = za; }
+        else if (v == 2) { S1 = B1; S2 = B2; c0 = zb; }
+        else { S1 = M * N - A1 - B1; S2 = M * N * N - 2 * N * (A1 + B1) + A2 + B2 + 2 * AB; c0 = N - za - zb; }   // c = N - a - b
+    }
+    const u128 P1 = S1 - c0, P2 = S2 - c0 * c0;                         // chains 1 .. M-1
     const double M_d = (double) net.n_graphs, n_d = M_d - 1.;
-    sums[2 * o] = (double) a[0] / Nd;
+    sums[2 * o] = (double) S1 / Nd;
     sums[2 * o + 1] = Nd > 1. ? (double) (N * S1 - S2) / (Nd * (Nd - 1.)) : 0.;
-    psums[o] = (double) a[2] / Nd;
+    psums[o] = (double) P1 / Nd;
     dev[o] = (double) (M * S2 - S1 * S1) / (M_d * Nd * Nd);
     pdev[o] = n_d >= 1. ? (double) ((M - 1) * P2 - P1 * P1) / (n_d * Nd * Nd) : 0.;
 }
@@ -280,36 +295,37 @@ __global__ void k_node_moments(DevNet net, DevChains ch, uint32_t c, double N, d
 
 }  // namespace
 
-void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double *sums, double *psums, cudaStream_t st)
+void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double *tsum, cudaStream_t st)
 {
     const uint32_t nT = net.const_params ? 0 : net.nX;                  // T nodes only: the rest is k_count_sums
     if (nT == 0) return;
     dim3 grid((nT + 31) / 32, net.n_datasets);
     const uint32_t n0 = net.sim ? 2 * net.nH : net.nX;                  // first T work item
-    k_moment_sums<<<grid, 32 * MS_SL, 0, st>>>(net, ch, N, sums, psums, n0, n0 + nT);
+    k_moment_sums<<<grid, 32 * MS_SL, 0, st>>>(net, ch, N, tsum, n0, n0 + nT);
 }
 
-void launch_count_sums(const DevNet &net, const DevChains &ch, double N, unsigned long long *isums, cudaStream_t st)
+size_t moment_isum_words(const DevNet &net) { return isum_words(net); }
+
+void launch_count_sums(const DevNet &net, const DevChains &ch, unsigned long long *isums, cudaStream_t st)
 {
     dim3 grid(((net.sim ? 2 * net.nH : net.nX + net.Ep) + 127) / 128, net.n_datasets);
-    k_count_sums<<<grid, 128, 0, st>>>(net, ch, (unsigned long long) N, isums);
+    k_count_sums<<<grid, 128, 0, st>>>(net, ch, isums);
 }
 
-void launch_expand_counts(const DevNet &net, double N, const unsigned long long *isums, double *sums, double *psums,
-                          double *dev, double *pdev, cudaStream_t st)
+void launch_expand_counts(const DevNet &net, double N, const unsigned long long *isums, const double *tsum, const double *tdev,
+                          double *sums, double *psums, double *dev, double *pdev, cudaStream_t st)
 {
     dim3 grid((n_stats_of(net) + 127) / 128, net.n_datasets);
-    k_expand_counts<<<grid, 128, 0, st>>>(net, N, isums, sums, psums, dev, pdev);
+    k_expand_counts<<<grid, 128, 0, st>>>(net, N, isums, tsum, tdev, sums, psums, dev, pdev);
 }
 
-void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const double *sums, const double *psums,
-                        double *dev, double *pdev, cudaStream_t st)
+void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const double *tsum, double *tdev, cudaStream_t st)
 {
     const uint32_t nT = net.const_params ? 0 : net.nX;                  // T nodes only
     if (nT == 0) return;
     dim3 grid((nT + 31) / 32, net.n_datasets);
     const uint32_t n0 = net.sim ? 2 * net.nH : net.nX;
-    k_moment_devs<<<grid, 32 * MS_SL, 0, st>>>(net, ch, N, sums, psums, dev, pdev, n0, n0 + nT);
+    k_moment_devs<<<grid, 32 * MS_SL, 0, st>>>(net, ch, N, tsum, tdev, n0, n0 + nT);
 }
 
 void launch_gelman_rubin(const DevNet &net, double N, const double *sums, const double *dev,

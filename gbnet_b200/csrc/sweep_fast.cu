@@ -43,14 +43,7 @@
 #include <utility>
 
 #include "topology.hpp"
-
-// Bounds checks of every data-dependent index, compiled in by the "chk" build variant
-// (GBN_LIB_VARIANT=chk; compute-sanitizer is closed on this pool): a violation traps the kernel.
-#ifdef GBN_BOUNDS
-#define GBN_CHECK(cond) do { if (!(cond)) { printf("GBN_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
-#else
-#define GBN_CHECK(cond) do { } while (0)
-#endif
+#include "fast_common.cuh"
 
 namespace gbn {
 
@@ -64,7 +57,7 @@ constexpr int FX_NT = GBN_X_NT;      // X kernel: one warp per TF of the specula
 #define GBN_XQ 2
 #endif
 #ifndef GBN_XU
-#define GBN_XU 2
+#define GBN_XU 4
 #endif
 constexpr int XU = GBN_XU;           // X kernel: independent gathers per lane and pipeline stage
 constexpr int XQ = GBN_XQ;           // X kernel: chains per CTA = chains interleaved in the product cache (power of two)
@@ -73,85 +66,6 @@ constexpr int XQ = GBN_XQ;           // X kernel: chains per CTA = chains interl
 #endif
 constexpr int FS_NT = GBN_S_NT;      // S kernel: one warp = one group of 32 targets
 constexpr int FT_NT = 128;           // T kernel
-
-struct SweepArgs {
-    uint32_t sweep;                  // absolute sweep index (Philox counter word)
-    uint32_t stat_n;                 // statistics count AFTER this sweep
-    uint32_t use_inj;                // 1: injected draws, row inj_row
-    uint32_t inj_row;                // sweep row inside the injection arrays
-    uint32_t chain0;                 // first local chain of this launch (chains are split over streams)
-    uint32_t rk0[10], rk1[10];       // Philox round keys (seed words bumped by the Weyl constants): as kernel
-                                     // parameters they are constant-bank operands of the round's XOR
-};
-
-static SweepArgs sweep_args(const DevNet &net)
-{
-    SweepArgs a{};
-    uint32_t k0 = (uint32_t) net.seed, k1 = (uint32_t) (net.seed >> 32);
-    for (int r = 0; r < 10; r++) { a.rk0[r] = k0; a.rk1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
-    return a;
-}
-
-// philox4x32_10 (device_math.cuh) with the key schedule taken from the kernel parameters
-__device__ __forceinline__ u32x4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const SweepArgs &a)
-{
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ a.rk0[r];
-        const uint32_t n2 = hi0 ^ c3 ^ a.rk1[r];
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    }
-    return u32x4{ c0, c1, c2, c3 };
-}
-
-// a *= f / n += k under a predicate, as ONE predicated instruction: the compiler turns `if (p) a *= f;` into a
-// multiply and two selects (three instructions for one), and the S kernel's edge loop is bound by issue
-__device__ __forceinline__ void mul_if(double &a, double f, bool p)
-{
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mul.rn.f64 %0, %0, %1;\n\t}" : "+d"(a) : "d"(f), "r"((int) p));
-}
-__device__ __forceinline__ void add_if(uint32_t &a, uint32_t k, bool p)
-{
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q add.u32 %0, %0, %1;\n\t}" : "+r"(a) : "r"(k), "r"((int) p));
-}
-
-// 2-bit S code at position pos of a packed array (16 codes per word)
-__device__ __forceinline__ uint32_t code_at(const uint32_t *w, uint32_t pos) { return (w[pos >> 4] >> (2 * (pos & 15))) & 3u; }
-
-// m * 2^e -> mantissa in [0.5, 1) and the exponent moved into e (frexp).  Likelihood products are
-// positive normal numbers, so the exponent field is rewritten directly; zero / subnormal / inf / nan
-// take the library path.
-// out of line on purpose: inlined, the library path's instructions are issued (predicated off) by every call
-__device__ __noinline__ double frexp_rare(double m, int *ex) { return frexp(m, ex); }
-
-__device__ __forceinline__ void normalise(double &m, int &e)
-{
-    const int hi = __double2hiint(m);
-    const int ef = (hi >> 20) & 0x7ff;
-    if (ef != 0 && ef != 0x7ff) {
-        e += ef - 1022;
-        m = __hiloint2double((hi & 0x800fffff) | (1022 << 20), __double2loint(m));
-    } else {
-        int ex;
-        m = frexp_rare(m, &ex);
-        e += ex;
-    }
-}
-
-// the two outcome likelihoods a * 2^ea and b * 2^eb (a, b in [0.25, 2)) brought to one scale.  Only
-// their ratio matters for the draw, except that the reference falls back to the prior when both
-// underflow (Multinomial.cpp:78-85) and rounds subnormals: near the bottom of the double range the
-// exact ldexp is used, elsewhere the smaller one is scaled by 2^(difference) with a bit pattern.
-__device__ __forceinline__ void common_scale(double a, int ea, double b, int eb, double &la, double &lb)
-{
-    const int emax = ea > eb ? ea : eb;
-    if (emax < -960) { la = ldexp(a, ea); lb = ldexp(b, eb); return; }
-    const int da = ea - emax, db = eb - emax;                       // one is 0, the other <= 0
-    la = da < -1000 ? 0. : a * __hiloint2double((1023 + da) << 20, 0);
-    lb = db < -1000 ? 0. : b * __hiloint2double((1023 + db) << 20, 0);
-}
 
 // ---------------------------------------------------------------------------------- X phase
 // One CTA sweeps the X nodes of XQ chains (a "bundle": chains XQ p .. XQ p + XQ - 1).  The kernel is bound
@@ -180,7 +94,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     __shared__ uint32_t s_dec[W];                                            // per window position: chains of the bundle that flipped
     const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;
     const uint32_t nXr = (nX + 3) & ~3u, C0N = 3 * D + 2, nStfW = (net.E + 15) >> 4;
-    double2 *sMul = reinterpret_cast<double2 *>(smem_x);                     // [W][Q][4] flip multipliers by S code
+    double2 *sMul = reinterpret_cast<double2 *>(smem_x);                     // [W][Q][4] ([0].x: flip factor of the (TF, chain))
     double *xC0all = reinterpret_cast<double *>(sMul + W * Q * 4);           // [Q][C0N] c0 by idx = y * D + n; [3 D] = 1 (dummy)
     uint32_t *sPtr = reinterpret_cast<uint32_t *>(xC0all + Q * C0N);         // [nX + 1 rounded up to 4] tf_ptr
     uint8_t *sX = reinterpret_cast<uint8_t *>(sPtr + ((nX + 4) & ~3u));      // [Q][nX rounded up to 4] value | prior class << 1
@@ -266,10 +180,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             // {beta, gamma} (S = 0), nothing (S = 1) or gamma only (S = 2)
             double fac = g;
             if (xcur) fac = 1. / g;
-            if (cs == 0) {
-                mul[0] = make_double2(fac, fac); mul[1] = make_double2(1., 1.); mul[2] = make_double2(1., fac);
-            }
-            __syncwarp();
+            if (cs == 0) mul[0] = make_double2(fac, fac);                     // read by the flip patch below
             double mc = 1., mf = 1.;
             int ec = 0, ef = 0, cnt = 0;
             for (; trips > 0; trips--) {
@@ -287,7 +198,9 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     GBN_CHECK(nyv[u] <= 3 * D);
-                    const double2 m = mul[sh[u]];
+                    // flip multipliers {m_beta, m_gamma} by S code (selects: a shared-memory row per (TF, chain) costs
+                    // four more L1 wavefronts per trip, measured 0.53 against 0.49 ms per sweep)
+                    const double2 m = make_double2(sh[u] == 0 ? fac : 1., sh[u] != 1 ? fac : 1.);
                     const double c0 = xC0[nyv[u]];
                     const double Lc = c0 + (bg[u].x + bg[u].y);
                     const double Lf = c0 + __fma_rn(m.x, bg[u].x, m.y * bg[u].y);
@@ -340,7 +253,12 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
                 if (!((fmask >> q) & 1u)) continue;
                 const double fq = sMul[(first * Q + q) * 4].x;
                 const uint32_t *gS = ch.Stfp + (size_t) (cbase + q) * nStfW;
+                uint32_t *gA = ch.Aw + (size_t) (cbase + q) * net.nSw;
                 for (uint32_t c2 = fb0 + tid; c2 < fe0; c2 += NT) {
+                    // the S kernel's "parent is active" bit of this edge follows the flip (whatever the edge's code)
+                    const uint32_t ab = net.tf_abit[c2];
+                    GBN_CHECK((ab >> 4) < net.nSw);
+                    atomicXor(gA + (ab >> 4), 1u << (ab & 15));
                     const uint32_t s = code_at(gS, c2);
                     if (s == 1) continue;
                     double2 *e = tcb + (size_t) net.tf_child[c2] * Q + q;
@@ -585,31 +503,27 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
 #ifndef GBN_S_MINB
 #define GBN_S_MINB 4          // 64 registers: 4 CTAs (32 warps) per SM measured best in round 1 (profiles/r1_summary.md)
 #endif
-template <int MODE, bool STAGE_FX, bool INJ>
+template <int MODE, bool INJ, bool PF>
 __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevChains ch, SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;
     double2 *sTab = reinterpret_cast<double2 *>(smem_raw);                      // [3][D] {c0[y][n], omz[class of y][n]}
-    double *sSp = reinterpret_cast<double *>(sTab + 3 * D);                     // [4][4] prior rows by code; row 3 = pad {0, 1, 0}
-    double2 *sFX = reinterpret_cast<double2 *>(sSp + 16);                       // [nX] if staged
+    double *sZp = reinterpret_cast<double *>(sTab + 3 * D);                     // [2][D] z^m by noise class
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t c = blockIdx.y + a.chain0;
     const uint32_t d = chain_dataset(net, c);
     const double2 *gFX = ch.FXp + (size_t) c * nX;
-    for (uint32_t j = tid; j < 3 * D; j += FS_NT) {
+    {
         const double *tab = net.stab + (size_t) d * STAB_ROWS * D;
-        const uint32_t yy = j / D, nn = j - yy * D;
-        sTab[j] = make_double2(tab[j], tab[(3 + (yy != 1 ? 0 : 1)) * D + nn]);
+        for (uint32_t j = tid; j < 3 * D; j += FS_NT) {
+            const uint32_t yy = j / D, nn = j - yy * D;
+            sTab[j] = make_double2(tab[j], tab[(3 + (yy != 1 ? 0 : 1)) * D + nn]);
+        }
+        for (uint32_t j = tid; j < 2 * D; j += FS_NT) sZp[j] = tab[13 * D + j];
     }
-    if (tid < 16) {
-        const uint32_t r = tid >> 2, v = tid & 3;
-        sSp[tid] = r < 3 ? (v < 3 ? net.sprob[r][v] : 0.) : (v == 1 ? 1. : 0.);
-    }
-    if (STAGE_FX) for (uint32_t k = tid; k < nX; k += FS_NT) sFX[k] = gFX[k];
     __syncthreads();
-    const double2 *fxp = STAGE_FX ? sFX : gFX;
 
     const uint32_t g = blockIdx.x * (FS_NT / 32) + (tid >> 5);
     if (g >= net.n_groups) return;
@@ -624,7 +538,8 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
     const double cb = net.ynoise[1][y] - net.ynoise[2][y];          // b
     const double2 *cot = sTab + y * D;                              // {c0, omz} over n for this target's y
     uint32_t *pSw = ch.Sw + (size_t) c * net.nSw + net.sbase[g] + lane;
-    const uint2 *pPar = net.par16 + net.dbase[g] + lane;
+    const uint32_t *pAw = ch.Aw + (size_t) c * net.nSw + net.sbase[g] + lane;
+    const uint16_t *pPar = reinterpret_cast<const uint16_t *>(net.par16 + net.dbase[g] + lane);   // step j: [128 (j / 4) + j % 4]
     const uint32_t W4 = (W + 3) >> 2;                                // 4-step blocks (the last may hold pads)
 
     if (MODE == 0) {
@@ -632,28 +547,33 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
         const uint2 *pc = ch.dC + (size_t) c * net.nD + net.dbase[g] + lane;
         for (uint32_t b = 0; b < W4; b++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + 32 * b));
     }
-    // products over the parents in append_parent order (HNodeORNOR.cpp:55-62, 72-81): A = a pr0, Bq = b pr0 pr2
-    // so that L = c0[n] + omz[n] (A + Bq) and the a, b constants stay out of the edge loop; pads hold S = 1
+    // Products over the parents (HNodeORNOR.cpp:55-62, 72-81): A = a pr0, Bq = b pr0 pr2, so that
+    // L = c0[n] + omz[n] (A + Bq) and the a, b constants stay out of the edge loop.  An inactive TF contributes
+    // the constant factor z (1 - t*0 = 1 exactly), so the products are z^(number of edges with that code) - two
+    // population counts per word of 16 steps - times the factors 1 - t of the ACTIVE parents, which the mask
+    // words name (about 1 % of the edges); pads hold S = 1.
     double A = ca, Bq = cb;
     uint32_t n = 0;
-    for (uint32_t b0 = 0; b0 < W4; b0 += 4) {
-        uint32_t sw = pSw[8 * b0];                                   // word b0 / 4 of this lane: 32 * (b0 / 4)
-        GBN_CHECK(net.sbase[g] + lane + 8 * b0 < net.nSw);
-        { const uint32_t x = sw ^ 0x55555555u; n += __popc((x | (x >> 1)) & 0x55555555u); }   // codes != 1
-        const uint32_t nb = min(4u, W4 - b0);
-        for (uint32_t b = 0; b < nb; b++) {
-            const uint2 pw = pPar[32 * (b0 + b)];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t s = sw & 3u;
-                sw >>= 2;
-                const uint32_t kk = (u & 1) ? ((u < 2 ? pw.x : pw.y) >> 16) : ((u < 2 ? pw.x : pw.y) & 0xffffu);
-                GBN_CHECK(kk < nX && s <= 2);
-                const double f = fxp[kk].x * z;
-                mul_if(A, f, s == 0);
-                mul_if(Bq, f, s != 1);
+    {
+        uint32_t n0 = 0;
+        for (uint32_t w = 0; 16 * w < W; w++) {
+            const uint32_t sw = pSw[32 * w];
+            GBN_CHECK(net.sbase[g] + lane + 32 * w < net.nSw);
+            const uint32_t x = sw ^ 0x55555555u;
+            n += __popc((x | (x >> 1)) & 0x55555555u);               // codes != 1
+            n0 += __popc(~(sw | (sw >> 1)) & 0x55555555u);           // codes == 0
+            for (uint32_t act = pAw[32 * w] & 0xffffu; act; act &= act - 1) {
+                const uint32_t u = __ffs(act) - 1, s = (sw >> (2 * u)) & 3u, j = 16 * w + u;
+                const uint32_t kk = pPar[128 * (j >> 2) + (j & 3)];
+                GBN_CHECK(kk < nX);
+                const double fx = __ldg(&gFX[kk].x);
+                if (s == 0) A *= fx;
+                if (s != 1) Bq *= fx;
             }
         }
+        GBN_CHECK(n < D && n0 <= n);
+        A *= sZp[cls * D + n0];
+        Bq *= sZp[cls * D + n];
     }
     if (MODE == 0) {
         const double rz = 1. / z;
@@ -662,34 +582,49 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
         const double *inj_flat = INJ ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + net.E) + nX : nullptr;
         const uint32_t *pEdge = net.par_edge + gb + lane;
         const uint32_t *pMor = net.mor2 + net.sbase[g] + lane;
+        const uint4 *pTp = net.tfpos4 + net.dbase[g] + lane;
         uint2 *pC = ch.dC + (size_t) c * net.nD + net.dbase[g] + lane;
         uint32_t *gStfp = ch.Stfp + (size_t) c * ((net.E + 15) >> 4);
-        for (uint32_t b0 = 0; b0 < W4; b0 += 4) {                    // one S word = up to four 4-step blocks
-            const uint32_t sw0 = pSw[8 * b0];
-            uint32_t sw = sw0, mw = pMor[8 * b0], chg = 0;
-            const uint32_t nb = min(4u, W4 - b0);
-            for (uint32_t b = 0; b < nb; b++) {
-                const uint32_t j0 = 4 * (b0 + b);
-                const uint2 pw = pPar[32 * (b0 + b)];
-                uint2 cw = __ldcs(pC + 32 * (b0 + b));
+        // blocks of four steps; every fourth block starts a new word of S codes / prior rows / activity bits.
+        // PF: the block's counters and by-TF positions are requested one block ahead
+        uint32_t sw0 = 0, sw = 0, mw = 0, aw = 0, chg = 0;
+        uint4 tp4n = make_uint4(0, 0, 0, 0);
+        uint2 cwn = make_uint2(0, 0);
+        if (PF) { tp4n = pTp[0]; cwn = __ldcs(pC); }
+        for (uint32_t bb = 0; bb < W4; bb++) {
+            {
+                if ((bb & 3u) == 0) { sw0 = pSw[8 * bb]; sw = sw0; mw = pMor[8 * bb]; aw = pAw[8 * bb]; chg = 0; }
+                const uint32_t j0 = 4 * bb;
+                uint4 tp4;
+                uint2 cw;
+                if (PF) {
+                    tp4 = tp4n; cw = cwn;
+                    if (bb + 1 < W4) { tp4n = pTp[32 * (bb + 1)]; cwn = __ldcs(pC + 32 * (bb + 1)); }
+                } else {
+                    tp4 = pTp[32 * bb]; cw = __ldcs(pC + 32 * bb);
+                }
                 u32x4 rnd = { 0, 0, 0, 0 };
-                if (!INJ) rnd = philox_rk(ref_i, a.sweep, gchain, KIND_S | ((b0 + b) << 8), a);
+                if (!INJ) rnd = philox_rk(ref_i, a.sweep, gchain, KIND_S | (bb << 8), a);
                 uint32_t chg4 = 0;
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (j0 + u < W) {                                // warp-uniform
                         const uint32_t s = (sw >> (2 * u)) & 3u, r = (mw >> (2 * u)) & 3u;
-                        const uint32_t kk = (u & 1) ? ((u < 2 ? pw.x : pw.y) >> 16) : ((u < 2 ? pw.x : pw.y) & 0xffffu);
-                        GBN_CHECK(kk < nX && s <= 2 && n + 1 < D);
-                        const double2 fx = fxp[kk];
-                        const double f = fx.x * z, finv = fx.y * rz;
+                        GBN_CHECK(s <= 2 && n + 1 < D);
+                        // f = (1 - t x) z and its reciprocal: z and 1 / z unless the parent TF is active
+                        double f = z, finv = rz;
+                        if ((aw >> u) & 1u) {
+                            const uint32_t kk = pPar[128 * bb + u];
+                            GBN_CHECK(kk < nX);
+                            const double2 fx = __ldg(gFX + kk);
+                            f = fx.x * z; finv = fx.y * rz;
+                        }
                         // the state without this edge
                         const double Af = A * finv, Bf = Bq * finv;
                         const double Ar = s == 0 ? Af : A, Br = s != 1 ? Bf : Bq;
                         const uint32_t nR = n - (s != 1);
                         const double2 t0 = cot[nR], t1 = cot[nR + 1];
-                        const double2 sp01 = *reinterpret_cast<const double2 *>(sSp + 4 * r);
-                        const double sp2 = sSp[4 * r + 2];
+                        const double *sp = net.sprob[r];             // constant bank, indexed (row 3: a pad step)
                         const double sum = Ar + Br;
                         // the file is compiled without FMA contraction (the reference's x86-64 build has none); these
                         // are explicit: this algebra differs from the reference's by rounding anyway (DESIGN.md
@@ -699,14 +634,14 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                         const double L2 = __fma_rn(t1.y, __fma_rn(f, Br, Ar), t1.x);       // S = 2: the factor joins pr2
                         // exp(log prior + log L) of Multinomial.cpp:66-75 as a product; the "0 +" and
                         // "0 * (1 - u)" terms of the reference's running sum / gsl_ran_flat add exact zeros
-                        double cum0 = sp01.x * L0;
-                        double cum1 = __fma_rn(sp01.y, L1, cum0);
-                        double cum2 = __fma_rn(sp2, L2, cum1);
+                        double cum0 = sp[0] * L0;
+                        double cum1 = __fma_rn(sp[1], L1, cum0);
+                        double cum2 = __fma_rn(sp[2], L2, cum1);
                         if (!(cum2 > 0.)) {                                                // Multinomial.cpp:78-85
                             // (L >= c0[n] > 0: only an all-zero or NaN prior row gets here.  Counted, so that the
                             // block stays a branch instead of six predicated instructions in the loop)
                             if (ch.dbg) atomicAdd(ch.dbg + 3, 1ull);
-                            cum0 = sp01.x; cum1 = cum0 + sp01.y; cum2 = cum1 + sp2;
+                            cum0 = sp[0]; cum1 = cum0 + sp[1]; cum2 = cum1 + sp[2];
                         }
                         const uint32_t word = u == 0 ? rnd.x : (u == 1 ? rnd.y : (u == 2 ? rnd.z : rnd.w));
                         double uu = unit_from_word(word);
@@ -725,17 +660,17 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                             A = ns == 0 ? Ar * f : Ar;
                             Bq = ns != 1 ? Br * f : Br;
                             n = nR + (ns != 1);
-                            const uint32_t tp = net.tfpos_of_slot[gb + lane + 32 * (j0 + u)];
+                            const uint32_t tp = u == 0 ? tp4.x : (u == 1 ? tp4.y : (u == 2 ? tp4.z : tp4.w));
                             GBN_CHECK(tp < net.E);
                             atomicXor(gStfp + (tp >> 4), x << (2 * (tp & 15)));
                         }
                     }
                 }
-                __stcs(pC + 32 * (b0 + b), cw);                      // streamed: the product cache stays in L2
-                chg |= chg4 << (8 * b);
-                sw >>= 8; mw >>= 8;
+                __stcs(pC + 32 * bb, cw);                            // streamed: the product cache stays in L2
+                chg |= chg4 << (8 * (bb & 3u));
+                sw >>= 8; mw >>= 8; aw >>= 4;
             }
-            if (chg) pSw[8 * b0] = sw0 ^ chg;
+            if (((bb & 3u) == 3 || bb + 1 == W4) && chg) pSw[8 * (bb & ~3u)] = sw0 ^ chg;
         }
     }
     GBN_CHECK(n + (y * D) < 3 * D);
@@ -757,14 +692,17 @@ __global__ void k_pack_s(DevNet net, DevChains ch)
     const uint32_t row = i >> 5, lane = i & 31, g = net.sw_grp[row];
     const uint32_t jw = row - (net.sbase[g] >> 5), gb = net.gbase[g], W = (net.gbase[g + 1] - gb) >> 5;
     const uint8_t *S = ch.S + (size_t) c * net.Ep + gb + lane;
-    uint32_t w = 0;
+    const uint8_t *X = ch.X + (size_t) c * net.nX;
+    uint32_t w = 0, aw = 0;
     for (uint32_t u = 0; u < 16; u++) {
         const uint32_t j = 16 * jw + u;
         const uint32_t code = j < W ? S[32 * j] : 1u;
         GBN_CHECK(code <= 2);
         w |= code << (2 * u);
+        if (j < W && net.par_edge[gb + lane + 32 * j] != 0xffffffffu) aw |= (uint32_t) (X[net.par_tf[gb + lane + 32 * j]] & 1u) << u;
     }
     ch.Sw[(size_t) c * net.nSw + i] = w;
+    ch.Aw[(size_t) c * net.nSw + i] = aw;
 }
 
 // 2-bit words -> S bytes (before anything reads ch.S after a fast sweep)
@@ -833,16 +771,10 @@ static int check(cudaError_t e, const char **err)
     return 0;
 }
 
-// shared memory of the S kernel: the per-dataset tables, the prior rows and, when it fits, FXp of the chain
-static size_t s_smem_bytes(const DevNet &net, bool stage_fx)
+// shared memory of the S kernel: the per-dataset tables over n
+static size_t s_smem_bytes(const DevNet &net)
 {
-    return sizeof(double2) * 3 * (size_t) net.stab_D + 16 * sizeof(double) + (stage_fx ? sizeof(double2) * (size_t) net.nX : 0) + 16;
-}
-
-static bool s_stage_fx(const DevNet &net)
-{
-    static const uint32_t want = env_u32("GBN_STAGE_FX", 1);      // 2 = off
-    return want != 2 && sizeof(double2) * (size_t) net.nX <= 48 * 1024;
+    return sizeof(double2) * 3 * (size_t) net.stab_D + sizeof(double) * 2 * (size_t) net.stab_D + 16;
 }
 
 // shared memory of the X kernel (XQ chains per CTA): flip multipliers of a window, tables, by-TF pointers, X and
@@ -872,29 +804,29 @@ bool fast_uses_x_stream(const DevNet &net) { return !net.const_params && env_u32
 bool fast_supported(const DevNet &net, const char **why)
 {
     if (net.nX > 65535) { *why = "n_tf does not fit the 16-bit parent id"; return false; }
-    if (s_smem_bytes(net, s_stage_fx(net)) > 200 * 1024) { *why = "in-degree too large for the S-phase tables"; return false; }
+    if (s_smem_bytes(net) > 200 * 1024) { *why = "in-degree too large for the S-phase tables"; return false; }
     if (net.Eu != net.E) { *why = "duplicate (TF, target) edges"; return false; }
     if (x_smem_bytes(net, false) + 256 > 200 * 1024) { *why = "n_tf too large for the X window kernel's shared memory"; return false; }
     if (3 * (size_t) net.stab_D + 1 > 65535) { *why = "in-degree does not fit the 16-bit (y, n) table index"; return false; }
     return true;
 }
 
-template <int MODE, bool STAGE, bool INJ>
+template <int MODE, bool INJ, bool PF>
 static int launch_s_t(const DevNet &net, const DevChains &ch, const SweepArgs &a, uint32_t nchains, cudaStream_t st, const char **err)
 {
-    const size_t smem = s_smem_bytes(net, STAGE);
-    if (check(cudaFuncSetAttribute(k_fast_s<MODE, STAGE, INJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), err)) return -1;
+    const size_t smem = s_smem_bytes(net);
+    if (check(cudaFuncSetAttribute(k_fast_s<MODE, INJ, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), err)) return -1;
     const uint32_t gpb = FS_NT / 32;                                  // groups per block
-    k_fast_s<MODE, STAGE, INJ><<<dim3((net.n_groups + gpb - 1) / gpb, nchains), FS_NT, smem, st>>>(net, ch, a);
+    k_fast_s<MODE, INJ, PF><<<dim3((net.n_groups + gpb - 1) / gpb, nchains), FS_NT, smem, st>>>(net, ch, a);
     return 0;
 }
 
 static int launch_s(const DevNet &net, const DevChains &ch, const SweepArgs &a, int mode, uint32_t nc, cudaStream_t st, const char **err)
 {
-    const bool stage = s_stage_fx(net);
-    if (mode == 1) return stage ? launch_s_t<1, true, false>(net, ch, a, nc, st, err) : launch_s_t<1, false, false>(net, ch, a, nc, st, err);
-    if (a.use_inj) return stage ? launch_s_t<0, true, true>(net, ch, a, nc, st, err) : launch_s_t<0, false, true>(net, ch, a, nc, st, err);
-    return stage ? launch_s_t<0, true, false>(net, ch, a, nc, st, err) : launch_s_t<0, false, false>(net, ch, a, nc, st, err);
+    static const bool pf = env_u32("GBN_S_PREFETCH", 0) == 1;         // 1 = on (measured: no gain at 64 registers)
+    if (mode == 1) return launch_s_t<1, false, false>(net, ch, a, nc, st, err);
+    if (a.use_inj) return launch_s_t<0, true, false>(net, ch, a, nc, st, err);
+    return pf ? launch_s_t<0, false, true>(net, ch, a, nc, st, err) : launch_s_t<0, false, false>(net, ch, a, nc, st, err);
 }
 
 int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err)

@@ -72,6 +72,8 @@ struct Topology {
     std::vector<uint32_t> sw_grp, dblk_grp;         // group of every row of 32 words / 32 blocks
     std::vector<uint32_t> mor2;                     // [nSw] prior row per step, 3 = pad (row {0, 1, 0}: never moves)
     std::vector<uint16_t> par16;                    // [4 nD] parent TF per step (0 for pads)
+    std::vector<uint32_t> tfpos4;                   // [4 nD] by-TF CSR position per step (UINT32_MAX for pads)
+    std::vector<uint32_t> tf_abit;                  // [Eu] by-TF position -> 16 * S word + step inside the word
     uint32_t nSw = 0, nD = 0;
 
     uint32_t slot(uint32_t dt, uint32_t j) const { return gbase[dt >> 5] + 32 * j + (dt & 31); }
@@ -205,6 +207,8 @@ inline Topology compile_topology(uint32_t n_edge, const uint32_t *src, const uin
     tp.nSw = tp.sbase[tp.n_groups]; tp.nD = tp.dbase[tp.n_groups];
     tp.mor2.assign(tp.nSw, 0xffffffffu);
     tp.par16.assign(4 * (size_t) tp.nD, 0);
+    tp.tfpos4.assign(4 * (size_t) tp.nD, UINT32_MAX);
+    tp.tf_abit.assign(tp.Eu, 0);
     if (nX <= 65536)
         for (uint32_t dt = 0; dt < nH; dt++) {
             const uint32_t g = dt >> 5, lane = dt & 31;
@@ -213,6 +217,8 @@ inline Topology compile_topology(uint32_t n_edge, const uint32_t *src, const uin
                 uint32_t &mw = tp.mor2[tp.sbase[g] + 32 * (j / 16) + lane];
                 mw = (mw & ~(3u << (2 * (j % 16)))) | ((uint32_t) tp.mor_idx[q] << (2 * (j % 16)));
                 tp.par16[4 * (size_t) (tp.dbase[g] + 32 * (j / 4) + lane) + (j % 4)] = (uint16_t) tp.par_tf[q];
+                tp.tfpos4[4 * (size_t) (tp.dbase[g] + 32 * (j / 4) + lane) + (j % 4)] = tp.tfpos_of_slot[q];
+                if (tp.tfpos_of_slot[q] != UINT32_MAX) tp.tf_abit[tp.tfpos_of_slot[q]] = 16 * (tp.sbase[g] + 32 * (j / 16) + lane) + (j % 16);
             }
         }
     tp.x_prior_active.assign(nX, 0);

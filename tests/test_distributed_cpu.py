@@ -1,5 +1,6 @@
-"""world_size-2 gloo test of the multi-rank protocol (host-side): chains sharded over ranks, the
-two-pass moment all-reduce, Gelman-Rubin and posterior summaries equal the unsharded oracle."""
+"""world_size-2 gloo tests of the multi-rank protocol (host-side): chains sharded over ranks, the exact
+integer count sums (discrete nodes) and the two-pass moment all-reduce (T nodes); Gelman-Rubin and the
+posterior summaries equal the unsharded oracle."""
 import os
 import sys
 
@@ -13,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from gbnet_b200.distributed import shard_chains, two_pass_gelman_rubin  # noqa: E402
+from gbnet_b200.distributed import (exact_count_moments, gelman_rubin_from_sums, shard_chains,  # noqa: E402
+                                    two_pass_gelman_rubin)
 
 
 def test_shard_chains_partitions():
@@ -76,6 +78,22 @@ def _worker(rank, world, port, q):
         ref_pm = np.concatenate([P.posterior_means(k) for k in "XTS"])
         ref_ps = np.concatenate([P.posterior_sdevs(k) for k in "XTS"])
         ok &= bool(np.max(np.abs(pmu - ref_pm)) < 1e-12) and bool(np.max(np.abs(psd - ref_ps)) < 1e-12)
+
+        # the integer route the library takes for the discrete nodes (csrc/moments.cu): per-chain counts are
+        # mean * N exactly; X then S statistics
+        nX, E, N = P.n_tf(), P.n_edges(), int(P.chain_length())
+        counts = np.rint(means * N).astype(np.int64)
+        is_s = node_of >= 2 * nX
+        cx1 = counts[:, node_of < nX].reshape(M, nX, 2)[:, :, 1]
+        cs = counts[:, is_s].reshape(M, E, 3)[:, :, [0, 2]]
+        ex = exact_count_moments(cx1[off:off + loc], cs[off:off + loc], N, M, off, allreduce_sum)
+        disc = np.concatenate([np.nonzero(node_of < nX)[0], np.nonzero(is_s)[0]])
+        R_int = gelman_rubin_from_sums(ex["sums"], ex["dev"], N, M)
+        both = np.isfinite(R[disc]) & np.isfinite(R_int)
+        ok &= np.array_equal(np.isfinite(R[disc]), np.isfinite(R_int))
+        ok &= bool(np.max(np.abs(R_int[both] - R[disc][both]) / R[disc][both]) < 1e-9)
+        ok &= bool(np.max(np.abs(ex["psums"] / (M - 1.) - pmu[disc])) < 1e-12)
+        ok &= bool(np.max(np.abs(np.sqrt(ex["pdev"] / (M - 2.)) - psd[disc])) < 1e-12)
         q.put((rank, bool(ok), float(np.max(gr_nodes[fin])), float(np.max(ref_gr[fin]))))
     finally:
         dist.destroy_process_group()
