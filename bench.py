@@ -46,9 +46,11 @@ def parse_args():
     ap.add_argument("--shape", default="C3", choices=["C1", "C2", "C3"])
     ap.add_argument("--chains", type=int, default=256, help="chains per GPU")
     ap.add_argument("--sweeps-per-step", type=int, default=30)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--roofline-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the other BASELINE configs (C5, C4, time to R-hat < 1.1) and the sharding self-check")
     ap.add_argument("--ref-sweeps-per-step", type=int, default=1)
     return ap.parse_args()
 
@@ -183,6 +185,151 @@ class _StdoutToStderr:
         os.close(self.saved)
 
 
+
+# ------------------------------------------------------------------------------------------ secondary configs
+def _attach(G, dist, rank, world):
+    """library-side NCCL communicator for the ranks of the torch process group (the id travels through torch)"""
+    if world == 1:
+        return
+    import gbnet_b200
+    with _StdoutToStderr():
+        uid = [gbnet_b200.Sampler.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        G.attach_comm(rank, world, uid[0])
+        G.max_gelman_rubin()
+
+
+def _timed_steps(G, dN, steps, warmup, barrier):
+    """device ms of `steps` x (dN sweeps + max R-hat) after `warmup` untimed ones"""
+    for _ in range(warmup):
+        G.sample_n(dN)
+        G.max_gelman_rubin()
+    barrier(G)
+    G.timer_start()
+    gr = None
+    for _ in range(steps):
+        G.sample_n(dN)
+        gr = G.max_gelman_rubin()
+    ms = G.timer_stop()
+    barrier(G)
+    return ms, gr
+
+
+def run_secondary(args, dist, rank, local_rank, world, reduce_max):
+    """The other BASELINE.json configs on the same GPUs, and the sharding self-check:
+    C5  4,096 chains of the C3 network in total, strong-scaled over the ranks (chains sharded, NCCL moments)
+    C4  C2 network, 512 contrasts x 8 chains, contrasts sharded over the ranks (independent models: no collective)
+    time to R-hat < 1.1 (protocol of gbnet/utils.py:93-135) for C1 and C2, CUDA against the reference C++ (N = 1)
+    parity_check (N > 1): a small model sharded over the ranks gives the R-hat / posterior means of the same
+    model held by one rank."""
+    import gbnet_b200
+    from gbnet_b200 import synth
+    from gbnet_b200.distributed import shard_chains
+    hy = synth.cli_default_hyper()
+    dN = args.sweeps_per_step
+    out = {}
+
+    def barrier(G):
+        if world > 1:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+        G.synchronize()
+
+    # ---- C5
+    net = synth.shape("C3")
+    off, loc = shard_chains(4096, rank, world)
+    G = gbnet_b200.Sampler(net.src, net.trg, net.mor, net.evid_trg, net.evid_val, n_graphs=4096, chain_offset=off,
+                           n_graphs_local=loc, seed=2026, device=local_rank, **hy)
+    _attach(G, dist, rank, world)
+    steps = 3
+    ms, gr = _timed_steps(G, dN, steps, 1, barrier)
+    ms = reduce_max(ms)
+    out["C5"] = {"workload": "C3 network, 4,096 chains in total (strong scaling), NCCL moment all-reduce every dN sweeps",
+                 "chains_total": 4096, "chains_per_gpu": loc, "value": 4096 * dN * steps * net.n_edges / (ms * 1e-3),
+                 "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "max_gelman_rubin": gr}
+    G.close()
+
+    # ---- C4
+    net2 = synth.shape("C2")
+    n_ds = 512
+    d0, dl = shard_chains(n_ds, rank, world)                         # contrasts are independent models: shard them
+    evs = np.stack([synth.redraw_evidence(net2, num_active_tfs=8, seed=100 + d0 + i)[0] for i in range(dl)])
+    G = gbnet_b200.Sampler(net2.src, net2.trg, net2.mor, net2.evid_trg, evs, n_graphs=8, seed=13, device=local_rank, **hy)
+    steps = 10
+    ms, gr = _timed_steps(G, dN, steps, 2, barrier)
+    ms = reduce_max(ms)
+    out["C4"] = {"workload": "C2 network, 512 contrasts x 8 chains, contrasts sharded over the GPUs (no collective)",
+                 "contrasts_per_gpu": dl, "chains_per_gpu": 8 * dl, "path": G.path(),
+                 "value": n_ds * 8 * dN * steps * net2.n_edges / (ms * 1e-3), "unit": UNIT,
+                 "ms_per_step": ms / steps, "steps": steps, "max_gelman_rubin_rank0": gr}
+    G.close()
+
+    # ---- time to R-hat < 1.1 (rank 0; the reference leg only at N = 1, as cpu_baseline)
+    if rank == 0:
+        ttr = {}
+        for shape, chains in (("C1", 3), ("C2", 64)):
+            netp = synth.shape(shape)
+            G = gbnet_b200.Sampler(netp.src, netp.trg, netp.mor, netp.evid_trg, netp.evid_val, n_graphs=chains, seed=12,
+                                   device=local_rank, **hy)
+            G.run_protocol(burn_its=1, max_its=2)                   # warm the path (kernel load, first launch)
+            G.close()
+            G = gbnet_b200.Sampler(netp.src, netp.trg, netp.mor, netp.evid_trg, netp.evid_val, n_graphs=chains, seed=12,
+                                   device=local_rank, **hy)
+            t0 = time.perf_counter()
+            its, mgr = G.run_protocol(burn_its=10, max_its=200)
+            tg = time.perf_counter() - t0
+            ttr[shape] = {"chains": chains, "edges": netp.n_edges, "gpu_s": tg, "gpu_iterations": its, "gpu_max_rhat": mgr,
+                          "path": G.path()}
+            G.close()
+            if world == 1 and not args.no_cpu_baseline:
+                import oracle
+                pb = oracle.Problem(src=netp.src, trg=netp.trg, mor=netp.mor, evid_trg=netp.evid_trg,
+                                    evid_val=netp.evid_val, n_graphs=chains, **hy)
+                R = oracle.RefModel(pb) if oracle.have_ref() else oracle.PortModel(pb)
+                R._f("omp_set_threads")(min(os.cpu_count() or 1, chains))
+                t0 = time.perf_counter()
+                it = 0
+                for _ in range(10):
+                    it += 1
+                    R.sample(20, 30)
+                R.burn_stats()
+                mgr = float("inf")
+                while mgr > 1.1 and it < 200:
+                    it += 1
+                    R.sample(20, 30)
+                    mgr = R.max_gelman_rubin()
+                ttr[shape].update({"reference_s": time.perf_counter() - t0, "reference_iterations": it,
+                                   "reference_max_rhat": mgr, "reference_cores": min(os.cpu_count() or 1, chains),
+                                   "reference_kind": "reference" if oracle.have_ref() else "port"})
+                R.close()
+        out["time_to_rhat"] = {"protocol": "gbnet/utils.py:93-135: 10 x sample(20), burn_stats, sample(20) until max R-hat <= 1.1",
+                               **ttr}
+
+    # ---- sharding self-check
+    if world > 1:
+        nets = synth.gen_network(NX=40, NY=800, AvgNTF=3.0, num_active_tfs=4, seed=17)
+        M = 4 * world
+        off, loc = shard_chains(M, rank, world)
+        G = gbnet_b200.Sampler(nets.src, nets.trg, nets.mor, nets.evid_trg, nets.evid_val, n_graphs=M, chain_offset=off,
+                               n_graphs_local=loc, seed=7, device=local_rank, **hy)
+        _attach(G, dist, rank, world)
+        G.sample_n(60)
+        gr, px, pt = G.max_gelman_rubin(), G.posterior_means("X"), G.posterior_means("T")
+        G.close()
+        if rank == 0:
+            F = gbnet_b200.Sampler(nets.src, nets.trg, nets.mor, nets.evid_trg, nets.evid_val, n_graphs=M, seed=7,
+                                   device=local_rank, **hy)
+            F.sample_n(60)
+            ok = bool(F.max_gelman_rubin() == gr and np.array_equal(F.posterior_means("X"), px)
+                      and np.max(np.abs(F.posterior_means("T") - pt)) < 1e-12)
+            F.close()
+            out["parity_check"] = ok
+            out["parity_check_what"] = (f"{M} chains of a 40-TF network sharded over {world} ranks vs the same model on one "
+                                        "rank after 60 sweeps: max R-hat and posterior X means identical, T means to 1e-12")
+    return out
+
+
 def run_native(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -276,6 +423,18 @@ def run_native(args):
     h2d = int(net.evid_trg.nbytes + evs[0].nbytes)
     d2h = int(post.nbytes + 8)
 
+    G.close()
+    secondary = None
+    if not args.no_secondary:
+        def reduce_max(v):
+            if world == 1:
+                return v
+            import torch
+            t = torch.tensor([v], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        secondary = run_secondary(args, dist, rank, local_rank, world, reduce_max)
+
     if world > 1:
         import torch
         t = torch.tensor([dev_ms, wall_ms, e2e_s, float(launches)], dtype=torch.float64, device="cuda")
@@ -342,8 +501,11 @@ def run_native(args):
                 "value": n_graphs * 3 * E / sum(times), "unit": UNIT, "cores": used, "kind": kind,
                 "sample": f"{n_graphs} of {C} chains (one per host thread), 3 sweeps after 1 warm-up sweep, "
                           "ModelBase::sample_n timed with omp_get_wtime, construction excluded"}
+        if secondary is not None:
+            line["secondary"] = secondary
+            if "parity_check" in secondary:
+                line["parity_check"] = secondary["parity_check"]
         print(json.dumps(line), flush=True)
-    G.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

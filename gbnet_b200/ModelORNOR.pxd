@@ -59,6 +59,9 @@ cdef extern from "gbnet_b200.h":
     int gbn_model_kernel(const gbn_model *m)
     int gbn_model_sample(gbn_model *m, uint32_t N, uint32_t dN) nogil
     int gbn_model_sample_n(gbn_model *m, uint32_t n) nogil
+    int gbn_model_run_protocol(gbn_model *m, uint32_t burn_its, uint32_t max_its, uint32_t N, uint32_t dN,
+                               uint32_t *its_out, double *rhat_out) nogil
+    int gbn_model_path(const gbn_model *m)
     int gbn_model_burn_stats(gbn_model *m)
     int gbn_model_max_gelman_rubin(gbn_model *m, double *out)
     int gbn_model_gelman_rubin(gbn_model *m, uint32_t dataset, double *out)

@@ -116,6 +116,19 @@ cdef class PyModelORNOR:
             rc = gbn_model_sample_n(self.h, n)
         self._check(rc)
 
+    def run_protocol(self, unsigned int burn_its=10, unsigned int max_its=100, unsigned int N=20, unsigned int dN=30):
+        """The schedule of gbnet/utils.py:93-135 (sample_model) as one library call: (calls made, last max R-hat)."""
+        cdef int rc
+        cdef uint32_t its = 0
+        cdef double rhat = 0
+        with nogil:
+            rc = gbn_model_run_protocol(self.h, burn_its, max_its, N, dN, &its, &rhat)
+        self._check(rc)
+        return int(its), float(rhat)
+
+    def path(self):
+        return gbn_model_path(self.h)
+
     def print_stats(self):
         self._check(gbn_model_print_stats(self.h))
 

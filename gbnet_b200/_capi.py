@@ -69,6 +69,10 @@ SYMBOLS = {
     "gbn_model_destroy": (None, [_vp]),
     "gbn_model_dims": (C.c_int, [_vp, _P(Dims)]),
     "gbn_model_kernel": (C.c_int, [_vp]),
+    "gbn_model_path": (C.c_int, [_vp]),
+    "gbn_model_run_protocol": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _P(_u32), _P(_dbl)]),
+    "gbn_fisher_counts": (C.c_int, [C.c_int, _P(Network), _u32, _u32, _P(_u32), _P(C.c_int8), _P(_u32), _P(_u32), _P(_u32)]),
+    "gbn_fisher_last_error": (C.c_char_p, []),
     "gbn_model_tf_ids": (C.c_int, [_vp, _P(_u32)]),
     "gbn_model_trg_ids": (C.c_int, [_vp, _P(_u32)]),
     "gbn_model_sample": (C.c_int, [_vp, _u32, _u32]),

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 # (experiment knobs: the shipped default keeps -fmad=false everywhere)
 VARIANT = os.environ.get("GBN_LIB_VARIANT", "")
 LIB = os.path.join(HERE, "libgbnet_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
-SOURCES = ["capi.cu", "eval_kernels.cu", "sweep_strict.cu", "sweep_fast.cu", "sim_kernels.cu", "moments.cu"]
+SOURCES = ["capi.cu", "eval_kernels.cu", "sweep_strict.cu", "sweep_fast.cu", "sweep_small.cu", "sim_kernels.cu", "moments.cu", "fisher.cu"]
 HEADERS = ["device_math.cuh", "device_model.cuh", "kernels.cuh", "topology.hpp", "fast_common.cuh",
            os.path.join("..", "..", "include", "gbnet_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

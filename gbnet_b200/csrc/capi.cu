@@ -46,7 +46,8 @@ extern "C" int gbn_abi_version(void) { return GBN_ABI_VERSION; }
 
 // ModelBase.cpp:3-33: a process-global flag polled between batches of sweeps
 static volatile std::sig_atomic_t g_signal = 0;
-static void sigint_handler(int signum) { g_signal = signum; }
+static volatile std::sig_atomic_t g_caught = 0;        // a real SIGINT arrived (as opposed to gbn_set_signal)
+static void sigint_handler(int signum) { g_signal = signum; g_caught = 1; }
 extern "C" void gbn_set_signal(int signum) { g_signal = signum; }
 extern "C" void gbn_install_sigint_handler(void) { std::signal(SIGINT, sigint_handler); }
 
@@ -62,8 +63,10 @@ struct SigintScope {
     ~SigintScope()
     {
         std::signal(SIGINT, prev == SIG_ERR ? SIG_DFL : prev);
-        if (g_signal == SIGINT && prev != SIG_ERR && prev != SIG_IGN && prev != SIG_DFL && prev != sigint_handler) std::raise(SIGINT);
+        const bool again = g_caught != 0 && prev != SIG_ERR && prev != SIG_IGN && prev != SIG_DFL && prev != sigint_handler;
+        g_caught = 0;
         g_signal = 0;                  // clearSignal(), ModelBase.cpp:126
+        if (again) std::raise(SIGINT);
     }
 };
 }  // namespace
@@ -123,7 +126,7 @@ struct gbn_model {
     uint64_t launches = 0;
     double last_ms = 0.;
     // device buffers
-    uint8_t *d_y = nullptr; double *d_yprob = nullptr, *d_stab = nullptr;
+    uint8_t *d_y = nullptr, *d_uf = nullptr; double *d_yprob = nullptr, *d_stab = nullptr;
     double *d_inj_flat = nullptr, *d_inj_beta = nullptr, *d_inj_exp = nullptr;
     double *d_sums = nullptr, *d_psums = nullptr, *d_dev = nullptr, *d_pdev = nullptr, *d_gr = nullptr, *d_max = nullptr;
     double *d_tsum = nullptr, *d_tdev = nullptr;      // T nodes: the two small buffers that cross the ranks
@@ -132,6 +135,8 @@ struct gbn_model {
     bool moments_valid = false;
     bool sim = false;                   // simulation mode (empty evidence)
     // fast kernel: the sweep works on packed views of S and counts into per-batch 8-bit counters
+    uint32_t *h_flags = nullptr;        // host-mapped flag word the fast kernels raise (DevChains::flags)
+    bool small = false;                 // the persistent shared-memory kernel (sweep_small.cu) sweeps this model
     bool s_bytes_valid = true;          // ch.S (bytes) agrees with ch.Sw (2-bit words)
     uint32_t pending = 0;               // sweeps counted in ch.dC and not yet folded into ch.cS
     // per-kernel timing (gbn_model_set_phase_timing)
@@ -294,6 +299,23 @@ int upload_evidence(gbn_model *m, const gbn_evidence *ev)
         }
         CUDA_TRY(cudaMemcpy(m->d_stab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     }
+    {
+        // (dataset, TF) pairs whose children's likelihood product could underflow a double: a target likelihood is a
+        // mixture sum_h P(h) YNOISE[h][y] >= min_h YNOISE[h][y]; only for these does the X kernel carry prod L
+        // (the prior fallback of Multinomial.cpp:78-85 needs its magnitude, sweep_fast.cu k_fast_x)
+        const double ynoise[3][3] = { { 0.945, 0.050, 0.005 }, { 0.050, 0.900, 0.050 }, { 0.005, 0.050, 0.945 } };
+        double lmin[3];
+        for (int y = 0; y < 3; y++) lmin[y] = std::log(std::min(ynoise[0][y], std::min(ynoise[1][y], ynoise[2][y])));
+        std::vector<uint8_t> uf((size_t) m->n_datasets * tp.nX, 0);
+        for (uint32_t d = 0; d < m->n_datasets; d++)
+            for (uint32_t k = 0; k < tp.nX; k++) {
+                double bound = 0.;
+                for (uint32_t c = tp.tf_ptr[k]; c < tp.tf_ptr[k + 1]; c++) bound += lmin[m->h_y[(size_t) d * tp.nH + tp.tf_child[c]]];
+                uf[(size_t) d * tp.nX + k] = bound < -600. ? 1 : 0;
+                if (env_u32("GBN_X_NOTRACK", 0) == 1) uf[(size_t) d * tp.nX + k] = 0;     // experiment: measures what the tracking costs
+            }
+        CUDA_TRY(cudaMemcpy(m->d_uf, uf.data(), uf.size(), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMemcpy(m->d_y, m->h_y.data(), m->h_y.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(m->d_yprob, m->h_yprob.data(), sizeof(double) * m->h_yprob.size(), cudaMemcpyHostToDevice));
     return 0;
@@ -325,6 +347,20 @@ int allreduce(gbn_model *m, void *buf, size_t n, int op, int dtype = NCCL_FLOAT6
     if (!m->comm || m->world <= 1) return 0;
     int rc = g_nccl.AllReduce(buf, buf, n, dtype, op, m->comm, m->stream);
     if (rc != 0) return fail(GBN_ERR_COMM, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return 0;
+}
+
+// after the stream has been synchronised: did a fast kernel meet a state it cannot represent?
+// T = 1.0 exactly with X = 1 makes the edge factor (1 - t x) z zero; the fast path divides it out of the
+// cached products (leave-one-out), so its reciprocal must exist.  The reference's arithmetic has no such
+// limit: the strict kernel (kernel = GBN_KERNEL_STRICT) follows it.  Reaching the value needs prev + dx to
+// round to 1.0 exactly and a Beta prior with b <= 1 (t_hmargin < 1), else its density there is 0 and the
+// proposal is rejected (Beta.cpp:66-72).
+int check_flags(gbn_model *m)
+{
+    if (m->h_flags && (*m->h_flags & 1u))
+        return fail(GBN_ERR_UNSUPPORTED, "a T node reached exactly 1.0: the fast kernels cannot represent the zero edge factor; "
+                                         "rebuild the model with kernel = GBN_KERNEL_STRICT");
     return 0;
 }
 
@@ -361,6 +397,7 @@ int max_gelman_rubin(gbn_model *m, double *out)
     std::vector<double> h(m->n_datasets);
     CUDA_TRY(cudaMemcpyAsync(h.data(), m->d_max, sizeof(double) * m->n_datasets, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (int rc = check_flags(m)) return rc;
     double mx = 0.;
     for (double v : h) mx = std::fmax(mx, v);
     *out = mx;
@@ -449,7 +486,12 @@ int sample_n(gbn_model *m, uint32_t n)
                 if (int rc = fold_counts(m)) return rc;
             const uint32_t chunk = std::min(n - done, FAST_MAX_PENDING - m->pending);
             g_error.clear();
-            int l = fast_batch(m, chunk, (uint32_t) m->sweeps_total + done, m->stat_n + done, &err);
+            int l;
+            if (m->small) {
+                l = launch_sweep_small(m->net, m->ch, chunk, (uint32_t) m->sweeps_total + done, m->stat_n + done, m->stream, &err);
+                if (l >= 0) { m->pending += chunk; m->s_bytes_valid = false; }
+            } else
+                l = fast_batch(m, chunk, (uint32_t) m->sweeps_total + done, m->stat_n + done, &err);
             if (l < 0) { launched = -1; break; }
             launched += l;
             done += chunk;
@@ -494,6 +536,7 @@ extern "C" void gbn_model_destroy(gbn_model *m)
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+    if (m->h_flags) cudaFreeHost(m->h_flags);
     for (void *p : m->owned) if (p) cudaFree(p);
     for (cudaEvent_t e : m->phase_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : m->gdone) cudaEventDestroy(e);
@@ -554,6 +597,15 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
         return bail(fail(GBN_ERR_CUDA, "cannot create stream / events"));
 
+    {
+        void *hp = nullptr, *dp = nullptr;
+        if (cudaHostAlloc(&hp, sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess)
+            return bail(fail(GBN_ERR_CUDA, "cannot allocate the host-mapped flag word"));
+        m->h_flags = (uint32_t *) hp;
+        *m->h_flags = 0;
+        m->ch.flags = (volatile uint32_t *) dp;
+    }
     // ---- network
     DevNet &n = m->net;
     n.nX = tp.nX; n.nH = tp.nH; n.E = tp.E; n.Eu = tp.Eu; n.max_indeg = tp.max_indeg; n.max_outdeg = tp.max_outdeg;
@@ -592,7 +644,8 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     if (int rc = dev_alloc(m, &m->d_yprob, (size_t) m->n_datasets * 3)) return bail(rc);
     n.stab_D = (tp.max_indeg + 2 + 1) & ~1u;     // even: the arrays behind the tables stay 16-byte aligned in shared memory
     if (int rc = dev_alloc(m, &m->d_stab, (size_t) m->n_datasets * STAB_ROWS * n.stab_D)) return bail(rc);
-    n.y = m->d_y; n.yprob = m->d_yprob; n.stab = m->d_stab;
+    if (int rc = dev_alloc(m, &m->d_uf, (size_t) m->n_datasets * tp.nX)) return bail(rc);
+    n.y = m->d_y; n.yprob = m->d_yprob; n.stab = m->d_stab; n.tf_uf = m->d_uf;
     if (int rc = upload_evidence(m, ev)) return bail(rc);
 
     // ---- kernel choice
@@ -602,12 +655,13 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         return bail(fail(GBN_ERR_UNSUPPORTED, std::string("fast kernel unavailable: ") + why));
     m->kernel = (p->kernel == GBN_KERNEL_STRICT) ? GBN_KERNEL_STRICT : (fast_ok ? GBN_KERNEL_FAST : GBN_KERNEL_STRICT);
     if (sim) m->kernel = GBN_KERNEL_STRICT;          // simulation has its own kernels (sim_kernels.cu), reference arithmetic
+    { const char *w2 = nullptr; m->small = m->kernel == GBN_KERNEL_FAST && small_supported(n, &w2); }
     if (!sim && m->kernel == GBN_KERNEL_STRICT && strict_smem_bytes(n) > 227 * 1024)
         return bail(fail(GBN_ERR_UNSUPPORTED, "strict kernel: n_tf too large for shared memory"));
 
     // ---- chains
     DevChains &ch = m->ch;
-    const size_t C = m->n_chains, nX = tp.nX, E = tp.E, Ep = tp.Ep, nH = tp.nH;
+    const size_t C = m->n_chains, nX = tp.nX, Ep = tp.Ep, nH = tp.nH;
     ch.n_chains = m->n_chains;
     if (int rc = dev_alloc(m, &ch.X, C * nX)) return bail(rc);
     if (int rc = dev_alloc(m, &ch.T, C * nX)) return bail(rc);
@@ -628,11 +682,16 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         const size_t n_tc2 = (C + xq - 1) / xq * xq * (nH + 1);                              // interleaved by chain bundle;
         if (int rc = dev_alloc(m, &ch.tc2, n_tc2)) return bail(rc);                          // entry nH of a bundle stays {0, 0}
         if (cudaMemset(ch.tc2, 0, sizeof(double2) * n_tc2) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "cudaMemset failed"));
-        if (int rc = dev_alloc(m, &ch.ny, C * nH)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.tL, n_tc2)) return bail(rc);
+        {
+            std::vector<double> ones(n_tc2, 1.);                                             // entry nH of a bundle stays 1
+            if (cudaMemcpy(ch.tL, ones.data(), sizeof(double) * n_tc2, cudaMemcpyHostToDevice) != cudaSuccess)
+                return bail(fail(GBN_ERR_CUDA, "cudaMemcpy failed"));
+        }
         if (int rc = dev_alloc(m, &ch.Sw, C * tp.nSw)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.Aw, C * tp.nSw)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.dC, C * tp.nD)) return bail(rc);
-        if (int rc = dev_alloc(m, &ch.Stfp, C * ((E + 15) / 16))) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.Stfp, C * n_stf_words(n))) return bail(rc);
         if (int rc = dev_alloc(m, &ch.xU, C * ((nX + 3) & ~(size_t) 3))) return bail(rc);
         if (int rc = dev_alloc(m, &ch.FXp, C * nX)) return bail(rc);
     }
@@ -668,6 +727,11 @@ extern "C" int gbn_model_dims(const gbn_model *m, gbn_dims *out)
 }
 
 extern "C" int gbn_model_kernel(const gbn_model *m) { return m ? m->kernel : (int) GBN_ERR_INVALID; }
+extern "C" int gbn_model_path(const gbn_model *m)
+{
+    if (!m) return (int) GBN_ERR_INVALID;
+    return m->kernel == GBN_KERNEL_FAST && !m->sim ? (m->small ? 2 : 1) : 0;
+}
 
 extern "C" int gbn_model_tf_ids(const gbn_model *m, uint32_t *out)
 {
@@ -706,6 +770,7 @@ extern "C" int gbn_model_sample_n(gbn_model *m, uint32_t n)
     if (int rc = use_device(m)) return rc;
     if (int rc = sample_n(m, n)) return rc;
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (int rc = check_flags(m)) return rc;
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
     m->last_ms = ms;
@@ -740,6 +805,30 @@ extern "C" int gbn_model_phase_ms(const gbn_model *m, double ms_out[3], uint64_t
 
 // ModelBase::sample (ModelBase.cpp:114-129).  The for-loop's increment expression clips dN
 // BEFORE adding it to n, so the batch that just ran is never clipped: sample(20, 30) draws 30.
+// want_rhat = false skips the Gelman-Rubin evaluation after a batch when it cannot end the call (N <= dN:
+// one batch whatever its value) and does not wait for the device; the caller synchronises.
+static int sample_loop(gbn_model *m, uint32_t N, uint32_t dN, bool want_rhat, double *total_ms)
+{
+    uint32_t n;
+    double gr = std::numeric_limits<double>::infinity();
+    const bool lazy = !want_rhat && N <= dN;
+    for (n = 0; n < N && gr > 1.10 && g_signal == 0; ) {
+        if (int rc = sample_n(m, dN)) return rc;
+        if (!lazy) {
+            CUDA_TRY(cudaStreamSynchronize(m->stream));
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+            *total_ms += ms;
+            if (int rc = collect_phase_times(m)) return rc;
+        }
+        dN = std::min(dN, N - n);
+        n += dN;
+        if (!lazy) if (int rc = max_gelman_rubin(m, &gr)) return rc;
+        if (dN == 0) break;        // N - n reached 0: the for-condition ends the loop
+    }
+    return 0;
+}
+
 extern "C" int gbn_model_sample(gbn_model *m, uint32_t N, uint32_t dN)
 {
     if (!m) return fail(GBN_ERR_INVALID, "null model");
@@ -749,21 +838,38 @@ extern "C" int gbn_model_sample(gbn_model *m, uint32_t N, uint32_t dN)
     if (dN == 0) return fail(GBN_ERR_INVALID, "deltaN must be positive (the reference's loop would never end)");
     SigintScope sigint;
     double total_ms = 0.;
-    uint32_t n;
-    double gr = std::numeric_limits<double>::infinity();
-    for (n = 0; n < N && gr > 1.10 && g_signal == 0; ) {
-        if (int rc = sample_n(m, dN)) return rc;
-        CUDA_TRY(cudaStreamSynchronize(m->stream));
-        float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
-        total_ms += ms;
-        if (int rc = collect_phase_times(m)) return rc;
-        dN = std::min(dN, N - n);
-        n += dN;
-        if (int rc = max_gelman_rubin(m, &gr)) return rc;
-        if (dN == 0) break;        // N - n reached 0: the for-condition ends the loop
-    }
+    if (int rc = sample_loop(m, N, dN, true, &total_ms)) return rc;
     m->last_ms = total_ms;
+    return 0;
+}
+
+// gbnet/utils.py:93-135 (sample_model) as one call
+extern "C" int gbn_model_run_protocol(gbn_model *m, uint32_t burn_its, uint32_t max_its, uint32_t N, uint32_t dN,
+                                      uint32_t *its_out, double *rhat_out)
+{
+    if (!m || !its_out || !rhat_out) return fail(GBN_ERR_INVALID, "null argument");
+    if (N == 0 || dN == 0) return fail(GBN_ERR_INVALID, "N and deltaN must be positive");
+    if (int rc = use_device(m)) return rc;
+    SigintScope sigint;
+    auto t0 = std::chrono::steady_clock::now();
+    uint32_t it = 0;
+    double ms = 0., rhat = std::numeric_limits<double>::infinity();
+    *its_out = 0; *rhat_out = rhat;
+    for (uint32_t i = 0; i < burn_its && g_signal == 0; i++) {                  // utils.py:94-96
+        it += 1;
+        if (int rc = sample_loop(m, N, dN, false, &ms)) return rc;
+    }
+    if (int rc = zero_stats(m)) return rc;                                      // utils.py:105: model.burn_stats()
+    while (rhat > 1.1 && g_signal == 0) {                                       // utils.py:123-135
+        it += 1;
+        if (int rc = sample_loop(m, N, dN, true, &ms)) return rc;
+        if (int rc = max_gelman_rubin(m, &rhat)) return rc;
+        if (it >= max_its) break;
+    }
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    m->phase_pending = 0;
+    m->last_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *its_out = it; *rhat_out = rhat;
     return 0;
 }
 
@@ -934,7 +1040,8 @@ extern "C" int gbn_topology_probe(const gbn_network *netin, const gbn_evidence *
     }
     auto put = [](uint32_t *dst, const std::vector<uint32_t> &v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), sizeof(uint32_t) * v.size()); };
     put(slot_of_edge, tp.slot_of_edge); put(deg, tp.deg); put(ref_of_dt, tp.ref_of_dt); put(gbase, tp.gbase);
-    put(tf_ptr, tp.tf_ptr); put(tf_child, tp.tf_child); put(tf_slot, tp.tf_slot);
+    put(tf_ptr, tp.tf_ptr); put(tf_slot, tp.tf_slot);
+    if (tf_child) std::memcpy(tf_child, tp.tf_child.data(), sizeof(uint32_t) * tp.Eu);       // without the sentinel entry
     if (ev && ev->n_evid > 0 && ev->n_datasets > 0 && (y || yprob)) {
         std::vector<uint8_t> yy(tp.nH);
         double yp[3];
@@ -1037,6 +1144,11 @@ extern "C" int gbn_model_set_state(gbn_model *m, uint32_t chain, const double *i
     for (uint32_t k = 0; k < nX; k++) { double v = in[o++]; if (v != 0. && v != 1.) return fail(GBN_ERR_INVALID, "X values must be 0 or 1"); X[k] = (uint8_t) v; }
     if (!m->net.const_params) for (uint32_t k = 0; k < nX; k++) T[k] = in[o++];
     for (uint32_t e = 0; e < E; e++) { double v = in[o++]; if (v != 0. && v != 1. && v != 2.) return fail(GBN_ERR_INVALID, "S values must be 0, 1 or 2"); S[m->tp.slot_of_edge[e]] = (uint8_t) v; }
+    if (m->kernel == GBN_KERNEL_FAST && !m->net.const_params)
+        for (uint32_t k = 0; k < nX; k++)
+            if (T[k] == 1.)                 // zero edge factor: see check_flags
+                return fail(GBN_ERR_UNSUPPORTED, "T = 1.0 exactly: the fast kernels cannot represent the zero edge factor; "
+                                                 "build the model with kernel = GBN_KERNEL_STRICT for this state");
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     if (!m->net.const_params)
         CUDA_TRY(cudaMemcpy(m->ch.T + (size_t) chain * nX, T.data(), sizeof(double) * nX, cudaMemcpyHostToDevice));
@@ -1268,21 +1380,21 @@ extern "C" int gbn_model_timer_stop(gbn_model *m, double *ms)
 }
 
 // diagnostics of the speculative X windows: rounds, TFs committed, flips (since enabled)
-extern "C" int gbn_model_debug_counters(gbn_model *m, int enable, uint64_t out[4])
+extern "C" int gbn_model_debug_counters(gbn_model *m, int enable, uint64_t out[8])
 {
     if (!m) return fail(GBN_ERR_INVALID, "null model");
     if (int rc = use_device(m)) return rc;
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     if (out) {
-        for (int i = 0; i < 4; i++) out[i] = 0;
-        if (m->ch.dbg) CUDA_TRY(cudaMemcpy(out, m->ch.dbg, 32, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 8; i++) out[i] = 0;
+        if (m->ch.dbg) CUDA_TRY(cudaMemcpy(out, m->ch.dbg, 64, cudaMemcpyDeviceToHost));
     }
     if (enable && !m->ch.dbg) {
         unsigned long long *p = nullptr;
-        if (int rc = dev_alloc(m, &p, 4)) return rc;
+        if (int rc = dev_alloc(m, &p, 8)) return rc;
         m->ch.dbg = p;
     }
-    if (m->ch.dbg) CUDA_TRY(cudaMemset(m->ch.dbg, 0, 32));
+    if (m->ch.dbg) CUDA_TRY(cudaMemset(m->ch.dbg, 0, 64));
     if (!enable) m->ch.dbg = nullptr;
     return 0;
 }

@@ -7,7 +7,7 @@
 //   statistics    cX1[c][nX] u32  (#sweeps with X=1; X=0 is N - cX1)
 //                 tMean[c][nX], tM2[c][nX] f64 (Welford, gsl_rstat order of operations)
 //                 cS[c][Ep] u32x2 in slot order: #sweeps with S=0 and with S=2 (S=1 is N - both)
-//   fast kernel   tc2[c][nH] {beta, gamma} f64x2 and ny[c][nH] u16 (y * D + n): the per-target product cache
+//   fast kernel   tc2[c][nH] {w0, w2} f64x2 flip weights and tL[c][nH] f64 likelihood: the per-target cache of the X phase
 //                 Sw[c][nSw] u32 S as 2-bit codes in slot order (the fast sweep's master copy of S)
 //                 dC[c][nD] u8x8 per-batch outcome counts of four steps, folded into cS on demand
 //                 Stfp[c][E/16] u32 copy of S in by-TF CSR order, 2-bit codes (coalesced reads in the X phase)
@@ -51,6 +51,8 @@ struct DevNet {
     const uint32_t *tf_abit;      // [Eu]  by-TF position -> 16 * (S word of the edge) + step inside the word
     uint32_t nSw, nD;
     const uint8_t *x_prior_active;// [nX]
+    const uint8_t *tf_uf;         // [n_datasets][nX] 1: the product of this TF's children's likelihoods could underflow a double
+                                  // (sum_children log min_h YNOISE[h][y] < -600), so the X kernel carries its magnitude
     const double *t_a, *t_b, *t_mean, *t_lnB;   // [nX]
     const uint8_t *y;             // [n_datasets][nH]
     const double *yprob;          // [n_datasets][3]
@@ -77,8 +79,8 @@ struct DevChains {
     double *tMean, *tM2;
     uint2 *cS;                    // {count S=0, count S=2}
     // fast kernel only
-    double2 *tc2;                 // [c/XQ][nH + 1][XQ] (interleaved by chain bundle; entry nH is a dummy {0, 0} for idle lanes) {beta, gamma} = {pr0 omz (N2-N0), pr0 pr2 omz (N1-N2)}: L = c0[ny] + beta + gamma
-    uint16_t *ny;                 // [c][nH] y * stab_D + n, n = number of parents with S != 1
+    double2 *tc2;                 // [c/XQ][nH + 1][XQ] (interleaved by chain bundle; entry nH is a dummy {0, 0} for idle lanes)
+    double *tL;                   // [c/XQ][nH + 1][XQ] the target likelihood L itself (dummy: 1) flip weights {w0, w2} = {pr0 omz (a + pr2 b), pr0 pr2 omz b} / L (sweep_fast.cu, k_fast_x)
     uint32_t *Sw;                 // [c][nSw] S as 2-bit codes, 16 steps per word: what the fast sweep reads and writes
                                   // (ch.S is refreshed from it on demand, capi.cu)
     uint32_t *Aw;                 // [c][nSw] bit u of a word: the parent TF of step u of the matching S word is active (X = 1);
@@ -91,7 +93,9 @@ struct DevChains {
     // simulation mode only: latent / observed state per (chain, device target) and their outcome counts
     uint8_t *H, *Y;
     uint2 *cH, *cY;               // {count outcome 0, count outcome 2}
-    unsigned long long *dbg;      // [4] diagnostics: X-window rounds, TFs committed, flips, (unused)
+    unsigned long long *dbg;      // [8] diagnostics (gbn_model_debug_counters)
+    volatile uint32_t *flags;     // host-mapped word: bit 0 = a T node reached exactly 1.0 on the fast path (factor 1 - t x = 0:
+                                  // its reciprocal does not exist; the model layer reports it, capi.cu)
     // injected draws (NULL = keyed Philox streams)
     const double *inj_flat;       // [chain][inj_sweeps][nX + E]  X then S in edge input order
     const double *inj_beta;       // [chain][inj_sweeps][nX]
@@ -103,6 +107,10 @@ struct DevChains {
 // local chain index -> dataset and global chain id (Philox counter word 2)
 // first slot of device target dt; its j-th parent is 32 j further
 __device__ __forceinline__ uint32_t slot0(const DevNet &n, uint32_t dt) { return n.gbase[dt >> 5] + (dt & 31); }
+
+// words of the by-TF copy of the S codes (16 codes per word): positions 0 .. E-1 and the sentinel position E
+// (code 1, child = the dummy target nH) that idle lanes of the X kernel's child loop read instead of branching
+__host__ __device__ inline uint32_t n_stf_words(const DevNet &n) { return (n.E + 16) >> 4; }
 
 __host__ __device__ inline uint32_t chain_dataset(const DevNet &n, uint32_t c) { return c / n.n_graphs_local; }
 __host__ __device__ inline uint32_t chain_global_id(const DevNet &n, uint32_t c)

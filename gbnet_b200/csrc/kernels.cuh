@@ -50,6 +50,12 @@ int launch_fast_fold(const DevNet &net, const DevChains &ch, cudaStream_t st, co
 constexpr uint32_t FAST_MAX_PENDING = 255;
 bool fast_supported(const DevNet &net, const char **why);
 
+// ---- sweep_small.cu: networks whose whole chain state fits one SM's shared memory - one persistent CTA per chain
+// runs all the sweeps of a batch in ONE launch (state in at the start, state and per-batch counters out at the end)
+bool small_supported(const DevNet &net, const char **why);
+int launch_sweep_small(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0, uint32_t stat_n0,
+                       cudaStream_t st, const char **err, uint32_t chain0 = 0, uint32_t nchains = UINT32_MAX);
+
 // ---- sim_kernels.cu: simulation mode (GraphORNOR.cpp:28,58-63,89-106): n_sweeps sweeps H, Y -> T
 int launch_sim_sweep(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
                      uint32_t stat_n0, cudaStream_t st, const char **err);

@@ -40,6 +40,7 @@
 #include <cstdio>
 #include "kernels.cuh"
 #include "device_math.cuh"
+#include <type_traits>
 #include <utility>
 
 #include "topology.hpp"
@@ -67,24 +68,49 @@ constexpr int XQ = GBN_XQ;           // X kernel: chains per CTA = chains interl
 constexpr int FS_NT = GBN_S_NT;      // S kernel: one warp = one group of 32 targets
 constexpr int FT_NT = 128;           // T kernel
 
+// One edge factor f = (1 - t x) z of a target is replaced by q f (phi = q - 1): the target's flip weights and
+// likelihood after the change.  With rho = 1 + phi w (w = the weight of the edge's code):
+//   S = 0 (f in both terms):  L' = L rho,  w0' = q w0 / rho,             w2' = q w2 / rho
+//   S = 2 (f in gamma only):  L' = L rho,  w0' = (w0 + phi w2) / rho,    w2' = q w2 / rho
+__device__ __forceinline__ void flip_weights(double2 &w, double &L, uint32_t s, double phi)
+{
+    const double q = 1. + phi;
+    const double rho = __fma_rn(phi, s == 0 ? w.x : w.y, 1.);
+    const double ir = 1. / rho;
+    w.x = (s == 0 ? q * w.x : __fma_rn(phi, w.y, w.x)) * ir;
+    w.y = q * w.y * ir;
+    L *= rho;
+}
+
 // ---------------------------------------------------------------------------------- X phase
-// One CTA sweeps the X nodes of XQ chains (a "bundle": chains XQ p .. XQ p + XQ - 1).  The kernel is bound
-// by L1 wavefronts and instruction issue: a warp-wide gather costs one wavefront (~2 cycles) per distinct
-// 128-byte line, and the children of a TF are scattered over the product cache.  The cache is therefore
-// interleaved by bundle - tc2[bundle][target][XQ] - and a warp's lanes are (32 / XQ children) x (XQ chains):
-// the XQ lanes of one child read adjacent 16-byte entries of one line, which divides the wavefronts per
-// (child, chain) by XQ.  The chains of a bundle share the window position: a window commits up to the
-// first TF that changed in ANY of them (flips are rare, so the shorter commit costs little), and every
-// committed TF still saw exactly the state the sequential sweep of its own chain would have seen.
+// One CTA sweeps the X nodes of XQ chains (a "bundle": chains XQ p .. XQ p + XQ - 1).
+//
+// Flip weights.  The S phase leaves per (target, chain) two numbers (tc2) and the likelihood itself (tL):
+//     w0 = pr0 omz (a + pr2 b) / L,     w2 = pr0 pr2 omz b / L,     L = c0[n] + pr0 omz (a + pr2 b)
+// (algebra at k_fast_s).  An edge with S = 0 carries its factor f = (1 - t x) z in both terms of the numerator of
+// w0, an edge with S = 2 in that of w2, so replacing f by q f turns L into L (1 + (q - 1) w), w = w0 or w2 by the
+// edge's code (an edge that is off: w = 0).  The conditional of X_k (Multinomial.cpp:56-86 with
+// XNode::get_children_loglikelihood, XNode.cpp:16-22) needs the product of L over the children for both values
+// of X_k; their RATIO is
+//     prod_children (1 + phi_k w),      phi_k = -t_k  (X_k = 0 -> 1),   t_k / (1 - t_k)  (X_k = 1 -> 0),
+// one 8-byte gather and one fused multiply-add per child - no table lookup, no second product.  Only the
+// underflow rule of Multinomial.cpp:78-85 (both outcome likelihoods round to zero: draw from the prior) needs the
+// magnitude prod L itself; it is carried along (one more 8-byte gather per child) for exactly the (dataset, TF)
+// pairs whose children COULD underflow a double: sum_children log min_h YNOISE[h][y] < -600 (net.tf_uf, computed
+// on the host when the evidence is set).
+//
+// The kernel is bound by L1 wavefronts and instruction issue: a warp-wide gather costs one wavefront per distinct
+// 128-byte line, and the children of a TF are scattered over the cache.  The cache is therefore interleaved by
+// bundle - tc2[bundle][target][XQ] - and a warp's lanes are (32 / XQ children) x (XQ chains): the XQ lanes of one
+// child read one sector.  The chains of a bundle share the window position: a window commits up to the first TF
+// that changed in ANY of them (flips are rare, so the shorter commit costs little), and every committed TF still
+// saw exactly the state the sequential sweep of its own chain would have seen.
 // LPT lanes of a warp work on one TF (32: a warp per TF; 16 / 8: two / four TFs per warp - the per-TF
 // instruction overhead is issued by all warps at once, and a longer window means fewer rounds).
-//
-// The child loop is written for instruction count (round 1: ~80 instructions per (child, chain), round 2:
-// see profiles/r2_sass_mix.txt): U children per lane and trip with the ids / S words of the NEXT trip
-// requested before the current trip's cache entries are used; idle lanes of a last trip read a dummy
-// target (entry nH: {0, 0}, table value 1) instead of branching; the flip multipliers {m_beta, m_gamma} of
-// an edge by S code come from a 3-entry shared-memory row per (TF, chain) instead of selects.
-template <int NT, bool NY_SMEM, int LPT, int U>
+// U children per lane and trip, the ids / S codes of the NEXT trip requested before the current trip's weights
+// are used; a lane past the end of its TF's list reads the sentinel position E (the dummy target nH: weights 0,
+// likelihood 1) instead of branching.
+template <int NT, int LPT, int U>
 __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, SweepArgs a, uint32_t nchains)
 {
     constexpr int NW = NT / 32, NS = 32 / LPT, W = NW * NS;                  // warps, TFs per warp, TFs per window
@@ -92,13 +118,11 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     static_assert(LPT >= 2 * XQ, "a TF needs at least two child slots");
     extern __shared__ __align__(16) unsigned char smem_x[];
     __shared__ uint32_t s_dec[W];                                            // per window position: chains of the bundle that flipped
-    const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;
-    const uint32_t nXr = (nX + 3) & ~3u, C0N = 3 * D + 2, nStfW = (net.E + 15) >> 4;
-    double2 *sMul = reinterpret_cast<double2 *>(smem_x);                     // [W][Q][4] ([0].x: flip factor of the (TF, chain))
-    double *xC0all = reinterpret_cast<double *>(sMul + W * Q * 4);           // [Q][C0N] c0 by idx = y * D + n; [3 D] = 1 (dummy)
-    uint32_t *sPtr = reinterpret_cast<uint32_t *>(xC0all + Q * C0N);         // [nX + 1 rounded up to 4] tf_ptr
-    uint8_t *sX = reinterpret_cast<uint8_t *>(sPtr + ((nX + 4) & ~3u));      // [Q][nX rounded up to 4] value | prior class << 1
-    uint16_t *sNy = reinterpret_cast<uint16_t *>(sX + Q * nXr);              // [nH + 1][Q] table index of every target (NY_SMEM)
+    __shared__ double s_phi[W * XQ];                                         // per window position and chain: phi of the flip
+    const uint32_t nX = net.nX, nH = net.nH;
+    const uint32_t nXr = (nX + 3) & ~3u, nStfW = n_stf_words(net);
+    uint32_t *sPtr = reinterpret_cast<uint32_t *>(smem_x);                   // [nX + 1 rounded up to 4] tf_ptr
+    uint8_t *sX = reinterpret_cast<uint8_t *>(sPtr + ((nX + 4) & ~3u));      // [Q][nX rounded up to 4] value | prior class << 1 | may underflow << 2
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sg = lane / LPT, sl = lane % LPT;                         // this lane's TF of the warp, lane within it
@@ -108,16 +132,16 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     const uint32_t nvalid = min(Q, nchains - Q * blockIdx.x);                // a last, partial bundle recomputes its last chain
     const uint32_t cmine = cbase + min(h, nvalid - 1);
     double2 *tcb = ch.tc2 + (size_t) (cbase / Q) * (nH + 1) * Q;             // bundle base: entry (i, chain) at Q i + chain
+    double *tlb = ch.tL + (size_t) (cbase / Q) * (nH + 1) * Q;
 
     // everything a round needs per TF is staged once: a round must not wait on global memory for
-    // anything but the children's ids and cache entries
+    // anything but the children's ids and weights
     for (uint32_t q = 0; q < Q; q++) {
         const uint32_t c = cbase + min(q, nvalid - 1);
         const uint32_t d = chain_dataset(net, c), gchain = chain_global_id(net, c);
         const uint8_t *gX = ch.X + (size_t) c * nX;
-        for (uint32_t k = tid; k < nX; k += NT) sX[q * nX + k] = (uint8_t) (gX[k] | (net.x_prior_active[k] << 1));
-        const double *tab = net.stab + (size_t) d * STAB_ROWS * D;
-        for (uint32_t j = tid; j < C0N; j += NT) xC0all[q * C0N + j] = j < 3 * D ? tab[j] : 1.;
+        const uint8_t *uf = net.tf_uf + (size_t) d * nX;
+        for (uint32_t k = tid; k < nX; k += NT) sX[q * nX + k] = (uint8_t) (gX[k] | (net.x_prior_active[k] << 1) | (uf[k] << 2));
         if (!a.use_inj) {   // every X uniform of this chain and sweep: one Philox block per four TFs, computed once
             uint4 *gU = reinterpret_cast<uint4 *>(ch.xU + (size_t) c * nXr);
             for (uint32_t blk = tid; blk < nXr / 4; blk += NT) {
@@ -125,103 +149,100 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
                 gU[blk] = make_uint4(r.x, r.y, r.z, r.w);
             }
         }
-        // (n, y) table index of every target: X flips do not change it, so one coalesced copy per sweep
-        // replaces a scattered 2-byte gather per child
-        if (NY_SMEM) {
-            const uint16_t *gny = ch.ny + (size_t) c * nH;
-            for (uint32_t i = tid; i < nH; i += NT) sNy[(size_t) i * Q + q] = gny[i];
-            if (tid == 0) sNy[(size_t) nH * Q + q] = (uint16_t) (3 * D);
-        }
     }
     for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.tf_ptr[k];
     __syncthreads();
 
-    const double *xC0 = xC0all + h * C0N;
-    const uint32_t *gStf = ch.Stfp + (size_t) cmine * nStfW;
     const double *gT = ch.T + (size_t) cmine * nX;
     const uint32_t *gU = ch.xU + (size_t) cmine * nXr;
-    const uint16_t *gNy = ch.ny + (size_t) cmine * nH;                       // networks too large for sNy gather it from here
     const double *inj = a.use_inj ? ch.inj_flat + ((size_t) cmine * ch.inj_sweeps + a.inj_row) * (nX + net.E) : nullptr;
-    double2 *mul = sMul + (pos * Q + h) * 4;
+    // this lane's chain inside the bundle-interleaved cache, as 32-bit element offsets: w0 of target i at
+    // tw_all[w_off + 2 Q i], w2 one further; L at ch.tL[l_off + Q i]; the chain's by-TF S words from stf_off
+    const double *tw_all = reinterpret_cast<const double *>(ch.tc2);
+    const uint32_t l_off = (cbase / Q) * (nH + 1) * Q + h, w_off = 2 * l_off, stf_off = cmine * nStfW;
+    const uint32_t E = net.E;
 
     uint32_t k0 = 0;
     while (k0 < nX) {
         const uint32_t kw = k0 + pos;
         const bool live = kw < nX;
         int dec = 0;                              // bit 0: drawn value, bit 1: value changed (this lane's chain)
+        double phi = 0.;
         if (NS > 1 || live) {                     // warp-uniform when a warp holds one TF; else dead TFs ride along empty
             const uint32_t kr = live ? kw : 0u;
-            const uint32_t xcur = sX[h * nX + kr] & 1u;
+            const uint32_t xs = sX[h * nX + kr], xcur = xs & 1u;
             // per-TF scalars come from global memory (written by this CTA or an earlier kernel): the loads
             // are issued with the first child ids and are off the critical path
-            const double g = 1. - gT[kr];         // (1 - t*x) at x = 1   (HNodeORNOR.cpp:59)
+            const double t = gT[kr];
             const uint32_t uword = a.use_inj ? 0u : gU[kr];
             uint32_t cbeg = 0, cend = 0;
             if (live) { cbeg = sPtr[kw]; cend = sPtr[kw + 1]; }
-            GBN_CHECK(cbeg <= cend && cend <= net.E);
-            // One (child, chain) per lane and gather.  The ids and S words of the next trip are requested
-            // before this trip's entries are used; the pipeline lives inside one round, so every entry is
-            // read after the flips of all earlier (committed) windows.
+            GBN_CHECK(cbeg <= cend && cend <= E);
             uint32_t cc = cbeg + cs;
-            uint32_t id[U], sw[U];
+            uint32_t id[U], sh[U];
+            // (32-bit element offsets off the kernel-parameter base pointers: one IMAD.WIDE per address, no
+            // 64-bit pointer kept or rebuilt in the loop)
             auto load_ids = [&](uint32_t c0) {
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const uint32_t c = c0 + u * CPW;
-                    const bool ok = c < cend;
-                    id[u] = nH; sw[u] = 0x55555555u;                         // idle lane: the dummy target, edge off
-                    if (ok) { id[u] = net.tf_child[c]; sw[u] = __ldg(gStf + (c >> 4)); }
+                    const uint32_t cr = c0 + u * CPW;
+                    const uint32_t c = cr < cend ? cr : E;
+                    id[u] = __ldg(net.tf_child + c);
+                    sh[u] = (__ldg(ch.Stfp + (stf_off + (c >> 4))) >> (2 * (c & 15))) & 3u;
                 }
             };
             load_ids(cc);
             uint32_t trips = (cend - cbeg + U * CPW - 1) / (U * CPW);        // trip count, uniform over the warp
             if (NS > 1) trips = __reduce_max_sync(0xffffffffu, trips);
-            // factor that turns the product into the flipped one; by S code of the edge it scales
-            // {beta, gamma} (S = 0), nothing (S = 1) or gamma only (S = 2)
-            double fac = g;
-            if (xcur) fac = 1. / g;
-            if (cs == 0) mul[0] = make_double2(fac, fac);                     // read by the flip patch below
-            double mc = 1., mf = 1.;
-            int ec = 0, ef = 0, cnt = 0;
-            for (; trips > 0; trips--) {
-                double2 bg[U];
-                uint32_t nyv[U], sh[U];
+            // f -> q f with q = 1 - t (X: 0 -> 1) or 1 / (1 - t) (X: 1 -> 0); phi = q - 1
+            phi = -t;
+            if (xcur) phi = t / (1. - t);
+            const bool track = (xs & 4u) != 0;                               // prod L could underflow: carry its magnitude
+            double mr = 1., ml = 1.;                                         // ratio flip / current, and prod L (if tracked)
+            int er = 0, el = 0;
+            auto child_loop = [&](auto with_l) {
+                constexpr bool WITH_L = decltype(with_l)::value;
+                int cnt = 0;
+                for (; trips > 0; trips--) {
+                    double w[U], lc[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    GBN_CHECK(id[u] <= nH);
-                    bg[u] = tcb[(size_t) id[u] * Q + h];
-                    nyv[u] = NY_SMEM ? sNy[(size_t) id[u] * Q + h] : (id[u] == nH ? 3 * D : gNy[id[u]]);
-                    sh[u] = (sw[u] >> (2 * ((cc + u * CPW) & 15))) & 3u;
-                }
-                cc += U * CPW;
-                load_ids(cc);                                                 // next trip
+                    for (int u = 0; u < U; u++) {
+                        GBN_CHECK(id[u] <= nH && sh[u] <= 2);
+                        const uint32_t iw = sh[u] == 1 ? nH : id[u];         // an edge that is off: the dummy's zero weight
+                        w[u] = tw_all[w_off + 2 * Q * iw + (sh[u] >> 1)];
+                        if (WITH_L) lc[u] = ch.tL[l_off + Q * id[u]];
+                    }
+                    cc += U * CPW;
+                    load_ids(cc);                                             // next trip
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    GBN_CHECK(nyv[u] <= 3 * D);
-                    // flip multipliers {m_beta, m_gamma} by S code (selects: a shared-memory row per (TF, chain) costs
-                    // four more L1 wavefronts per trip, measured 0.53 against 0.49 ms per sweep)
-                    const double2 m = make_double2(sh[u] == 0 ? fac : 1., sh[u] != 1 ? fac : 1.);
-                    const double c0 = xC0[nyv[u]];
-                    const double Lc = c0 + (bg[u].x + bg[u].y);
-                    const double Lf = c0 + __fma_rn(m.x, bg[u].x, m.y * bg[u].y);
-                    mc *= Lc; mf *= Lf;
+                    for (int u = 0; u < U; u++) {
+                        mr *= __fma_rn(phi, w[u], 1.);
+                        if (WITH_L) ml *= lc[u];
+                    }
+                    if ((cnt += U) >= 16) { normalise(mr, er); if (WITH_L) normalise(ml, el); cnt = 0; }
                 }
-                if ((cnt += U) >= 16) { normalise(mc, ec); normalise(mf, ef); cnt = 0; }
-            }
-            normalise(mc, ec);
-            normalise(mf, ef);
+            };
+            if (__any_sync(0xffffffffu, track)) child_loop(std::true_type{});
+            else child_loop(std::false_type{});
+            if (!track) { ml = 1.; el = 0; }
+            normalise(mr, er);
+            normalise(ml, el);
 #pragma unroll
             for (int o = LPT / 2; o >= (int) Q; o >>= 1) {
-                mc *= __shfl_xor_sync(0xffffffffu, mc, o);
-                mf *= __shfl_xor_sync(0xffffffffu, mf, o);
-                ec += __shfl_xor_sync(0xffffffffu, ec, o);
-                ef += __shfl_xor_sync(0xffffffffu, ef, o);
+                mr *= __shfl_xor_sync(0xffffffffu, mr, o);
+                ml *= __shfl_xor_sync(0xffffffffu, ml, o);
+                er += __shfl_xor_sync(0xffffffffu, er, o);
+                el += __shfl_xor_sync(0xffffffffu, el, o);
             }
-            normalise(mc, ec);
+            normalise(mr, er);
+            normalise(ml, el);
+            // outcome likelihoods exp(log prior + sum log L) of Multinomial.cpp:66-75: current = p prod L, flipped = p' prod L ratio
+            const double *prob = net.xprob[(xs >> 1) & 1u];
+            double mf = ml * mr;
+            int ef = el + er;
             normalise(mf, ef);
-            const double *prob = net.xprob[sX[h * nX + kr] >> 1];
             double lik_cur, lik_flip;
-            common_scale(prob[xcur] * mc, ec, prob[1 - xcur] * mf, ef, lik_cur, lik_flip);
+            common_scale(prob[xcur] * ml, el, prob[1 - xcur] * mf, ef, lik_cur, lik_flip);
             const double l0 = xcur ? lik_flip : lik_cur, l1 = xcur ? lik_cur : lik_flip;
             double cum0 = 0. + l0, cum1 = cum0 + l1;
             if (!(cum1 > 0.)) { cum0 = 0. + prob[0]; cum1 = cum0 + prob[1]; }     // Multinomial.cpp:78-85
@@ -234,6 +255,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
         const uint32_t fb = __ballot_sync(0xffffffffu, (dec & 2) && cs == 0);
         const uint32_t flipped = (fb >> (sg * LPT)) & ((1u << Q) - 1u);
         if (sl == 0) s_dec[pos] = flipped;
+        if (cs == 0) s_phi[pos * Q + h] = phi;
         __syncthreads();
         uint32_t first = W;
 #pragma unroll
@@ -242,16 +264,16 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             if (f && first == (uint32_t) W) first = w0 + (uint32_t) __ffs(f) - 1;
         }
         const uint32_t ncommit = first < W ? first + 1 : W;
-        if (pos < ncommit && live && cs == 0) sX[h * nX + kw] = (uint8_t) ((sX[h * nX + kw] & 2u) | (dec & 1));
+        if (pos < ncommit && live && cs == 0) sX[h * nX + kw] = (uint8_t) ((sX[h * nX + kw] & 6u) | (dec & 1));
         if (first < (uint32_t) W) {
             // The window ends at the one TF that flipped (in one or more chains of the bundle): apply the flip
-            // to the cached terms of each child that depends on it.  The whole CTA does this - every other
+            // to the weights of each child that depends on it.  The whole CTA does this - every other
             // warp would only wait at the barrier, and a hub's children walked by one warp cost tens of
             // microseconds of dependent loads.
             const uint32_t kf = k0 + first, fb0 = sPtr[kf], fe0 = sPtr[kf + 1], fmask = s_dec[first];
             for (uint32_t q = 0; q < Q; q++) {
                 if (!((fmask >> q) & 1u)) continue;
-                const double fq = sMul[(first * Q + q) * 4].x;
+                const double ph = s_phi[first * Q + q];
                 const uint32_t *gS = ch.Stfp + (size_t) (cbase + q) * nStfW;
                 uint32_t *gA = ch.Aw + (size_t) (cbase + q) * net.nSw;
                 for (uint32_t c2 = fb0 + tid; c2 < fe0; c2 += NT) {
@@ -261,11 +283,8 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
                     atomicXor(gA + (ab >> 4), 1u << (ab & 15));
                     const uint32_t s = code_at(gS, c2);
                     if (s == 1) continue;
-                    double2 *e = tcb + (size_t) net.tf_child[c2] * Q + q;
-                    double2 bg = *e;
-                    if (s == 0) bg.x *= fq;
-                    bg.y *= fq;
-                    *e = bg;
+                    const size_t i = (size_t) net.tf_child[c2] * Q + q;
+                    flip_weights(tcb[i], tlb[i], s, ph);
                 }
             }
         }
@@ -316,6 +335,7 @@ __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, Swee
         t = mh_decide(prev, prop, prev_ll, prop_ll, mean, dx, al, be, lnB,
                       a.use_inj != 0, a.use_inj ? ch.inj_exp[row] : 0., net.seed, gchain, a.sweep, k);
         Tout[o] = t;
+        if (t == 1.) *ch.flags = 1u;
         double m = ch.tMean[o], m2 = ch.tM2[o];
         welford_add(m, m2, t, (double) a.stat_n);
         ch.tMean[o] = m; ch.tM2[o] = m2;
@@ -340,29 +360,25 @@ __global__ void __launch_bounds__(FT_NT) k_fast_fx(DevNet net, DevChains ch, Swe
 // T nodes that LISTEN to their children (TNode.cpp:15-25; the pyx default), active TFs only: one CTA
 // per chain walks the chain's active TFs in index order (the reference's order; T updates of TFs
 // that share a target do not commute).  The blanket difference  sum_children log L(t') - log L(t)
-// comes from the product cache: the edge's factor (1 - t) z sits in beta and gamma (S = 0) or in
-// gamma only (S = 2), so L(t') = c0 + r (beta + gamma) resp. c0 + beta + r gamma with
-// r = (1 - t') / (1 - t); the product of the ratios is kept as mantissa x 2^e and one log is taken.
+// comes from the flip weights (see k_fast_x): the edge's factor (1 - t) z changes by r = (1 - t') / (1 - t),
+// so L(t') / L(t) = 1 + (r - 1) w; the product of the ratios is kept as mantissa x 2^e and one log is taken.
 constexpr int FTL_NT = 256;
 __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, SweepArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_tl[];
     __shared__ uint32_t s_count;
-    __shared__ double s_m[2][FTL_NT / 32];
-    __shared__ int s_e[2][FTL_NT / 32];
-    const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;
-    double *xC0 = reinterpret_cast<double *>(smem_tl);               // [3][D]
-    uint32_t *list = reinterpret_cast<uint32_t *>(xC0 + 3 * D);      // [nX] active TFs, ascending
+    __shared__ double s_m[FTL_NT / 32];
+    __shared__ int s_e[FTL_NT / 32];
+    const uint32_t nX = net.nX, nH = net.nH;
+    uint32_t *list = reinterpret_cast<uint32_t *>(smem_tl);          // [nX] active TFs, ascending
     const uint32_t c = blockIdx.x + a.chain0;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t d = chain_dataset(net, c);
     const uint32_t gchain = chain_global_id(net, c);
     const uint8_t *gX = ch.X + (size_t) c * nX;
-    const uint32_t *gStf = ch.Stfp + (size_t) c * ((net.E + 15) >> 4);
+    const uint32_t *gStf = ch.Stfp + (size_t) c * n_stf_words(net);
     double2 *tc2 = ch.tc2 + (size_t) (c / XQ) * (nH + 1) * XQ + (c % XQ);    // bundle-interleaved: entry i at XQ i
-    const uint16_t *gny = ch.ny + (size_t) c * nH;
+    double *tL = ch.tL + (size_t) (c / XQ) * (nH + 1) * XQ + (c % XQ);
 
-    for (uint32_t j = tid; j < 3 * D; j += FTL_NT) xC0[j] = net.stab[(size_t) d * STAB_ROWS * D + j];
     if (warp == 0) {
         uint32_t count = 0;
         for (uint32_t base = 0; base < nX; base += 32) {
@@ -407,35 +423,30 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
             const uint32_t cbeg = net.tf_ptr[k], cend = net.tf_ptr[k + 1];
             double dll = 0.;
             if (s_lpp[idx] > -INFINITY) {               // out-of-range proposals are rejected before the children matter
-                double mo = 1., mn = 1.;
-                int eo = 0, en = 0, cnt = 0;
+                // sum_children log L(t') - log L(t) = log prod (1 + (r - 1) w), w = the flip weight of the edge's code
+                double mr = 1.;
+                int er = 0, cnt = 0;
                 for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
                     const uint32_t s = code_at(gStf, cc);
                     if (s == 1) continue;
                     const uint32_t i = net.tf_child[cc];
-                    GBN_CHECK(i < nH && gny[i] < 3 * D);
-                    const double2 bg = tc2[XQ * (size_t) i];
-                    const double c0 = xC0[gny[i]];
-                    mo *= c0 + (bg.x + bg.y);
-                    mn *= s == 0 ? c0 + r * (bg.x + bg.y) : c0 + (bg.x + r * bg.y);
-                    if (++cnt == 8) { normalise(mo, eo); normalise(mn, en); cnt = 0; }
+                    GBN_CHECK(i < nH);
+                    const double2 w = tc2[XQ * (size_t) i];
+                    mr *= __fma_rn(r - 1., s == 0 ? w.x : w.y, 1.);
+                    if (++cnt == 8) { normalise(mr, er); cnt = 0; }
                 }
-                normalise(mo, eo);
-                normalise(mn, en);
+                normalise(mr, er);
 #pragma unroll
                 for (int w = 16; w > 0; w >>= 1) {
-                    mo *= __shfl_xor_sync(0xffffffffu, mo, w);
-                    mn *= __shfl_xor_sync(0xffffffffu, mn, w);
-                    eo += __shfl_xor_sync(0xffffffffu, eo, w);
-                    en += __shfl_xor_sync(0xffffffffu, en, w);
+                    mr *= __shfl_xor_sync(0xffffffffu, mr, w);
+                    er += __shfl_xor_sync(0xffffffffu, er, w);
                 }
-                normalise(mo, eo);
-                normalise(mn, en);
-                if (lane == 0) { s_m[0][warp] = mo; s_m[1][warp] = mn; s_e[0][warp] = eo; s_e[1][warp] = en; }
+                normalise(mr, er);
+                if (lane == 0) { s_m[warp] = mr; s_e[warp] = er; }
                 __syncthreads();
-                mo = 1.; mn = 1.; eo = 0; en = 0;
-                for (int w = 0; w < FTL_NT / 32; w++) { mo *= s_m[0][w]; mn *= s_m[1][w]; eo += s_e[0][w]; en += s_e[1][w]; }
-                dll = log(mn / mo) + (double) (en - eo) * 0.69314718055994530942;
+                mr = 1.; er = 0;
+                for (int w = 0; w < FTL_NT / 32; w++) { mr *= s_m[w]; er += s_e[w]; }
+                dll = log(mr) + (double) er * 0.69314718055994530942;
                 __syncthreads();                        // s_m / s_e free for the next TF
             }
             // Beta::metropolis_hastings_with_prior_proposal (Beta.cpp:60-91), as mh_decide with its pieces precomputed
@@ -450,19 +461,17 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
                 }
             }
             if (t != prev) {
-                // accepted: move the edge factors of this TF inside the cached terms of its children
+                // accepted: the edge factors of this TF change by the ratio r inside its children's weights
                 for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
                     const uint32_t s = code_at(gStf, cc);
                     if (s == 1) continue;
-                    const uint32_t i = net.tf_child[cc];
-                    double2 bg = tc2[XQ * (size_t) i];
-                    if (s == 0) bg.x *= r;
-                    bg.y *= r;
-                    tc2[XQ * (size_t) i] = bg;
+                    const size_t i = XQ * (size_t) net.tf_child[cc];
+                    flip_weights(tc2[i], tL[i], s, r - 1.);
                 }
             }
             if (tid == 0) {
                 ch.T[o] = t;
+                if (t == 1.) *ch.flags = 1u;
                 double m = ch.tMean[o], m2 = ch.tM2[o];
                 welford_add(m, m2, t, (double) a.stat_n);
                 ch.tMean[o] = m; ch.tM2[o] = m2;
@@ -537,15 +546,16 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
     const double ca = net.ynoise[2][y] - net.ynoise[0][y];          // a
     const double cb = net.ynoise[1][y] - net.ynoise[2][y];          // b
     const double2 *cot = sTab + y * D;                              // {c0, omz} over n for this target's y
-    uint32_t *pSw = ch.Sw + (size_t) c * net.nSw + net.sbase[g] + lane;
-    const uint32_t *pAw = ch.Aw + (size_t) c * net.nSw + net.sbase[g] + lane;
-    const uint16_t *pPar = reinterpret_cast<const uint16_t *>(net.par16 + net.dbase[g] + lane);   // step j: [128 (j / 4) + j % 4]
+    // 32-bit element offsets off the kernel-parameter base pointers (one IMAD.WIDE per address; 64-bit pointers
+    // kept in registers get rebuilt from the constant bank in every block under the 64-register cap)
+    const uint32_t sb = net.sbase[g] + lane, db = net.dbase[g] + lane;
+    const uint32_t sw_off = c * net.nSw + sb, dc_off = c * net.nD + db;
+    const uint16_t *par16 = reinterpret_cast<const uint16_t *>(net.par16);   // step j of this lane: [4 (db + 32 (j / 4)) + j % 4]
     const uint32_t W4 = (W + 3) >> 2;                                // 4-step blocks (the last may hold pads)
 
     if (MODE == 0) {
         // the counters are first touched by the second pass: start pulling their lines into L2 now
-        const uint2 *pc = ch.dC + (size_t) c * net.nD + net.dbase[g] + lane;
-        for (uint32_t b = 0; b < W4; b++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + 32 * b));
+        for (uint32_t b = 0; b < W4; b++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ch.dC + (dc_off + 32 * b)));
     }
     // Products over the parents (HNodeORNOR.cpp:55-62, 72-81): A = a pr0, Bq = b pr0 pr2, so that
     // L = c0[n] + omz[n] (A + Bq) and the a, b constants stay out of the edge loop.  An inactive TF contributes
@@ -557,14 +567,14 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
     {
         uint32_t n0 = 0;
         for (uint32_t w = 0; 16 * w < W; w++) {
-            const uint32_t sw = pSw[32 * w];
+            const uint32_t sw = ch.Sw[sw_off + 32 * w];
             GBN_CHECK(net.sbase[g] + lane + 32 * w < net.nSw);
             const uint32_t x = sw ^ 0x55555555u;
             n += __popc((x | (x >> 1)) & 0x55555555u);               // codes != 1
             n0 += __popc(~(sw | (sw >> 1)) & 0x55555555u);           // codes == 0
-            for (uint32_t act = pAw[32 * w] & 0xffffu; act; act &= act - 1) {
+            for (uint32_t act = ch.Aw[sw_off + 32 * w] & 0xffffu; act; act &= act - 1) {
                 const uint32_t u = __ffs(act) - 1, s = (sw >> (2 * u)) & 3u, j = 16 * w + u;
-                const uint32_t kk = pPar[128 * (j >> 2) + (j & 3)];
+                const uint32_t kk = par16[4 * (db + 32 * (j >> 2)) + (j & 3)];
                 GBN_CHECK(kk < nX);
                 const double fx = __ldg(&gFX[kk].x);
                 if (s == 0) A *= fx;
@@ -581,27 +591,24 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
         const uint32_t ref_i = valid ? net.ref_of_dt[dt] : 0u;
         const double *inj_flat = INJ ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + net.E) + nX : nullptr;
         const uint32_t *pEdge = net.par_edge + gb + lane;
-        const uint32_t *pMor = net.mor2 + net.sbase[g] + lane;
-        const uint4 *pTp = net.tfpos4 + net.dbase[g] + lane;
-        uint2 *pC = ch.dC + (size_t) c * net.nD + net.dbase[g] + lane;
-        uint32_t *gStfp = ch.Stfp + (size_t) c * ((net.E + 15) >> 4);
+        const uint32_t stf_off = c * n_stf_words(net);
         // blocks of four steps; every fourth block starts a new word of S codes / prior rows / activity bits.
         // PF: the block's counters and by-TF positions are requested one block ahead
         uint32_t sw0 = 0, sw = 0, mw = 0, aw = 0, chg = 0;
         uint4 tp4n = make_uint4(0, 0, 0, 0);
         uint2 cwn = make_uint2(0, 0);
-        if (PF) { tp4n = pTp[0]; cwn = __ldcs(pC); }
+        if (PF) { tp4n = net.tfpos4[db]; cwn = __ldcs(ch.dC + dc_off); }
         for (uint32_t bb = 0; bb < W4; bb++) {
             {
-                if ((bb & 3u) == 0) { sw0 = pSw[8 * bb]; sw = sw0; mw = pMor[8 * bb]; aw = pAw[8 * bb]; chg = 0; }
+                if ((bb & 3u) == 0) { sw0 = ch.Sw[sw_off + 8 * bb]; sw = sw0; mw = net.mor2[sb + 8 * bb]; aw = ch.Aw[sw_off + 8 * bb]; chg = 0; }
                 const uint32_t j0 = 4 * bb;
                 uint4 tp4;
                 uint2 cw;
                 if (PF) {
                     tp4 = tp4n; cw = cwn;
-                    if (bb + 1 < W4) { tp4n = pTp[32 * (bb + 1)]; cwn = __ldcs(pC + 32 * (bb + 1)); }
+                    if (bb + 1 < W4) { tp4n = net.tfpos4[db + 32 * (bb + 1)]; cwn = __ldcs(ch.dC + (dc_off + 32 * (bb + 1))); }
                 } else {
-                    tp4 = pTp[32 * bb]; cw = __ldcs(pC + 32 * bb);
+                    tp4 = net.tfpos4[db + 32 * bb]; cw = __ldcs(ch.dC + (dc_off + 32 * bb));
                 }
                 u32x4 rnd = { 0, 0, 0, 0 };
                 if (!INJ) rnd = philox_rk(ref_i, a.sweep, gchain, KIND_S | (bb << 8), a);
@@ -612,12 +619,15 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                         const uint32_t s = (sw >> (2 * u)) & 3u, r = (mw >> (2 * u)) & 3u;
                         GBN_CHECK(s <= 2 && n + 1 < D);
                         // f = (1 - t x) z and its reciprocal: z and 1 / z unless the parent TF is active
+                        // (a warp-wide vote first: as a per-lane branch the lookup is predicated into every step)
                         double f = z, finv = rz;
-                        if ((aw >> u) & 1u) {
-                            const uint32_t kk = pPar[128 * bb + u];
-                            GBN_CHECK(kk < nX);
-                            const double2 fx = __ldg(gFX + kk);
-                            f = fx.x * z; finv = fx.y * rz;
+                        if (__any_sync(0xffffffffu, (aw >> u) & 1u)) {
+                            if ((aw >> u) & 1u) {
+                                const uint32_t kk = par16[4 * (db + 32 * bb) + u];
+                                GBN_CHECK(kk < nX);
+                                const double2 fx = __ldg(gFX + kk);
+                                f = fx.x * z; finv = fx.y * rz;
+                            }
                         }
                         // the state without this edge
                         const double Af = A * finv, Bf = Bq * finv;
@@ -662,22 +672,27 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                             n = nR + (ns != 1);
                             const uint32_t tp = u == 0 ? tp4.x : (u == 1 ? tp4.y : (u == 2 ? tp4.z : tp4.w));
                             GBN_CHECK(tp < net.E);
-                            atomicXor(gStfp + (tp >> 4), x << (2 * (tp & 15)));
+                            atomicXor(ch.Stfp + (stf_off + (tp >> 4)), x << (2 * (tp & 15)));
                         }
                     }
                 }
-                __stcs(pC + 32 * bb, cw);                            // streamed: the product cache stays in L2
+                __stcs(ch.dC + (dc_off + 32 * bb), cw);              // streamed: the product cache stays in L2
                 chg |= chg4 << (8 * (bb & 3u));
                 sw >>= 8; mw >>= 8; aw >>= 4;
             }
-            if (((bb & 3u) == 3 || bb + 1 == W4) && chg) pSw[8 * (bb & ~3u)] = sw0 ^ chg;
+            if (((bb & 3u) == 3 || bb + 1 == W4) && chg) ch.Sw[sw_off + 8 * (bb & ~3u)] = sw0 ^ chg;
         }
     }
-    GBN_CHECK(n + (y * D) < 3 * D);
+    GBN_CHECK(n < D);
     if (valid) {
-        ch.tc2[((size_t) (c / XQ) * (nH + 1) + dt) * XQ + (c % XQ)] =
-            make_double2(cot[n].y * A, cot[n].y * Bq);                 // {beta, gamma}, interleaved by chain bundle
-        ch.ny[(size_t) c * nH + dt] = (uint16_t) (y * D + n);          // index into the X phase tables
+        // what the X phase reads (see k_fast_x): L = c0[n] + omz[n] (A + Bq) and the flip weights
+        // w0 = omz (A + Bq) / L (an S = 0 edge's factor sits in both terms), w2 = omz Bq / L (an S = 2 edge's)
+        const double2 t = cot[n];
+        const double g2 = t.y * Bq, g02 = t.y * A + g2;
+        const double L = t.x + g02, iL = 1. / L;
+        const size_t o = ((size_t) (c / XQ) * (nH + 1) + dt) * XQ + (c % XQ);   // interleaved by chain bundle
+        ch.tc2[o] = make_double2(g02 * iL, g2 * iL);
+        ch.tL[o] = L;
     }
 }
 
@@ -751,7 +766,7 @@ __global__ void k_fast_stf(DevNet net, DevChains ch)
 {
     const uint32_t c = blockIdx.y;
     const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t nStfW = (net.E + 15) >> 4;
+    const uint32_t nStfW = n_stf_words(net);
     if (wi >= nStfW) return;
     uint32_t w = 0;
     for (uint32_t u = 0; u < 16; u++) {
@@ -777,18 +792,11 @@ static size_t s_smem_bytes(const DevNet &net)
     return sizeof(double2) * 3 * (size_t) net.stab_D + sizeof(double) * 2 * (size_t) net.stab_D + 16;
 }
 
-// shared memory of the X kernel (XQ chains per CTA): flip multipliers of a window, tables, by-TF pointers, X and
-// - when it fits - the (n, y) index of every target
-static size_t x_smem_bytes(const DevNet &net, bool ny_smem)
+// shared memory of the X kernel (XQ chains per CTA): by-TF pointers and X
+static size_t x_smem_bytes(const DevNet &net)
 {
     const size_t nX = net.nX, nXr = (nX + 3) & ~(size_t) 3, Q = XQ;
-    return sizeof(double2) * 64 * Q * 4 + sizeof(double) * Q * (3 * (size_t) net.stab_D + 2) + 4 * ((nX + 4) & ~(size_t) 3) + Q * nXr
-           + (ny_smem ? 2 * ((size_t) net.nH + 1) * Q : 0) + 16;
-}
-static bool x_ny_smem(const DevNet &net)
-{
-    if (env_u32("GBN_X_NY", 1) == 2) return false;        // 2 = gather from global memory (tests of the large-network path)
-    return x_smem_bytes(net, true) + 256 <= 200 * 1024;
+    return 4 * ((nX + 4) & ~(size_t) 3) + Q * nXr + 16;
 }
 
 uint32_t fast_x_bundle() { return XQ; }
@@ -806,8 +814,11 @@ bool fast_supported(const DevNet &net, const char **why)
     if (net.nX > 65535) { *why = "n_tf does not fit the 16-bit parent id"; return false; }
     if (s_smem_bytes(net) > 200 * 1024) { *why = "in-degree too large for the S-phase tables"; return false; }
     if (net.Eu != net.E) { *why = "duplicate (TF, target) edges"; return false; }
-    if (x_smem_bytes(net, false) + 256 > 200 * 1024) { *why = "n_tf too large for the X window kernel's shared memory"; return false; }
-    if (3 * (size_t) net.stab_D + 1 > 65535) { *why = "in-degree does not fit the 16-bit (y, n) table index"; return false; }
+    {   // the X kernel addresses the per-chain caches with 32-bit element offsets
+        const uint64_t C = (uint64_t) net.n_datasets * net.n_graphs_local + XQ;
+        if (2 * C * (net.nH + 1) >= (1ull << 32) || C * n_stf_words(net) >= (1ull << 32) || C * net.nD >= (1ull << 32)) { *why = "chains x targets exceeds the 32-bit cache offsets"; return false; }
+    }
+    if (x_smem_bytes(net) + 2048 > 200 * 1024) { *why = "n_tf too large for the X window kernel's shared memory"; return false; }
     return true;
 }
 
@@ -834,7 +845,7 @@ int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st,
     if (ch.n_chains == 0) return 0;
     SweepArgs a = sweep_args(net);
     k_pack_s<<<dim3((net.nSw + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
-    k_fast_stf<<<dim3(((net.E + 15) / 16 + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
+    k_fast_stf<<<dim3((n_stf_words(net) + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
     k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, 0, ch.T, 1);
     if (launch_s(net, ch, a, 1, ch.n_chains, st, err)) return -1;
     if (check(cudaGetLastError(), err)) return -1;
@@ -866,26 +877,23 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
     if (stx == nullptr) stx = st;                      // X kernels on their own (high-priority) stream when given
     if (nchains == UINT32_MAX) nchains = ch.n_chains - chain0;
     if (n_sweeps == 0 || nchains == 0) return 0;
-    const bool ny_smem = x_ny_smem(net);
-    const size_t smem_x = x_smem_bytes(net, ny_smem);
+    const size_t smem_x = x_smem_bytes(net);
     if (chain0 % XQ) { *err = "chain groups must start at a multiple of the X kernel's bundle size"; return -1; }
-    // Lanes per TF by the mean number of targets of a TF: half a warp (a 64-TF window; two gathers per lane and
-    // stage when TFs are large), or a quarter in CTAs of 16 warps (two CTAs per SM when there are more bundles
-    // than SMs).  Fewer lanes per TF = less per-TF instruction overhead and, with the longer window, fewer
+    // Lanes per TF by the mean number of targets of a TF: half a warp (a 64-TF window), or a quarter in CTAs of 16
+    // warps.  Fewer lanes per TF = less per-TF instruction overhead and, with the longer window, fewer
     // rounds: the fixed latency of a round grows when the S kernels of other chain groups load the memory
-    // system (C3, 4 chain groups: a warp per TF 7.43e10, half a warp 7.81e10 edge-updates/s at equal
-    // stand-alone kernel time).  A whole warp per TF is kept for GBN_X_LPT=32.
+    // system.  A whole warp per TF is kept for GBN_X_LPT=32.
     uint32_t lpt = env_u32("GBN_X_LPT", 0);                  // 8 / 16 / 32 force a path (tests)
     const bool big = (uint64_t) net.E >= 48ull * net.nX;
     if (lpt != 8 && lpt != 16 && lpt != 32) lpt = (uint64_t) net.E >= 20ull * net.nX ? 16 : 8;
     void (*kx)(DevNet, DevChains, SweepArgs, uint32_t);
     uint32_t x_nt = FX_NT;
-    if (lpt == 32) kx = ny_smem ? k_fast_x<FX_NT, true, 32, XU> : k_fast_x<FX_NT, false, 32, XU>;
-    else if (lpt == 16 && big) kx = ny_smem ? k_fast_x<FX_NT, true, 16, XU> : k_fast_x<FX_NT, false, 16, XU>;
-    else if (lpt == 16) kx = ny_smem ? k_fast_x<FX_NT, true, 16, 1> : k_fast_x<FX_NT, false, 16, 1>;
-    else { kx = ny_smem ? k_fast_x<FX_NT / 2, true, 8, 1> : k_fast_x<FX_NT / 2, false, 8, 1>; x_nt = FX_NT / 2; }
+    if (lpt == 32) kx = k_fast_x<FX_NT, 32, XU>;
+    else if (lpt == 16 && big) kx = k_fast_x<FX_NT, 16, XU>;
+    else if (lpt == 16) kx = k_fast_x<FX_NT, 16, 1>;
+    else { kx = k_fast_x<FX_NT / 2, 8, 1>; x_nt = FX_NT / 2; }
     if (check(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x), err)) return -1;
-    const size_t smem_tl = sizeof(double) * 3 * (size_t) net.stab_D + 4 * (size_t) net.nX + 16;
+    const size_t smem_tl = 4 * (size_t) net.nX + 16;
     if (net.listen && !net.const_params &&
         check(cudaFuncSetAttribute(k_fast_tl, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int) (smem_tl > 48 * 1024 ? smem_tl : 48 * 1024)), err)) return -1;

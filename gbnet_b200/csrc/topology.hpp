@@ -177,7 +177,7 @@ inline Topology compile_topology(uint32_t n_edge, const uint32_t *src, const uin
             tp.tf_ptr[k + 1] += tp.tf_ptr[k];
         }
         tp.Eu = tp.tf_ptr[nX];
-        tp.tf_child.resize(tp.Eu); tp.tf_slot.resize(tp.Eu);
+        tp.tf_child.assign((size_t) tp.Eu + 1, nH); tp.tf_slot.resize(tp.Eu);     // tf_child[Eu]: sentinel (the dummy target)
         std::vector<uint32_t> pos(nX, 0);
         std::fill(last.begin(), last.end(), -1);
         for (uint32_t r = 0; r < nH; r++) {

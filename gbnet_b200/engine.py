@@ -99,6 +99,9 @@ class Sampler:
     def n_chains(self): return int(self.dims.n_datasets * self.dims.n_graphs_local)
     def n_datasets(self): return int(self.dims.n_datasets)
     def kernel(self): return int(self._lib.gbn_model_kernel(self._h))
+    def path(self):
+        """0 strict kernel, 1 fast multi-kernel path (state in HBM), 2 fast persistent kernel (state in shared memory)"""
+        return int(self._lib.gbn_model_path(self._h))
     def simulation(self): return bool(self.dims.simulation)
 
     def tf_ids(self):
@@ -117,6 +120,14 @@ class Sampler:
 
     def sample_n(self, n):
         _capi.check(self._lib.gbn_model_sample_n(self._h, int(n)))
+
+    def run_protocol(self, burn_its=10, max_its=100, N=20, dN=30):
+        """The burn-in / convergence schedule of the reference's sample_model (gbnet/utils.py:93-135) as ONE
+        library call: returns (calls made, last max R-hat)."""
+        its, rhat = C.c_uint32(0), C.c_double(0.)
+        _capi.check(self._lib.gbn_model_run_protocol(self._h, int(burn_its), int(max_its), int(N), int(dN),
+                                                     C.byref(its), C.byref(rhat)))
+        return int(its.value), float(rhat.value)
 
     def burn_stats(self):
         _capi.check(self._lib.gbn_model_burn_stats(self._h))
@@ -289,12 +300,45 @@ class Sampler:
         return v.value
 
     def debug_counters(self, enable=True):
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 8)()
         _capi.check(self._lib.gbn_model_debug_counters(self._h, int(bool(enable)), out))
         return [int(v) for v in out]
 
     def synchronize(self):
         _capi.check(self._lib.gbn_model_synchronize(self._h))
+
+
+EVID_ABSENT = 127
+
+
+def fisher_counts(src, trg, mor, evid_trg, evid_val, device=0):
+    """Per contrast and source TF the six edge counts behind the reference's get_tests (gbnet/utils.py:10-35),
+    reduced on the device for all contrasts at once.  ``evid_val``: [n_datasets, n_evid] values -1 / 0 / +1 or
+    EVID_ABSENT.  Returns (sorted unique source ids, counts[n_datasets, n_tf, 6])."""
+    lib = _capi.load()
+    src = np.ascontiguousarray(src, np.uint32)
+    trg = np.ascontiguousarray(trg, np.uint32)
+    mor = np.ascontiguousarray(mor, np.int32)
+    evid_trg = np.ascontiguousarray(evid_trg, np.uint32)
+    evid_val = np.ascontiguousarray(evid_val, np.int8)
+    if evid_val.ndim == 1:
+        evid_val = evid_val[None, :]
+    if evid_val.shape[1] != evid_trg.size:
+        raise ValueError("evid_val must have one column per evid_trg entry")
+    net = _capi.Network(src.size, _capi.u32ptr(src), _capi.u32ptr(trg), _capi.i32ptr(mor), 0, None)
+    n_tf = C.c_uint32(0)
+
+    def call(ids, counts):
+        st = lib.gbn_fisher_counts(int(device), C.byref(net), evid_val.shape[0], evid_trg.size, _capi.u32ptr(evid_trg),
+                                   evid_val.ctypes.data_as(C.POINTER(C.c_int8)), C.byref(n_tf), ids, counts)
+        if st != 0:
+            raise GbnError(st, lib.gbn_fisher_last_error().decode())
+
+    call(None, None)
+    ids = np.empty(n_tf.value, np.uint32)
+    counts = np.zeros((evid_val.shape[0], n_tf.value, 6), np.uint32)
+    call(_capi.u32ptr(ids), _capi.u32ptr(counts))
+    return ids, counts
 
 
 def philox_kat(ctr, key, device=0):

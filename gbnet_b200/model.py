@@ -75,6 +75,40 @@ def marshal_frames(ents, rels, evid=None, active_tf_set_py=frozenset()):
         tf_symbols=tf_symbols, trg_symbols=trg_symbols, edges=edges)
 
 
+def marshal_contrasts(ents, rels, evids, active_tf_set_py=frozenset()):
+    """``marshal_frames`` once for a network and MANY evidence frames (batched contrasts, BASELINE config C4):
+    the symbol tables and the integer edge list are built a single time; every contrast contributes one row of
+    the evidence matrix over the union of its targets (0 = no evidence: the reference's default state of a
+    target without evidence is "not DE", GraphORNOR.cpp:131)."""
+    if len(evids) == 0:
+        raise ValueError("from_contrasts needs at least one evidence frame")
+    base = marshal_frames(ents, rels, evids[0], active_tf_set_py)
+    trg_rank = {s: i for i, s in enumerate(base["trg_symbols"])}
+    names = ents[["uid", "name"]].dropna().set_index("uid")["name"]
+    rows = [dict(zip(base["evid_trg"].tolist(), base["evid_val"].tolist()))]
+    for evid in evids[1:]:
+        if isinstance(evid, dict):
+            evid = pd.DataFrame([dict(uid=k, val=v) for k, v in evid.items()])
+        elif not isinstance(evid, pd.DataFrame):
+            raise TypeError("Please make sure that provided DEG file is either a dictionary or a Pandas Series with uids as keys/index")
+        evid = evid[["uid", "val"]].dropna()
+        sym = names.loc[evid.uid].values
+        row = {}
+        for s, v in zip(sym, evid["val"].values):                # dict semantics of pyx:54: the last value of a symbol wins
+            if s in trg_rank:
+                row[trg_rank[s]] = int(v)
+        rows.append(row)
+    keys = sorted(set().union(*[r.keys() for r in rows]))
+    val = np.zeros((len(rows), len(keys)), np.int32)
+    col = {k: i for i, k in enumerate(keys)}
+    for d, r in enumerate(rows):
+        for k, v in r.items():
+            val[d, col[k]] = v
+    base["evid_trg"] = np.array(keys, np.uint32)
+    base["evid_val"] = val
+    return base
+
+
 def check_sprior(sprior):
     """pyx:70-82"""
     if sprior is None:
@@ -95,7 +129,9 @@ class ModelORNOR:
                  seed=0, device=0, kernel=KERNEL_AUTO):
         z0_alpha = z_alpha if z0_alpha is None else z0_alpha          # pyx:18-19
         z0_beta = z_beta if z0_beta is None else z0_beta
-        m = marshal_frames(ents, rels, evid, active_tf_set_py)
+        # evid may be a LIST of evidence frames (see from_contrasts): one network, many contrasts
+        m = marshal_contrasts(ents, rels, evid, active_tf_set_py) if isinstance(evid, (list, tuple)) \
+            else marshal_frames(ents, rels, evid, active_tf_set_py)
         sprior_py = check_sprior(sprior)
         self._tf_symbols, self._trg_symbols, self._edges = m["tf_symbols"], m["trg_symbols"], m["edges"]
         src, trg, mor, evid_trg, evid_val, active = m["src"], m["trg"], m["mor"], m["evid_trg"], m["evid_val"], m["active"]
@@ -108,6 +144,22 @@ class ModelORNOR:
                                 t_hmargin=t_hmargin, zn_focus=zn_focus, zn_lmargin=zn_lmargin,
                                 zn_hmargin=zn_hmargin, seed=seed, device=device, kernel=kernel)
         self._const_params = bool(const_params)
+
+    @classmethod
+    def from_contrasts(cls, ents, rels, evids, **options):
+        """One network, many DE contrasts (BASELINE config C4): the frames are marshalled ONCE (the reference
+        rebuilds its string maps per model and per chain, ModelORNOR.pyx:13-83, ModelORNOR.cpp:23-27) and every
+        contrast gets ``n_graphs`` chains of the same device-resident network.  The getters take ``dataset=``;
+        ``get_max_gelman_rubin`` is the maximum over the contrasts."""
+        return cls(ents, rels, list(evids), **options)
+
+    @property
+    def n_contrasts(self):
+        return self._sampler.n_datasets()
+
+    def run_protocol(self, burn_its=10, max_its=100, N=20, dN=30):
+        """gbnet/utils.py:93-135 as one library call (gbn_model_run_protocol): (calls made, last max R-hat)"""
+        return self._sampler.run_protocol(burn_its=burn_its, max_its=max_its, N=N, dN=dN)
 
     # ids exactly as RVNode builds them (RVNode.cpp:29-33; GraphORNOR.cpp:243): name + "_" + uid
     def _node_ids(self):
@@ -122,8 +174,8 @@ class ModelORNOR:
         ids += [["S", f"{s}-->{t}"] for s, t in self._edges]
         return ids
 
-    def get_gelman_rubin(self):
-        gr = self._sampler.gelman_rubin()
+    def get_gelman_rubin(self, dataset=0):
+        gr = self._sampler.gelman_rubin(dataset)
         # the reference splits "<name>_<uid>" on "_" and keeps two fields (pyx:85-87)
         return [f"{name}_{uid}".split('_')[:2] + [float(v)] for (name, uid), v in zip(self._node_ids(), gr)]
 
@@ -155,11 +207,11 @@ class ModelORNOR:
                 out.append(f"{name}_{uid}_{j}".split('_') + [float(values[n * per + j])])   # pyx:120-126
         return out
 
-    def get_posterior_means(self, var_name):
-        return self._posterior(self._sampler.posterior_means(var_name), var_name)
+    def get_posterior_means(self, var_name, dataset=0):
+        return self._posterior(self._sampler.posterior_means(var_name, dataset), var_name)
 
-    def get_posterior_sdevs(self, var_name):
-        return self._posterior(self._sampler.posterior_sdevs(var_name), var_name)
+    def get_posterior_sdevs(self, var_name, dataset=0):
+        return self._posterior(self._sampler.posterior_sdevs(var_name, dataset), var_name)
 
     @property
     def sampler(self) -> Sampler:

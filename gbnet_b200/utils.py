@@ -74,6 +74,43 @@ def get_tests(evid, rels):
     return table
 
 
+def _tests_from_counts(index, counts, n_de, n_not_de):
+    """The table of ``get_tests`` from the six per-TF edge counts (columns of ``_COUNT_COLUMNS``)."""
+    table = pd.DataFrame(np.asarray(counts, np.int64), index=pd.Index(index, name="srcuid"),
+                         columns=[c[0] for c in _COUNT_COLUMNS])
+    table["enrichment"] = _fisher_greater(table.trg_ydeg, n_de - table.trg_ydeg, table.trg_ndeg, n_not_de - table.trg_ndeg)
+    table["mor_binary"] = _fisher_greater(table.morp_degp, table.morn_degp, table.morp_degn, table.morn_degn)
+    rho = (table.enrichment * table.mor_binary).to_numpy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        table["combined"] = np.where(rho > 0, rho * (1 - np.log(np.where(rho > 0, rho, 1.))), rho)
+    table["trg_tot"] = table.trg_ndeg + table.trg_ydeg
+    agree = table.morp_degp + table.morn_degn
+    disagree = table.morp_degn + table.morn_degp
+    table["score"] = (agree - disagree) / table.trg_ydeg
+    table["gt_act"] = False
+    return table
+
+
+def get_tests_batched(evids, rels, device=0):
+    """``get_tests`` (reference gbnet/utils.py:10-68) for MANY contrasts that share ``rels``: one list of result
+    tables, one per evidence frame.  The per-TF contingency counts - the reference's six pandas group-bys per
+    contrast - are ONE segmented reduction over the by-TF edge list on the GPU (csrc/fisher.cu); the Fisher
+    p-values are evaluated from them for all TFs at once as in ``get_tests``."""
+    from .engine import EVID_ABSENT, fisher_counts
+    frames = [e.reset_index().set_index("uid")["val"] for e in evids]
+    uids = np.unique(np.concatenate([f.index.to_numpy() for f in frames])) if frames else np.zeros(0, np.int64)
+    vals = np.full((len(frames), uids.size), EVID_ABSENT, np.int8)
+    for d, f in enumerate(frames):
+        f = f[~f.index.duplicated(keep="first")]
+        vals[d, np.searchsorted(uids, f.index.to_numpy())] = f.to_numpy().astype(np.int8)
+    ids, counts = fisher_counts(rels["srcuid"].to_numpy(), rels["trguid"].to_numpy(), rels["type"].to_numpy(),
+                                uids, vals, device=device)
+    out = []
+    for d, f in enumerate(frames):
+        out.append(_tests_from_counts(ids.astype(np.int64), counts[d], int((f != 0).sum()), int((f == 0).sum())))
+    return out
+
+
 def s_prior_from_leniency(s_leniency):
     """The 3x3 prior of the edge mode S given the annotated sign (rows: sign -1, 0, +1; columns: S = 0, 1, 2)
     that reference gbnet/utils.py:78-81 derives from one leniency number."""
@@ -108,6 +145,10 @@ def run_protocol(model, max_its=100, burn_its=10, verbosity=0, batch=20):
         if verbosity >= 1:
             print(f"[{datetime.now()}] {tag}mgr={value: 10.4f}", flush=True)
 
+    fused = getattr(model, "run_protocol", None)
+    if fused is not None and verbosity < 1:
+        # one library call (gbn_model_run_protocol): no Python round trip, no stream sync during burn-in
+        return fused(burn_its=burn_its, max_its=max_its, N=batch)
     done = 0
     for _ in range(burn_its):
         model.sample(batch)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GBN_ABI_VERSION 1
+#define GBN_ABI_VERSION 2
 
 typedef enum gbn_status {
     GBN_OK = 0,
@@ -108,6 +108,10 @@ typedef struct gbn_dims {
 int gbn_model_dims(const gbn_model *m, gbn_dims *out);
 /* the gbn_kernel_kind the model runs (GBN_KERNEL_AUTO resolved) */
 int gbn_model_kernel(const gbn_model *m);
+/* which sweep path serves the model: 0 = strict kernel (sweep_strict.cu), 1 = fast multi-kernel path with the
+ * chain state in HBM (sweep_fast.cu), 2 = fast persistent kernel with the chain state in shared memory for a
+ * whole batch of sweeps (sweep_small.cu: networks that fit one SM, non-listening T nodes) */
+int gbn_model_path(const gbn_model *m);
 /* sorted unique ids (std::set order of GraphORNOR.cpp:31-42), for building result ids */
 int gbn_model_tf_ids(const gbn_model *m, uint32_t *out /* [n_tf] */);
 int gbn_model_trg_ids(const gbn_model *m, uint32_t *out /* [n_trg] */);
@@ -146,6 +150,32 @@ int gbn_model_set_evidence(gbn_model *m, const gbn_evidence *ev);
 #define GBN_COMM_ID_BYTES 128
 int gbn_comm_unique_id(void *id_out /* [GBN_COMM_ID_BYTES] */);
 int gbn_model_attach_comm(gbn_model *m, int rank, int world, const void *id /* [GBN_COMM_ID_BYTES] */);
+
+/* ---- the burn-in / convergence protocol as one call (reference gbnet/utils.py:93-135, sample_model) ----
+ * burn_its times sample(N, dN); burn_stats(); then sample(N, dN) followed by the max Gelman-Rubin statistic until
+ * that is <= 1.1 or max_its calls (burn-in included) have been made - the schedule that defines "time to
+ * R-hat < 1.1".  The reference evaluates R-hat inside every sample() call as well (ModelBase.cpp:122); during
+ * burn-in that value can end a call early only when N > dN, so with N <= dN (the reference's sample(20),
+ * dN = 30) the burn-in batches are enqueued back to back without a host round trip, and every later batch
+ * costs one 8-byte read.  *its_out = calls made, *rhat_out = the last max R-hat (inf if none was evaluated).
+ * SIGINT ends the protocol after the current batch (ModelBase.cpp:121). */
+int gbn_model_run_protocol(gbn_model *m, uint32_t burn_its, uint32_t max_its, uint32_t N, uint32_t dN,
+                           uint32_t *its_out, double *rhat_out);
+
+/* ---- enrichment pre-screen counts (reference gbnet/utils.py:10-35, get_tests) for many contrasts at once ----
+ * Per contrast d and source TF (sorted unique src ids, as gbn_model_tf_ids): the six edge counts the Fisher
+ * tests of get_tests are built from - a segmented reduction over the by-TF edge list on the device:
+ *   counts[d][tf][0..5] = { val != 0 (targets without evidence included, as pandas' NaN != 0), val == 0,
+ *                           type +1 & val +1, type +1 & val -1, type -1 & val +1, type -1 & val -1 }
+ * evid_val[d][i] is the value of target evid_trg[i] in contrast d: -1, 0, +1, or GBN_EVID_ABSENT.
+ * Every edge row counts (duplicates and type 0 included), as the reference's group-by does.
+ * tf_ids_out may be NULL; *n_tf_out receives the number of sources (call with counts == NULL for the size). */
+#define GBN_EVID_ABSENT 127
+int gbn_fisher_counts(int device, const gbn_network *net, uint32_t n_datasets, uint32_t n_evid,
+                      const uint32_t *evid_trg, const int8_t *evid_val /* [n_datasets][n_evid] */,
+                      uint32_t *n_tf_out, uint32_t *tf_ids_out /* [n_tf] */, uint32_t *counts /* [n_datasets][n_tf][6] */);
+/* message of the last failed gbn_fisher_counts call on this thread (that entry point needs no model) */
+const char *gbn_fisher_last_error(void);
 
 /* ---- parity / test hooks (per LOCAL chain index: dataset-major, chain-minor) ---- */
 /* state in random_nodes order: X[nX], T[nX] (absent if const_params), S[E, edge input order] */
@@ -213,9 +243,11 @@ int gbn_model_sweep_count(const gbn_model *m, uint64_t *n);
 /* device time between two points chosen by the caller (CUDA events on the model's stream) */
 int gbn_model_timer_start(gbn_model *m);
 int gbn_model_timer_stop(gbn_model *m, double *ms);
-/* diagnostics of the fast X kernel's speculative windows since the last call: rounds, TFs committed,
- * rounds that ended in a flip; enable != 0 switches counting on, 0 off */
-int gbn_model_debug_counters(gbn_model *m, int enable, uint64_t out[4]);
+/* diagnostics since the last call: [0..2] the X phase's speculative windows (rounds, TFs committed, rounds
+ * that ended in a flip), [3] prior fallbacks of S draws (Multinomial.cpp:78-85), [4..6] cycles one thread of the
+ * persistent small-network kernel spent in the X, T and S phases (summed over chains and sweeps);
+ * enable != 0 switches counting on, 0 off */
+int gbn_model_debug_counters(gbn_model *m, int enable, uint64_t out[8]);
 int gbn_model_synchronize(gbn_model *m);
 
 #ifdef __cplusplus

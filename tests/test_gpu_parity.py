@@ -153,10 +153,10 @@ def test_trajectory_variants_fast(case):
     _run_trajectory(pb, KERNEL_FAST, 10, injected=True, chunks=(2,))
 
 
-def test_fast_x_large_network_path(monkeypatch):
-    """Networks whose (n, y) index does not fit the X kernel's shared memory gather it from global
-    memory; forced here on a small problem (5 chains: a last, partial chain bundle as well)."""
-    monkeypatch.setenv("GBN_X_NY", "2")
+def test_fast_x_partial_chain_bundle(monkeypatch):
+    """The X kernel sweeps chain pairs; 5 chains leave a last, partial bundle (multi-kernel path forced: the
+    network would otherwise run on the persistent small-network kernel)."""
+    monkeypatch.setenv("GBN_SMALL", "2")
     pb, _ = make_problem(NX=30, NY=400, AvgNTF=3.0, seed=36, n_graphs=5)
     _run_trajectory(pb, KERNEL_FAST, 60, injected=False, chunks=(20,))
     _run_trajectory(pb, KERNEL_FAST, 10, injected=True, chunks=(5,))

@@ -101,6 +101,18 @@ def test_cython_binding_matches_ctypes_binding():
         assert A.get_posterior_sdevs(k) == B.get_posterior_sdevs(k)
     A.burn_stats()
     assert A.get_max_gelman_rubin() == float("inf")
+    assert A.run_protocol(burn_its=2, max_its=6) == B.run_protocol(burn_its=2, max_its=6)
+    assert A.get_posterior_means("X") == B.get_posterior_means("X")
+    # simulation mode (evid=None: H and Y sampled forward, GraphORNOR.cpp:28): same ids and values from both bindings
+    active = set(ents.loc[ents.uid.isin(net.gt_active), "name"])
+    As = PyModelORNOR(ents, rels.copy(), None, active, n_graphs=3, seed=5)
+    Bs = gbnet_b200.ModelORNOR(ents, rels.copy(), None, active, n_graphs=3, seed=5)
+    As.sample(60, 30)
+    Bs.sample(60, 30)
+    assert As.get_gelman_rubin() == Bs.get_gelman_rubin()
+    for k in ("H", "Y", "T", "X"):
+        assert As.get_posterior_means(k) == Bs.get_posterior_means(k)
+    assert len(As.get_posterior_means("H")) == 3 * len(set(rels.trguid))
     with pytest.raises(IndexError, match="MOR values"):          # std::out_of_range in the reference (GraphORNOR.cpp:40-41)
         bad = rels.copy()
         bad.loc[0, "type"] = 5
