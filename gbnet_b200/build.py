@@ -70,6 +70,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             flags += ["-DGBN_XQ=" + xv.group(1), "-DGBN_XU=" + xv.group(2)]
             if xv.group(3):
                 flags.append("-DGBN_X_NT=" + xv.group(3))
+        if VARIANT.startswith("xexp") and src == "sweep_fast.cu":
+            flags.append("-DGBN_XEXP=" + VARIANT[4:])
         if VARIANT == "chk":
             flags.append("-DGBN_BOUNDS")
         if VARIANT.startswith("s") and VARIANT[1:].isdigit() and src == "sweep_fast.cu":

@@ -311,8 +311,7 @@ int upload_evidence(gbn_model *m, const gbn_evidence *ev)
             for (uint32_t k = 0; k < tp.nX; k++) {
                 double bound = 0.;
                 for (uint32_t c = tp.tf_ptr[k]; c < tp.tf_ptr[k + 1]; c++) bound += lmin[m->h_y[(size_t) d * tp.nH + tp.tf_child[c]]];
-                uf[(size_t) d * tp.nX + k] = bound < -600. ? 1 : 0;
-                if (env_u32("GBN_X_NOTRACK", 0) == 1) uf[(size_t) d * tp.nX + k] = 0;     // experiment: measures what the tracking costs
+                uf[(size_t) d * tp.nX + k] = bound < -600. ? 1 : 0;                // -600 in natural logs ~ 2^-865
             }
         CUDA_TRY(cudaMemcpy(m->d_uf, uf.data(), uf.size(), cudaMemcpyHostToDevice));
     }
@@ -683,6 +682,8 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         if (int rc = dev_alloc(m, &ch.tc2, n_tc2)) return bail(rc);                          // entry nH of a bundle stays {0, 0}
         if (cudaMemset(ch.tc2, 0, sizeof(double2) * n_tc2) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "cudaMemset failed"));
         if (int rc = dev_alloc(m, &ch.tL, n_tc2)) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.tq, n_tc2)) return bail(rc);
+        if (cudaMemset(ch.tq, 0, n_tc2) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "cudaMemset failed"));
         {
             std::vector<double> ones(n_tc2, 1.);                                             // entry nH of a bundle stays 1
             if (cudaMemcpy(ch.tL, ones.data(), sizeof(double) * n_tc2, cudaMemcpyHostToDevice) != cudaSuccess)
@@ -693,6 +694,8 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         if (int rc = dev_alloc(m, &ch.dC, C * tp.nD)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.Stfp, C * n_stf_words(n))) return bail(rc);
         if (int rc = dev_alloc(m, &ch.xU, C * ((nX + 3) & ~(size_t) 3))) return bail(rc);
+        if (int rc = dev_alloc(m, &ch.xqp, C * nX)) return bail(rc);
+        if (cudaMemset(ch.xqp, 0, sizeof(uint16_t) * C * nX) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "cudaMemset failed"));
         if (int rc = dev_alloc(m, &ch.FXp, C * nX)) return bail(rc);
     }
     const size_t ns = (size_t) m->n_datasets * n_stats_of(n);
@@ -1380,21 +1383,21 @@ extern "C" int gbn_model_timer_stop(gbn_model *m, double *ms)
 }
 
 // diagnostics of the speculative X windows: rounds, TFs committed, flips (since enabled)
-extern "C" int gbn_model_debug_counters(gbn_model *m, int enable, uint64_t out[8])
+extern "C" int gbn_model_debug_counters(gbn_model *m, int enable, uint64_t out[16])
 {
     if (!m) return fail(GBN_ERR_INVALID, "null model");
     if (int rc = use_device(m)) return rc;
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     if (out) {
-        for (int i = 0; i < 8; i++) out[i] = 0;
-        if (m->ch.dbg) CUDA_TRY(cudaMemcpy(out, m->ch.dbg, 64, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 16; i++) out[i] = 0;
+        if (m->ch.dbg) CUDA_TRY(cudaMemcpy(out, m->ch.dbg, 128, cudaMemcpyDeviceToHost));
     }
     if (enable && !m->ch.dbg) {
         unsigned long long *p = nullptr;
-        if (int rc = dev_alloc(m, &p, 8)) return rc;
+        if (int rc = dev_alloc(m, &p, 16)) return rc;
         m->ch.dbg = p;
     }
-    if (m->ch.dbg) CUDA_TRY(cudaMemset(m->ch.dbg, 0, 64));
+    if (m->ch.dbg) CUDA_TRY(cudaMemset(m->ch.dbg, 0, 128));
     if (!enable) m->ch.dbg = nullptr;
     return 0;
 }

@@ -80,7 +80,9 @@ struct DevChains {
     uint2 *cS;                    // {count S=0, count S=2}
     // fast kernel only
     double2 *tc2;                 // [c/XQ][nH + 1][XQ] (interleaved by chain bundle; entry nH is a dummy {0, 0} for idle lanes)
-    double *tL;                   // [c/XQ][nH + 1][XQ] the target likelihood L itself (dummy: 1) flip weights {w0, w2} = {pr0 omz (a + pr2 b), pr0 pr2 omz b} / L (sweep_fast.cu, k_fast_x)
+    double *tL;                   // [c/XQ][nH + 1][XQ] the target likelihood L itself (dummy: 1)
+    uint8_t *tq;                  // [c/XQ][nH + 1][XQ] q with L >= 2^-q (from L's exponent field; dummy: 0): the X kernel's cheap
+                                  // bound on the magnitude of a product of child likelihoods flip weights {w0, w2} = {pr0 omz (a + pr2 b), pr0 pr2 omz b} / L (sweep_fast.cu, k_fast_x)
     uint32_t *Sw;                 // [c][nSw] S as 2-bit codes, 16 steps per word: what the fast sweep reads and writes
                                   // (ch.S is refreshed from it on demand, capi.cu)
     uint32_t *Aw;                 // [c][nSw] bit u of a word: the parent TF of step u of the matching S word is active (X = 1);
@@ -88,6 +90,8 @@ struct DevChains {
     uint2 *dC;                    // [c][nD] per-batch counts {S=0, S=2} of four steps as 4 x u8 each, folded into cS
                                   // before anything reads the statistics (and before a byte could overflow)
     uint32_t *Stfp;               // [c][ceil(E / 16)] copy of S in by-TF CSR order, 2-bit codes (coalesced reads in the X phase)
+    uint16_t *xqp;                // [c][nX] X kernel: the magnitude bound (bits) a TF's children gave at its last update - predicts
+                                  // which TFs will need the exact product, so that it is gathered in the same pass
     uint32_t *xU;                 // [c][nX rounded up to 4] Philox words of the current sweep's X draws (X kernel scratch)
     double2 *FXp;                 // {1 - t*x, 1 / (1 - t*x)}
     // simulation mode only: latent / observed state per (chain, device target) and their outcome counts

@@ -59,6 +59,39 @@ __device__ __forceinline__ void add_if(uint32_t &a, uint32_t k, bool p)
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q add.u32 %0, %0, %1;\n\t}" : "+r"(a) : "r"(k), "r"((int) p));
 }
 
+// log(gsl_ran_beta_pdf(x, a, b)) (Beta.cpp:50,82,83 under the log of Beta.cpp:69-78).  Inside (0, 1) the density is
+// exp(lnB + (a-1) log x + (b-1) log1p(-x)) and the reference takes the log of that exp: here the exponent is
+// used directly (one exp and one log less per density - four densities per T update - at a difference of an
+// ulp or two in the log-ratio, the size of the libm differences the fast path already has; the strict kernel
+// keeps the reference's form).  Outside and at the end points the density's own special cases decide.
+__device__ __forceinline__ double beta_logpdf(double x, double a, double b, double lnB)
+{
+    if (x > 0. && x < 1.) return lnB + log(x) * (a - 1) + log1p(-x) * (b - 1);
+    return log(beta_pdf(x, a, b, lnB));
+}
+
+// Beta::metropolis_hastings_with_prior_proposal (Beta.cpp:60-91) on log densities; returns the value the node keeps
+__device__ __forceinline__ double mh_decide_log(double prev, double proposal, double prev_loglik, double prop_loglik,
+                                                double prior_mean, double sample_dx, double a, double b, double lnB,
+                                                bool have_expo, double expo,
+                                                uint64_t seed, uint32_t gchain, uint32_t sweep, uint32_t k)
+{
+    if (!(prop_loglik > -INFINITY)) return prev;
+    if (prev_loglik > -INFINITY) {
+        // log(q01 / q10): a zero density on either side keeps the reference's quotient (0 / q, q / 0, 0 / 0)
+        const double lq01 = beta_logpdf(prior_mean - sample_dx, a, b, lnB), lq10 = beta_logpdf(prior_mean + sample_dx, a, b, lnB);
+        const double log_q = (lq01 > -INFINITY && lq10 > -INFINITY) ? lq01 - lq10 : log(exp(lq01) / exp(lq10));
+        const double logratio = prop_loglik - prev_loglik + log_q;
+        bool accept = logratio >= 0.;
+        if (!accept) {
+            if (!have_expo) expo = draw_exp(seed, gchain, sweep, k);
+            accept = logratio > -expo;
+        }
+        if (!accept) return prev;
+    }
+    return proposal;
+}
+
 // 2-bit S code at position pos of a packed array (16 codes per word)
 __device__ __forceinline__ uint32_t code_at(const uint32_t *w, uint32_t pos) { return (w[pos >> 4] >> (2 * (pos & 15))) & 3u; }
 
@@ -82,6 +115,15 @@ __device__ __forceinline__ void normalise(double &m, int &e)
     }
 }
 
+// a * 2^e for e < -900 with ONE rounding (what exp() of the reference delivers near the bottom of the double range:
+// subnormal, or zero): the first product is exact, the second rounds into the subnormal range
+__device__ __forceinline__ double scale_down(double a, int e)
+{
+    if (e < -1080) return 0.;                                               // a < 2: below half the smallest subnormal
+    const double t = a * __hiloint2double((1023 + (e + 1000)) << 20, 0);    // e + 1000 in [-80, 40]: exact
+    return t * __hiloint2double((1023 - 1000) << 20, 0);
+}
+
 // the two outcome likelihoods a * 2^ea and b * 2^eb (a, b in [0.25, 2)) brought to one scale.  Only
 // their ratio matters for the draw, except that the reference falls back to the prior when both
 // underflow (Multinomial.cpp:78-85) and rounds subnormals: near the bottom of the double range the
@@ -89,7 +131,7 @@ __device__ __forceinline__ void normalise(double &m, int &e)
 __device__ __forceinline__ void common_scale(double a, int ea, double b, int eb, double &la, double &lb)
 {
     const int emax = ea > eb ? ea : eb;
-    if (emax < -960) { la = ldexp(a, ea); lb = ldexp(b, eb); return; }
+    if (emax < -960) { la = scale_down(a, ea); lb = scale_down(b, eb); return; }
     const int da = ea - emax, db = eb - emax;                       // one is 0, the other <= 0
     la = da < -1000 ? 0. : a * __hiloint2double((1023 + da) << 20, 0);
     lb = db < -1000 ? 0. : b * __hiloint2double((1023 + db) << 20, 0);

@@ -46,6 +46,10 @@
 #include "topology.hpp"
 #include "fast_common.cuh"
 
+#ifndef GBN_XEXP
+#define GBN_XEXP 0        // experiments (profiles/r2_summary.md)
+#endif
+
 namespace gbn {
 
 namespace {
@@ -67,6 +71,25 @@ constexpr int XQ = GBN_XQ;           // X kernel: chains per CTA = chains interl
 #endif
 constexpr int FS_NT = GBN_S_NT;      // S kernel: one warp = one group of 32 targets
 constexpr int FT_NT = 128;           // T kernel
+
+// q with L >= 2^(-q / 32), read off the bits of L (a likelihood: 0.005 <= L < 1, so q <= 245): L = m 2^e with
+// 1 <= m < 2, and LOG2_TAB[i] = floor(32 log2(1 + i / 256)) is a lower bound of 32 log2 m for the eight leading
+// mantissa bits i.  The bound overshoots -32 log2 L by less than 1.3, i.e. 0.04 bits per child.
+__constant__ uint8_t LOG2_TAB[256] = {
+    0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5,
+    5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 8, 8, 8, 8, 8, 8, 8, 9, 9, 9, 9, 9, 9, 10, 10,
+    10, 10, 10, 10, 10, 11, 11, 11, 11, 11, 11, 11, 12, 12, 12, 12, 12, 12, 12, 12, 13, 13, 13, 13, 13, 13, 13, 14, 14, 14, 14, 14,
+    14, 14, 14, 15, 15, 15, 15, 15, 15, 15, 15, 16, 16, 16, 16, 16, 16, 16, 17, 17, 17, 17, 17, 17, 17, 17, 17, 18, 18, 18, 18, 18,
+    18, 18, 18, 19, 19, 19, 19, 19, 19, 19, 19, 20, 20, 20, 20, 20, 20, 20, 20, 20, 21, 21, 21, 21, 21, 21, 21, 21, 21, 22, 22, 22,
+    22, 22, 22, 22, 22, 22, 23, 23, 23, 23, 23, 23, 23, 23, 23, 24, 24, 24, 24, 24, 24, 24, 24, 24, 25, 25, 25, 25, 25, 25, 25, 25,
+    25, 25, 26, 26, 26, 26, 26, 26, 26, 26, 26, 26, 27, 27, 27, 27, 27, 27, 27, 27, 27, 27, 28, 28, 28, 28, 28, 28, 28, 28, 28, 28,
+    29, 29, 29, 29, 29, 29, 29, 29, 29, 29, 29, 30, 30, 30, 30, 30, 30, 30, 30, 30, 30, 30, 31, 31, 31, 31, 31, 31, 31, 31, 31, 31 };
+__device__ __forceinline__ uint8_t l_bound_bits(double L)
+{
+    const int hi = __double2hiint(L);
+    const int q = 32 * (1023 - ((hi >> 20) & 0x7ff)) - (int) LOG2_TAB[(hi >> 12) & 255];
+    return (uint8_t) min(max(q, 0), 255);
+}
 
 // One edge factor f = (1 - t x) z of a target is replaced by q f (phi = q - 1): the target's flip weights and
 // likelihood after the change.  With rho = 1 + phi w (w = the weight of the edge's code):
@@ -110,7 +133,7 @@ __device__ __forceinline__ void flip_weights(double2 &w, double &L, uint32_t s, 
 // U children per lane and trip, the ids / S codes of the NEXT trip requested before the current trip's weights
 // are used; a lane past the end of its TF's list reads the sentinel position E (the dummy target nH: weights 0,
 // likelihood 1) instead of branching.
-template <int NT, int LPT, int U>
+template <int NT, int LPT, int U, bool Q_SMEM>
 __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, SweepArgs a, uint32_t nchains)
 {
     constexpr int NW = NT / 32, NS = 32 / LPT, W = NW * NS;                  // warps, TFs per warp, TFs per window
@@ -123,6 +146,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     const uint32_t nXr = (nX + 3) & ~3u, nStfW = n_stf_words(net);
     uint32_t *sPtr = reinterpret_cast<uint32_t *>(smem_x);                   // [nX + 1 rounded up to 4] tf_ptr
     uint8_t *sX = reinterpret_cast<uint8_t *>(sPtr + ((nX + 4) & ~3u));      // [Q][nX rounded up to 4] value | prior class << 1 | may underflow << 2
+    uint8_t *sQ = sX + Q * nXr;                                              // [nH + 1][Q] q with L >= 2^-q per (target, chain) (Q_SMEM)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sg = lane / LPT, sl = lane % LPT;                         // this lane's TF of the warp, lane within it
@@ -151,7 +175,36 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
         }
     }
     for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.tf_ptr[k];
+    const uint8_t *gQ = ch.tq + (size_t) (cbase / Q) * (nH + 1) * Q;         // this bundle's bounds, interleaved like the weights
+    if (Q_SMEM) {
+        static_assert(XQ % 2 == 0, "the bounds are copied two bytes at a time");
+        const uint32_t nq = (nH + 1) * Q / 2;
+        for (uint32_t i = tid; i < nq; i += NT) reinterpret_cast<uint16_t *>(sQ)[i] = reinterpret_cast<const uint16_t *>(gQ)[i];
+    }
     __syncthreads();
+    const uint8_t *qh = (Q_SMEM ? sQ : gQ) + h;
+    // The TFs that will want the likelihoods of their children (below: their bound came close at the last update -
+    // an active hub or two per chain) gather them from an array nothing else reads: pull those entries into L2
+    // now, or each trip of such a TF waits for DRAM while the rest of the CTA waits at the round's barrier.
+    {
+        __shared__ uint32_t s_hot[32], s_nhot;
+        if (tid == 0) s_nhot = 0;
+        __syncthreads();
+        for (uint32_t q = 0; q < nvalid; q++)
+            for (uint32_t k = tid; k < nX; k += NT)
+                if ((sX[q * nX + k] & 4u) && ch.xqp[(cbase + q) * nX + k] >= 900) {
+                    const uint32_t slot = atomicAdd(&s_nhot, 1u);
+                    if (slot < 32) s_hot[slot] = k | (q << 31);
+                }
+        __syncthreads();
+        const uint32_t nhot = min(s_nhot, 32u);
+        for (uint32_t i = 0; i < nhot; i++) {
+            const uint32_t k = s_hot[i] & 0x7fffffffu, q = s_hot[i] >> 31;
+            const double *base = tlb + q;
+            for (uint32_t c2 = sPtr[k] + tid; c2 < sPtr[k + 1]; c2 += NT)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t) net.tf_child[c2] * Q));
+        }
+    }
 
     const double *gT = ch.T + (size_t) cmine * nX;
     const uint32_t *gU = ch.xU + (size_t) cmine * nXr;
@@ -197,11 +250,23 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             // f -> q f with q = 1 - t (X: 0 -> 1) or 1 / (1 - t) (X: 1 -> 0); phi = q - 1
             phi = -t;
             if (xcur) phi = t / (1. - t);
-            const bool track = (xs & 4u) != 0;                               // prod L could underflow: carry its magnitude
-            double mr = 1., ml = 1.;                                         // ratio flip / current, and prod L (if tracked)
+            // Could prod L underflow a double for this TF?  Never for most (tf_uf = 0, decided on the host from the
+            // evidence).  For the rest a cheap bound rides along: q_i with L_i >= 2^(-q_i / 32) (a byte per target and
+            // chain, staged in shared memory) summed over the children; only when the sum says "maybe" is the exact
+            // product taken (the slow path below).
+            const bool track = (xs & 4u) != 0;
+            // ... and a TF whose bound came close last time gathers the likelihoods in the same pass (active hubs:
+            // about three updates per chain and sweep at C3), so that the exact product rarely needs a second one
+#if GBN_XEXP == 2 || GBN_XEXP == 3
+            const bool want_l = false;
+#else
+            const bool want_l = track && ch.xqp[cmine * nX + kr] >= 900;
+#endif
+            double mr = 1., ml = 1.;                                         // ratio flipped / current; prod L (if gathered)
             int er = 0, el = 0;
-            auto child_loop = [&](auto with_l) {
-                constexpr bool WITH_L = decltype(with_l)::value;
+            uint32_t qs = 0;
+            auto child_loop = [&](auto with_q, auto with_l) {
+                constexpr bool WITH_Q = decltype(with_q)::value, WITH_L = decltype(with_l)::value;
                 int cnt = 0;
                 for (; trips > 0; trips--) {
                     double w[U], lc[U];
@@ -210,7 +275,12 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
                         GBN_CHECK(id[u] <= nH && sh[u] <= 2);
                         const uint32_t iw = sh[u] == 1 ? nH : id[u];         // an edge that is off: the dummy's zero weight
                         w[u] = tw_all[w_off + 2 * Q * iw + (sh[u] >> 1)];
-                        if (WITH_L) lc[u] = ch.tL[l_off + Q * id[u]];
+#if GBN_XEXP == 1
+                        if (WITH_Q) qs += id[u] & 1u;
+#else
+                        if (WITH_Q) qs += qh[Q * id[u]];
+#endif
+                        if (WITH_L) { lc[u] = 1.; if (want_l) lc[u] = ch.tL[l_off + Q * id[u]]; }
                     }
                     cc += U * CPW;
                     load_ids(cc);                                             // next trip
@@ -222,20 +292,67 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
                     if ((cnt += U) >= 16) { normalise(mr, er); if (WITH_L) normalise(ml, el); cnt = 0; }
                 }
             };
-            if (__any_sync(0xffffffffu, track)) child_loop(std::true_type{});
-            else child_loop(std::false_type{});
-            if (!track) { ml = 1.; el = 0; }
+            const bool any_l = __any_sync(0xffffffffu, want_l);
+            if (any_l) child_loop(std::true_type{}, std::true_type{});
+            else if (__any_sync(0xffffffffu, track)) child_loop(std::true_type{}, std::false_type{});
+            else child_loop(std::false_type{}, std::false_type{});
             normalise(mr, er);
-            normalise(ml, el);
 #pragma unroll
             for (int o = LPT / 2; o >= (int) Q; o >>= 1) {
                 mr *= __shfl_xor_sync(0xffffffffu, mr, o);
-                ml *= __shfl_xor_sync(0xffffffffu, ml, o);
                 er += __shfl_xor_sync(0xffffffffu, er, o);
-                el += __shfl_xor_sync(0xffffffffu, el, o);
+                qs += __shfl_xor_sync(0xffffffffu, qs, o);
             }
             normalise(mr, er);
-            normalise(ml, el);
+            if (any_l) {                                                     // warp-uniform
+                normalise(ml, el);
+#pragma unroll
+                for (int o = LPT / 2; o >= (int) Q; o >>= 1) {
+                    ml *= __shfl_xor_sync(0xffffffffu, ml, o);
+                    el += __shfl_xor_sync(0xffffffffu, el, o);
+                }
+                normalise(ml, el);
+            }
+            if (track && cs == 0 && live && h < nvalid) ch.xqp[cmine * nX + kr] = (uint16_t) min(qs >> 5, 65535u);
+#if GBN_XEXP == 3
+            const bool exact = false;
+#else
+            const bool exact = track && qs >= 32 * 990;                      // prior (>= 2^-7) x prod L could leave the normal range
+#endif
+            if (!exact) { ml = 1.; el = 0; }                                 // far from underflow: only the ratio matters
+            const bool second = exact && !want_l;
+            const uint32_t xmask = __ballot_sync(0xffffffffu, second);       // the lanes of one (TF, chain) agree
+            if (ch.dbg && cs == 0 && live && track) atomicAdd(ch.dbg + 9, 1ull);
+            if (ch.dbg && cs == 0 && exact) atomicAdd(ch.dbg + 8, 1ull);
+            if (ch.dbg && cs == 0 && want_l) atomicAdd(ch.dbg + 11, 1ull);
+            if (second) {
+                // not predicted (the bound jumped since the TF's last update): a second pass over all the children
+                if (ch.dbg && cs == 0) atomicAdd(ch.dbg + 10, 1ull);
+                uint32_t hm = 0;
+#pragma unroll
+                for (uint32_t b = 0; b < 32; b += Q) hm |= 1u << b;
+                const uint32_t tmask = xmask & (hm << h) & (LPT == 32 ? 0xffffffffu : (((1u << LPT) - 1u) << (sg * LPT)));
+                ml = 1.; el = 0;
+                for (uint32_t c2 = cbeg + cs; c2 < cend; c2 += 4 * CPW) {        // four independent gathers in flight
+                    double l4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t cr = c2 + u * CPW;
+                        l4[u] = ch.tL[l_off + Q * __ldg(net.tf_child + (cr < cend ? cr : E))];   // past the end: the dummy's 1
+                    }
+                    ml *= (l4[0] * l4[1]) * (l4[2] * l4[3]);
+                    normalise(ml, el);
+                }
+#pragma unroll
+                for (int o = LPT / 2; o >= (int) Q; o >>= 1) {
+                    ml *= __shfl_xor_sync(tmask, ml, o);
+                    el += __shfl_xor_sync(tmask, el, o);
+                }
+                normalise(ml, el);
+            }
+#if GBN_XEXP == 4
+            ml = 1.; el = 0;
+#endif
             // outcome likelihoods exp(log prior + sum log L) of Multinomial.cpp:66-75: current = p prod L, flipped = p' prod L ratio
             const double *prob = net.xprob[(xs >> 1) & 1u];
             double mf = ml * mr;
@@ -285,6 +402,8 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
                     if (s == 1) continue;
                     const size_t i = (size_t) net.tf_child[c2] * Q + q;
                     flip_weights(tcb[i], tlb[i], s, ph);
+                    if (Q_SMEM) sQ[i] = l_bound_bits(tlb[i]);                 // later windows of this sweep read the bound here
+                    else ch.tq[(size_t) (cbase / Q) * (nH + 1) * Q + i] = l_bound_bits(tlb[i]);
                 }
             }
         }
@@ -327,12 +446,12 @@ __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, Swee
         const double al = net.t_a[k], be = net.t_b[k], mean = net.t_mean[k], lnB = net.t_lnB[k];
         const size_t row = ((size_t) c * ch.inj_sweeps + a.inj_row) * nX + k;
         const double prev = t;
-        const double prev_ll = (0. + log(beta_pdf(prev, al, be, lnB))) + 0.;
+        const double prev_ll = (0. + beta_logpdf(prev, al, be, lnB)) + 0.;
         const double draw = a.use_inj ? ch.inj_beta[row] : draw_beta(net.seed, gchain, a.sweep, k, al, be);
         const double dx = draw - mean;
         const double prop = prev + dx;
-        const double prop_ll = (0. + log(beta_pdf(prop, al, be, lnB))) + 0.;
-        t = mh_decide(prev, prop, prev_ll, prop_ll, mean, dx, al, be, lnB,
+        const double prop_ll = (0. + beta_logpdf(prop, al, be, lnB)) + 0.;
+        t = mh_decide_log(prev, prop, prev_ll, prop_ll, mean, dx, al, be, lnB,
                       a.use_inj != 0, a.use_inj ? ch.inj_exp[row] : 0., net.seed, gchain, a.sweep, k);
         Tout[o] = t;
         if (t == 1.) *ch.flags = 1u;
@@ -407,12 +526,14 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
             const double draw = a.use_inj ? ch.inj_beta[row] : draw_beta(net.seed, gchain, a.sweep, k, al, be);
             const double dx = draw - mean;
             const double prop = prev + dx;
-            const double pdf_prev = beta_pdf(prev, al, be, lnB), pdf_prop = beta_pdf(prop, al, be, lnB);
             s_prop[tid] = prop;
             s_r[tid] = (1. - prop) / (1. - prev);
-            s_prev_ll[tid] = (0. + log(pdf_prev)) + 0.;
-            s_lpp[tid] = 0. + log(pdf_prop);                // -inf for an out-of-range proposal
-            s_logq[tid] = log(beta_pdf(mean - dx, al, be, lnB) / beta_pdf(mean + dx, al, be, lnB));   // Beta.cpp:74-78
+            s_prev_ll[tid] = (0. + beta_logpdf(prev, al, be, lnB)) + 0.;
+            s_lpp[tid] = 0. + beta_logpdf(prop, al, be, lnB);   // -inf for an out-of-range proposal
+            {                                                   // Beta.cpp:74-78
+                const double lq01 = beta_logpdf(mean - dx, al, be, lnB), lq10 = beta_logpdf(mean + dx, al, be, lnB);
+                s_logq[tid] = (lq01 > -INFINITY && lq10 > -INFINITY) ? lq01 - lq10 : log(exp(lq01) / exp(lq10));
+            }
             s_expo[tid] = a.use_inj ? ch.inj_exp[row] : draw_exp(net.seed, gchain, a.sweep, k);
         }
         __syncthreads();
@@ -619,15 +740,15 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                         const uint32_t s = (sw >> (2 * u)) & 3u, r = (mw >> (2 * u)) & 3u;
                         GBN_CHECK(s <= 2 && n + 1 < D);
                         // f = (1 - t x) z and its reciprocal: z and 1 / z unless the parent TF is active
-                        // (a warp-wide vote first: as a per-lane branch the lookup is predicated into every step)
+                        // (about 1 % of the edges.  The diagnostic count keeps the block a branch: without it the
+                        // compiler predicates the lookup's 14 instructions into every step of every lane)
                         double f = z, finv = rz;
-                        if (__any_sync(0xffffffffu, (aw >> u) & 1u)) {
-                            if ((aw >> u) & 1u) {
-                                const uint32_t kk = par16[4 * (db + 32 * bb) + u];
-                                GBN_CHECK(kk < nX);
-                                const double2 fx = __ldg(gFX + kk);
-                                f = fx.x * z; finv = fx.y * rz;
-                            }
+                        if ((aw >> u) & 1u) {
+                            if (ch.dbg) atomicAdd(ch.dbg + 7, 1ull);
+                            const uint32_t kk = par16[4 * (db + 32 * bb) + u];
+                            GBN_CHECK(kk < nX);
+                            const double2 fx = __ldg(gFX + kk);
+                            f = fx.x * z; finv = fx.y * rz;
                         }
                         // the state without this edge
                         const double Af = A * finv, Bf = Bq * finv;
@@ -693,6 +814,7 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
         const size_t o = ((size_t) (c / XQ) * (nH + 1) + dt) * XQ + (c % XQ);   // interleaved by chain bundle
         ch.tc2[o] = make_double2(g02 * iL, g2 * iL);
         ch.tL[o] = L;
+        ch.tq[o] = l_bound_bits(L);
     }
 }
 
@@ -792,11 +914,17 @@ static size_t s_smem_bytes(const DevNet &net)
     return sizeof(double2) * 3 * (size_t) net.stab_D + sizeof(double) * 2 * (size_t) net.stab_D + 16;
 }
 
-// shared memory of the X kernel (XQ chains per CTA): by-TF pointers and X
-static size_t x_smem_bytes(const DevNet &net)
+// shared memory of the X kernel (XQ chains per CTA): by-TF pointers, X and - when it fits - the per-target
+// magnitude bounds of the bundle
+static size_t x_smem_bytes(const DevNet &net, bool q_smem)
 {
     const size_t nX = net.nX, nXr = (nX + 3) & ~(size_t) 3, Q = XQ;
-    return 4 * ((nX + 4) & ~(size_t) 3) + Q * nXr + 16;
+    return 4 * ((nX + 4) & ~(size_t) 3) + Q * nXr + (q_smem ? Q * ((size_t) net.nH + 1) + 4 : 0) + 16;
+}
+static bool x_q_smem(const DevNet &net)
+{
+    if (env_u32("GBN_X_Q", 1) == 2) return false;        // 2 = read the bounds from global memory (tests of the large-network path)
+    return x_smem_bytes(net, true) + 2048 <= 200 * 1024;
 }
 
 uint32_t fast_x_bundle() { return XQ; }
@@ -818,7 +946,7 @@ bool fast_supported(const DevNet &net, const char **why)
         const uint64_t C = (uint64_t) net.n_datasets * net.n_graphs_local + XQ;
         if (2 * C * (net.nH + 1) >= (1ull << 32) || C * n_stf_words(net) >= (1ull << 32) || C * net.nD >= (1ull << 32)) { *why = "chains x targets exceeds the 32-bit cache offsets"; return false; }
     }
-    if (x_smem_bytes(net) + 2048 > 200 * 1024) { *why = "n_tf too large for the X window kernel's shared memory"; return false; }
+    if (x_smem_bytes(net, false) + 2048 > 200 * 1024) { *why = "n_tf too large for the X window kernel's shared memory"; return false; }
     return true;
 }
 
@@ -877,7 +1005,8 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
     if (stx == nullptr) stx = st;                      // X kernels on their own (high-priority) stream when given
     if (nchains == UINT32_MAX) nchains = ch.n_chains - chain0;
     if (n_sweeps == 0 || nchains == 0) return 0;
-    const size_t smem_x = x_smem_bytes(net);
+    const bool qs = x_q_smem(net);
+    const size_t smem_x = x_smem_bytes(net, qs);
     if (chain0 % XQ) { *err = "chain groups must start at a multiple of the X kernel's bundle size"; return -1; }
     // Lanes per TF by the mean number of targets of a TF: half a warp (a 64-TF window), or a quarter in CTAs of 16
     // warps.  Fewer lanes per TF = less per-TF instruction overhead and, with the longer window, fewer
@@ -888,10 +1017,10 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
     if (lpt != 8 && lpt != 16 && lpt != 32) lpt = (uint64_t) net.E >= 20ull * net.nX ? 16 : 8;
     void (*kx)(DevNet, DevChains, SweepArgs, uint32_t);
     uint32_t x_nt = FX_NT;
-    if (lpt == 32) kx = k_fast_x<FX_NT, 32, XU>;
-    else if (lpt == 16 && big) kx = k_fast_x<FX_NT, 16, XU>;
-    else if (lpt == 16) kx = k_fast_x<FX_NT, 16, 1>;
-    else { kx = k_fast_x<FX_NT / 2, 8, 1>; x_nt = FX_NT / 2; }
+    if (lpt == 32) kx = qs ? k_fast_x<FX_NT, 32, XU, true> : k_fast_x<FX_NT, 32, XU, false>;
+    else if (lpt == 16 && big) kx = qs ? k_fast_x<FX_NT, 16, XU, true> : k_fast_x<FX_NT, 16, XU, false>;
+    else if (lpt == 16) kx = qs ? k_fast_x<FX_NT, 16, 1, true> : k_fast_x<FX_NT, 16, 1, false>;
+    else { kx = qs ? k_fast_x<FX_NT / 2, 8, 1, true> : k_fast_x<FX_NT / 2, 8, 1, false>; x_nt = FX_NT / 2; }
     if (check(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x), err)) return -1;
     const size_t smem_tl = 4 * (size_t) net.nX + 16;
     if (net.listen && !net.const_params &&

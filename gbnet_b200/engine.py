@@ -300,7 +300,7 @@ class Sampler:
         return v.value
 
     def debug_counters(self, enable=True):
-        out = (C.c_uint64 * 8)()
+        out = (C.c_uint64 * 16)()
         _capi.check(self._lib.gbn_model_debug_counters(self._h, int(bool(enable)), out))
         return [int(v) for v in out]
 

@@ -245,9 +245,12 @@ int gbn_model_timer_start(gbn_model *m);
 int gbn_model_timer_stop(gbn_model *m, double *ms);
 /* diagnostics since the last call: [0..2] the X phase's speculative windows (rounds, TFs committed, rounds
  * that ended in a flip), [3] prior fallbacks of S draws (Multinomial.cpp:78-85), [4..6] cycles one thread of the
- * persistent small-network kernel spent in the X, T and S phases (summed over chains and sweeps);
+ * persistent small-network kernel spent in the X, T and S phases (summed over chains and sweeps), [7] S updates whose
+ * parent TF was active (the only ones that look the TF's factor up), [8] X updates that took the exact product of their
+ * children's likelihoods (the magnitude bound said it could underflow), [9] X updates that carried the bound, [10] exact products that needed a
+ * second pass over the children (not predicted by the TF's previous update);
  * enable != 0 switches counting on, 0 off */
-int gbn_model_debug_counters(gbn_model *m, int enable, uint64_t out[8]);
+int gbn_model_debug_counters(gbn_model *m, int enable, uint64_t out[16]);
 int gbn_model_synchronize(gbn_model *m);
 
 #ifdef __cplusplus

@@ -20,7 +20,7 @@ G.debug_counters(True)
 bundles = M // 2
 for blk in range(6):
     G.sample_n(10)
-    r, t, f, _ = G.debug_counters(True)
+    r, t, f = G.debug_counters(True)[:3]
     print("%s sweeps %d-%d: rounds/sweep/bundle %.1f  TFs/round %.2f  flip rounds/sweep/bundle %.1f"
           % (shape, blk * 10, blk * 10 + 9, r / (10 * bundles), t / max(r, 1), f / (10 * bundles)))
 st = G.get_state(0)

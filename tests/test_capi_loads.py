@@ -24,7 +24,7 @@ def test_header_symbols_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/gbnet_b200.h but not exported"
     assert set(declared) == set(_capi.SYMBOLS), set(declared) ^ set(_capi.SYMBOLS)
-    assert lib.gbn_abi_version() == 1
+    assert lib.gbn_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
