@@ -445,6 +445,7 @@ def run_native(args):
         launches = int(tl[0])
 
     if rank == 0:
+        r_targets = net.realised()["n_trg"]
         total_updates = world * C * dN * args.steps * E
         value = total_updates / (dev_ms * 1e-3)
         e2e_value = world * C * dN * args.e2e_steps * E / e2e_s
@@ -467,13 +468,28 @@ def run_native(args):
         bytes_per_launch = per_unit[dom] * C * E                    # serialised: one launch covers all C chains
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(names[dom])
+        for tname in ("r2_traffic.json", "traffic.json"):          # per launch, from the latest `ncu --set full` capture
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get(names[dom])
+                break
         sweep_gbs = value / world * b_edge / 1e9          # per GPU: the peak is one GPU's
+        # compulsory bytes of the round-2 layout per edge-update of the S kernel: byte counters
+        # 2 B read + 2 B written, S code 0.25 B read, activity bit 0.125 B, per-target outputs (flip weights 16 B,
+        # likelihood 8 B, bound 1 B) amortised over the target's edges, network words shared by the C chains
+        comp_edge = 4.0 + 0.25 + 0.125 + 25.0 * r_targets / E + 4.6 / C
+        comp_bytes = comp_edge * C * E
         roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+                    "bytes_per_unit": per_unit[dom],
+                    "what": "SURVEY.md section 8(d) bytes per edge-update (u32 counter pairs read + written every sweep): "
+                            "the figure round 1 was reported against",
+                    "compulsory": {"bytes_per_unit": comp_edge, "bytes_per_launch": comp_bytes,
+                                   "achieved": comp_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0,
+                                   "frac": comp_bytes / (avg_ms * 1e-3) / 1e9 / peak if avg_ms > 0 else 0.0,
+                                   "what": "bytes the round-2 layout has to move (8-bit per-batch counters, 2-bit S codes); "
+                                           "the kernel is bound by instruction issue, not by HBM (profiles/r2_summary.md)"},
                     "how": "CUDA events on the model's stream around every launch, kernels serialised "
                            f"(stream groups = 1) for {args.roofline_steps} steps right after the timed region",
                     "kernel_ms_per_sweep": {n: phase_ms[i] / max(phase_launches, 1) for i, n in enumerate(names)},

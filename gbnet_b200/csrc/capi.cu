@@ -654,7 +654,16 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         return bail(fail(GBN_ERR_UNSUPPORTED, std::string("fast kernel unavailable: ") + why));
     m->kernel = (p->kernel == GBN_KERNEL_STRICT) ? GBN_KERNEL_STRICT : (fast_ok ? GBN_KERNEL_FAST : GBN_KERNEL_STRICT);
     if (sim) m->kernel = GBN_KERNEL_STRICT;          // simulation has its own kernels (sim_kernels.cu), reference arithmetic
-    { const char *w2 = nullptr; m->small = m->kernel == GBN_KERNEL_FAST && small_supported(n, &w2); }
+    {
+        // the persistent shared-memory kernel wins while every chain has an SM to itself (one CTA per chain, its phases
+        // bound by latency: C1 24 vs 33 us per sweep, C2 x 64 chains 51 vs 72); with several waves of chains the
+        // multi-kernel path's throughput wins (C2 x 512: 184 vs 203 us).  GBN_SMALL=3 forces it for any chain count.
+        const char *w2 = nullptr;
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device) != cudaSuccess) sms = 0;
+        m->small = m->kernel == GBN_KERNEL_FAST && small_supported(n, &w2) &&
+                   (m->n_datasets * m->n_graphs_local <= (uint32_t) sms || env_u32("GBN_SMALL", 1) == 3);
+    }
     if (!sim && m->kernel == GBN_KERNEL_STRICT && strict_smem_bytes(n) > 227 * 1024)
         return bail(fail(GBN_ERR_UNSUPPORTED, "strict kernel: n_tf too large for shared memory"));
 

@@ -7,6 +7,7 @@
 
 #include "device_model.cuh"
 #include "device_math.cuh"
+#include "topology.hpp"
 
 // Bounds checks of every data-dependent index, compiled in by the "chk" build variant
 // (GBN_LIB_VARIANT=chk; compute-sanitizer is closed on this pool): a violation traps the kernel.
@@ -26,6 +27,7 @@ struct SweepArgs {
     uint32_t use_inj;                // 1: injected draws, row inj_row
     uint32_t inj_row;                // sweep row inside the injection arrays
     uint32_t chain0;                 // first local chain of this launch (chains are split over streams)
+    uint32_t x_adapt;                // X kernel: adaptive window on (GBN_X_ADAPT=2 switches it off)
     uint32_t rk0[10], rk1[10];       // Philox round keys (seed words bumped by the Weyl constants): as kernel
                                      // parameters they are constant-bank operands of the round's XOR
 };
@@ -35,6 +37,7 @@ inline SweepArgs sweep_args(const DevNet &net)
     SweepArgs a{};
     uint32_t k0 = (uint32_t) net.seed, k1 = (uint32_t) (net.seed >> 32);
     for (int r = 0; r < 10; r++) { a.rk0[r] = k0; a.rk1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    a.x_adapt = env_u32("GBN_X_ADAPT", 1) != 2;
     return a;
 }
 

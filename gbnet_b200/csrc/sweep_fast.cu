@@ -215,10 +215,17 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     const uint32_t l_off = (cbase / Q) * (nH + 1) * Q + h, w_off = 2 * l_off, stf_off = cmine * nStfW;
     const uint32_t E = net.E;
 
+    // Adaptive window.  A round that ends in a flip throws away the evaluations behind the flip.  With the CLI
+    // defaults 18 % of the rounds end that way and the full window is right; when X values move often (a diffuse
+    // posterior, many active TFs: most rounds end in a flip after ~20 TFs) the window follows the recent commit
+    // length: after two flip-ended rounds in a row it is twice the last committed length (at least 8), and a round
+    // that commits its whole window doubles it again.  Every thread derives the same length from the same votes;
+    // the visiting order is untouched (profiles/r2_summary.md: flip regimes).
+    uint32_t wlen = W, streak = 0;
     uint32_t k0 = 0;
     while (k0 < nX) {
         const uint32_t kw = k0 + pos;
-        const bool live = kw < nX;
+        const bool live = kw < nX && pos < wlen;
         int dec = 0;                              // bit 0: drawn value, bit 1: value changed (this lane's chain)
         double phi = 0.;
         if (NS > 1 || live) {                     // warp-uniform when a warp holds one TF; else dead TFs ride along empty
@@ -380,8 +387,12 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             const uint32_t f = __ballot_sync(0xffffffffu, w0 + lane < (uint32_t) W && s_dec[(w0 + lane) % W] != 0);
             if (f && first == (uint32_t) W) first = w0 + (uint32_t) __ffs(f) - 1;
         }
-        const uint32_t ncommit = first < W ? first + 1 : W;
+        const uint32_t ncommit = first < W ? first + 1 : wlen;
         if (pos < ncommit && live && cs == 0) sX[h * nX + kw] = (uint8_t) ((sX[h * nX + kw] & 6u) | (dec & 1));
+        if (a.x_adapt) {
+            if (first < (uint32_t) W) { if (++streak >= 2) wlen = min((uint32_t) W, max(8u, 2 * ncommit)); }
+            else { streak = 0; wlen = min((uint32_t) W, 2 * wlen); }
+        }
         if (first < (uint32_t) W) {
             // The window ends at the one TF that flipped (in one or more chains of the bundle): apply the flip
             // to the weights of each child that depends on it.  The whole CTA does this - every other

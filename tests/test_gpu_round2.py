@@ -268,17 +268,20 @@ def test_zero_length_calls_are_no_ops():
 
 
 # ------------------------------------------------------------------------------------------- full shapes
-def test_c4_full_shape_batched_contrasts():
-    """BASELINE config C4 at full size on one device: the C2 network, 512 contrasts x 8 chains (4,096 chains).
+@pytest.mark.parametrize("small", ["1", "3"])
+def test_c4_full_shape_batched_contrasts(monkeypatch, small):
+    """BASELINE config C4 at full size on one device: the C2 network, 512 contrasts x 8 chains (4,096 chains), on
+    the multi-kernel path (the default for more chains than SMs) and on the persistent kernel (GBN_SMALL=3).
     Contrast 0 draws the chains of the single-contrast model bit for bit; a late contrast's conditionals match
     the oracle holding that contrast's evidence; the maximum R-hat is the maximum over contrasts."""
     from gbnet_b200 import synth
     import gbnet_b200
+    monkeypatch.setenv("GBN_SMALL", small)
     net = synth.shape("C2")
     hy = synth.cli_default_hyper()
     evs = np.stack([net.evid_val] + [synth.redraw_evidence(net, num_active_tfs=8, seed=100 + i)[0] for i in range(511)])
     G = gbnet_b200.Sampler(net.src, net.trg, net.mor, net.evid_trg, evs, n_graphs=8, seed=13, **hy)
-    assert G.n_chains() == 4096 and G.path() == (1 if os.environ.get("GBN_SMALL") == "2" else 2)
+    assert G.n_chains() == 4096 and G.path() == (2 if small == "3" else 1)
     S = gbnet_b200.Sampler(net.src, net.trg, net.mor, net.evid_trg, net.evid_val, n_graphs=8, seed=13, **hy)
     G.sample_n(30)
     S.sample_n(30)
