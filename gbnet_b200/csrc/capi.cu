@@ -698,6 +698,15 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
             if (cudaMemcpy(ch.tL, ones.data(), sizeof(double) * n_tc2, cudaMemcpyHostToDevice) != cudaSuccess)
                 return bail(fail(GBN_ERR_CUDA, "cudaMemcpy failed"));
         }
+        n.x1 = fast_x1_supported(n) ? 1 : 0;
+        if (n.x1) {                                                                          // rows of the single-chain X kernel; entries
+            const size_t nw = C * n_w32(n), nq = C * n_q8(n);                                // nH .. of a row stay 0
+            if (int rc = dev_alloc(m, &ch.w0f, nw)) return bail(rc);
+            if (int rc = dev_alloc(m, &ch.w2f, nw)) return bail(rc);
+            if (int rc = dev_alloc(m, &ch.tq1, nq)) return bail(rc);
+            if (cudaMemset(ch.w0f, 0, sizeof(float) * nw) != cudaSuccess || cudaMemset(ch.w2f, 0, sizeof(float) * nw) != cudaSuccess ||
+                cudaMemset(ch.tq1, 0, nq) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "cudaMemset failed"));
+        }
         if (int rc = dev_alloc(m, &ch.Sw, C * tp.nSw)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.Aw, C * tp.nSw)) return bail(rc);
         if (int rc = dev_alloc(m, &ch.dC, C * tp.nD)) return bail(rc);

@@ -65,6 +65,7 @@ struct DevNet {
     double z_y, z_n;              // ZY / ZN constants   GraphORNOR.cpp:155-164
     uint32_t n_datasets, n_graphs_local, chain_offset, n_graphs;
     int32_t listen, const_params;
+    int32_t x1;                   // X phase by the single-chain kernel (k_fast_x1: fp32 flip weights of the whole chain in shared memory)
     int32_t sim;                  // simulation mode (empty evidence, GraphORNOR.cpp:28): X and S fixed, H and Y sampled
     uint64_t seed;
 };
@@ -90,6 +91,9 @@ struct DevChains {
     uint2 *dC;                    // [c][nD] per-batch counts {S=0, S=2} of four steps as 4 x u8 each, folded into cS
                                   // before anything reads the statistics (and before a byte could overflow)
     uint32_t *Stfp;               // [c][ceil(E / 16)] copy of S in by-TF CSR order, 2-bit codes (coalesced reads in the X phase)
+    float *w0f, *w2f;             // [c][n_w32(net)] the flip weights rounded to fp32, one contiguous row per chain (net.x1): what the
+                                  // single-chain X kernel stages in shared memory (entry nH .. : 0)
+    uint8_t *tq1;                 // [c][n_q8(net)] the bound bytes of tq, one contiguous row per chain (net.x1; entry nH .. : 0)
     uint16_t *xqp;                // [c][nX] X kernel: the magnitude bound (bits) a TF's children gave at its last update - predicts
                                   // which TFs will need the exact product, so that it is gathered in the same pass
     uint32_t *xU;                 // [c][nX rounded up to 4] Philox words of the current sweep's X draws (X kernel scratch)
@@ -115,6 +119,11 @@ __device__ __forceinline__ uint32_t slot0(const DevNet &n, uint32_t dt) { return
 // words of the by-TF copy of the S codes (16 codes per word): positions 0 .. E-1 and the sentinel position E
 // (code 1, child = the dummy target nH) that idle lanes of the X kernel's child loop read instead of branching
 __host__ __device__ inline uint32_t n_stf_words(const DevNet &n) { return (n.E + 16) >> 4; }
+
+// row lengths of the per-chain fp32 weight rows / bound-byte rows (targets 0 .. nH-1, the dummy nH; rounded so that
+// every row starts on a 16-byte boundary: the rows are copied to shared memory with cp.async.bulk)
+__host__ __device__ inline uint32_t n_w32(const DevNet &n) { return (n.nH + 4) & ~3u; }
+__host__ __device__ inline uint32_t n_q8(const DevNet &n) { return (n.nH + 16) & ~15u; }
 
 __host__ __device__ inline uint32_t chain_dataset(const DevNet &n, uint32_t c) { return c / n.n_graphs_local; }
 __host__ __device__ inline uint32_t chain_global_id(const DevNet &n, uint32_t c)

@@ -34,6 +34,7 @@ size_t strict_smem_bytes(const DevNet &net);
 // separate streams so that one group's X kernel overlaps another group's S kernel)
 bool fast_t_beside_x(const DevNet &net);   // launch_sweep_fast leaves the current T in ch.T2 after an odd number of sweeps
 bool fast_uses_x_stream(const DevNet &net);
+bool fast_x1_supported(const DevNet &net);   // the X phase runs on the single-chain shared-memory kernel (needs ch.w0f / w2f / tq1)
 uint32_t fast_x_bundle();    // chains per X-kernel CTA = interleave factor of the product cache
 int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps, uint32_t sweep0,
                       uint32_t stat_n0, cudaStream_t st, const char **err, cudaEvent_t *phase_ev = nullptr,

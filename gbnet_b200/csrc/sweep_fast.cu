@@ -434,6 +434,423 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     }
 }
 
+// ---------------------------------------------------------------------------------- X phase, one chain per CTA
+// k_fast_x (above) gathers 8 bytes per (child, chain) from the flip-weight cache in L2: one L1 wavefront per
+// distinct line, 16 lines per warp-wide gather - the kernel is bound by those wavefronts.  Here the flip weights of
+// ONE chain, rounded to fp32 by the S kernel (2 x 4 bytes per target: 160 KB at 20,000 targets), and the bound
+// bytes are staged in shared memory by bulk asynchronous copies (cp.async.bulk -> mbarrier), and the children's
+// gathers become shared-memory loads (a warp-wide gather of 32 random words costs ~3.5 bank-conflict cycles).
+//
+// The draw must not depend on the rounding.  The fp32 product R~ of the factors 1 + phi w carries a RIGOROUS
+// relative error bound B (below); the draw is decided from R~ only if R~ (1 - 2B) and R~ (1 + 2B) give the same
+// value - i.e. the uniform is not within the error of the boundary (probability ~ B p0 p1, around 1e-4 per
+// update).  Otherwise, and for the TFs whose children's product may underflow a double (the underflow rule of
+// Multinomial.cpp:78-85 needs the exact magnitude), the WHOLE CTA evaluates the TF in fp64 from the global cache:
+// the arithmetic of k_fast_x, one trip even for a hub.  Only undecided TFs in front of the window's first flip
+// are resolved; the others are evaluated again by a later window anyway.
+//
+// Error bound.  Per factor f = 1 + phi w computed as fmaf(fl(phi), fl(w), 1): |f~ - f| <= |phi w| 2^-23 + |f| 2^-24
+// (+ second-order terms), and |phi w| = |f - 1| <= f + 1, so the relative error is <= 2^-23 (1.5 + 1 / f).  The
+// running fp32 product of U factors and its conversion add 2^-24 per factor; the fp64 accumulation is exact at
+// this scale.  With n factors and m = the smallest computed factor:  B = 1.05 n 2^-23 (2 + 1 / m).  Lanes past the
+// end of a list multiply by exactly 1 (the dummy's weight is 0) and are counted in n anyway.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is counted on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// the draw of Multinomial.cpp:66-99 for a binary node from the likelihood ratio flipped / current = mr 2^er and, where
+// the magnitude matters, the current product ml 2^el (1, 0 otherwise); returns the drawn value
+__device__ __forceinline__ uint32_t x_draw(const double *prob, uint32_t xcur, double ml, int el, double mr, int er, double u)
+{
+    double mf = ml * mr;
+    int ef = el + er;
+    normalise(mf, ef);
+    double lik_cur, lik_flip;
+    common_scale(prob[xcur] * ml, el, prob[1 - xcur] * mf, ef, lik_cur, lik_flip);
+    const double l0 = xcur ? lik_flip : lik_cur, l1 = xcur ? lik_cur : lik_flip;
+    double cum0 = 0. + l0, cum1 = cum0 + l1;
+    if (!(cum1 > 0.)) { cum0 = 0. + prob[0]; cum1 = cum0 + prob[1]; }     // Multinomial.cpp:78-85
+    const double dice = 0. * (1 - u) + cum1 * u;
+    return dice < cum0 ? 0u : (dice < cum1 ? 1u : xcur);
+}
+
+constexpr uint32_t X1_BULK = 16384;          // bytes per bulk copy
+
+template <int NT, int LPT, int U>
+__global__ void __launch_bounds__(NT, 1) k_fast_x1(DevNet net, DevChains ch, SweepArgs a)
+{
+    constexpr int NW = NT / 32, NS = 32 / LPT, W = NW * NS;                  // warps, TFs per warp, TFs per window
+    constexpr uint32_t Q = XQ;                                               // interleave of the fp64 cache (the fallback reads it)
+    static_assert(NW <= 32, "the block-wide reduction takes one partial per lane");
+    extern __shared__ __align__(128) unsigned char smem_x[];
+    __shared__ uint32_t s_dec[W];                                            // per window position: 0 kept, 1 flipped, 2 undecided
+    __shared__ double s_phi[W];                                              // per window position: phi of the flip
+    __shared__ double s_rm[NW], s_rl[NW];                                    // block-wide reduction of a resolved TF
+    __shared__ int s_re[NW], s_rel[NW];
+    __shared__ uint32_t s_rq[NW];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const uint32_t nX = net.nX, nH = net.nH, nHp = n_w32(net), nHq = n_q8(net);
+    const uint32_t nXr = (nX + 3) & ~3u, nStfW = n_stf_words(net);
+    float *sW0 = reinterpret_cast<float *>(smem_x);                          // [nHp] w0 per target (entry nH: 0)
+    float *sW2 = sW0 + nHp;                                                  // [nHp] w2
+    uint8_t *sQ = reinterpret_cast<uint8_t *>(sW2 + nHp);                    // [nHq] q with L >= 2^(-q / 32)
+    uint32_t *sPtr = reinterpret_cast<uint32_t *>(sQ + nHq);                 // [nX + 1 rounded up to 4] tf_ptr
+    uint8_t *sX = reinterpret_cast<uint8_t *>(sPtr + ((nX + 4) & ~3u));      // [nX] value | prior class << 1 | may underflow << 2
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sg = lane / LPT, cs = lane % LPT;                         // this lane's TF of the warp, child slot within it
+    const uint32_t pos = warp * NS + sg;                                     // window position of this lane's TF
+    const uint32_t c = a.chain0 + blockIdx.x;
+    const uint32_t d = chain_dataset(net, c), gchain = chain_global_id(net, c);
+
+    // ---- stage the chain: weights and bounds by bulk copies, the rest by the threads while the copies fly
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bw = 4 * nHp, bq = nHq;
+        mbar_expect_tx(&s_bar, 2 * bw + bq);
+        const unsigned char *g0 = reinterpret_cast<const unsigned char *>(ch.w0f + (size_t) c * nHp);
+        const unsigned char *g2 = reinterpret_cast<const unsigned char *>(ch.w2f + (size_t) c * nHp);
+        const unsigned char *gq = ch.tq1 + (size_t) c * nHq;
+        for (uint32_t o = 0; o < bw; o += X1_BULK) bulk_g2s(reinterpret_cast<unsigned char *>(sW0) + o, g0 + o, min(X1_BULK, bw - o), &s_bar);
+        for (uint32_t o = 0; o < bw; o += X1_BULK) bulk_g2s(reinterpret_cast<unsigned char *>(sW2) + o, g2 + o, min(X1_BULK, bw - o), &s_bar);
+        for (uint32_t o = 0; o < bq; o += X1_BULK) bulk_g2s(sQ + o, gq + o, min(X1_BULK, bq - o), &s_bar);
+    }
+    {
+        const uint8_t *gX = ch.X + (size_t) c * nX;
+        const uint8_t *uf = net.tf_uf + (size_t) d * nX;
+        for (uint32_t k = tid; k < nX; k += NT) sX[k] = (uint8_t) (gX[k] | (net.x_prior_active[k] << 1) | (uf[k] << 2));
+        if (!a.use_inj) {   // every X uniform of this chain and sweep: one Philox block per four TFs, computed once
+            uint4 *gU = reinterpret_cast<uint4 *>(ch.xU + (size_t) c * nXr);
+            for (uint32_t blk = tid; blk < nXr / 4; blk += NT) {
+                const u32x4 r = philox_rk(blk, a.sweep, gchain, KIND_X, a);
+                gU[blk] = make_uint4(r.x, r.y, r.z, r.w);
+            }
+        }
+        for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.tf_ptr[k];
+    }
+    __syncthreads();
+    // this chain inside the bundle-interleaved fp64 cache, as 32-bit element offsets: w0 of target i at
+    // tw_all[w_off + 2 Q i], w2 one further; L at ch.tL[l_off + Q i]
+    const double *tw_all = reinterpret_cast<const double *>(ch.tc2);
+    const uint32_t l_off = (c / Q) * (nH + 1) * Q + (c % Q), w_off = 2 * l_off, stf_off = c * nStfW;
+    const uint32_t E = net.E;
+    // The TFs whose magnitude bound reached the exact-product threshold at their last update (an active hub per chain at
+    // C3) will most likely be resolved in fp64 again, from cache lines nothing else touches: pull them into L2 now.
+    {
+        __shared__ uint32_t s_hot[32], s_nhot;
+        if (tid == 0) s_nhot = 0;
+        __syncthreads();
+        for (uint32_t k = tid; k < nX; k += NT)
+            if ((sX[k] & 4u) && ch.xqp[c * nX + k] >= 985) {
+                const uint32_t slot = atomicAdd(&s_nhot, 1u);
+                if (slot < 32) s_hot[slot] = k;
+            }
+        __syncthreads();
+        const uint32_t nhot = min(s_nhot, 32u);
+        for (uint32_t i = 0; i < nhot; i++) {
+            const uint32_t k = s_hot[i];
+            for (uint32_t c2 = sPtr[k] + tid; c2 < sPtr[k + 1]; c2 += NT) {
+                const uint32_t t = net.tf_child[c2];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ch.tL + (l_off + Q * t)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(tw_all + (w_off + 2 * Q * t)));
+            }
+        }
+    }
+    while (!mbar_try_wait(&s_bar, 0)) { }
+
+    const double *gT = ch.T + (size_t) c * nX;
+    const uint32_t *gU = ch.xU + (size_t) c * nXr;
+    const double *inj = a.use_inj ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + net.E) : nullptr;
+    uint16_t *xqp = ch.xqp + (size_t) c * nX;
+
+    uint32_t wlen = W, streak = 0;                                           // adaptive window: see k_fast_x
+    uint32_t k0 = 0;
+    while (k0 < nX) {
+        const uint32_t kw = k0 + pos;
+        const bool live = kw < nX && pos < wlen;
+        uint32_t state = 0;                        // this lane's TF: 0 kept, 1 flipped, 2 undecided
+        uint32_t nxv = 0;
+        double phi = 0.;
+        if (NS > 1 || live) {                     // warp-uniform when a warp holds one TF; else dead TFs ride along empty
+            const uint32_t kr = live ? kw : 0u;
+            const uint32_t xs = sX[kr], xcur = xs & 1u;
+            const double t = gT[kr];
+            const uint32_t uword = a.use_inj ? 0u : gU[kr];
+            const bool track = live && (xs & 4u) != 0;
+            uint32_t cbeg = 0, cend = 0;
+            if (live) { cbeg = sPtr[kw]; cend = sPtr[kw + 1]; }
+            GBN_CHECK(cbeg <= cend && cend <= E);
+            uint32_t cc = cbeg + cs;
+            uint32_t id[U], sh[U];
+            auto load_ids = [&](uint32_t c0) {
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const uint32_t cr = c0 + u * LPT;
+                    const uint32_t ce = cr < cend ? cr : E;                  // past the end: the sentinel (dummy target, code 1)
+                    id[u] = __ldg(net.tf_child + ce);
+                    sh[u] = (__ldg(ch.Stfp + (stf_off + (ce >> 4))) >> (2 * (ce & 15))) & 3u;
+                }
+            };
+            load_ids(cc);
+            uint32_t trips = (cend - cbeg + U * LPT - 1) / (U * LPT);        // trip count, uniform over the warp
+            if (NS > 1) trips = __reduce_max_sync(0xffffffffu, trips);
+            const uint32_t nfac = trips * U * LPT;                           // factors of this TF's product, idle lanes included
+            phi = -t;                                                        // f -> q f, q = 1 - t (X: 0 -> 1) or 1 / (1 - t) (1 -> 0)
+            if (xcur) phi = t / (1. - t);
+            const float phf = (float) phi;
+            double mr = 1.;
+            int er = 0;
+            float minf = 1.f;
+            uint32_t qs = 0;
+            auto child_loop = [&](auto with_q) {
+                constexpr bool WITH_Q = decltype(with_q)::value;
+                int cnt = 0;
+                for (; trips > 0; trips--) {
+                    float w[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        GBN_CHECK(id[u] <= nH && sh[u] <= 2);
+                        const float *base = (sh[u] & 2u) ? sW2 : sW0;
+                        w[u] = base[sh[u] == 1 ? nH : id[u]];                // an edge that is off: the dummy's zero weight
+                        if (WITH_Q) qs += sQ[id[u]];
+                    }
+                    cc += U * LPT;
+                    load_ids(cc);                                             // next trip
+                    float pm = 1.f;
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const float f = __fmaf_rn(phf, w[u], 1.f);
+                        minf = fminf(minf, f);
+                        pm *= f;
+                    }
+                    mr *= (double) pm;
+                    if ((cnt += U) >= 16) { normalise(mr, er); cnt = 0; }
+                }
+            };
+            if (__any_sync(0xffffffffu, track)) child_loop(std::true_type{}); else child_loop(std::false_type{});
+            normalise(mr, er);
+#pragma unroll
+            for (int o = LPT / 2; o >= 1; o >>= 1) {
+                mr *= __shfl_xor_sync(0xffffffffu, mr, o);
+                er += __shfl_xor_sync(0xffffffffu, er, o);
+                qs += __shfl_xor_sync(0xffffffffu, qs, o);
+                minf = fminf(minf, __shfl_xor_sync(0xffffffffu, minf, o));
+            }
+            normalise(mr, er);
+            if (live) {
+                const bool exact = track && qs >= 32 * 990;                  // prior (>= 2^-7) x prod L could leave the normal range
+                if (track && cs == 0) xqp[kr] = (uint16_t) min(qs >> 5, 65535u);
+                // (a NaN or non-positive factor fails the first test; phi beyond 2^20 only when t is within 1e-6 of 1)
+                // (a NaN or non-positive factor fails the first test; phi beyond 2^20 only when t is within 1e-6 of 1)
+                const bool r_ok = minf >= 0x1p-10f && fabsf(phf) <= 0x1p20f;
+                // twice the bound (rounded up: the reciprocal is an approximation within 2 ulp)
+                const double B2 = (double) (2.2f * 0x1p-23f * (float) nfac * (2.f + __frcp_ru(fmaxf(minf, 0x1p-10f))));
+                bool sure = !exact && r_ok && B2 < 0.125;
+                const double u = a.use_inj ? inj[kr] : unit_from_word(uword);
+                const double *prob = net.xprob[(xs >> 1) & 1u];
+                if (sure) {
+                    // the draw of x_draw() from R~, and its distance from the boundary: a relative change delta of the
+                    // flipped outcome's likelihood moves dice - cum0 by delta l_flip u (flipped outcome = 1) or
+                    // delta l_flip (u - 1) (flipped outcome = 0)
+                    double lik_cur, lik_flip;
+                    common_scale(prob[xcur], 0, prob[1 - xcur] * mr, er, lik_cur, lik_flip);
+                    const double l0 = xcur ? lik_flip : lik_cur, l1 = xcur ? lik_cur : lik_flip;
+                    const double cum0 = 0. + l0, cum1 = cum0 + l1;
+                    const double dice = 0. * (1 - u) + cum1 * u;
+                    nxv = dice < cum0 ? 0u : 1u;
+                    sure = fabs(dice - cum0) > B2 * lik_flip * (xcur ? 1. - u : u) && dice < cum1;
+                } else if (exact && r_ok && B2 < 0.125) {
+                    // Far below the double range: the bytes also bound the product from above, L < 2^(-(q - 1.3) / 32), so
+                    // log2 prod L < ub, and log2 of the flipped outcome's product < ub + er + 1.  When both are below -1090
+                    // both outcome likelihoods are exactly zero in fp64 (as the reference's exp() delivers them), and the
+                    // draw is from the prior (Multinomial.cpp:78-85) - no exact product needed.
+                    const float ub = (1.3f * (float) nfac - (float) qs) * (1.f / 32.f);
+                    if (ub < -1090.f && ub + (float) er + 1.f < -1090.f) {
+                        const double cum0 = 0. + prob[0], cum1 = cum0 + prob[1];
+                        const double dice = 0. * (1 - u) + cum1 * u;
+                        nxv = dice < cum0 ? 0u : (dice < cum1 ? 1u : xcur);
+                        sure = true;
+                        if (ch.dbg && cs == 0) atomicAdd(ch.dbg + 11, 1ull);
+                    }
+                }
+                if (a.x1_force && kw % a.x1_force == 0) sure = false;
+                state = sure ? (nxv != xcur ? 1u : 0u) : 2u;
+                if (ch.dbg && cs == 0 && track) atomicAdd(ch.dbg + 9, 1ull);
+            }
+        }
+        if (cs == 0) { s_dec[pos] = state; s_phi[pos] = phi; }
+        __syncthreads();
+        // Undecided TFs in front of the window's first decided flip are resolved in fp64 from the global cache (the
+        // arithmetic of k_fast_x), all at once: G = NW / (their number) warps per TF - the whole CTA for the usual single
+        // hub, one warp each when there are many.  Then the first TF of the window that flipped is known.
+        uint32_t first;
+        {
+            constexpr int NB = (W + 31) / 32;
+            uint32_t um[NB];                                                 // undecided positions
+            uint32_t fs = W, n_u = 0;                                        // first decided flip
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const uint32_t v = 32 * b + lane < (uint32_t) W ? s_dec[(32 * b + lane) % W] : 0u;
+                const uint32_t f1 = __ballot_sync(0xffffffffu, v == 1u);
+                um[b] = __ballot_sync(0xffffffffu, v == 2u);
+                if (f1 && fs == (uint32_t) W) fs = 32 * b + (uint32_t) __ffs(f1) - 1;
+            }
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                if ((uint32_t) (32 * b) >= fs) um[b] = 0;
+                else if (fs < (uint32_t) (32 * b + 32)) um[b] &= (1u << (fs - 32 * b)) - 1u;
+                n_u += __popc(um[b]);
+            }
+            if (n_u) {                                                       // uniform over the CTA
+                uint32_t G = NW;
+                while (G > 1 && NW / G < n_u) G >>= 1;
+                const uint32_t P = NW / G, wg = warp / G, wl = warp % G;
+                for (uint32_t j0 = 0; j0 < n_u; j0 += P) {
+                    const uint32_t j = j0 + wg;
+                    const bool act = j < n_u;                                // warp-uniform
+                    uint32_t up = 0;                                         // the j-th undecided position
+                    {
+                        uint32_t r = j;
+                        bool found = !act;
+#pragma unroll
+                        for (int b = 0; b < NB; b++) {
+                            const uint32_t cb = __popc(um[b]);
+                            if (!found && r < cb) { up = 32 * b + __fns(um[b], 0, r + 1); found = true; }
+                            if (!found) r -= cb;
+                        }
+                    }
+                    const uint32_t kf = k0 + up, xs = sX[kf], xcur = xs & 1u;
+                    const bool track = (xs & 4u) != 0;
+                    const double ph = s_phi[up];
+                    double mr = 1., ml = 1.;
+                    int er = 0, el = 0;
+                    uint32_t qs = 0;
+                    if (act) {
+                        const uint32_t fb0 = sPtr[kf], fe0 = sPtr[kf + 1];
+                        int cnt = 0;
+                        for (uint32_t c2 = fb0 + 32 * wl + lane; c2 < fe0; c2 += 32 * G) {
+                            const uint32_t i = net.tf_child[c2];
+                            const uint32_t sc = (ch.Stfp[stf_off + (c2 >> 4)] >> (2 * (c2 & 15))) & 3u;
+                            GBN_CHECK(i < nH && sc <= 2);
+                            const double w = tw_all[w_off + 2 * Q * (sc == 1 ? nH : i) + (sc >> 1)];
+                            mr *= __fma_rn(ph, w, 1.);
+                            if (track) { ml *= ch.tL[l_off + Q * i]; qs += sQ[i]; }
+                            if (++cnt == 8) { normalise(mr, er); normalise(ml, el); cnt = 0; }
+                        }
+                        normalise(mr, er); normalise(ml, el);
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) {
+                            mr *= __shfl_xor_sync(0xffffffffu, mr, o); er += __shfl_xor_sync(0xffffffffu, er, o);
+                            ml *= __shfl_xor_sync(0xffffffffu, ml, o); el += __shfl_xor_sync(0xffffffffu, el, o);
+                            qs += __shfl_xor_sync(0xffffffffu, qs, o);
+                            normalise(mr, er); normalise(ml, el);
+                        }
+                    }
+                    if (lane == 0) { s_rm[warp] = mr; s_re[warp] = er; s_rl[warp] = ml; s_rel[warp] = el; s_rq[warp] = qs; }
+                    __syncthreads();
+                    if (act) {
+                        // every warp of the group folds the group's G partials the same way
+                        const bool in = lane < G;
+                        const uint32_t src = wg * G + (in ? lane : 0u);
+                        mr = in ? s_rm[src] : 1.; er = in ? s_re[src] : 0;
+                        ml = in ? s_rl[src] : 1.; el = in ? s_rel[src] : 0;
+                        qs = in ? s_rq[src] : 0u;
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) {
+                            mr *= __shfl_xor_sync(0xffffffffu, mr, o); er += __shfl_xor_sync(0xffffffffu, er, o);
+                            ml *= __shfl_xor_sync(0xffffffffu, ml, o); el += __shfl_xor_sync(0xffffffffu, el, o);
+                            qs += __shfl_xor_sync(0xffffffffu, qs, o);
+                            normalise(mr, er); normalise(ml, el);
+                        }
+                        const bool exact = track && qs >= 32 * 990;
+                        if (!exact) { ml = 1.; el = 0; }                     // far from underflow: only the ratio matters
+                        const double u = a.use_inj ? inj[kf] : unit_from_word(gU[kf]);
+                        const uint32_t nx = x_draw(net.xprob[(xs >> 1) & 1u], xcur, ml, el, mr, er, u);
+                        if (wl == 0 && lane == 0) {
+                            s_dec[up] = nx != xcur ? 1u : 0u;
+                            if (ch.dbg) { atomicAdd(ch.dbg + 10, 1ull); if (exact) atomicAdd(ch.dbg + 8, 1ull); }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            first = W;
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                const uint32_t f1 = __ballot_sync(0xffffffffu, 32 * b + lane < (uint32_t) W && s_dec[(32 * b + lane) % W] == 1u);
+                if (f1 && first == (uint32_t) W) first = 32 * b + (uint32_t) __ffs(f1) - 1;
+            }
+        }
+        const uint32_t ncommit = first < W ? first + 1 : wlen;
+        if (pos < ncommit && live && cs == 0) sX[kw] = (uint8_t) (sX[kw] ^ (s_dec[pos] & 1u));    // decided: 0 kept, 1 flipped
+        if (a.x_adapt) {
+            if (first < (uint32_t) W) { if (++streak >= 2) wlen = min((uint32_t) W, max(8u, 2 * ncommit)); }
+            else { streak = 0; wlen = min((uint32_t) W, 2 * wlen); }
+        }
+        if (first < (uint32_t) W) {
+            // The window ends at the TF that flipped: apply the flip to the weights of each child that depends on it -
+            // the fp64 cache (what a later resolve reads), its fp32 image and the bound byte in shared memory, and the
+            // S kernel's "parent is active" bit of the edge.  The whole CTA walks the children.
+            const uint32_t kf = k0 + first, fb0 = sPtr[kf], fe0 = sPtr[kf + 1];
+            const double ph = s_phi[first];
+            const uint32_t *gS = ch.Stfp + (size_t) c * nStfW;
+            uint32_t *gA = ch.Aw + (size_t) c * net.nSw;
+            double2 *tcb = ch.tc2 + (size_t) (c / Q) * (nH + 1) * Q + (c % Q);
+            double *tlb = ch.tL + (size_t) (c / Q) * (nH + 1) * Q + (c % Q);
+            for (uint32_t c2 = fb0 + tid; c2 < fe0; c2 += NT) {
+                const uint32_t ab = net.tf_abit[c2];
+                GBN_CHECK((ab >> 4) < net.nSw);
+                atomicXor(gA + (ab >> 4), 1u << (ab & 15));
+                const uint32_t s = code_at(gS, c2);
+                if (s == 1) continue;
+                const uint32_t i = net.tf_child[c2];
+                double2 w = tcb[(size_t) Q * i];
+                double L = tlb[(size_t) Q * i];
+                flip_weights(w, L, s, ph);
+                tcb[(size_t) Q * i] = w;
+                tlb[(size_t) Q * i] = L;
+                sW0[i] = (float) w.x;
+                sW2[i] = (float) w.y;
+                sQ[i] = l_bound_bits(L);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && ch.dbg) {
+            atomicAdd(ch.dbg + 0, 1ull);
+            atomicAdd(ch.dbg + 1, (unsigned long long) (k0 + ncommit <= nX ? ncommit : nX - k0));
+            atomicAdd(ch.dbg + 2, first < W ? 1ull : 0ull);
+        }
+        k0 += ncommit;
+    }
+    // every TF was committed exactly once: write X back and count (Multinomial.cpp:101-105 as a count)
+    {
+        uint8_t *gX = ch.X + (size_t) c * nX;
+        uint32_t *cX1 = ch.cX1 + (size_t) c * nX;
+        for (uint32_t k = tid; k < nX; k += NT) { const uint32_t x = sX[k] & 1u; gX[k] = (uint8_t) x; cX1[k] += x; }
+    }
+}
+
 // ---------------------------------------------------------------------------------- T phase
 // Beta::sample (Beta.cpp:60-104) for T nodes that do not listen to their children: the blanket is
 // the Beta prior alone.  Also publishes FXp = {1 - t*x, 1 / (1 - t*x)} (HNodeORNOR.cpp:59) for
@@ -823,9 +1240,17 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
         const double g2 = t.y * Bq, g02 = t.y * A + g2;
         const double L = t.x + g02, iL = 1. / L;
         const size_t o = ((size_t) (c / XQ) * (nH + 1) + dt) * XQ + (c % XQ);   // interleaved by chain bundle
-        ch.tc2[o] = make_double2(g02 * iL, g2 * iL);
+        const double w0 = g02 * iL, w2 = g2 * iL;
+        ch.tc2[o] = make_double2(w0, w2);
         ch.tL[o] = L;
-        ch.tq[o] = l_bound_bits(L);
+        if (net.x1) {                                               // the single-chain X kernel's rows (k_fast_x1)
+            const size_t of = (size_t) c * n_w32(net) + dt;
+            ch.w0f[of] = (float) w0;
+            ch.w2f[of] = (float) w2;
+            ch.tq1[(size_t) c * n_q8(net) + dt] = l_bound_bits(L);
+        } else {
+            ch.tq[o] = l_bound_bits(L);
+        }
     }
 }
 
@@ -940,6 +1365,20 @@ static bool x_q_smem(const DevNet &net)
 
 uint32_t fast_x_bundle() { return XQ; }
 
+// shared memory of the single-chain X kernel: fp32 flip weights and bound bytes of every target, by-TF pointers, X
+static size_t x1_smem_bytes(const DevNet &net)
+{
+    return 8 * (size_t) n_w32(net) + n_q8(net) + 4 * (((size_t) net.nX + 4) & ~(size_t) 3) + net.nX + 16;
+}
+// the X phase runs on k_fast_x1 when one chain's weights fit an SM's shared memory (GBN_X1=2: never)
+bool fast_x1_supported(const DevNet &net)
+{
+    if (env_u32("GBN_X1", 1) == 2) return false;
+    const uint64_t C = (uint64_t) net.n_datasets * net.n_graphs_local + XQ;
+    if (C * net.nX >= (1ull << 32)) return false;
+    return x1_smem_bytes(net) + 4096 <= 227 * 1024;
+}
+
 // the T draws of a sweep run beside its X phase (see launch_sweep_fast); the caller swaps ch.T / ch.T2 after
 // an odd number of sweeps
 bool fast_t_beside_x(const DevNet &net) { return !net.listen && !net.const_params && env_u32("GBN_T_BESIDE_X", 1) != 2; }
@@ -1033,6 +1472,15 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
     else if (lpt == 16) kx = qs ? k_fast_x<FX_NT, 16, 1, true> : k_fast_x<FX_NT, 16, 1, false>;
     else { kx = qs ? k_fast_x<FX_NT / 2, 8, 1, true> : k_fast_x<FX_NT / 2, 8, 1, false>; x_nt = FX_NT / 2; }
     if (check(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x), err)) return -1;
+    void (*kx1)(DevNet, DevChains, SweepArgs) = nullptr;
+    const size_t smem_x1 = x1_smem_bytes(net);
+    if (net.x1) {
+        // one chain per CTA: half as many lanes per TF as the pair kernel for the same children per gather
+        uint32_t l1 = env_u32("GBN_X_LPT", 0);
+        if (l1 != 4 && l1 != 8 && l1 != 16 && l1 != 32) l1 = big ? 8 : 4;
+        kx1 = l1 == 32 ? k_fast_x1<FX_NT, 32, XU> : l1 == 16 ? k_fast_x1<FX_NT, 16, XU> : l1 == 8 ? k_fast_x1<FX_NT, 8, XU> : k_fast_x1<FX_NT, 4, XU>;
+        if (check(cudaFuncSetAttribute(kx1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x1), err)) return -1;
+    }
     const size_t smem_tl = 4 * (size_t) net.nX + 16;
     if (net.listen && !net.const_params &&
         check(cudaFuncSetAttribute(k_fast_tl, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1054,7 +1502,8 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         a.chain0 = chain0;
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw], st);
         if (stx != st && sw > 0) cudaStreamWaitEvent(stx, evs, 0);      // this chain group's previous S phase
-        kx<<<(nchains + XQ - 1) / XQ, x_nt, smem_x, stx>>>(net, chl, a, nchains);
+        if (kx1) kx1<<<nchains, FX_NT, smem_x1, stx>>>(net, chl, a);
+        else kx<<<(nchains + XQ - 1) / XQ, x_nt, smem_x, stx>>>(net, chl, a, nchains);
         if (stx != st) cudaEventRecord(evx, stx);
         if (t_beside_x) {
             if (phase_ev) cudaEventRecord(phase_ev[3 * sw + 1], st);
