@@ -413,6 +413,9 @@ int fast_batch(gbn_model *m, uint32_t n, uint32_t sweep0, uint32_t stat0, const 
     static const uint32_t env_groups = env_u32("GBN_STREAM_GROUPS", 0);
     uint32_t G = m->stream_groups ? m->stream_groups
                : (env_groups ? env_groups : (m->n_chains >= 192 ? 3 : (m->n_chains >= 96 ? 2 : 1)));
+    // ... and a sweep of little work (C2 network x 512 chains: 0.19 ms) is bound by the host's launch rate when
+    // three groups multiply the launches: one group below 1.5e7 edge-updates per sweep
+    if (!m->stream_groups && !env_groups && (uint64_t) m->n_chains * m->tp.E < 15000000ull) G = 1;
     const uint32_t xq = fast_x_bundle();
     G = std::min(G, (m->n_chains + xq - 1) / xq);       // no empty groups (boundaries fall on whole bundles)
     if (G < 1) G = 1;

@@ -497,7 +497,7 @@ __device__ __forceinline__ uint32_t x_draw(const double *prob, uint32_t xcur, do
 constexpr uint32_t X1_BULK = 16384;          // bytes per bulk copy
 
 template <int NT, int LPT, int U>
-__global__ void __launch_bounds__(NT, 1) k_fast_x1(DevNet net, DevChains ch, SweepArgs a)
+__global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fast_x1(DevNet net, DevChains ch, SweepArgs a)
 {
     constexpr int NW = NT / 32, NS = 32 / LPT, W = NW * NS;                  // warps, TFs per warp, TFs per window
     constexpr uint32_t Q = XQ;                                               // interleave of the fp64 cache (the fallback reads it)
@@ -1473,12 +1473,27 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
     else { kx = qs ? k_fast_x<FX_NT / 2, 8, 1, true> : k_fast_x<FX_NT / 2, 8, 1, false>; x_nt = FX_NT / 2; }
     if (check(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x), err)) return -1;
     void (*kx1)(DevNet, DevChains, SweepArgs) = nullptr;
+    uint32_t x1_nt = FX_NT;
     const size_t smem_x1 = x1_smem_bytes(net);
     if (net.x1) {
         // one chain per CTA: half as many lanes per TF as the pair kernel for the same children per gather
         uint32_t l1 = env_u32("GBN_X_LPT", 0);
         if (l1 != 4 && l1 != 8 && l1 != 16 && l1 != 32) l1 = big ? 8 : 4;
-        kx1 = l1 == 32 ? k_fast_x1<FX_NT, 32, XU> : l1 == 16 ? k_fast_x1<FX_NT, 16, XU> : l1 == 8 ? k_fast_x1<FX_NT, 8, XU> : k_fast_x1<FX_NT, 4, XU>;
+        // TFs with few targets and more chains than SMs: CTAs of 256 threads (a 64-TF window), four chains per SM -
+        // a round is bound by its latency, not by the lanes (GBN_X1_NT=256 / 1024 force one)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        uint32_t nt1 = env_u32("GBN_X1_NT", 0);
+        // TFs with many targets: CTAs of 512 threads - the kernel is bound by the latency of its rounds, not by its
+        // lanes (1,024 threads: 0.347 ms per launch at C3, 512: 0.358), and half the registers of the SM stay free
+        // for S-kernel CTAs of another chain group (step 23.0 -> 22.5 ms)
+        if (nt1 != 256 && nt1 != 512 && nt1 != 1024) nt1 = big ? 512 : (nchains > 2u * (uint32_t) sms ? 256 : 1024);
+        if (l1 != 4 && nt1 == 256) nt1 = 1024;
+        x1_nt = nt1;
+        if (nt1 == 256) kx1 = k_fast_x1<256, 4, XU>;
+        else if (nt1 == 512) kx1 = l1 >= 16 ? k_fast_x1<512, 16, XU> : l1 == 8 ? k_fast_x1<512, 8, XU> : k_fast_x1<512, 4, XU>;
+        else kx1 = l1 == 32 ? k_fast_x1<FX_NT, 32, XU> : l1 == 16 ? k_fast_x1<FX_NT, 16, XU> : l1 == 8 ? k_fast_x1<FX_NT, 8, XU> : k_fast_x1<FX_NT, 4, XU>;
         if (check(cudaFuncSetAttribute(kx1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x1), err)) return -1;
     }
     const size_t smem_tl = 4 * (size_t) net.nX + 16;
@@ -1502,7 +1517,7 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         a.chain0 = chain0;
         if (phase_ev) cudaEventRecord(phase_ev[3 * sw], st);
         if (stx != st && sw > 0) cudaStreamWaitEvent(stx, evs, 0);      // this chain group's previous S phase
-        if (kx1) kx1<<<nchains, FX_NT, smem_x1, stx>>>(net, chl, a);
+        if (kx1) kx1<<<nchains, x1_nt, smem_x1, stx>>>(net, chl, a);
         else kx<<<(nchains + XQ - 1) / XQ, x_nt, smem_x, stx>>>(net, chl, a, nchains);
         if (stx != st) cudaEventRecord(evx, stx);
         if (t_beside_x) {
