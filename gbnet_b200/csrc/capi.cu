@@ -621,7 +621,9 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         UP(tf_ptr, tp.tf_ptr, u32) UP(tf_child, tp.tf_child, u32) UP(tf_slot, tp.tf_slot, u32)
         UP(tfpos_of_slot, tp.tfpos_of_slot, u32) UP(par_pack, tp.par_pack, u32)
         UP(sbase, tp.sbase, u32) UP(dbase, tp.dbase, u32) UP(sw_grp, tp.sw_grp, u32) UP(dblk_grp, tp.dblk_grp, u32)
-        UP(mor2, tp.mor2, u32) UP(tf_abit, tp.tf_abit, u32)
+        UP(mor2, tp.mor2, u32)
+        UP(fp_ptr, tp.fp_ptr, u32) UP(fp_child, tp.fp_child, u32) UP(fp_slot, tp.fp_slot, u32) UP(fp_abit, tp.fp_abit, u32)
+        n.Efp = tp.Efp;
         { uint32_t *t4 = nullptr; if (int rc = dev_upload(m, &t4, tp.tfpos4)) return bail(rc); n.tfpos4 = reinterpret_cast<const uint4 *>(t4); }
         { uint16_t *u16 = nullptr; if (int rc = dev_upload(m, &u16, tp.par16)) return bail(rc); n.par16 = reinterpret_cast<const uint2 *>(u16); }
         n.nSw = tp.nSw; n.nD = tp.nD;

@@ -10,7 +10,7 @@
 //   fast kernel   tc2[c][nH] {w0, w2} f64x2 flip weights and tL[c][nH] f64 likelihood: the per-target cache of the X phase
 //                 Sw[c][nSw] u32 S as 2-bit codes in slot order (the fast sweep's master copy of S)
 //                 dC[c][nD] u8x8 per-batch outcome counts of four steps, folded into cS on demand
-//                 Stfp[c][E/16] u32 copy of S in by-TF CSR order, 2-bit codes (coalesced reads in the X phase)
+//                 Stfp[c][Efp/16] u32 copy of S in by-TF order (padded lists, topology.hpp), 2-bit codes (coalesced reads in the X phase)
 //                 FXp[c][nX] f64x2   1 - t*x and its reciprocal
 // Integer counts replace the reference's gsl_rstat workspaces of 0/1 indicators
 // (Multinomial.cpp:101-105): mean = c/N, variance = N/(N-1) p (1-p).
@@ -47,8 +47,13 @@ struct DevNet {
     const uint32_t *dblk_grp;     // [nD / 32]   group of every row of 32 blocks
     const uint32_t *mor2;         // [nSw] prior row per step (3 = pad)
     const uint2 *par16;           // [nD]  four 16-bit parent TFs per block
-    const uint4 *tfpos4;          // [nD]  by-TF CSR position of the block's four steps (UINT32_MAX for pads)
-    const uint32_t *tf_abit;      // [Eu]  by-TF position -> 16 * (S word of the edge) + step inside the word
+    const uint4 *tfpos4;          // [nD]  fp position (padded by-TF lists) of the block's four steps (UINT32_MAX for pads)
+    // by-TF lists of the fast path, every TF's list padded to a multiple of four with sentinel children (topology.hpp)
+    const uint32_t *fp_ptr;       // [nX+1]
+    const uint32_t *fp_child;     // [Efp + 4] device targets; pads and the four entries past the end: the dummy target nH
+    const uint32_t *fp_slot;      // [Efp] slot of the edge (UINT32_MAX: pad)
+    const uint32_t *fp_abit;      // [Efp] fp position -> 16 * (S word of the edge) + step inside the word (UINT32_MAX: pad)
+    uint32_t Efp;
     uint32_t nSw, nD;
     const uint8_t *x_prior_active;// [nX]
     const uint8_t *tf_uf;         // [n_datasets][nX] 1: the product of this TF's children's likelihoods could underflow a double
@@ -90,7 +95,7 @@ struct DevChains {
                                   // kept current by the X kernel's flip patch, so the S kernel looks a TF's factor up only then
     uint2 *dC;                    // [c][nD] per-batch counts {S=0, S=2} of four steps as 4 x u8 each, folded into cS
                                   // before anything reads the statistics (and before a byte could overflow)
-    uint32_t *Stfp;               // [c][ceil(E / 16)] copy of S in by-TF CSR order, 2-bit codes (coalesced reads in the X phase)
+    uint32_t *Stfp;               // [c][n_stf_words] copy of S in by-TF order (padded lists), 2-bit codes (coalesced reads in the X phase)
     float *w0f, *w2f;             // [c][n_w32(net)] the flip weights rounded to fp32, one contiguous row per chain (net.x1): what the
                                   // single-chain X kernel stages in shared memory (entry nH .. : 0)
     uint8_t *tq1;                 // [c][n_q8(net)] the bound bytes of tq, one contiguous row per chain (net.x1; entry nH .. : 0)
@@ -116,9 +121,9 @@ struct DevChains {
 // first slot of device target dt; its j-th parent is 32 j further
 __device__ __forceinline__ uint32_t slot0(const DevNet &n, uint32_t dt) { return n.gbase[dt >> 5] + (dt & 31); }
 
-// words of the by-TF copy of the S codes (16 codes per word): positions 0 .. E-1 and the sentinel position E
-// (code 1, child = the dummy target nH) that idle lanes of the X kernel's child loop read instead of branching
-__host__ __device__ inline uint32_t n_stf_words(const DevNet &n) { return (n.E + 16) >> 4; }
+// words of the by-TF copy of the S codes (16 codes per word): fp positions 0 .. Efp-1 and the four sentinel positions
+// Efp .. Efp+3 (code 1, child = the dummy target nH) that idle lanes of the X kernels' child loops read instead of branching
+__host__ __device__ inline uint32_t n_stf_words(const DevNet &n) { return (n.Efp + 19) >> 4; }
 
 // row lengths of the per-chain fp32 weight rows / bound-byte rows (targets 0 .. nH-1, the dummy nH; rounded so that
 // every row starts on a 16-byte boundary: the rows are copied to shared memory with cp.async.bulk)

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             }
         }
     }
-    for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.tf_ptr[k];
+    for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.fp_ptr[k];
     const uint8_t *gQ = ch.tq + (size_t) (cbase / Q) * (nH + 1) * Q;         // this bundle's bounds, interleaved like the weights
     if (Q_SMEM) {
         static_assert(XQ % 2 == 0, "the bounds are copied two bytes at a time");
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
             const uint32_t k = s_hot[i] & 0x7fffffffu, q = s_hot[i] >> 31;
             const double *base = tlb + q;
             for (uint32_t c2 = sPtr[k] + tid; c2 < sPtr[k + 1]; c2 += NT)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t) net.tf_child[c2] * Q));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t) net.fp_child[c2] * Q));
         }
     }
 
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
     // tw_all[w_off + 2 Q i], w2 one further; L at ch.tL[l_off + Q i]; the chain's by-TF S words from stf_off
     const double *tw_all = reinterpret_cast<const double *>(ch.tc2);
     const uint32_t l_off = (cbase / Q) * (nH + 1) * Q + h, w_off = 2 * l_off, stf_off = cmine * nStfW;
-    const uint32_t E = net.E;
+    const uint32_t E = net.Efp;                     // the sentinel position of the padded by-TF lists
 
     // Adaptive window.  A round that ends in a flip throws away the evaluations behind the flip.  With the CLI
     // defaults 18 % of the rounds end that way and the full window is right; when X values move often (a diffuse
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
                 for (int u = 0; u < U; u++) {
                     const uint32_t cr = c0 + u * CPW;
                     const uint32_t c = cr < cend ? cr : E;
-                    id[u] = __ldg(net.tf_child + c);
+                    id[u] = __ldg(net.fp_child + c);
                     sh[u] = (__ldg(ch.Stfp + (stf_off + (c >> 4))) >> (2 * (c & 15))) & 3u;
                 }
             };
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const uint32_t cr = c2 + u * CPW;
-                        l4[u] = ch.tL[l_off + Q * __ldg(net.tf_child + (cr < cend ? cr : E))];   // past the end: the dummy's 1
+                        l4[u] = ch.tL[l_off + Q * __ldg(net.fp_child + (cr < cend ? cr : E))];   // past the end: the dummy's 1
                     }
                     ml *= (l4[0] * l4[1]) * (l4[2] * l4[3]);
                     normalise(ml, el);
@@ -406,12 +406,13 @@ __global__ void __launch_bounds__(NT, 1) k_fast_x(DevNet net, DevChains ch, Swee
                 uint32_t *gA = ch.Aw + (size_t) (cbase + q) * net.nSw;
                 for (uint32_t c2 = fb0 + tid; c2 < fe0; c2 += NT) {
                     // the S kernel's "parent is active" bit of this edge follows the flip (whatever the edge's code)
-                    const uint32_t ab = net.tf_abit[c2];
+                    const uint32_t ab = net.fp_abit[c2];
+                    if (ab == UINT32_MAX) continue;                           // a pad of the by-TF list
                     GBN_CHECK((ab >> 4) < net.nSw);
                     atomicXor(gA + (ab >> 4), 1u << (ab & 15));
                     const uint32_t s = code_at(gS, c2);
                     if (s == 1) continue;
-                    const size_t i = (size_t) net.tf_child[c2] * Q + q;
+                    const size_t i = (size_t) net.fp_child[c2] * Q + q;
                     flip_weights(tcb[i], tlb[i], s, ph);
                     if (Q_SMEM) sQ[i] = l_bound_bits(tlb[i]);                 // later windows of this sweep read the bound here
                     else ch.tq[(size_t) (cbase / Q) * (nH + 1) * Q + i] = l_bound_bits(tlb[i]);
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
     constexpr int NW = NT / 32, NS = 32 / LPT, W = NW * NS;                  // warps, TFs per warp, TFs per window
     constexpr uint32_t Q = XQ;                                               // interleave of the fp64 cache (the fallback reads it)
     static_assert(NW <= 32, "the block-wide reduction takes one partial per lane");
-    extern __shared__ __align__(128) unsigned char smem_x[];
+    extern __shared__ __align__(16) unsigned char smem_x[];
     __shared__ uint32_t s_dec[W];                                            // per window position: 0 kept, 1 flipped, 2 undecided
     __shared__ double s_phi[W];                                              // per window position: phi of the flip
     __shared__ double s_rm[NW], s_rl[NW];                                    // block-wide reduction of a resolved TF
@@ -547,14 +548,14 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
                 gU[blk] = make_uint4(r.x, r.y, r.z, r.w);
             }
         }
-        for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.tf_ptr[k];
+        for (uint32_t k = tid; k <= nX; k += NT) sPtr[k] = net.fp_ptr[k];
     }
     __syncthreads();
     // this chain inside the bundle-interleaved fp64 cache, as 32-bit element offsets: w0 of target i at
     // tw_all[w_off + 2 Q i], w2 one further; L at ch.tL[l_off + Q i]
     const double *tw_all = reinterpret_cast<const double *>(ch.tc2);
     const uint32_t l_off = (c / Q) * (nH + 1) * Q + (c % Q), w_off = 2 * l_off, stf_off = c * nStfW;
-    const uint32_t E = net.E;
+    const uint32_t E = net.Efp;                     // the sentinel position of the padded by-TF lists
     // The TFs whose magnitude bound reached the exact-product threshold at their last update (an active hub per chain at
     // C3) will most likely be resolved in fp64 again, from cache lines nothing else touches: pull them into L2 now.
     {
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
         for (uint32_t i = 0; i < nhot; i++) {
             const uint32_t k = s_hot[i];
             for (uint32_t c2 = sPtr[k] + tid; c2 < sPtr[k + 1]; c2 += NT) {
-                const uint32_t t = net.tf_child[c2];
+                const uint32_t t = net.fp_child[c2];
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ch.tL + (l_off + Q * t)));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(tw_all + (w_off + 2 * Q * t)));
             }
@@ -583,6 +584,8 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
     const uint32_t *gU = ch.xU + (size_t) c * nXr;
     const double *inj = a.use_inj ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + net.E) : nullptr;
     uint16_t *xqp = ch.xqp + (size_t) c * nX;
+    const uint4 *child4 = reinterpret_cast<const uint4 *>(net.fp_child);                                  // chunk q: children 4q .. 4q+3
+    const uint8_t *code4 = reinterpret_cast<const uint8_t *>(ch.Stfp + (size_t) c * nStfW);              // byte q: their S codes
 
     uint32_t wlen = W, streak = 0;                                           // adaptive window: see k_fast_x
     uint32_t k0 = 0;
@@ -598,24 +601,26 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
             const double t = gT[kr];
             const uint32_t uword = a.use_inj ? 0u : gU[kr];
             const bool track = live && (xs & 4u) != 0;
-            uint32_t cbeg = 0, cend = 0;
-            if (live) { cbeg = sPtr[kw]; cend = sPtr[kw + 1]; }
-            GBN_CHECK(cbeg <= cend && cend <= E);
-            uint32_t cc = cbeg + cs;
-            uint32_t id[U], sh[U];
-            auto load_ids = [&](uint32_t c0) {
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const uint32_t cr = c0 + u * LPT;
-                    const uint32_t ce = cr < cend ? cr : E;                  // past the end: the sentinel (dummy target, code 1)
-                    id[u] = __ldg(net.tf_child + ce);
-                    sh[u] = (__ldg(ch.Stfp + (stf_off + (ce >> 4))) >> (2 * (ce & 15))) & 3u;
-                }
-            };
-            load_ids(cc);
-            uint32_t trips = (cend - cbeg + U * LPT - 1) / (U * LPT);        // trip count, uniform over the warp
+            // The by-TF lists are padded to multiples of four per TF (topology.hpp): a lane takes CHUNKS of four consecutive
+            // children - one 16-byte load of the ids, one byte load of their four S codes - LPT chunks apart, and requests
+            // the chunks of the next two trips before it touches this trip's weights (a trip's shared-memory gathers are
+            // short; with one trip of look-ahead every trip waited for an L2 round trip).
+            uint32_t q4 = 0, q4e = 0;                                        // this lane's chunk; the end of the TF's chunks
+            if (live) { q4 = sPtr[kw] >> 2; q4e = sPtr[kw + 1] >> 2; }
+            GBN_CHECK(q4 <= q4e && 4 * q4e <= E);
+            uint32_t trips = (q4e - q4 + LPT - 1) / LPT;                     // trip count, uniform over the warp
             if (NS > 1) trips = __reduce_max_sync(0xffffffffu, trips);
-            const uint32_t nfac = trips * U * LPT;                           // factors of this TF's product, idle lanes included
+            const uint32_t nfac = trips * 4 * LPT;                           // factors of this TF's product, idle lanes included
+            q4 += cs;
+            struct Chunk { uint4 id; uint32_t cd; };
+            auto load_chunk = [&](uint32_t q) {
+                const uint32_t qq = q < q4e ? q : (E >> 2);                  // past the end: the sentinel chunk (dummy target, code 1)
+                Chunk r;
+                r.id = __ldg(child4 + qq);
+                r.cd = __ldg(code4 + qq);
+                return r;
+            };
+            Chunk c0 = load_chunk(q4), c1 = load_chunk(q4 + LPT);
             phi = -t;                                                        // f -> q f, q = 1 - t (X: 0 -> 1) or 1 / (1 - t) (1 -> 0)
             if (xcur) phi = t / (1. - t);
             const float phf = (float) phi;
@@ -627,25 +632,27 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
                 constexpr bool WITH_Q = decltype(with_q)::value;
                 int cnt = 0;
                 for (; trips > 0; trips--) {
-                    float w[U];
+                    const Chunk c2 = load_chunk(q4 + 2 * LPT);               // two trips ahead
+                    const uint32_t id[4] = { c0.id.x, c0.id.y, c0.id.z, c0.id.w };
+                    float w[4];
 #pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        GBN_CHECK(id[u] <= nH && sh[u] <= 2);
-                        const float *base = (sh[u] & 2u) ? sW2 : sW0;
-                        w[u] = base[sh[u] == 1 ? nH : id[u]];                // an edge that is off: the dummy's zero weight
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t sh = (c0.cd >> (2 * u)) & 3u;
+                        GBN_CHECK(id[u] <= nH && sh <= 2);
+                        const float *base = (sh & 2u) ? sW2 : sW0;
+                        w[u] = base[sh == 1 ? nH : id[u]];                   // an edge that is off: the dummy's zero weight
                         if (WITH_Q) qs += sQ[id[u]];
                     }
-                    cc += U * LPT;
-                    load_ids(cc);                                             // next trip
                     float pm = 1.f;
 #pragma unroll
-                    for (int u = 0; u < U; u++) {
+                    for (int u = 0; u < 4; u++) {
                         const float f = __fmaf_rn(phf, w[u], 1.f);
                         minf = fminf(minf, f);
                         pm *= f;
                     }
                     mr *= (double) pm;
-                    if ((cnt += U) >= 16) { normalise(mr, er); cnt = 0; }
+                    if ((cnt += 4) >= 16) { normalise(mr, er); cnt = 0; }
+                    c0 = c1; c1 = c2; q4 += LPT;
                 }
             };
             if (__any_sync(0xffffffffu, track)) child_loop(std::true_type{}); else child_loop(std::false_type{});
@@ -750,9 +757,9 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
                         const uint32_t fb0 = sPtr[kf], fe0 = sPtr[kf + 1];
                         int cnt = 0;
                         for (uint32_t c2 = fb0 + 32 * wl + lane; c2 < fe0; c2 += 32 * G) {
-                            const uint32_t i = net.tf_child[c2];
+                            const uint32_t i = net.fp_child[c2];
                             const uint32_t sc = (ch.Stfp[stf_off + (c2 >> 4)] >> (2 * (c2 & 15))) & 3u;
-                            GBN_CHECK(i < nH && sc <= 2);
+                            GBN_CHECK(i <= nH && sc <= 2 && (i < nH || sc == 1));
                             const double w = tw_all[w_off + 2 * Q * (sc == 1 ? nH : i) + (sc >> 1)];
                             mr *= __fma_rn(ph, w, 1.);
                             if (track) { ml *= ch.tL[l_off + Q * i]; qs += sQ[i]; }
@@ -819,12 +826,13 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
             double2 *tcb = ch.tc2 + (size_t) (c / Q) * (nH + 1) * Q + (c % Q);
             double *tlb = ch.tL + (size_t) (c / Q) * (nH + 1) * Q + (c % Q);
             for (uint32_t c2 = fb0 + tid; c2 < fe0; c2 += NT) {
-                const uint32_t ab = net.tf_abit[c2];
+                const uint32_t ab = net.fp_abit[c2];
+                if (ab == UINT32_MAX) continue;                               // a pad of the by-TF list
                 GBN_CHECK((ab >> 4) < net.nSw);
                 atomicXor(gA + (ab >> 4), 1u << (ab & 15));
                 const uint32_t s = code_at(gS, c2);
                 if (s == 1) continue;
-                const uint32_t i = net.tf_child[c2];
+                const uint32_t i = net.fp_child[c2];
                 double2 w = tcb[(size_t) Q * i];
                 double L = tlb[(size_t) Q * i];
                 flip_weights(w, L, s, ph);
@@ -969,7 +977,7 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
             const uint32_t k = list[b0 + idx];
             const size_t o = (size_t) c * nX + k;
             const double prev = ch.T[o], prop = s_prop[idx], r = s_r[idx];
-            const uint32_t cbeg = net.tf_ptr[k], cend = net.tf_ptr[k + 1];
+            const uint32_t cbeg = net.fp_ptr[k], cend = net.fp_ptr[k + 1];
             double dll = 0.;
             if (s_lpp[idx] > -INFINITY) {               // out-of-range proposals are rejected before the children matter
                 // sum_children log L(t') - log L(t) = log prod (1 + (r - 1) w), w = the flip weight of the edge's code
@@ -978,8 +986,8 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
                 for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
                     const uint32_t s = code_at(gStf, cc);
                     if (s == 1) continue;
-                    const uint32_t i = net.tf_child[cc];
-                    GBN_CHECK(i < nH);
+                    const uint32_t i = net.fp_child[cc];
+                    GBN_CHECK(i < nH);                      // (pads carry code 1 and were skipped)
                     const double2 w = tc2[XQ * (size_t) i];
                     mr *= __fma_rn(r - 1., s == 0 ? w.x : w.y, 1.);
                     if (++cnt == 8) { normalise(mr, er); cnt = 0; }
@@ -1014,7 +1022,7 @@ __global__ void __launch_bounds__(FTL_NT) k_fast_tl(DevNet net, DevChains ch, Sw
                 for (uint32_t cc = cbeg + tid; cc < cend; cc += FTL_NT) {
                     const uint32_t s = code_at(gStf, cc);
                     if (s == 1) continue;
-                    const size_t i = XQ * (size_t) net.tf_child[cc];
+                    const size_t i = XQ * (size_t) net.fp_child[cc];
                     flip_weights(tc2[i], tL[i], s, r - 1.);
                 }
             }
@@ -1220,7 +1228,7 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                             Bq = ns != 1 ? Br * f : Br;
                             n = nR + (ns != 1);
                             const uint32_t tp = u == 0 ? tp4.x : (u == 1 ? tp4.y : (u == 2 ? tp4.z : tp4.w));
-                            GBN_CHECK(tp < net.E);
+                            GBN_CHECK(tp < net.Efp);
                             atomicXor(ch.Stfp + (stf_off + (tp >> 4)), x << (2 * (tp & 15)));
                         }
                     }
@@ -1330,7 +1338,7 @@ __global__ void k_fast_stf(DevNet net, DevChains ch)
     for (uint32_t u = 0; u < 16; u++) {
         const uint32_t pos = 16 * wi + u;
         uint32_t code = 1u;
-        if (pos < net.E) { GBN_CHECK(net.tf_slot[pos] < net.Ep); code = ch.S[(size_t) c * net.Ep + net.tf_slot[pos]]; }
+        if (pos < net.Efp && net.fp_slot[pos] != UINT32_MAX) { GBN_CHECK(net.fp_slot[pos] < net.Ep); code = ch.S[(size_t) c * net.Ep + net.fp_slot[pos]]; }
         w |= code << (2 * u);
     }
     ch.Stfp[(size_t) c * nStfW + wi] = w;

@@ -154,7 +154,7 @@ __device__ __forceinline__ void small_s_group(const DevNet &net, const DevChains
                         Bq = ns != 1 ? Br * f : Br;
                         n = nR + (ns != 1);
                         const uint32_t tp = u == 0 ? pTp[32 * bb].x : (u == 1 ? pTp[32 * bb].y : (u == 2 ? pTp[32 * bb].z : pTp[32 * bb].w));
-                        GBN_CHECK(tp < net.E);
+                        GBN_CHECK(tp < net.Efp);
                         atomicXor(sStf + (tp >> 4), x << (2 * (tp & 15)));
                     }
                 }
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small_sweep(DevNet net, DevChains 
         sFX[k] = make_double2(fx, 1. / fx);
         sCX1[k] = 0;
     }
-    for (uint32_t k = tid; k <= nX; k += SM_NT) sPtr[k] = net.tf_ptr[k];
+    for (uint32_t k = tid; k <= nX; k += SM_NT) sPtr[k] = net.fp_ptr[k];
     for (uint32_t i = tid; i < net.nSw; i += SM_NT) sSw[i] = gSw[i];
     for (uint32_t i = tid; i < net.nD; i += SM_NT) sDC[i] = make_uint2(0u, 0u);
     {
@@ -231,10 +231,8 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small_sweep(DevNet net, DevChains 
         uint32_t w = 0x55555555u;
         for (uint32_t u = 0; u < 16; u++) {
             const uint32_t pos = 16 * wi + u;
-            if (pos < E) {
-                const uint32_t ab = net.tf_abit[pos];
-                w = (w & ~(3u << (2 * u))) | (((sSw[ab >> 4] >> (2 * (ab & 15))) & 3u) << (2 * u));
-            }
+            const uint32_t ab = pos < net.Efp ? net.fp_abit[pos] : UINT32_MAX;     // pads of the by-TF lists keep code 1
+            if (ab != UINT32_MAX) w = (w & ~(3u << (2 * u))) | (((sSw[ab >> 4] >> (2 * (ab & 15))) & 3u) << (2 * u));
         }
         sStf[wi] = w;
     }
@@ -284,7 +282,7 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small_sweep(DevNet net, DevChains 
                 uint32_t cc = cbeg + sl;
                 for (; trips > 0; trips--, cc += LPT) {
                     uint32_t id = nH, s = 1u;                         // idle lane: the dummy target, edge off
-                    if (cc < cend) { id = net.tf_child[cc]; s = code_at(sStf, cc); }
+                    if (cc < cend) { id = net.fp_child[cc]; s = code_at(sStf, cc); }
                     GBN_CHECK(id <= nH && s <= 2);
                     const double2 bg = sTc[id];
                     const double c0 = sTab[sNy[id]].x;
@@ -332,10 +330,10 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small_sweep(DevNet net, DevChains 
                 for (uint32_t c2 = fb0 + tid; c2 < fe0; c2 += SM_NT) {
                     const uint32_t s = code_at(sStf, c2);
                     if (s == 1) continue;
-                    double2 bg = sTc[net.tf_child[c2]];
+                    double2 bg = sTc[net.fp_child[c2]];
                     if (s == 0) bg.x *= fq;
                     bg.y *= fq;
-                    sTc[net.tf_child[c2]] = bg;
+                    sTc[net.fp_child[c2]] = bg;
                 }
             }
             __syncthreads();

@@ -73,7 +73,14 @@ struct Topology {
     std::vector<uint32_t> mor2;                     // [nSw] prior row per step, 3 = pad (row {0, 1, 0}: never moves)
     std::vector<uint16_t> par16;                    // [4 nD] parent TF per step (0 for pads)
     std::vector<uint32_t> tfpos4;                   // [4 nD] by-TF CSR position per step (UINT32_MAX for pads)
-    std::vector<uint32_t> tf_abit;                  // [Eu] by-TF position -> 16 * S word + step inside the word
+    // by-TF lists of the FAST path: every TF's list starts at a multiple of four and is padded to one with sentinel
+    // children (the dummy target nH, slot UINT32_MAX; their S code in the by-TF copy stays 1 = edge off), so that a lane
+    // of the X kernels reads four children with one 16-byte load and their four S codes with one byte load.  Positions
+    // in these lists ("fp" positions) index the by-TF copy of S (Stfp), tfpos4 and fp_abit.
+    std::vector<uint32_t> fp_ptr;                   // [nX+1] multiples of 4; fp_ptr[nX] = Efp
+    std::vector<uint32_t> fp_child, fp_slot;        // [Efp + 4] (four sentinels at the end: what idle lanes read), [Efp]
+    std::vector<uint32_t> fp_abit;                  // [Efp] fp position -> 16 * S word + step inside the word (UINT32_MAX: pad)
+    uint32_t Efp = 0;
     uint32_t nSw = 0, nD = 0;
 
     uint32_t slot(uint32_t dt, uint32_t j) const { return gbase[dt >> 5] + 32 * j + (dt & 31); }
@@ -208,7 +215,18 @@ inline Topology compile_topology(uint32_t n_edge, const uint32_t *src, const uin
     tp.mor2.assign(tp.nSw, 0xffffffffu);
     tp.par16.assign(4 * (size_t) tp.nD, 0);
     tp.tfpos4.assign(4 * (size_t) tp.nD, UINT32_MAX);
-    tp.tf_abit.assign(tp.Eu, 0);
+    tp.fp_ptr.assign(nX + 1, 0);
+    for (uint32_t k = 0; k < nX; k++) tp.fp_ptr[k + 1] = tp.fp_ptr[k] + ((tp.tf_ptr[k + 1] - tp.tf_ptr[k] + 3) & ~3u);
+    tp.Efp = tp.fp_ptr[nX];
+    tp.fp_child.assign((size_t) tp.Efp + 4, nH); tp.fp_slot.assign(tp.Efp, UINT32_MAX); tp.fp_abit.assign(tp.Efp, UINT32_MAX);
+    std::vector<uint32_t> fp_of_slot(tp.Ep, UINT32_MAX);
+    for (uint32_t k = 0; k < nX; k++)
+        for (uint32_t c = tp.tf_ptr[k]; c < tp.tf_ptr[k + 1]; c++) {
+            const uint32_t fpos = tp.fp_ptr[k] + (c - tp.tf_ptr[k]);
+            tp.fp_child[fpos] = tp.tf_child[c];
+            tp.fp_slot[fpos] = tp.tf_slot[c];
+            fp_of_slot[tp.tf_slot[c]] = fpos;
+        }
     if (nX <= 65536)
         for (uint32_t dt = 0; dt < nH; dt++) {
             const uint32_t g = dt >> 5, lane = dt & 31;
@@ -217,8 +235,8 @@ inline Topology compile_topology(uint32_t n_edge, const uint32_t *src, const uin
                 uint32_t &mw = tp.mor2[tp.sbase[g] + 32 * (j / 16) + lane];
                 mw = (mw & ~(3u << (2 * (j % 16)))) | ((uint32_t) tp.mor_idx[q] << (2 * (j % 16)));
                 tp.par16[4 * (size_t) (tp.dbase[g] + 32 * (j / 4) + lane) + (j % 4)] = (uint16_t) tp.par_tf[q];
-                tp.tfpos4[4 * (size_t) (tp.dbase[g] + 32 * (j / 4) + lane) + (j % 4)] = tp.tfpos_of_slot[q];
-                if (tp.tfpos_of_slot[q] != UINT32_MAX) tp.tf_abit[tp.tfpos_of_slot[q]] = 16 * (tp.sbase[g] + 32 * (j / 16) + lane) + (j % 16);
+                tp.tfpos4[4 * (size_t) (tp.dbase[g] + 32 * (j / 4) + lane) + (j % 4)] = fp_of_slot[q];
+                if (fp_of_slot[q] != UINT32_MAX) tp.fp_abit[fp_of_slot[q]] = 16 * (tp.sbase[g] + 32 * (j / 16) + lane) + (j % 16);
             }
         }
     tp.x_prior_active.assign(nX, 0);
