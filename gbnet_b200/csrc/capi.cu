@@ -298,6 +298,26 @@ int upload_evidence(gbn_model *m, const gbn_evidence *ev)
             }
         }
         CUDA_TRY(cudaMemcpy(m->d_stab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+        // k_fast_s2 drops the all-zero fallback of Multinomial.cpp:78-85: prior x likelihood must be positive for some
+        // outcome.  That holds when every prior row has an entry that is not tiny and the likelihood tables are
+        // positive: L = omz (a convex combination of YNOISE entries) + zc K with K = sum_h YPROB[h] YNOISE[h][y], so
+        // YPROB >= 0 with a positive sum suffices (comp_yprob can make an entry negative, GraphORNOR.cpp:113-125,
+        // when evidence outside the network is counted).  Anything else runs on k_fast_s, which keeps the fallback.
+        uint32_t safe = 1;
+        for (int r = 0; r < 3; r++) {
+            bool pos = false;
+            for (int v = 0; v < 3; v++) {
+                const double q = m->net.sprob[r][v];
+                if (!(q == 0. || (q >= 1e-200 && q <= 1e200))) safe = 0;         // negative, NaN, inf, or tiny
+                if (q >= 1e-200) pos = true;
+            }
+            if (!pos) safe = 0;
+        }
+        for (uint32_t d = 0; d < m->n_datasets; d++) {
+            const double *yp = &m->h_yprob[(size_t) d * 3];
+            if (!(yp[0] >= 0. && yp[1] >= 0. && yp[2] >= 0. && yp[0] + yp[1] + yp[2] >= 1e-100 && yp[0] + yp[1] + yp[2] <= 1e100)) safe = 0;
+        }
+        m->net.sprior_safe = safe;
     }
     {
         // (dataset, TF) pairs whose children's likelihood product could underflow a double: a target likelihood is a
@@ -647,6 +667,9 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     if (int rc = dev_alloc(m, &m->d_y, (size_t) m->n_datasets * tp.nH)) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_yprob, (size_t) m->n_datasets * 3)) return bail(rc);
     n.stab_D = (tp.max_indeg + 2 + 1) & ~1u;     // even: the arrays behind the tables stay 16-byte aligned in shared memory
+    n.groups_desc = 1;
+    for (uint32_t g = 0; g + 1 < tp.n_groups; g++)
+        if (tp.gbase[g + 2] - tp.gbase[g + 1] > tp.gbase[g + 1] - tp.gbase[g]) n.groups_desc = 0;
     if (int rc = dev_alloc(m, &m->d_stab, (size_t) m->n_datasets * STAB_ROWS * n.stab_D)) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_uf, (size_t) m->n_datasets * tp.nX)) return bail(rc);
     n.y = m->d_y; n.yprob = m->d_yprob; n.stab = m->d_stab; n.tf_uf = m->d_uf;

@@ -64,6 +64,11 @@ struct DevNet {
     const double *stab;           // [n_datasets][STAB_ROWS][stab_D] fast-path tables over n: c0[y=0..2], omz[cls], zc[cls],
                                   // A[y] = omz (N2 - N0), B[y] = omz (N1 - N2), z^n[cls]
     uint32_t stab_D;              // max_indeg + 2 rounded up to even
+    uint32_t sprior_safe;         // 1: every S prior row has an entry that is not tiny and the likelihood tables are positive (YPROB >= 0),
+                                  // so prior x likelihood cannot vanish for all outcomes: k_fast_s2 drops the fallback of
+                                  // Multinomial.cpp:78-85 (set with the evidence, capi.cu; 0 = the S phase runs on k_fast_s)
+    uint32_t groups_desc;         // 1: group widths never grow with the group index (targets sorted by in-degree): a CTA of the
+                                  // fast S kernel stages only the table rows its first group can reach
     double xprob[2][2];           // [prior_active][v]   GraphORNOR.h:40-41
     double sprob[4][3];           // [mor+1][v]          GraphORNOR.cpp:25; row 3 = {0, 1, 0}: pad steps of the fast S kernel
     double ynoise[3][3];          // [h][y]              GraphORNOR.h:46-48

@@ -46,6 +46,9 @@
 #include "topology.hpp"
 #include "fast_common.cuh"
 
+#ifndef GBN_S2_PRIOR_SMEM
+#define GBN_S2_PRIOR_SMEM 1   // k_fast_s2: prior rows from shared memory (0: from the constant bank)
+#endif
 #ifndef GBN_XEXP
 #define GBN_XEXP 0        // experiments (profiles/r2_summary.md)
 #endif
@@ -1262,6 +1265,261 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
     }
 }
 
+// a *= k under a predicate as ONE predicated multiply (see add_if): the state of a target is updated in place
+__device__ __forceinline__ void mul_if(double &a, double k, bool p)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mul.rn.f64 %0, %0, %1;\n\t}" : "+d"(a) : "d"(k), "r"((int) p));
+}
+// {c0, omz} table pair at a 32-bit shared-memory address (+ 16: the next row).  The address is an ordinary register:
+// behind a generic pointer the compiler rebuilds the shared window base (S2UR / UMOV / ULEA) in every step
+__device__ __forceinline__ double2 lds_pair(uint32_t addr)
+{
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 lds_pair_next(uint32_t addr)
+{
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64_next(uint32_t addr)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1+16];" : "=d"(v) : "r"(addr));
+    return v;
+}
+// a ^= k under a predicate as one predicated instruction
+__device__ __forceinline__ void xor_if(uint32_t &a, uint32_t k, bool p)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q xor.b32 %0, %0, %1;\n\t}" : "+r"(a) : "r"(k), "r"((int) p));
+}
+// a copy of a positive double made by the fp64 pipe (one instruction; a register move of a double is two, and the
+// S kernel is bound by instruction issue, not by the fp64 pipe)
+__device__ __forceinline__ double copy_f64(double x, const SweepArgs &a) { return x * a.one; }
+__device__ __forceinline__ uint32_t smem_addr_opaque(const void *p)
+{
+    unsigned long long a;
+    asm("cvta.to.shared.u64 %0, %1;" : "=l"(a) : "l"(p));
+    return (uint32_t) a;
+}
+
+// S phase, second form (the default; GBN_S_V=1 selects k_fast_s).  Same layout, same draws, same visiting order; what
+// changes is the bookkeeping around the seventeen fp64 operations of a step:
+//  * the state is updated IN PLACE by predicated multiplies: the edge's factor leaves A / Bq (if its code put it
+//    there), the three candidates are evaluated, the drawn code's factor goes back in.  No select pairs on
+//    doubles, no second copy of the state, no state update inside a divergent branch.  An unchanged edge costs the
+//    state two roundings (A f^-1 f); the cache the X phase reads is rebuilt from the codes every sweep (pass 1),
+//    so the drift is bounded by the in-degree (< 2e-14 relative at 72 parents - the size of the rounding
+//    differences the fast path already has against the reference's own order of operations);
+//  * the new codes of a word of 16 steps are collected unconditionally (one shift-add per step); a changed word
+//    is written back and its changed codes are patched into the by-TF copy once per word, with the by-TF position
+//    loaded only then (k_fast_s: a branch taken by 47 % of the warp-steps for 2 % of the lanes, and a 16-byte
+//    position load per block);
+//  * table pairs through a 32-bit shared-memory address that moves with n (no address arithmetic per step);
+//  * an outer loop over words and an inner one over blocks: no predicated word loads in every block;
+//  * only the table rows the CTA's widest group can reach are staged.
+template <bool INJ>
+__global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s2(DevNet net, DevChains ch, SweepArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t nX = net.nX, nH = net.nH, D = net.stab_D;
+    double2 *sTab = reinterpret_cast<double2 *>(smem_raw);                      // [3][D] {c0[y][n], omz[class of y][n]}
+    double *sZp = reinterpret_cast<double *>(sTab + 3 * D);                     // [2][D] z^m by noise class
+    double *sPr = sZp + 2 * D;                                                  // [4][4] prior rows (row 3: a pad step), 32 bytes each
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t c = blockIdx.y + a.chain0;
+    const uint32_t d = chain_dataset(net, c);
+    const double2 *gFX = ch.FXp + (size_t) c * nX;
+    {
+        // n never exceeds the in-degree: with groups in descending order of width the CTA's first group bounds it
+        uint32_t rows = D;
+        if (net.groups_desc) {
+            const uint32_t g0 = blockIdx.x * (FS_NT / 32);
+            rows = min(D, ((net.gbase[g0 + 1] - net.gbase[g0]) >> 5) + 2);
+        }
+        const double *tab = net.stab + (size_t) d * STAB_ROWS * D;
+        for (uint32_t j = tid; j < 3 * rows; j += FS_NT) {
+            const uint32_t yy = j / rows, nn = j - yy * rows;
+            sTab[yy * D + nn] = make_double2(tab[yy * D + nn], tab[(3 + (yy != 1 ? 0 : 1)) * D + nn]);
+        }
+        for (uint32_t j = tid; j < 2 * rows; j += FS_NT) {
+            const uint32_t cc = j / rows, nn = j - cc * rows;
+            sZp[cc * D + nn] = tab[(13 + cc) * D + nn];
+        }
+        if (tid < 16) sPr[tid] = (tid & 3) < 3 ? net.sprob[tid >> 2][tid & 3] : 0.;
+    }
+    __syncthreads();
+
+    const uint32_t g = blockIdx.x * (FS_NT / 32) + (tid >> 5);
+    if (g >= net.n_groups) return;
+    const uint32_t dt = 32 * g + lane;
+    const bool valid = dt < nH;
+    const uint32_t gb = net.gbase[g];
+    const uint32_t W = (net.gbase[g + 1] - gb) >> 5;                 // group width = largest in-degree
+    const uint32_t y = valid ? net.y[(size_t) d * nH + dt] : 1u;
+    const uint32_t cls = (y != 1) ? 0 : 1;                          // ZY for DE targets, ZN otherwise
+    const double z = cls ? net.z_n : net.z_y;
+    const double ca = net.ynoise[2][y] - net.ynoise[0][y];          // a
+    const double cb = net.ynoise[1][y] - net.ynoise[2][y];          // b
+    const uint32_t cot_s = smem_addr_opaque(sTab + y * D);          // {c0, omz} over n for this target's y
+    const uint32_t pr_s = smem_addr_opaque(sPr);
+    const uint32_t sb = net.sbase[g] + lane, db = net.dbase[g] + lane;
+    const uint32_t sw_off = c * net.nSw + sb, dc_off = c * net.nD + db;
+    const uint16_t *par16 = reinterpret_cast<const uint16_t *>(net.par16);   // step j of this lane: [4 (db + 32 (j / 4)) + j % 4]
+    const uint32_t *tfpos = reinterpret_cast<const uint32_t *>(net.tfpos4);  // likewise
+    const uint32_t W4 = (W + 3) >> 2;                                // 4-step blocks (the last may hold pads)
+
+    // the counters are first touched by the second pass: start pulling their lines into L2 now
+    for (uint32_t b = 0; b < W4; b++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ch.dC + (dc_off + 32 * b)));
+    // pass 1 (as in k_fast_s): A = a pr0, Bq = b pr0 pr2, n from two population counts per word and the factors of
+    // the active parents
+    double A = ca, Bq = cb;
+    uint32_t n = 0;
+    {
+        uint32_t n0 = 0;
+        for (uint32_t w = 0; 16 * w < W; w++) {
+            const uint32_t sw = ch.Sw[sw_off + 32 * w];
+            GBN_CHECK(net.sbase[g] + lane + 32 * w < net.nSw);
+            const uint32_t x = sw ^ 0x55555555u;
+            n += __popc((x | (x >> 1)) & 0x55555555u);               // codes != 1
+            n0 += __popc(~(sw | (sw >> 1)) & 0x55555555u);           // codes == 0
+            for (uint32_t act = ch.Aw[sw_off + 32 * w] & 0xffffu; act; act &= act - 1) {
+                const uint32_t u = __ffs(act) - 1, s = (sw >> (2 * u)) & 3u, j = 16 * w + u;
+                const uint32_t kk = par16[4 * (db + 32 * (j >> 2)) + (j & 3)];
+                GBN_CHECK(kk < nX);
+                const double fx = __ldg(&gFX[kk].x);
+                if (s == 0) A *= fx;
+                if (s != 1) Bq *= fx;
+            }
+        }
+        GBN_CHECK(n < D && n0 <= n);
+        A *= sZp[cls * D + n0];
+        Bq *= sZp[cls * D + n];
+    }
+    const double rz = 1. / z;
+    const uint32_t gchain = chain_global_id(net, c);
+    const uint32_t ref_i = valid ? net.ref_of_dt[dt] : 0u;
+    const double *inj_flat = INJ ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + net.E) + nX : nullptr;
+    const uint32_t *pEdge = net.par_edge + gb + lane;
+    const uint32_t stf_off = c * n_stf_words(net);
+    uint32_t na = cot_s + 16 * n;                                    // shared-memory address of cot[n]
+    for (uint32_t w = 0; 16 * w < W; w++) {
+        const uint32_t sw0 = ch.Sw[sw_off + 32 * w];
+        uint32_t sw = sw0, mw = net.mor2[sb + 32 * w], aw = ch.Aw[sw_off + 32 * w], nsw = 0;
+        const uint32_t nb = min(4u, W4 - 4 * w);
+        for (uint32_t b = 0; b < nb; b++) {
+            const uint32_t bb = 4 * w + b, j0 = 4 * bb;
+            uint2 cw = __ldcs(ch.dC + (dc_off + 32 * bb));
+            u32x4 rnd = { 0, 0, 0, 0 };
+            if (!INJ) rnd = philox_rk(ref_i, a.sweep, gchain, KIND_S | (bb << 8), a);
+            uint32_t ns4 = 0x55u;                                    // four codes "off"; pads stay so
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (j0 + u < W) {                                    // warp-uniform
+                    const bool s_is0 = (sw & (3u << (2 * u))) == 0, s_ne1 = (sw & (1u << (2 * u))) == 0;
+                    const uint32_t r32 = (u <= 2 ? mw << (5 - 2 * u) : mw >> (2 * u - 5)) & 0x60u;   // 32 x the prior row
+                    GBN_CHECK(((sw >> (2 * u)) & 3u) <= 2 && na >= cot_s && (na - cot_s) / 16 + 1 < D);
+                    // f = (1 - t x) z and its reciprocal: z and 1 / z unless the parent TF is active (about 1 % of
+                    // the edges; the diagnostic count keeps the block a branch)
+                    double f = copy_f64(z, a), finv = copy_f64(rz, a);
+                    if ((aw >> u) & 1u) {
+                        if (ch.dbg) atomicAdd(ch.dbg + 7, 1ull);
+                        const uint32_t kk = par16[4 * (db + 32 * bb) + u];
+                        GBN_CHECK(kk < nX);
+                        const double2 fx = __ldg(gFX + kk);
+                        f = fx.x * z; finv = fx.y * rz;
+                    }
+                    // the state without this edge
+                    mul_if(A, finv, s_is0);
+                    mul_if(Bq, finv, s_ne1);
+                    add_if(na, 0xfffffff0u, s_ne1);
+                    const double2 t0 = lds_pair(na), t1 = lds_pair_next(na);
+#if GBN_S2_PRIOR_SMEM
+                    const double2 sp01 = lds_pair(pr_s + r32);
+                    const double sp2 = lds_f64_next(pr_s + r32);
+#else
+                    const double *spc = net.sprob[r32 >> 5];         // constant bank, indexed
+                    const double2 sp01 = make_double2(spc[0], spc[1]);
+                    const double sp2 = spc[2];
+#endif
+                    const double sum = A + Bq;
+                    const double L0 = __fma_rn(t1.y, f * sum, t1.x);                   // S = 0: the factor joins pr0
+                    const double L1 = __fma_rn(t0.y, sum, t0.x);                       // S = 1: edge off
+                    const double L2 = __fma_rn(t1.y, __fma_rn(f, Bq, A), t1.x);        // S = 2: the factor joins pr2
+                    // exp(log prior + log L) of Multinomial.cpp:66-75 as a product.  The fallback of Multinomial.cpp:78-85
+                    // (all three terms zero) cannot happen here: L >= c0[n] >= min_h YNOISE > 0, and the model layer
+                    // sends prior rows that could make a product vanish to k_fast_s (sprior_safe)
+                    const double cum0 = sp01.x * L0;
+                    const double cum1 = __fma_rn(sp01.y, L1, cum0);
+                    const double cum2 = __fma_rn(sp2, L2, cum1);
+                    const uint32_t word = u == 0 ? rnd.x : (u == 1 ? rnd.y : (u == 2 ? rnd.z : rnd.w));
+                    double uu = unit_from_word(word);
+                    if (INJ) { const uint32_t e = pEdge[32 * (j0 + u)]; uu = e != 0xffffffffu ? inj_flat[e] : 0.5; }
+                    const double dice = cum2 * uu;
+                    // first v with dice < cum[v] (Multinomial.cpp:92-99); cum0 <= cum1, so "2" is "not below cum1"
+                    bool ns_is0 = dice < cum0, ns_is2 = !(dice < cum1);
+                    if (INJ && !(dice < cum2)) {                     // an injected double can round up to cum[2]: the value is kept
+                        ns_is0 = s_is0; ns_is2 = s_ne1 && !s_is0;
+                    }
+                    const bool ns_ne1 = ns_is0 || ns_is2;
+#ifdef GBN_BOUNDS
+                    if (r32 == 0x60u && ns_ne1) printf("pad moved: lane %u step %u y %u n %u sp %g %g %g t0 %g %g t1 %g %g A %g Bq %g f %g L %g %g %g cum %g %g %g uu %g dice %g\n", lane, j0 + u, y, (na - cot_s) >> 4, sp01.x, sp01.y, sp2, t0.x, t0.y, t1.x, t1.y, A, Bq, f, L0, L1, L2, cum0, cum1, cum2, uu, dice);
+#endif
+                    add_if(cw.x, 1u << (8 * u), ns_is0);                               // Multinomial.cpp:101-105 as counts
+                    add_if(cw.y, 1u << (8 * u), ns_is2);
+                    mul_if(A, f, ns_is0);
+                    mul_if(Bq, f, ns_ne1);
+                    add_if(na, 16u, ns_ne1);
+                    xor_if(ns4, 1u << (2 * u), ns_ne1);              // code 1 -> 0 ...
+                    xor_if(ns4, 2u << (2 * u), ns_is2);              // ... -> 2
+                }
+            }
+            __stcs(ch.dC + (dc_off + 32 * bb), cw);                  // streamed: the product cache stays in L2
+            nsw |= ns4 << (8 * b);
+            sw >>= 8; mw >>= 8; aw >>= 4;
+        }
+        // blocks past the group's width keep their pads
+        uint32_t chg = nb == 4 ? sw0 ^ nsw : (sw0 ^ nsw) & ((1u << (8 * nb)) - 1u);
+        if (chg) {
+            ch.Sw[sw_off + 32 * w] = sw0 ^ chg;
+            do {                                                     // the by-TF copy follows, code by code
+                const uint32_t u16 = (__ffs(chg) - 1) >> 1, j = 16 * w + u16;
+                const uint32_t x = (chg >> (2 * u16)) & 3u;
+                chg &= ~(3u << (2 * u16));
+                const uint32_t tp = tfpos[4 * (db + 32 * (j >> 2)) + (j & 3)];
+#ifdef GBN_BOUNDS
+                if (!(tp < net.Efp)) printf("pad changed: chain %u group %u lane %u W %u word %u step %u x %u sw0 %08x nsw %08x nb %u y %u n %u A %g Bq %g\n", c, g, lane, W, w, u16, x, sw0, nsw, nb, y, (na - cot_s) >> 4, A, Bq);
+#endif
+                GBN_CHECK(tp < net.Efp);
+                atomicXor(ch.Stfp + (stf_off + (tp >> 4)), x << (2 * (tp & 15)));
+            } while (chg);
+        }
+    }
+    n = (na - cot_s) >> 4;
+    GBN_CHECK(n < D);
+    if (valid) {
+        // what the X phase reads (see k_fast_x): L = c0[n] + omz[n] (A + Bq) and the flip weights
+        const double2 t = lds_pair(na);
+        const double g2 = t.y * Bq, g02 = t.y * A + g2;
+        const double L = t.x + g02, iL = 1. / L;
+        const size_t o = ((size_t) (c / XQ) * (nH + 1) + dt) * XQ + (c % XQ);   // interleaved by chain bundle
+        const double w0 = g02 * iL, w2 = g2 * iL;
+        ch.tc2[o] = make_double2(w0, w2);
+        ch.tL[o] = L;
+        if (net.x1) {                                               // the single-chain X kernel's rows (k_fast_x1)
+            const size_t of = (size_t) c * n_w32(net) + dt;
+            ch.w0f[of] = (float) w0;
+            ch.w2f[of] = (float) w2;
+            ch.tq1[(size_t) c * n_q8(net) + dt] = l_bound_bits(L);
+        } else {
+            ch.tq[o] = l_bound_bits(L);
+        }
+    }
+}
+
 // ---- conversions between the byte view of S (ch.S: parity hooks, state get / set, checkpoints, strict kernel)
 // and the packed views the fast sweep works on
 // S bytes -> 2-bit words (after creation, set_state, checkpoint load)
@@ -1355,7 +1613,7 @@ static int check(cudaError_t e, const char **err)
 // shared memory of the S kernel: the per-dataset tables over n
 static size_t s_smem_bytes(const DevNet &net)
 {
-    return sizeof(double2) * 3 * (size_t) net.stab_D + sizeof(double) * 2 * (size_t) net.stab_D + 16;
+    return sizeof(double2) * 3 * (size_t) net.stab_D + sizeof(double) * 2 * (size_t) net.stab_D + 128 + 16;   // + the prior rows of k_fast_s2
 }
 
 // shared memory of the X kernel (XQ chains per CTA): by-TF pointers, X and - when it fits - the per-target
@@ -1418,10 +1676,22 @@ static int launch_s_t(const DevNet &net, const DevChains &ch, const SweepArgs &a
     return 0;
 }
 
+template <bool INJ>
+static int launch_s2_t(const DevNet &net, const DevChains &ch, const SweepArgs &a, uint32_t nchains, cudaStream_t st, const char **err)
+{
+    const size_t smem = s_smem_bytes(net);
+    if (check(cudaFuncSetAttribute(k_fast_s2<INJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), err)) return -1;
+    const uint32_t gpb = FS_NT / 32;                                  // groups per block
+    k_fast_s2<INJ><<<dim3((net.n_groups + gpb - 1) / gpb, nchains), FS_NT, smem, st>>>(net, ch, a);
+    return 0;
+}
+
 static int launch_s(const DevNet &net, const DevChains &ch, const SweepArgs &a, int mode, uint32_t nc, cudaStream_t st, const char **err)
 {
     static const bool pf = env_u32("GBN_S_PREFETCH", 0) == 1;         // 1 = on (measured: no gain at 64 registers)
+    const bool v1 = env_u32("GBN_S_V", 2) == 1;                       // 1 = the first form of the S kernel (k_fast_s)
     if (mode == 1) return launch_s_t<1, false, false>(net, ch, a, nc, st, err);
+    if (!v1 && net.sprior_safe) return a.use_inj ? launch_s2_t<true>(net, ch, a, nc, st, err) : launch_s2_t<false>(net, ch, a, nc, st, err);
     if (a.use_inj) return launch_s_t<0, true, false>(net, ch, a, nc, st, err);
     return pf ? launch_s_t<0, false, true>(net, ch, a, nc, st, err) : launch_s_t<0, false, false>(net, ch, a, nc, st, err);
 }

@@ -55,8 +55,9 @@ def have_gpu():
 # Networks that fit one SM run on the persistent shared-memory kernel (sweep_small.cu) unless GBN_SMALL=2; the
 # parity suites run every test on BOTH fast paths, so that the multi-kernel path (sweep_fast.cu: the one the
 # BASELINE shapes C3 / C5 use) is held to the same small-network oracle comparisons - with its X phase on the
-# single-chain shared-memory kernel (k_fast_x1, the default: "multi"), on the chain-pair kernel ("pair") and with
-# every TF of the single-chain kernel resolved in fp64 ("resolve").
+# single-chain shared-memory kernel (k_fast_x1, the default: "multi"), on the chain-pair kernel together with the first
+# form of the S kernel (k_fast_x + k_fast_s: "pair"; every other mode runs the S phase on k_fast_s2) and with every TF
+# of the single-chain kernel resolved in fp64 ("resolve").
 _BOTH_PATHS = ("test_gpu_parity", "test_gpu_edgecases", "test_gpu_golden")
 
 
@@ -72,6 +73,7 @@ def fast_path(request, monkeypatch):
         monkeypatch.setenv("GBN_SMALL", "2")
     if mode == "pair":                       # X phase on the chain-pair kernel that gathers from the fp64 cache (k_fast_x)
         monkeypatch.setenv("GBN_X1", "2")
+        monkeypatch.setenv("GBN_S_V", "1")   # ... and the S phase on k_fast_s (state copies and selects) instead of k_fast_s2
     if mode == "resolve":                    # single-chain X kernel with every TF resolved in fp64 by the whole CTA
         monkeypatch.setenv("GBN_X1", "3")
     if mode == "resolve8":                   # ... every eighth TF (several warps per resolved TF)

@@ -80,6 +80,31 @@ def test_hub_underflow_prior_fallback(kernel):
     assert G.posterior_means("X")[1] < 0.3
 
 
+@pytest.mark.parametrize("n_child", [350, 360])
+def test_hub_in_the_subnormal_band(n_child):
+    """A hub TF whose better outcome likelihood hovers around the bottom of the double range (sum log L between
+    -709 and -790 over the sweeps; exp() goes subnormal below -708.4 and to zero below -745.1): the draw switches
+    between "the subnormal outcome wins", and "both are zero: the prior decides" (Multinomial.cpp:78-85) from sweep to
+    sweep.  The X kernels must take the exact product of the children's likelihoods here (k_fast_x: gathered
+    likelihoods; k_fast_x1: the fp64 resolve with the exact product - the bound bytes cannot decide inside the band)
+    and reproduce the oracle's chain bit for bit."""
+    rng = np.random.default_rng(9)
+    src = [0] * n_child + list(rng.integers(1, 6, 60))
+    trg = list(100 + np.arange(n_child)) + list(100 + rng.integers(0, n_child, 60))
+    mor = [1] * n_child + list(rng.choice([-1, 1], 60))
+    keep = np.sort(np.unique(np.stack([src, trg]), axis=1, return_index=True)[1])
+    src, trg, mor = np.array(src)[keep], np.array(trg)[keep], np.array(mor)[keep]
+    evid = {int(t): int(v) for t, v in zip(100 + np.arange(n_child), rng.choice([-1, 1], n_child))}
+    pb = _problem(src, trg, mor, evid, n_graphs=2)
+    P = oracle.PortModel(pb)
+    seen = []
+    for _ in range(12):
+        seen.append(P.all_conditionals(0)[0, :2].max())
+        P.sample_n(1)
+    assert min(seen) < -745.2 and -745. < max(seen) < -708.4        # both sides of the underflow threshold, never normal
+    _run_trajectory(pb, KERNEL_FAST, 40, injected=False, chunks=(5,))
+
+
 def test_evidence_quirks():
     # all targets unchanged; all evidence for targets outside the network (every y defaults to "not DE")
     pb0 = _problem([0, 1, 1], [5, 5, 6], [1, -1, 1], {5: 0, 6: 0})
