@@ -647,6 +647,23 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
         { uint32_t *t4 = nullptr; if (int rc = dev_upload(m, &t4, tp.tfpos4)) return bail(rc); n.tfpos4 = reinterpret_cast<const uint4 *>(t4); }
         { uint16_t *u16 = nullptr; if (int rc = dev_upload(m, &u16, tp.par16)) return bail(rc); n.par16 = reinterpret_cast<const uint2 *>(u16); }
         n.nSw = tp.nSw; n.nD = tp.nD;
+        {
+            std::vector<uint32_t> rec(4 * (size_t) tp.n_groups), cmap(2 * (size_t) m->n_chains);
+            for (uint32_t g = 0; g < tp.n_groups; g++) {
+                rec[4 * g] = tp.gbase[g]; rec[4 * g + 1] = (tp.gbase[g + 1] - tp.gbase[g]) >> 5;
+                rec[4 * g + 2] = tp.sbase[g]; rec[4 * g + 3] = tp.dbase[g];
+            }
+            for (uint32_t c = 0; c < m->n_chains; c++) {
+                cmap[2 * c] = c / m->n_graphs_local;
+                cmap[2 * c + 1] = (c / m->n_graphs_local) * m->n_graphs + m->chain_offset + c % m->n_graphs_local;
+            }
+            uint32_t *t = nullptr;
+            if (int rc = dev_upload(m, &t, rec)) return bail(rc);
+            n.grec = reinterpret_cast<const uint4 *>(t);
+            t = nullptr;
+            if (int rc = dev_upload(m, &t, cmap)) return bail(rc);
+            n.chain_map = reinterpret_cast<const uint2 *>(t);
+        }
         UP(x_prior_active, tp.x_prior_active, u8)
         UP(t_a, tp.t_a, f64) UP(t_b, tp.t_b, f64) UP(t_mean, tp.t_mean, f64) UP(t_lnB, tp.t_lnB, f64)
 #undef UP
@@ -659,6 +676,7 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     n.sprob[3][0] = 0.; n.sprob[3][1] = 1.; n.sprob[3][2] = 0.;                       // pad steps of the fast S kernel: never move
     n.z_y = p->z_alpha / (p->z_alpha + p->z_beta);                                    // GraphORNOR.cpp:155-164
     n.z_n = p->z0_alpha / (p->z0_alpha + p->z0_beta);
+    n.rz_y = 1. / n.z_y; n.rz_n = 1. / n.z_n;
     n.n_datasets = m->n_datasets; n.n_graphs_local = m->n_graphs_local; n.chain_offset = m->chain_offset; n.n_graphs = m->n_graphs;
     n.sim = sim ? 1 : 0;
     n.listen = p->noise_listen_children ? 1 : 0;

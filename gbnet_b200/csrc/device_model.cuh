@@ -47,6 +47,8 @@ struct DevNet {
     const uint32_t *dblk_grp;     // [nD / 32]   group of every row of 32 blocks
     const uint32_t *mor2;         // [nSw] prior row per step (3 = pad)
     const uint2 *par16;           // [nD]  four 16-bit parent TFs per block
+    const uint4 *grec;            // [n_groups] {gbase, width, sbase, dbase} of a group in one 16-byte record (k_fast_s2)
+    const uint2 *chain_map;       // [n_chains] local chain -> {dataset, global chain id} (chain_dataset / chain_global_id tabulated)
     const uint4 *tfpos4;          // [nD]  fp position (padded by-TF lists) of the block's four steps (UINT32_MAX for pads)
     // by-TF lists of the fast path, every TF's list padded to a multiple of four with sentinel children (topology.hpp)
     const uint32_t *fp_ptr;       // [nX+1]
@@ -73,6 +75,7 @@ struct DevNet {
     double sprob[4][3];           // [mor+1][v]          GraphORNOR.cpp:25; row 3 = {0, 1, 0}: pad steps of the fast S kernel
     double ynoise[3][3];          // [h][y]              GraphORNOR.h:46-48
     double z_y, z_n;              // ZY / ZN constants   GraphORNOR.cpp:155-164
+    double rz_y, rz_n;            // their reciprocals (the same correctly rounded quotient the device would compute)
     uint32_t n_datasets, n_graphs_local, chain_offset, n_graphs;
     int32_t listen, const_params;
     int32_t x1;                   // X phase by the single-chain kernel (k_fast_x1: fp32 flip weights of the whole chain in shared memory)

@@ -1331,49 +1331,53 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s2(DevNet net, DevCh
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t c = blockIdx.y + a.chain0;
-    const uint32_t d = chain_dataset(net, c);
+    const uint2 cmap = net.chain_map[c];                             // {dataset, global chain id}
+    const uint32_t d = cmap.x, gchain = cmap.y;
     const double2 *gFX = ch.FXp + (size_t) c * nX;
+    const uint32_t g0 = blockIdx.x * (FS_NT / 32), g = g0 + (tid >> 5);
+    const bool live = g < net.n_groups;
+    // The warp's first requests go out before the tables are staged, so that their latency (the S words and the
+    // counters come from DRAM) overlaps the staging and the barrier: the group's record, the lane's evidence and
+    // Philox key, the first word of S codes / activity bits / prior rows, the counters' lines (into L2)
+    const uint4 gr = live ? net.grec[g] : make_uint4(0u, 0u, 0u, 0u);          // {gbase, width, sbase, dbase}
+    const uint32_t gb = gr.x, W = gr.y;                              // group width = largest in-degree
+    const uint32_t dt = 32 * g + lane;
+    const bool valid = live && dt < nH;
+    const uint32_t y = valid ? net.y[(size_t) d * nH + dt] : 1u;
+    const uint32_t ref_i = valid ? net.ref_of_dt[dt] : 0u;
+    const uint32_t sb = gr.z + lane, db = gr.w + lane;
+    // 32-bit element offsets off the kernel-parameter base pointers (one IMAD.WIDE per address)
+    const uint32_t sw_off = c * net.nSw + sb, dc_off = c * net.nD + db;
+    const uint32_t W4 = (W + 3) >> 2;                                // 4-step blocks (the last may hold pads)
+    uint32_t swA = 0x55555555u, awA = 0, mwA = 0xffffffffu;
+    if (W) { swA = ch.Sw[sw_off]; awA = ch.Aw[sw_off]; mwA = net.mor2[sb]; }
+    for (uint32_t b = 0; b < W4; b++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ch.dC + (dc_off + 32 * b)));
     {
         // n never exceeds the in-degree: with groups in descending order of width the CTA's first group bounds it
-        uint32_t rows = D;
-        if (net.groups_desc) {
-            const uint32_t g0 = blockIdx.x * (FS_NT / 32);
-            rows = min(D, ((net.gbase[g0 + 1] - net.gbase[g0]) >> 5) + 2);
-        }
+        const uint32_t rows = net.groups_desc ? min(D, net.grec[g0].y + 2) : D;
         const double *tab = net.stab + (size_t) d * STAB_ROWS * D;
-        for (uint32_t j = tid; j < 3 * rows; j += FS_NT) {
-            const uint32_t yy = j / rows, nn = j - yy * rows;
-            sTab[yy * D + nn] = make_double2(tab[yy * D + nn], tab[(3 + (yy != 1 ? 0 : 1)) * D + nn]);
+        for (uint32_t nn = tid; nn < rows; nn += FS_NT) {
+            const double o0 = tab[3 * D + nn], o1 = tab[4 * D + nn];            // omz of the two noise classes
+            sTab[nn] = make_double2(tab[nn], o0);
+            sTab[D + nn] = make_double2(tab[D + nn], o1);
+            sTab[2 * D + nn] = make_double2(tab[2 * D + nn], o0);
+            sZp[nn] = tab[13 * D + nn];
+            sZp[D + nn] = tab[14 * D + nn];
         }
-        for (uint32_t j = tid; j < 2 * rows; j += FS_NT) {
-            const uint32_t cc = j / rows, nn = j - cc * rows;
-            sZp[cc * D + nn] = tab[(13 + cc) * D + nn];
-        }
-        if (tid < 16) sPr[tid] = (tid & 3) < 3 ? net.sprob[tid >> 2][tid & 3] : 0.;
+        if (tid >= FS_NT - 16) { const uint32_t q = tid - (FS_NT - 16); sPr[q] = (q & 3) < 3 ? net.sprob[q >> 2][q & 3] : 0.; }
     }
     __syncthreads();
+    if (!live) return;
 
-    const uint32_t g = blockIdx.x * (FS_NT / 32) + (tid >> 5);
-    if (g >= net.n_groups) return;
-    const uint32_t dt = 32 * g + lane;
-    const bool valid = dt < nH;
-    const uint32_t gb = net.gbase[g];
-    const uint32_t W = (net.gbase[g + 1] - gb) >> 5;                 // group width = largest in-degree
-    const uint32_t y = valid ? net.y[(size_t) d * nH + dt] : 1u;
     const uint32_t cls = (y != 1) ? 0 : 1;                          // ZY for DE targets, ZN otherwise
     const double z = cls ? net.z_n : net.z_y;
     const double ca = net.ynoise[2][y] - net.ynoise[0][y];          // a
     const double cb = net.ynoise[1][y] - net.ynoise[2][y];          // b
     const uint32_t cot_s = smem_addr_opaque(sTab + y * D);          // {c0, omz} over n for this target's y
     const uint32_t pr_s = smem_addr_opaque(sPr);
-    const uint32_t sb = net.sbase[g] + lane, db = net.dbase[g] + lane;
-    const uint32_t sw_off = c * net.nSw + sb, dc_off = c * net.nD + db;
     const uint16_t *par16 = reinterpret_cast<const uint16_t *>(net.par16);   // step j of this lane: [4 (db + 32 (j / 4)) + j % 4]
     const uint32_t *tfpos = reinterpret_cast<const uint32_t *>(net.tfpos4);  // likewise
-    const uint32_t W4 = (W + 3) >> 2;                                // 4-step blocks (the last may hold pads)
 
-    // the counters are first touched by the second pass: start pulling their lines into L2 now
-    for (uint32_t b = 0; b < W4; b++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ch.dC + (dc_off + 32 * b)));
     // pass 1 (as in k_fast_s): A = a pr0, Bq = b pr0 pr2, n from two population counts per word and the factors of
     // the active parents
     double A = ca, Bq = cb;
@@ -1381,12 +1385,12 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s2(DevNet net, DevCh
     {
         uint32_t n0 = 0;
         for (uint32_t w = 0; 16 * w < W; w++) {
-            const uint32_t sw = ch.Sw[sw_off + 32 * w];
-            GBN_CHECK(net.sbase[g] + lane + 32 * w < net.nSw);
+            const uint32_t sw = w == 0 ? swA : ch.Sw[sw_off + 32 * w];
+            GBN_CHECK(sb + 32 * w < net.nSw);
             const uint32_t x = sw ^ 0x55555555u;
             n += __popc((x | (x >> 1)) & 0x55555555u);               // codes != 1
             n0 += __popc(~(sw | (sw >> 1)) & 0x55555555u);           // codes == 0
-            for (uint32_t act = ch.Aw[sw_off + 32 * w] & 0xffffu; act; act &= act - 1) {
+            for (uint32_t act = (w == 0 ? awA : ch.Aw[sw_off + 32 * w]) & 0xffffu; act; act &= act - 1) {
                 const uint32_t u = __ffs(act) - 1, s = (sw >> (2 * u)) & 3u, j = 16 * w + u;
                 const uint32_t kk = par16[4 * (db + 32 * (j >> 2)) + (j & 3)];
                 GBN_CHECK(kk < nX);
@@ -1399,16 +1403,15 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s2(DevNet net, DevCh
         A *= sZp[cls * D + n0];
         Bq *= sZp[cls * D + n];
     }
-    const double rz = 1. / z;
-    const uint32_t gchain = chain_global_id(net, c);
-    const uint32_t ref_i = valid ? net.ref_of_dt[dt] : 0u;
+    const double rz = cls ? net.rz_n : net.rz_y;
     const double *inj_flat = INJ ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + net.E) + nX : nullptr;
     const uint32_t *pEdge = net.par_edge + gb + lane;
     const uint32_t stf_off = c * n_stf_words(net);
     uint32_t na = cot_s + 16 * n;                                    // shared-memory address of cot[n]
     for (uint32_t w = 0; 16 * w < W; w++) {
-        const uint32_t sw0 = ch.Sw[sw_off + 32 * w];
-        uint32_t sw = sw0, mw = net.mor2[sb + 32 * w], aw = ch.Aw[sw_off + 32 * w], nsw = 0;
+        uint32_t sw0 = swA, mw = mwA, aw = awA, nsw = 0;
+        if (w) { sw0 = ch.Sw[sw_off + 32 * w]; mw = net.mor2[sb + 32 * w]; aw = ch.Aw[sw_off + 32 * w]; }
+        uint32_t sw = sw0;
         const uint32_t nb = min(4u, W4 - 4 * w);
         for (uint32_t b = 0; b < nb; b++) {
             const uint32_t bb = 4 * w + b, j0 = 4 * bb;
