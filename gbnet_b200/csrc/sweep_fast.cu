@@ -1284,6 +1284,12 @@ __device__ __forceinline__ double2 lds_pair_next(uint32_t addr)
     asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ double2 lds_pair_volatile(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ double lds_f64_next(uint32_t addr)
 {
     double v;
@@ -1297,7 +1303,6 @@ __device__ __forceinline__ void xor_if(uint32_t &a, uint32_t k, bool p)
 }
 // a copy of a positive double made by the fp64 pipe (one instruction; a register move of a double is two, and the
 // S kernel is bound by instruction issue, not by the fp64 pipe)
-__device__ __forceinline__ double copy_f64(double x, const SweepArgs &a) { return x * a.one; }
 __device__ __forceinline__ uint32_t smem_addr_opaque(const void *p)
 {
     unsigned long long a;
@@ -1328,6 +1333,7 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s2(DevNet net, DevCh
     double2 *sTab = reinterpret_cast<double2 *>(smem_raw);                      // [3][D] {c0[y][n], omz[class of y][n]}
     double *sZp = reinterpret_cast<double *>(sTab + 3 * D);                     // [2][D] z^m by noise class
     double *sPr = sZp + 2 * D;                                                  // [4][4] prior rows (row 3: a pad step), 32 bytes each
+    double *sZr = sPr + 16;                                                     // [2][2] {z, 1 / z} by noise class
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t c = blockIdx.y + a.chain0;
@@ -1365,6 +1371,7 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s2(DevNet net, DevCh
             sZp[D + nn] = tab[14 * D + nn];
         }
         if (tid >= FS_NT - 16) { const uint32_t q = tid - (FS_NT - 16); sPr[q] = (q & 3) < 3 ? net.sprob[q >> 2][q & 3] : 0.; }
+        if (tid == FS_NT - 17) { sZr[0] = net.z_y; sZr[1] = net.rz_y; sZr[2] = net.z_n; sZr[3] = net.rz_n; }
     }
     __syncthreads();
     if (!live) return;
@@ -1408,98 +1415,110 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s2(DevNet net, DevCh
     const uint32_t *pEdge = net.par_edge + gb + lane;
     const uint32_t stf_off = c * n_stf_words(net);
     uint32_t na = cot_s + 16 * n;                                    // shared-memory address of cot[n]
-    for (uint32_t w = 0; 16 * w < W; w++) {
-        uint32_t sw0 = swA, mw = mwA, aw = awA, nsw = 0;
-        if (w) { sw0 = ch.Sw[sw_off + 32 * w]; mw = net.mor2[sb + 32 * w]; aw = ch.Aw[sw_off + 32 * w]; }
-        uint32_t sw = sw0;
-        const uint32_t nb = min(4u, W4 - 4 * w);
-        for (uint32_t b = 0; b < nb; b++) {
-            const uint32_t bb = 4 * w + b, j0 = 4 * bb;
-            uint2 cw = __ldcs(ch.dC + (dc_off + 32 * bb));
-            u32x4 rnd = { 0, 0, 0, 0 };
-            if (!INJ) rnd = philox_rk(ref_i, a.sweep, gchain, KIND_S | (bb << 8), a);
-            uint32_t ns4 = 0x55u;                                    // four codes "off"; pads stay so
+    // f = (1 - t x) z and its reciprocal live in registers as z and 1 / z; an active parent (about 1 % of the edges)
+    // changes them for its step and puts them back, both in branches that read z and 1 / z from shared memory
+    // (volatile loads: hoisted into registers they would be rebuilt from the constant bank in every step)
+    const uint32_t zz_s = smem_addr_opaque(sZr + 2 * cls);
+    double f = z, finv = rz;
+    uint32_t sw0 = swA, mw = mwA, aw = awA;
+    // one block of four steps; GUARD: the group's last block, which may end before its fourth step
+    auto block = [&](auto guard_tag, const uint32_t w, const uint32_t b, uint32_t &sw, uint32_t &nsw) {
+        constexpr bool GUARD = decltype(guard_tag)::value;
+        const uint32_t bb = 4 * w + b, j0 = 4 * bb;
+        uint2 cw = __ldcs(ch.dC + (dc_off + 32 * bb));
+        u32x4 rnd = { 0, 0, 0, 0 };
+        if (!INJ) rnd = philox_rk(ref_i, a.sweep, gchain, KIND_S | (bb << 8), a);
+        uint32_t ns4 = 0x55u;                                        // four codes "off"; pads stay so
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (j0 + u < W) {                                    // warp-uniform
-                    const bool s_is0 = (sw & (3u << (2 * u))) == 0, s_ne1 = (sw & (1u << (2 * u))) == 0;
-                    const uint32_t r32 = (u <= 2 ? mw << (5 - 2 * u) : mw >> (2 * u - 5)) & 0x60u;   // 32 x the prior row
-                    GBN_CHECK(((sw >> (2 * u)) & 3u) <= 2 && na >= cot_s && (na - cot_s) / 16 + 1 < D);
-                    // f = (1 - t x) z and its reciprocal: z and 1 / z unless the parent TF is active (about 1 % of
-                    // the edges; the diagnostic count keeps the block a branch)
-                    double f = copy_f64(z, a), finv = copy_f64(rz, a);
-                    if ((aw >> u) & 1u) {
-                        if (ch.dbg) atomicAdd(ch.dbg + 7, 1ull);
-                        const uint32_t kk = par16[4 * (db + 32 * bb) + u];
-                        GBN_CHECK(kk < nX);
-                        const double2 fx = __ldg(gFX + kk);
-                        f = fx.x * z; finv = fx.y * rz;
-                    }
-                    // the state without this edge
-                    mul_if(A, finv, s_is0);
-                    mul_if(Bq, finv, s_ne1);
-                    add_if(na, 0xfffffff0u, s_ne1);
-                    const double2 t0 = lds_pair(na), t1 = lds_pair_next(na);
+        for (int u = 0; u < 4; u++) {
+            if (!GUARD || j0 + u < W) {                              // warp-uniform
+                const bool s_is0 = (sw & (3u << (2 * u))) == 0, s_ne1 = (sw & (1u << (2 * u))) == 0;
+                const uint32_t r32 = (u <= 2 ? mw << (5 - 2 * u) : mw >> (2 * u - 5)) & 0x60u;   // 32 x the prior row
+                GBN_CHECK(((sw >> (2 * u)) & 3u) <= 2 && na >= cot_s && (na - cot_s) / 16 + 1 < D);
+                const bool active = (aw >> u) & 1u;
+                if (active) {                                        // (the diagnostic count keeps the block a branch)
+                    if (ch.dbg) atomicAdd(ch.dbg + 7, 1ull);
+                    const uint32_t kk = par16[4 * (db + 32 * bb) + u];
+                    GBN_CHECK(kk < nX);
+                    const double2 fx = __ldg(gFX + kk);
+                    const double2 zr = lds_pair_volatile(zz_s);
+                    f = fx.x * zr.x; finv = fx.y * zr.y;
+                }
+                // the state without this edge
+                mul_if(A, finv, s_is0);
+                mul_if(Bq, finv, s_ne1);
+                add_if(na, 0xfffffff0u, s_ne1);
+                const double2 t0 = lds_pair(na), t1 = lds_pair_next(na);
 #if GBN_S2_PRIOR_SMEM
-                    const double2 sp01 = lds_pair(pr_s + r32);
-                    const double sp2 = lds_f64_next(pr_s + r32);
+                const double2 sp01 = lds_pair(pr_s + r32);
+                const double sp2 = lds_f64_next(pr_s + r32);
 #else
-                    const double *spc = net.sprob[r32 >> 5];         // constant bank, indexed
-                    const double2 sp01 = make_double2(spc[0], spc[1]);
-                    const double sp2 = spc[2];
+                const double *spc = net.sprob[r32 >> 5];             // constant bank, indexed
+                const double2 sp01 = make_double2(spc[0], spc[1]);
+                const double sp2 = spc[2];
 #endif
-                    const double sum = A + Bq;
-                    const double L0 = __fma_rn(t1.y, f * sum, t1.x);                   // S = 0: the factor joins pr0
-                    const double L1 = __fma_rn(t0.y, sum, t0.x);                       // S = 1: edge off
-                    const double L2 = __fma_rn(t1.y, __fma_rn(f, Bq, A), t1.x);        // S = 2: the factor joins pr2
-                    // exp(log prior + log L) of Multinomial.cpp:66-75 as a product.  The fallback of Multinomial.cpp:78-85
-                    // (all three terms zero) cannot happen here: L >= c0[n] >= min_h YNOISE > 0, and the model layer
-                    // sends prior rows that could make a product vanish to k_fast_s (sprior_safe)
-                    const double cum0 = sp01.x * L0;
-                    const double cum1 = __fma_rn(sp01.y, L1, cum0);
-                    const double cum2 = __fma_rn(sp2, L2, cum1);
-                    const uint32_t word = u == 0 ? rnd.x : (u == 1 ? rnd.y : (u == 2 ? rnd.z : rnd.w));
-                    double uu = unit_from_word(word);
-                    if (INJ) { const uint32_t e = pEdge[32 * (j0 + u)]; uu = e != 0xffffffffu ? inj_flat[e] : 0.5; }
-                    const double dice = cum2 * uu;
-                    // first v with dice < cum[v] (Multinomial.cpp:92-99); cum0 <= cum1, so "2" is "not below cum1"
-                    bool ns_is0 = dice < cum0, ns_is2 = !(dice < cum1);
-                    if (INJ && !(dice < cum2)) {                     // an injected double can round up to cum[2]: the value is kept
-                        ns_is0 = s_is0; ns_is2 = s_ne1 && !s_is0;
-                    }
-                    const bool ns_ne1 = ns_is0 || ns_is2;
-#ifdef GBN_BOUNDS
-                    if (r32 == 0x60u && ns_ne1) printf("pad moved: lane %u step %u y %u n %u sp %g %g %g t0 %g %g t1 %g %g A %g Bq %g f %g L %g %g %g cum %g %g %g uu %g dice %g\n", lane, j0 + u, y, (na - cot_s) >> 4, sp01.x, sp01.y, sp2, t0.x, t0.y, t1.x, t1.y, A, Bq, f, L0, L1, L2, cum0, cum1, cum2, uu, dice);
-#endif
-                    add_if(cw.x, 1u << (8 * u), ns_is0);                               // Multinomial.cpp:101-105 as counts
-                    add_if(cw.y, 1u << (8 * u), ns_is2);
-                    mul_if(A, f, ns_is0);
-                    mul_if(Bq, f, ns_ne1);
-                    add_if(na, 16u, ns_ne1);
-                    xor_if(ns4, 1u << (2 * u), ns_ne1);              // code 1 -> 0 ...
-                    xor_if(ns4, 2u << (2 * u), ns_is2);              // ... -> 2
+                const double sum = A + Bq;
+                const double L0 = __fma_rn(t1.y, f * sum, t1.x);                       // S = 0: the factor joins pr0
+                const double L1 = __fma_rn(t0.y, sum, t0.x);                           // S = 1: edge off
+                const double L2 = __fma_rn(t1.y, __fma_rn(f, Bq, A), t1.x);            // S = 2: the factor joins pr2
+                // exp(log prior + log L) of Multinomial.cpp:66-75 as a product.  The fallback of Multinomial.cpp:78-85
+                // (all three terms zero) cannot happen here: L >= c0[n] >= min_h YNOISE > 0, and the model layer
+                // sends prior rows that could make a product vanish to k_fast_s (sprior_safe)
+                const double cum0 = sp01.x * L0;
+                const double cum1 = __fma_rn(sp01.y, L1, cum0);
+                const double cum2 = __fma_rn(sp2, L2, cum1);
+                const uint32_t word = u == 0 ? rnd.x : (u == 1 ? rnd.y : (u == 2 ? rnd.z : rnd.w));
+                double uu = unit_from_word(word);
+                if (INJ) { const uint32_t e = pEdge[32 * (j0 + u)]; uu = e != 0xffffffffu ? inj_flat[e] : 0.5; }
+                const double dice = cum2 * uu;
+                // first v with dice < cum[v] (Multinomial.cpp:92-99); cum0 <= cum1, so "2" is "not below cum1"
+                bool ns_is0 = dice < cum0, ns_is2 = !(dice < cum1);
+                if (INJ && !(dice < cum2)) {                         // an injected double can round up to cum[2]: the value is kept
+                    ns_is0 = s_is0; ns_is2 = s_ne1 && !s_is0;
+                }
+                const bool ns_ne1 = ns_is0 || ns_is2;
+                add_if(cw.x, 1u << (8 * u), ns_is0);                                   // Multinomial.cpp:101-105 as counts
+                add_if(cw.y, 1u << (8 * u), ns_is2);
+                mul_if(A, f, ns_is0);
+                mul_if(Bq, f, ns_ne1);
+                add_if(na, 16u, ns_ne1);
+                xor_if(ns4, 1u << (2 * u), ns_ne1);                  // code 1 -> 0 ...
+                xor_if(ns4, 2u << (2 * u), ns_is2);                  // ... -> 2
+                if (active) {
+                    if (ch.dbg) atomicAdd(ch.dbg + 6, 1ull);
+                    const double2 zr = lds_pair_volatile(zz_s);
+                    f = zr.x; finv = zr.y;
                 }
             }
-            __stcs(ch.dC + (dc_off + 32 * bb), cw);                  // streamed: the product cache stays in L2
-            nsw |= ns4 << (8 * b);
-            sw >>= 8; mw >>= 8; aw >>= 4;
         }
+        __stcs(ch.dC + (dc_off + 32 * bb), cw);                      // streamed: the product cache stays in L2
+        nsw |= ns4 << (8 * b);
+        sw >>= 8; mw >>= 8; aw >>= 4;
+    };
+    const uint32_t Wf = W >> 2;                                      // blocks with all four steps inside the group's width
+    for (uint32_t w = 0;;) {
+        uint32_t sw = sw0, nsw = 0;
+        const uint32_t nb = min(4u, W4 - 4 * w), nbf = min(nb, Wf - min(Wf, 4 * w));
+        uint32_t b = 0;
+        for (; b < nbf; b++) block(std::false_type{}, w, b, sw, nsw);
+        if (b < nb) block(std::true_type{}, w, b, sw, nsw);
         // blocks past the group's width keep their pads
         uint32_t chg = nb == 4 ? sw0 ^ nsw : (sw0 ^ nsw) & ((1u << (8 * nb)) - 1u);
         if (chg) {
             ch.Sw[sw_off + 32 * w] = sw0 ^ chg;
+            const uint32_t tb = 4 * db + 512 * w;                    // by-TF positions of this lane's steps of the word
             do {                                                     // the by-TF copy follows, code by code
-                const uint32_t u16 = (__ffs(chg) - 1) >> 1, j = 16 * w + u16;
+                const uint32_t u16 = (__ffs(chg) - 1) >> 1;
                 const uint32_t x = (chg >> (2 * u16)) & 3u;
                 chg &= ~(3u << (2 * u16));
-                const uint32_t tp = tfpos[4 * (db + 32 * (j >> 2)) + (j & 3)];
-#ifdef GBN_BOUNDS
-                if (!(tp < net.Efp)) printf("pad changed: chain %u group %u lane %u W %u word %u step %u x %u sw0 %08x nsw %08x nb %u y %u n %u A %g Bq %g\n", c, g, lane, W, w, u16, x, sw0, nsw, nb, y, (na - cot_s) >> 4, A, Bq);
-#endif
+                const uint32_t tp = tfpos[tb + 128 * (u16 >> 2) + (u16 & 3)];
                 GBN_CHECK(tp < net.Efp);
                 atomicXor(ch.Stfp + (stf_off + (tp >> 4)), x << (2 * (tp & 15)));
             } while (chg);
         }
+        w++;
+        if (16 * w >= W) break;
+        sw0 = ch.Sw[sw_off + 32 * w]; mw = net.mor2[sb + 32 * w]; aw = ch.Aw[sw_off + 32 * w];
     }
     n = (na - cot_s) >> 4;
     GBN_CHECK(n < D);
@@ -1616,7 +1635,7 @@ static int check(cudaError_t e, const char **err)
 // shared memory of the S kernel: the per-dataset tables over n
 static size_t s_smem_bytes(const DevNet &net)
 {
-    return sizeof(double2) * 3 * (size_t) net.stab_D + sizeof(double) * 2 * (size_t) net.stab_D + 128 + 16;   // + the prior rows of k_fast_s2
+    return sizeof(double2) * 3 * (size_t) net.stab_D + sizeof(double) * 2 * (size_t) net.stab_D + 128 + 32 + 16;   // + the prior rows and {z, 1 / z} of k_fast_s2
 }
 
 // shared memory of the X kernel (XQ chains per CTA): by-TF pointers, X and - when it fits - the per-target
