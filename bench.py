@@ -471,7 +471,10 @@ def run_native(args):
             peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        names = ["k_fast_x", "k_fast_t", "k_fast_s"]
+        # the kernels behind the three phases of a sweep at this shape (sweep_fast.cu; GBN_X1=2 / GBN_S_V=1 select the
+        # chain-pair X kernel / the first form of the S kernel)
+        names = ["k_fast_x" if os.environ.get("GBN_X1") == "2" else "k_fast_x1", "k_fast_t",
+                 "k_fast_s" if os.environ.get("GBN_S_V") == "1" else "k_fast_s2"]
         # algorithmic bytes per edge-update for C chains sharing one network:
         #   S kernel: S state 2 x 0.25 B + two u32 counters read+write 16 B + by-target parent id / prior row 4.25 B / C
         #   X kernel: by-TF target id + sign 4.25 B / C + per-TF terms amortised over the out-degree 0.2 B

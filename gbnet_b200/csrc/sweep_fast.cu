@@ -1507,14 +1507,29 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s2(DevNet net, DevCh
         if (chg) {
             ch.Sw[sw_off + 32 * w] = sw0 ^ chg;
             const uint32_t tb = 4 * db + 512 * w;                    // by-TF positions of this lane's steps of the word
-            do {                                                     // the by-TF copy follows, code by code
-                const uint32_t u16 = (__ffs(chg) - 1) >> 1;
-                const uint32_t x = (chg >> (2 * u16)) & 3u;
-                chg &= ~(3u << (2 * u16));
-                const uint32_t tp = tfpos[tb + 128 * (u16 >> 2) + (u16 & 3)];
-                GBN_CHECK(tp < net.Efp);
-                atomicXor(ch.Stfp + (stf_off + (tp >> 4)), x << (2 * (tp & 15)));
-            } while (chg);
+            // the by-TF copy follows: a trip patches up to N changed codes, their by-TF positions requested together (one
+            // code per trip waits for an L2 round trip per code: S prior 0.4/0.4/0.2, where 60 % of the codes move, 0.73 ->
+            // 0.51 ms per launch).  Two codes cover the usual word; whatever is left goes four at a time.
+            auto patch = [&](auto n_tag) {
+                constexpr int N = decltype(n_tag)::value;
+                uint32_t tp[N], xx[N];
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    xx[i] = 0; tp[i] = 0;
+                    if (chg) {
+                        const uint32_t u16 = (__ffs(chg) - 1) >> 1;
+                        xx[i] = (chg >> (2 * u16)) & 3u;
+                        chg &= ~(3u << (2 * u16));
+                        tp[i] = tfpos[tb + 128 * (u16 >> 2) + (u16 & 3)];
+                        GBN_CHECK(tp[i] < net.Efp);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < N; i++)
+                    if (xx[i]) atomicXor(ch.Stfp + (stf_off + (tp[i] >> 4)), xx[i] << (2 * (tp[i] & 15)));
+            };
+            patch(std::integral_constant<int, 2>{});
+            while (chg) patch(std::integral_constant<int, 4>{});
         }
         w++;
         if (16 * w >= W) break;
