@@ -500,6 +500,32 @@ __device__ __forceinline__ uint32_t x_draw(const double *prob, uint32_t xcur, do
 
 constexpr uint32_t X1_BULK = 16384;          // bytes per bulk copy
 
+// shared-memory loads at 32-bit addresses (volatile: the flip patch rewrites the entries between rounds)
+__device__ __forceinline__ float lds_f32_volatile(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8_volatile(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t x)
+{
+    uint32_t v;
+    asm volatile("mov.u32 %0, %1;" : "=r"(v) : "r"(x));
+    return v;
+}
+__device__ __forceinline__ uint32_t smem_addr_opaque(const void *p)
+{
+    unsigned long long a;
+    asm("cvta.to.shared.u64 %0, %1;" : "=l"(a) : "l"(p));
+    return (uint32_t) a;
+}
+
 template <int NT, int LPT, int U>
 __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fast_x1(DevNet net, DevChains ch, SweepArgs a)
 {
@@ -588,7 +614,10 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
     const double *inj = a.use_inj ? ch.inj_flat + ((size_t) c * ch.inj_sweeps + a.inj_row) * (nX + net.E) : nullptr;
     uint16_t *xqp = ch.xqp + (size_t) c * nX;
     const uint4 *child4 = reinterpret_cast<const uint4 *>(net.fp_child);                                  // chunk q: children 4q .. 4q+3
-    const uint8_t *code4 = reinterpret_cast<const uint8_t *>(ch.Stfp + (size_t) c * nStfW);              // byte q: their S codes
+    const uint8_t *code_base = reinterpret_cast<const uint8_t *>(ch.Stfp);                                // byte code_off + q: their S codes
+    const uint32_t code_off = opaque_u32(4 * stf_off);                       // (kept in a register: left to the compiler, the offset is
+                                                                             // rebuilt from the CTA index and the network size in every trip)
+    const uint32_t sW0_s = smem_addr_opaque(sW0), sW2_s = smem_addr_opaque(sW2), sQ_s = smem_addr_opaque(sQ);
 
     uint32_t wlen = W, streak = 0;                                           // adaptive window: see k_fast_x
     uint32_t k0 = 0;
@@ -620,10 +649,10 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
                 const uint32_t qq = q < q4e ? q : (E >> 2);                  // past the end: the sentinel chunk (dummy target, code 1)
                 Chunk r;
                 r.id = __ldg(child4 + qq);
-                r.cd = __ldg(code4 + qq);
+                r.cd = __ldg(code_base + (code_off + qq));                   // a 32-bit offset off the parameter's pointer
                 return r;
             };
-            Chunk c0 = load_chunk(q4), c1 = load_chunk(q4 + LPT);
+            Chunk c0 = load_chunk(q4), c1 = load_chunk(q4 + LPT), c2;
             phi = -t;                                                        // f -> q f, q = 1 - t (X: 0 -> 1) or 1 / (1 - t) (1 -> 0)
             if (xcur) phi = t / (1. - t);
             const float phf = (float) phi;
@@ -634,17 +663,20 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
             auto child_loop = [&](auto with_q) {
                 constexpr bool WITH_Q = decltype(with_q)::value;
                 int cnt = 0;
-                for (; trips > 0; trips--) {
-                    const Chunk c2 = load_chunk(q4 + 2 * LPT);               // two trips ahead
-                    const uint32_t id[4] = { c0.id.x, c0.id.y, c0.id.z, c0.id.w };
+                // one trip: the chunk two trips ahead is requested into the buffer the previous trip used, then this
+                // trip's four children are gathered from shared memory (32-bit addresses: behind generic pointers the
+                // shared window base is rebuilt in every trip)
+                auto trip = [&](const Chunk &cur, Chunk &ahead) {
+                    ahead = load_chunk(q4 + 2 * LPT);
+                    const uint32_t id[4] = { cur.id.x, cur.id.y, cur.id.z, cur.id.w };
                     float w[4];
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const uint32_t sh = (c0.cd >> (2 * u)) & 3u;
+                        const uint32_t sh = (cur.cd >> (2 * u)) & 3u;
                         GBN_CHECK(id[u] <= nH && sh <= 2);
-                        const float *base = (sh & 2u) ? sW2 : sW0;
-                        w[u] = base[sh == 1 ? nH : id[u]];                   // an edge that is off: the dummy's zero weight
-                        if (WITH_Q) qs += sQ[id[u]];
+                        const uint32_t base = (sh & 2u) ? sW2_s : sW0_s;
+                        w[u] = lds_f32_volatile(base + 4 * (sh == 1 ? nH : id[u]));   // an edge that is off: the dummy's zero weight
+                        if (WITH_Q) qs += lds_u8_volatile(sQ_s + id[u]);
                     }
                     float pm = 1.f;
 #pragma unroll
@@ -655,8 +687,16 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
                     }
                     mr *= (double) pm;
                     if ((cnt += 4) >= 16) { normalise(mr, er); cnt = 0; }
-                    c0 = c1; c1 = c2; q4 += LPT;
-                }
+                    q4 += LPT;
+                    return --trips == 0;
+                };
+                // the three chunk buffers take turns (no register moves between trips)
+                if (trips > 0)
+                    for (;;) {
+                        if (trip(c0, c2)) break;
+                        if (trip(c1, c0)) break;
+                        if (trip(c2, c1)) break;
+                    }
             };
             if (__any_sync(0xffffffffu, track)) child_loop(std::true_type{}); else child_loop(std::false_type{});
             normalise(mr, er);
@@ -1303,12 +1343,6 @@ __device__ __forceinline__ void xor_if(uint32_t &a, uint32_t k, bool p)
 }
 // a copy of a positive double made by the fp64 pipe (one instruction; a register move of a double is two, and the
 // S kernel is bound by instruction issue, not by the fp64 pipe)
-__device__ __forceinline__ uint32_t smem_addr_opaque(const void *p)
-{
-    unsigned long long a;
-    asm("cvta.to.shared.u64 %0, %1;" : "=l"(a) : "l"(p));
-    return (uint32_t) a;
-}
 
 // S phase, second form (the default; GBN_S_V=1 selects k_fast_s).  Same layout, same draws, same visiting order; what
 // changes is the bookkeeping around the seventeen fp64 operations of a step:
@@ -1678,7 +1712,7 @@ bool fast_x1_supported(const DevNet &net)
 {
     if (env_u32("GBN_X1", 1) == 2) return false;
     const uint64_t C = (uint64_t) net.n_datasets * net.n_graphs_local + XQ;
-    if (C * net.nX >= (1ull << 32)) return false;
+    if (C * net.nX >= (1ull << 32) || 4 * C * n_stf_words(net) >= (1ull << 32)) return false;
     return x1_smem_bytes(net) + 4096 <= 227 * 1024;
 }
 
