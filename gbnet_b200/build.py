@@ -72,9 +72,11 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
                 flags.append("-DGBN_X_NT=" + xv.group(3))
         if VARIANT.startswith("xexp") and src == "sweep_fast.cu":
             flags.append("-DGBN_XEXP=" + VARIANT[4:])
-        dv = re.fullmatch(r"D(\w+?)_(\d+)", VARIANT)          # D<MACRO>_<value>: one macro of sweep_fast.cu (experiments)
-        if dv and src == "sweep_fast.cu":
-            flags.append("-D%s=%s" % dv.groups())
+        if VARIANT.startswith("D") and src == "sweep_fast.cu":      # D<MACRO>_<value>[+<MACRO>_<value>...]: macros of sweep_fast.cu (experiments)
+            for part in VARIANT[1:].split("+"):
+                dv = re.fullmatch(r"(\w+?)_(\d+)", part)
+                if dv:
+                    flags.append("-D%s=%s" % dv.groups())
         if VARIANT == "chk":
             flags.append("-DGBN_BOUNDS")
         if VARIANT.startswith("s") and VARIANT[1:].isdigit() and src == "sweep_fast.cu":

@@ -49,6 +49,9 @@
 #ifndef GBN_S2_PRIOR_SMEM
 #define GBN_S2_PRIOR_SMEM 1   // k_fast_s2: prior rows from shared memory (0: from the constant bank)
 #endif
+#ifndef GBN_X1_AHEAD
+#define GBN_X1_AHEAD 3        // k_fast_x1: trips of look-ahead of the child-chunk loads (2 or 3)
+#endif
 #ifndef GBN_XEXP
 #define GBN_XEXP 0        // experiments (profiles/r2_summary.md)
 #endif
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
             const bool track = live && (xs & 4u) != 0;
             // The by-TF lists are padded to multiples of four per TF (topology.hpp): a lane takes CHUNKS of four consecutive
             // children - one 16-byte load of the ids, one byte load of their four S codes - LPT chunks apart, and requests
-            // the chunks of the next two trips before it touches this trip's weights (a trip's shared-memory gathers are
+            // the chunks of the next three trips before it touches this trip's weights (a trip's shared-memory gathers are
             // short; with one trip of look-ahead every trip waited for an L2 round trip).
             uint32_t q4 = 0, q4e = 0;                                        // this lane's chunk; the end of the TF's chunks
             if (live) { q4 = sPtr[kw] >> 2; q4e = sPtr[kw + 1] >> 2; }
@@ -652,7 +655,9 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
                 r.cd = __ldg(code_base + (code_off + qq));                   // a 32-bit offset off the parameter's pointer
                 return r;
             };
-            Chunk c0 = load_chunk(q4), c1 = load_chunk(q4 + LPT), c2;
+            Chunk cb[GBN_X1_AHEAD + 1];                                      // the chunk in use and those requested ahead
+#pragma unroll
+            for (int i = 0; i < GBN_X1_AHEAD; i++) cb[i] = load_chunk(q4 + i * LPT);
             phi = -t;                                                        // f -> q f, q = 1 - t (X: 0 -> 1) or 1 / (1 - t) (1 -> 0)
             if (xcur) phi = t / (1. - t);
             const float phf = (float) phi;
@@ -663,11 +668,11 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
             auto child_loop = [&](auto with_q) {
                 constexpr bool WITH_Q = decltype(with_q)::value;
                 int cnt = 0;
-                // one trip: the chunk two trips ahead is requested into the buffer the previous trip used, then this
+                // one trip: the chunk three trips ahead is requested into the buffer the previous trip used, then this
                 // trip's four children are gathered from shared memory (32-bit addresses: behind generic pointers the
                 // shared window base is rebuilt in every trip)
                 auto trip = [&](const Chunk &cur, Chunk &ahead) {
-                    ahead = load_chunk(q4 + 2 * LPT);
+                    ahead = load_chunk(q4 + GBN_X1_AHEAD * LPT);
                     const uint32_t id[4] = { cur.id.x, cur.id.y, cur.id.z, cur.id.w };
                     float w[4];
 #pragma unroll
@@ -690,13 +695,13 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4)) k_fa
                     q4 += LPT;
                     return --trips == 0;
                 };
-                // the three chunk buffers take turns (no register moves between trips)
-                if (trips > 0)
-                    for (;;) {
-                        if (trip(c0, c2)) break;
-                        if (trip(c1, c0)) break;
-                        if (trip(c2, c1)) break;
-                    }
+                // the chunk buffers take turns (no register moves between trips)
+                if (trips == 0) return;
+                for (;;) {
+#pragma unroll
+                    for (int i = 0; i <= GBN_X1_AHEAD; i++)
+                        if (trip(cb[i], cb[(i + GBN_X1_AHEAD) % (GBN_X1_AHEAD + 1)])) return;
+                }
             };
             if (__any_sync(0xffffffffu, track)) child_loop(std::true_type{}); else child_loop(std::false_type{});
             normalise(mr, er);
