@@ -15,7 +15,11 @@ rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 ie, sm = col["Instructions Executed"], col["# Samples"]
-body = [r for r in rows[2:] if len(r) > ie and r[0].startswith("0x")]
+body, seen = [], set()
+for r in rows[2:]:                       # (the page lists every SASS line twice with the same counts)
+    if len(r) > ie and r[0].startswith("0x") and r[0] not in seen:
+        seen.add(r[0])
+        body.append(r)
 base = int(body[0][0], 16)
 U = float(sys.argv[2])
 L = [(int(r[0], 16) - base, int(r[ie]) / U, int(r[sm]), r[1].strip()) for r in body]
