@@ -1263,10 +1263,11 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s(DevNet net, DevCha
                         if (INJ) { const uint32_t e = pEdge[32 * (j0 + u)]; uu = e != 0xffffffffu ? inj_flat[e] : 0.5; }
                         const double dice = cum2 * uu;
                         // first v with dice < cum[v] (Multinomial.cpp:92-99); dice < cum[2] always holds (u < 1)
-                        // (a 32-bit uniform; an injected double can round up to cum[2]: the value is then kept)
+                        // (an injected double can round up to cum[2], and an all-zero prior row leaves cum[2] = 0: no
+                        // outcome is below the dice and the value is kept, Multinomial.cpp:92-99)
                         const bool q0 = dice < cum0, q1 = dice < cum1;
                         uint32_t ns = q0 ? 0u : (q1 ? 1u : 2u);
-                        if (INJ && !(dice < cum2)) ns = s;
+                        if (!(dice < cum2)) ns = s;
                         add_if(cw.x, 1u << (8 * u), ns == 0);                              // Multinomial.cpp:101-105 as counts
                         add_if(cw.y, 1u << (8 * u), ns == 2);
                         const uint32_t x = s ^ ns;

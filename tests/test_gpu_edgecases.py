@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import rel_err, sampler_from_problem
+from conftest import make_problem, rel_err, sampler_from_problem
 from test_gpu_parity import _assert_state_equal, _run_trajectory
 
 pytestmark = pytest.mark.gpu
@@ -103,6 +103,37 @@ def test_hub_in_the_subnormal_band(n_child):
         P.sample_n(1)
     assert min(seen) < -745.2 and -745. < max(seen) < -708.4        # both sides of the underflow threshold, never normal
     _run_trajectory(pb, KERNEL_FAST, 40, injected=False, chunks=(5,))
+
+
+def test_unsorted_targets_are_the_same_chain(monkeypatch):
+    """GBN_SORT_TARGETS=2 keeps the device targets in reference order: group widths are no longer descending, so a
+    CTA of the S kernel stages every table row (DevNet.groups_desc = 0) and wide and narrow groups share CTAs.  The
+    chain does not depend on the device order (the Philox keys use reference indices)."""
+    monkeypatch.setenv("GBN_SORT_TARGETS", "2")
+    rng = np.random.default_rng(11)
+    nX, nT = 40, 400
+    deg = rng.integers(1, 30, nT)
+    deg[::37] = 70                                                 # a few wide targets scattered through the order
+    src = np.concatenate([rng.choice(nX, min(d, nX), replace=False) for d in deg])
+    trg = np.concatenate([np.full(min(d, nX), 500 + i) for i, d in enumerate(deg)])
+    mor = rng.choice([-1, 0, 1], len(src))
+    evid = {int(t): int(rng.choice([-1, 0, 1])) for t in np.unique(trg)}
+    pb = _problem(src, trg, mor, evid, n_graphs=2)
+    _run_trajectory(pb, KERNEL_FAST, 25, injected=False, chunks=(5,))
+
+
+@pytest.mark.parametrize("sprior", [
+    (1., 0., 0., 0., 1., 0., 0., 0., 1.),                            # certain priors: zero entries, nothing tiny
+    (1e-250, 1. - 1e-250, 0., 0.5, 0.25, 0.25, 0., 1. - 1e-250, 1e-250),   # tiny entries: not certified, runs on k_fast_s
+    (0., 0., 0., 0.3, 0.4, 0.3, 0.2, 0.4, 0.4),                      # an all-zero row: the fallback of Multinomial.cpp:78-85
+])
+def test_degenerate_prior_rows(sprior):
+    """Prior rows with zeros, with entries so small that prior x likelihood could vanish, and an all-zero row: the
+    model layer certifies rows for k_fast_s2 (which has no all-zero fallback) or keeps the S phase on k_fast_s; either
+    way the chain is the oracle's."""
+    pb, _ = make_problem(NX=15, NY=120, AvgNTF=3.0, seed=8, n_graphs=3, sprior=sprior)
+    for injected in (False, True):
+        _run_trajectory(pb, KERNEL_FAST, 30, injected=injected, chunks=(7,))
 
 
 def test_evidence_quirks():
