@@ -1758,6 +1758,10 @@ static int launch_s2_t(const DevNet &net, const DevChains &ch, const SweepArgs &
 {
     const size_t smem = s_smem_bytes(net);
     if (check(cudaFuncSetAttribute(k_fast_s2<INJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem), err)) return -1;
+    {
+        static const uint32_t carve = env_u32("GBN_S_CARVE", 0);          // experiment knob, see GBN_X1_CARVE
+        if (carve && check(cudaFuncSetAttribute(k_fast_s2<INJ>, cudaFuncAttributePreferredSharedMemoryCarveout, (int) carve), err)) return -1;
+    }
     const uint32_t gpb = FS_NT / 32;                                  // groups per block
     k_fast_s2<INJ><<<dim3((net.n_groups + gpb - 1) / gpb, nchains), FS_NT, smem, st>>>(net, ch, a);
     return 0;
@@ -1850,6 +1854,10 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
         else if (nt1 == 512) kx1 = l1 >= 16 ? k_fast_x1<512, 16, XU> : l1 == 8 ? k_fast_x1<512, 8, XU> : k_fast_x1<512, 4, XU>;
         else kx1 = l1 == 32 ? k_fast_x1<FX_NT, 32, XU> : l1 == 16 ? k_fast_x1<FX_NT, 16, XU> : l1 == 8 ? k_fast_x1<FX_NT, 8, XU> : k_fast_x1<FX_NT, 4, XU>;
         if (check(cudaFuncSetAttribute(kx1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_x1), err)) return -1;
+        {   // experiment knob: the shared-memory carve-out the kernel asks for, in percent of the maximum (0 = the driver's choice)
+            static const uint32_t carve = env_u32("GBN_X1_CARVE", 0);
+            if (carve && check(cudaFuncSetAttribute(kx1, cudaFuncAttributePreferredSharedMemoryCarveout, (int) carve), err)) return -1;
+        }
     }
     const size_t smem_tl = 4 * (size_t) net.nX + 16;
     if (net.listen && !net.const_params &&
