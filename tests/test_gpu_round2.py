@@ -36,6 +36,24 @@ def test_path_selection(monkeypatch):
     assert sampler_from_problem(pb).path() == 1
 
 
+@pytest.mark.parametrize("listen", [False, True])
+@pytest.mark.parametrize("xq", ["1", "2"])
+def test_pair_x_kernel_with_the_second_s_kernel(monkeypatch, listen, xq):
+    """Networks whose flip weights do not fit an SM sweep X on the chain-pair kernel (k_fast_x, GBN_X1=2) and S on
+    k_fast_s2, which then writes the bundle-interleaved bound bytes instead of the per-chain rows (the parity suites'
+    "pair" mode runs k_fast_x with k_fast_s): the oracle's chain, with the bounds in shared memory (GBN_X_Q=1) and
+    read from global memory (GBN_X_Q=2), listening and non-listening T nodes, keyed and injected streams."""
+    from test_gpu_parity import _run_trajectory
+    import gbnet_b200
+    monkeypatch.setenv("GBN_SMALL", "2")
+    monkeypatch.setenv("GBN_X1", "2")
+    monkeypatch.setenv("GBN_X_Q", xq)
+    monkeypatch.delenv("GBN_S_V", raising=False)
+    pb, _ = make_problem(NX=25, NY=300, AvgNTF=4.0, seed=31, n_graphs=5, noise_listen_children=listen)
+    for injected in (False, True):
+        _run_trajectory(pb, gbnet_b200.KERNEL_FAST, 30, injected, chunks=(4, 9))
+
+
 @pytest.mark.parametrize("lpt", [0, 4, 8, 16, 32])
 def test_persistent_kernel_is_the_same_chain(monkeypatch, lpt):
     """The persistent shared-memory kernel, the multi-kernel fast path and the oracle draw the same chains:
