@@ -184,7 +184,9 @@ int dev_upload(gbn_model *m, T **out, const std::vector<T> &v)
 // T at the prior mean, S at mor + 1.  The two cumulative likelihoods exp(log(prob[v])) are evaluated
 // here with the host libm so that the initial state is the oracle's bit for bit; the draw itself
 // (keyed Philox, kind INIT) happens on the device.
-int init_chains(gbn_model *m)
+// fast_views: the caller fills the packed views of the fast path from the network's initial words next
+// (refresh_fast(m, true)), so the byte view of S is not written here (it is unpacked on demand)
+int init_chains(gbn_model *m, bool fast_views = false)
 {
     const double xprob[2][2] = { { 0.99, 0.01 }, { 0.10, 0.90 } };
     double cum[2][2];
@@ -192,7 +194,7 @@ int init_chains(gbn_model *m)
         cum[a][0] = std::exp(std::log(xprob[a][0]));
         cum[a][1] = cum[a][0] + std::exp(std::log(xprob[a][1]));
     }
-    launch_init_chains(m->net, m->ch, cum, m->stream);
+    launch_init_chains(m->net, m->ch, cum, m->stream, fast_views);
     m->launches += 1;
     if (m->sim) {       // H starts at 1 ("no deg"), Y copies it (GraphORNOR.cpp:94-96, YDataNode.cpp:20-25)
         CUDA_TRY(cudaMemsetAsync(m->ch.H, 1, (size_t) m->n_chains * m->tp.nH, m->stream));
@@ -221,14 +223,16 @@ int zero_stats(gbn_model *m)
 }
 
 // the fast kernel's packed views and caches from X, T and the byte view of S
-int refresh_fast(gbn_model *m)
+// initial: the chains were just initialised (init_chains(m, true)): S words and the by-TF copy are broadcast from the
+// network's initial words instead of being packed / gathered from the byte view, which is left stale
+int refresh_fast(gbn_model *m, bool initial = false)
 {
     if (m->kernel != GBN_KERNEL_FAST) return 0;
     const char *err = nullptr;
-    int n = launch_fast_refresh(m->net, m->ch, m->stream, &err);
+    int n = launch_fast_refresh(m->net, m->ch, m->stream, &err, initial);
     if (n < 0) return fail(GBN_ERR_CUDA, std::string("fast refresh: ") + err);
     m->launches += (uint64_t) n;
-    m->s_bytes_valid = true;
+    m->s_bytes_valid = !initial;
     return 0;
 }
 
@@ -657,7 +661,28 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
                 cmap[2 * c] = c / m->n_graphs_local;
                 cmap[2 * c + 1] = (c / m->n_graphs_local) * m->n_graphs + m->chain_offset + c % m->n_graphs_local;
             }
+            // the packed views of the initial state (every chain starts with S = mor + 1 on every edge)
+            std::vector<uint32_t> swi(tp.nSw, 0x55555555u), sti((tp.Efp + 19) >> 4, 0x55555555u);
+            for (uint32_t i = 0; i < tp.nSw; i++) {
+                const uint32_t row = i >> 5, lane = i & 31, g = tp.sw_grp[row], jw = row - (tp.sbase[g] >> 5);
+                const uint32_t gb = tp.gbase[g], W = (tp.gbase[g + 1] - gb) >> 5;
+                uint32_t w = 0;
+                for (uint32_t u = 0; u < 16; u++) {
+                    const uint32_t j = 16 * jw + u;
+                    w |= (j < W ? (uint32_t) tp.mor_idx[gb + lane + 32 * j] : 1u) << (2 * u);
+                }
+                swi[i] = w;
+            }
+            for (uint32_t pos = 0; pos < tp.Efp; pos++)
+                if (tp.fp_slot[pos] != UINT32_MAX)
+                    sti[pos >> 4] = (sti[pos >> 4] & ~(3u << (2 * (pos & 15)))) | ((uint32_t) tp.mor_idx[tp.fp_slot[pos]] << (2 * (pos & 15)));
             uint32_t *t = nullptr;
+            if (int rc = dev_upload(m, &t, swi)) return bail(rc);
+            n.sw_init = t;
+            t = nullptr;
+            if (int rc = dev_upload(m, &t, sti)) return bail(rc);
+            n.stfp_init = t;
+            t = nullptr;
             if (int rc = dev_upload(m, &t, rec)) return bail(rc);
             n.grec = reinterpret_cast<const uint4 *>(t);
             t = nullptr;
@@ -773,9 +798,12 @@ extern "C" int gbn_model_create(const gbn_network *netin, const gbn_evidence *ev
     if (int rc = dev_alloc(m, &m->d_gr, (size_t) n_nodes_of(n))) return bail(rc);
     if (int rc = dev_alloc(m, &m->d_max, (size_t) m->n_datasets)) return bail(rc);
 
-    if (int rc = init_chains(m)) return bail(rc);
-    if (int rc = zero_stats(m)) return bail(rc);
-    if (int rc = refresh_fast(m)) return bail(rc);
+    {
+        const bool fv = m->kernel == GBN_KERNEL_FAST;
+        if (int rc = init_chains(m, fv)) return bail(rc);
+        if (int rc = zero_stats(m)) return bail(rc);
+        if (int rc = refresh_fast(m, fv)) return bail(rc);
+    }
     if (cudaStreamSynchronize(m->stream) != cudaSuccess) return bail(fail(GBN_ERR_CUDA, "initialisation failed on the device"));
     *out = m;
     return 0;
@@ -1079,11 +1107,12 @@ extern "C" int gbn_model_set_evidence(gbn_model *m, const gbn_evidence *ev)
     lap("upload");
     m->sweeps_total = 0;
     m->ch.inj_flat = m->ch.inj_beta = m->ch.inj_exp = nullptr; m->ch.inj_sweeps = m->ch.inj_pos = 0;
-    if (int rc = init_chains(m)) return rc;
+    const bool fv = m->kernel == GBN_KERNEL_FAST;
+    if (int rc = init_chains(m, fv)) return rc;
     lap("init_chains");
     if (int rc = zero_stats(m)) return rc;
     lap("zero_stats");
-    if (int rc = refresh_fast(m)) return rc;
+    if (int rc = refresh_fast(m, fv)) return rc;
     lap("refresh_fast");
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     return 0;

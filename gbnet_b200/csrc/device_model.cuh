@@ -47,6 +47,9 @@ struct DevNet {
     const uint32_t *dblk_grp;     // [nD / 32]   group of every row of 32 blocks
     const uint32_t *mor2;         // [nSw] prior row per step (3 = pad)
     const uint2 *par16;           // [nD]  four 16-bit parent TFs per block
+    const uint32_t *sw_init;      // [nSw] the S words of a freshly initialised chain (S = mor + 1 on every edge, GraphORNOR.cpp:237-263;
+                                  // the same for every chain): set_evidence / create fill the packed views from these
+    const uint32_t *stfp_init;    // [n_stf_words] likewise the by-TF copy
     const uint4 *grec;            // [n_groups] {gbase, width, sbase, dbase} of a group in one 16-byte record (k_fast_s2)
     const uint2 *chain_map;       // [n_chains] local chain -> {dataset, global chain id} (chain_dataset / chain_global_id tabulated)
     const uint4 *tfpos4;          // [nD]  fp position (padded by-TF lists) of the block's four steps (UINT32_MAX for pads)

@@ -148,7 +148,7 @@ __global__ void k_export_draws(DevNet net, uint32_t gchain, uint32_t sweep0, uin
 }
 
 // Multinomial ctor draw for X (Multinomial.cpp:42-49), T = prior mean, S = mor + 1
-__global__ void k_init_chains(DevNet net, DevChains ch, double c00, double c01, double c10, double c11)
+__global__ void k_init_chains(DevNet net, DevChains ch, double c00, double c01, double c10, double c11, int skip_s)
 {
     const uint32_t c = blockIdx.y;
     const uint32_t gchain = chain_global_id(net, c);
@@ -162,15 +162,17 @@ __global__ void k_init_chains(DevNet net, DevChains ch, double c00, double c01, 
         ch.X[(size_t) c * net.nX + j] = net.sim ? (act ? 1 : 0) : (dice < c0 ? 0 : 1);
         ch.T[(size_t) c * net.nX + j] = net.t_mean[j];
     }
-    if (j < net.Ep) ch.S[(size_t) c * net.Ep + j] = net.mor_idx[j];     // pads: 1 = edge off
+    if (!skip_s && j < net.Ep) ch.S[(size_t) c * net.Ep + j] = net.mor_idx[j];     // pads: 1 = edge off
 }
 
 }  // namespace
 
-void launch_init_chains(const DevNet &net, const DevChains &ch, const double cum[2][2], cudaStream_t st)
+// skip_s_bytes: the fast path fills its packed views from the network's initial words (launch_fast_refresh, initial);
+// the byte view of S is then unpacked on demand
+void launch_init_chains(const DevNet &net, const DevChains &ch, const double cum[2][2], cudaStream_t st, bool skip_s_bytes)
 {
-    uint32_t n = net.nX > net.Ep ? net.nX : net.Ep;
-    k_init_chains<<<dim3((n + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch, cum[0][0], cum[0][1], cum[1][0], cum[1][1]);
+    uint32_t n = skip_s_bytes ? net.nX : (net.nX > net.Ep ? net.nX : net.Ep);
+    k_init_chains<<<dim3((n + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch, cum[0][0], cum[0][1], cum[1][0], cum[1][1], skip_s_bytes ? 1 : 0);
 }
 
 void launch_conditionals(const DevNet &net, const DevChains &ch, uint32_t c, double *out, cudaStream_t st)

@@ -17,7 +17,7 @@ void launch_export_draws(const DevNet &net, uint32_t gchain, uint32_t sweep0, ui
                          double *flat_u, double *beta_v, double *exp_v, cudaStream_t st);
 
 // initial state of every local chain; cum[a][v] = cumulative prior likelihood of X (host libm)
-void launch_init_chains(const DevNet &net, const DevChains &ch, const double cum[2][2], cudaStream_t st);
+void launch_init_chains(const DevNet &net, const DevChains &ch, const double cum[2][2], cudaStream_t st, bool skip_s_bytes = false);
 
 // ---- sweep_strict.cu: n_sweeps full sweeps X -> T -> S of every local chain, one CTA per chain,
 // every likelihood recomputed from the state in the reference's operand order.
@@ -42,7 +42,7 @@ int launch_sweep_fast(const DevNet &net, const DevChains &ch, uint32_t n_sweeps,
                       cudaStream_t stx = nullptr, cudaEvent_t evx = nullptr, cudaEvent_t evs = nullptr);
 // rebuild the packed S words, the by-TF copy, FXp and the product cache from X, T and the BYTE view of S
 // (after creation, set_state, checkpoint load)
-int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
+int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err, bool initial = false);
 // the byte view of S (ch.S) from the packed words a fast sweep leaves behind
 int launch_fast_unpack(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
 // the S nodes' per-batch 8-bit outcome counts (ch.dC) added to the 32-bit totals (ch.cS); at most

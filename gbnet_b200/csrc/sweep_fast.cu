@@ -1599,7 +1599,9 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s2(DevNet net, DevCh
 
 // ---- conversions between the byte view of S (ch.S: parity hooks, state get / set, checkpoints, strict kernel)
 // and the packed views the fast sweep works on
-// S bytes -> 2-bit words (after creation, set_state, checkpoint load)
+// S bytes -> 2-bit words (after set_state, checkpoint load).  INITIAL (after creation, set_evidence): the S words of
+// a freshly initialised chain are the network's initial words; only the activity bits depend on the chain (its X)
+template <bool INITIAL>
 __global__ void k_pack_s(DevNet net, DevChains ch)
 {
     const uint32_t c = blockIdx.y;
@@ -1609,12 +1611,14 @@ __global__ void k_pack_s(DevNet net, DevChains ch)
     const uint32_t jw = row - (net.sbase[g] >> 5), gb = net.gbase[g], W = (net.gbase[g + 1] - gb) >> 5;
     const uint8_t *S = ch.S + (size_t) c * net.Ep + gb + lane;
     const uint8_t *X = ch.X + (size_t) c * net.nX;
-    uint32_t w = 0, aw = 0;
+    uint32_t w = INITIAL ? net.sw_init[i] : 0u, aw = 0;
     for (uint32_t u = 0; u < 16; u++) {
         const uint32_t j = 16 * jw + u;
-        const uint32_t code = j < W ? S[32 * j] : 1u;
-        GBN_CHECK(code <= 2);
-        w |= code << (2 * u);
+        if (!INITIAL) {
+            const uint32_t code = j < W ? S[32 * j] : 1u;
+            GBN_CHECK(code <= 2);
+            w |= code << (2 * u);
+        }
         if (j < W && net.par_edge[gb + lane + 32 * j] != 0xffffffffu) aw |= (uint32_t) (X[net.par_tf[gb + lane + 32 * j]] & 1u) << u;
     }
     ch.Sw[(size_t) c * net.nSw + i] = w;
@@ -1662,13 +1666,15 @@ __global__ void k_fold_counts(DevNet net, DevChains ch)
     *pd = make_uint2(0u, 0u);
 }
 
-// Stfp from S (refresh only): one thread per word of the by-TF list
+// Stfp from S (refresh only): one thread per word of the by-TF list.  INITIAL: the network's initial words
+template <bool INITIAL>
 __global__ void k_fast_stf(DevNet net, DevChains ch)
 {
     const uint32_t c = blockIdx.y;
     const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nStfW = n_stf_words(net);
     if (wi >= nStfW) return;
+    if (INITIAL) { ch.Stfp[(size_t) c * nStfW + wi] = net.stfp_init[wi]; return; }
     uint32_t w = 0;
     for (uint32_t u = 0; u < 16; u++) {
         const uint32_t pos = 16 * wi + u;
@@ -1777,12 +1783,13 @@ static int launch_s(const DevNet &net, const DevChains &ch, const SweepArgs &a, 
     return pf ? launch_s_t<0, false, true>(net, ch, a, nc, st, err) : launch_s_t<0, false, false>(net, ch, a, nc, st, err);
 }
 
-int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err)
+int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err, bool initial)
 {
     if (ch.n_chains == 0) return 0;
     SweepArgs a = sweep_args(net);
-    k_pack_s<<<dim3((net.nSw + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
-    k_fast_stf<<<dim3((n_stf_words(net) + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
+    const dim3 gp((net.nSw + 255) / 256, ch.n_chains), gs((n_stf_words(net) + 255) / 256, ch.n_chains);
+    if (initial) { k_pack_s<true><<<gp, 256, 0, st>>>(net, ch); k_fast_stf<true><<<gs, 256, 0, st>>>(net, ch); }
+    else { k_pack_s<false><<<gp, 256, 0, st>>>(net, ch); k_fast_stf<false><<<gs, 256, 0, st>>>(net, ch); }
     k_fast_t<<<dim3((net.nX + FT_NT - 1) / FT_NT, ch.n_chains), FT_NT, 0, st>>>(net, ch, a, 0, ch.T, 1);
     if (launch_s(net, ch, a, 1, ch.n_chains, st, err)) return -1;
     if (check(cudaGetLastError(), err)) return -1;
