@@ -394,10 +394,12 @@ int compute_moments(gbn_model *m)
     const double N = (double) m->stat_n;
     // counts of the discrete nodes overflow the exact integer path only beyond M * N^2 >= 2^63
     if ((double) m->n_graphs * N * N >= 9.0e18) return fail(GBN_ERR_UNSUPPORTED, "chain length too large for the exact moment sums");
-    if (int rc = fold_counts(m)) return rc;
+    // the fast path's per-batch byte counters are read beside the totals, not folded into them: the fold (a rewrite
+    // of every total) waits until a byte could overflow or something reads the totals themselves
+    const bool pend = m->kernel == GBN_KERNEL_FAST && m->pending > 0;
     // one u64 all-reduce of the stored counts' sums, two small fp64 ones for the T nodes (3 nX, then 2 nX)
     const size_t nt = (size_t) m->n_datasets * n_t_of(m->net);
-    launch_count_sums(m->net, m->ch, m->d_isums, m->stream);
+    launch_count_sums(m->net, m->ch, m->d_isums, m->stream, pend);
     launch_moment_sums(m->net, m->ch, N, m->d_tsum, m->stream);
     if (int rc = allreduce(m, m->d_isums, (size_t) m->n_datasets * moment_isum_words(m->net), NCCL_SUM, NCCL_UINT64)) return rc;
     if (nt) if (int rc = allreduce(m, m->d_tsum, 3 * nt, NCCL_SUM)) return rc;

@@ -165,7 +165,9 @@ __global__ void __launch_bounds__(32 * MS_SL) k_moment_devs(DevNet net, DevChain
 constexpr uint32_t IS_X = 3, IS_S = 6;
 __host__ __device__ inline size_t isum_words(const DevNet &n) { return n.sim ? (size_t) IS_S * 2 * n.nH : (size_t) IS_X * n.nX + (size_t) IS_S * n.E; }
 
-__global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long *isums)
+// with_pending: the fast path's per-batch byte counters (ch.dC) have not been folded into the totals: add them here
+// (the fold rewrites 2.5 MB of totals per chain; between folds the R-hat check only reads)
+__global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long *isums, int with_pending)
 {
     const uint32_t d = blockIdx.y;
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;          // X_k for w < nX, then slots
@@ -182,7 +184,9 @@ __global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long *isums
         return;
     }
     const uint2 *cnt;
-    size_t stride, idx, o;
+    const uint2 *dC = nullptr;                                          // pending counts of this slot: byte sh of entry didx
+    size_t stride, idx, o, didx = 0;
+    uint32_t sh = 0;
     if (net.sim) {                                                      // H_dt for w < nH, then Y_dt
         const uint32_t isY = w >= net.nH, dt = w - (isY ? net.nH : 0);
         cnt = isY ? ch.cY : ch.cH; stride = net.nH; idx = dt;
@@ -192,11 +196,19 @@ __global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long *isums
         if (e == 0xffffffffu) return;                                   // pad slot
         cnt = ch.cS; stride = net.Ep; idx = q;
         o = (size_t) IS_X * net.nX + (size_t) IS_S * e;
+        if (with_pending) {                                             // slot q = gbase[g] + 32 j + lane (topology.hpp)
+            const uint32_t g = net.slot_trg[q] >> 5, j = (q - net.gbase[g]) >> 5;
+            dC = ch.dC; didx = net.dbase[g] + 32 * (j >> 2) + (q & 31); sh = 8 * (j & 3);
+        }
     }
     unsigned long long a1 = 0, a2 = 0, b1 = 0, b2 = 0, ab = 0, z = 0;
     for (uint32_t l = 0; l < net.n_graphs_local; l++) {
         const uint2 cs = cnt[(size_t) (d * net.n_graphs_local + l) * stride + idx];
-        const unsigned long long a = cs.x, b = cs.y;
+        unsigned long long a = cs.x, b = cs.y;
+        if (dC) {
+            const uint2 dv = dC[(size_t) (d * net.n_graphs_local + l) * net.nD + didx];
+            a += (dv.x >> sh) & 0xffu; b += (dv.y >> sh) & 0xffu;
+        }
         a1 += a; a2 += a * a; b1 += b; b2 += b * b; ab += a * b;
         if (net.chain_offset + l == 0) z = a | (b << 32);
     }
@@ -306,10 +318,10 @@ void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double
 
 size_t moment_isum_words(const DevNet &net) { return isum_words(net); }
 
-void launch_count_sums(const DevNet &net, const DevChains &ch, unsigned long long *isums, cudaStream_t st)
+void launch_count_sums(const DevNet &net, const DevChains &ch, unsigned long long *isums, cudaStream_t st, bool with_pending)
 {
     dim3 grid(((net.sim ? 2 * net.nH : net.nX + net.Ep) + 127) / 128, net.n_datasets);
-    k_count_sums<<<grid, 128, 0, st>>>(net, ch, isums);
+    k_count_sums<<<grid, 128, 0, st>>>(net, ch, isums, with_pending && !net.sim && ch.dC != nullptr ? 1 : 0);
 }
 
 void launch_expand_counts(const DevNet &net, double N, const unsigned long long *isums, const double *tsum, const double *tdev,
