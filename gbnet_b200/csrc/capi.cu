@@ -139,6 +139,8 @@ struct gbn_model {
     bool small = false;                 // the persistent shared-memory kernel (sweep_small.cu) sweeps this model
     bool s_bytes_valid = true;          // ch.S (bytes) agrees with ch.Sw (2-bit words)
     uint32_t pending = 0;               // sweeps counted in ch.dC and not yet folded into ch.cS
+    bool cs_zero = false;               // fast path: the S totals (ch.cS) are logically zero and their memory is not written yet:
+                                        // the first fold overwrites instead of adding, the R-hat check does not read them
     // per-kernel timing (gbn_model_set_phase_timing)
     bool phase_timing = false;
     std::vector<cudaEvent_t> phase_ev;  // [group][3 n + 1]
@@ -210,7 +212,9 @@ int zero_stats(gbn_model *m)
     CUDA_TRY(cudaMemsetAsync(m->ch.cX1, 0, sizeof(uint32_t) * C * nX, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->ch.tMean, 0, sizeof(double) * C * nX, m->stream));
     CUDA_TRY(cudaMemsetAsync(m->ch.tM2, 0, sizeof(double) * C * nX, m->stream));
-    CUDA_TRY(cudaMemsetAsync(m->ch.cS, 0, sizeof(uint2) * C * E, m->stream));
+    // (the fast path leaves the 2.5 MB of S totals per chain untouched until a fold or a reader needs them)
+    if (m->kernel == GBN_KERNEL_FAST && !m->sim && m->ch.dC) m->cs_zero = true;
+    else CUDA_TRY(cudaMemsetAsync(m->ch.cS, 0, sizeof(uint2) * C * E, m->stream));
     if (m->ch.dC) CUDA_TRY(cudaMemsetAsync(m->ch.dC, 0, sizeof(uint2) * C * m->tp.nD, m->stream));
     m->pending = 0;
     if (m->sim) {
@@ -251,12 +255,20 @@ int ensure_s_bytes(gbn_model *m)
 // before anything reads ch.cS: the fast sweep counts S outcomes into per-batch 8-bit counters
 int fold_counts(gbn_model *m)
 {
-    if (m->kernel != GBN_KERNEL_FAST || m->pending == 0) return 0;
+    if (m->kernel != GBN_KERNEL_FAST) return 0;
+    if (m->pending == 0) {
+        if (m->cs_zero) {                                   // a reader of totals that were never written
+            CUDA_TRY(cudaMemsetAsync(m->ch.cS, 0, sizeof(uint2) * (size_t) m->n_chains * m->tp.Ep, m->stream));
+            m->cs_zero = false;
+        }
+        return 0;
+    }
     const char *err = nullptr;
-    int n = launch_fast_fold(m->net, m->ch, m->stream, &err);
+    int n = launch_fast_fold(m->net, m->ch, m->stream, &err, m->cs_zero);
     if (n < 0) return fail(GBN_ERR_CUDA, std::string("fast fold: ") + err);
     m->launches += (uint64_t) n;
     m->pending = 0;
+    m->cs_zero = false;
     return 0;
 }
 
@@ -399,7 +411,7 @@ int compute_moments(gbn_model *m)
     const bool pend = m->kernel == GBN_KERNEL_FAST && m->pending > 0;
     // one u64 all-reduce of the stored counts' sums, two small fp64 ones for the T nodes (3 nX, then 2 nX)
     const size_t nt = (size_t) m->n_datasets * n_t_of(m->net);
-    launch_count_sums(m->net, m->ch, m->d_isums, m->stream, pend);
+    launch_count_sums(m->net, m->ch, m->d_isums, m->stream, pend, m->cs_zero);
     launch_moment_sums(m->net, m->ch, N, m->d_tsum, m->stream);
     if (int rc = allreduce(m, m->d_isums, (size_t) m->n_datasets * moment_isum_words(m->net), NCCL_SUM, NCCL_UINT64)) return rc;
     if (nt) if (int rc = allreduce(m, m->d_tsum, 3 * nt, NCCL_SUM)) return rc;
@@ -1426,6 +1438,7 @@ extern "C" int gbn_model_checkpoint_load(gbn_model *m, const void *in, size_t by
     m->moments_valid = false;
     if (m->ch.dC) CUDA_TRY(cudaMemsetAsync(m->ch.dC, 0, sizeof(uint2) * (size_t) m->n_chains * m->tp.nD, m->stream));
     m->pending = 0;
+    m->cs_zero = false;                                     // the totals came with the checkpoint
     m->ch.inj_flat = m->ch.inj_beta = m->ch.inj_exp = nullptr; m->ch.inj_sweeps = m->ch.inj_pos = 0;
     if (int rc = refresh_fast(m)) return rc;
     CUDA_TRY(cudaStreamSynchronize(m->stream));

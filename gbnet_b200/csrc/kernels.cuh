@@ -47,7 +47,7 @@ int launch_fast_refresh(const DevNet &net, const DevChains &ch, cudaStream_t st,
 int launch_fast_unpack(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
 // the S nodes' per-batch 8-bit outcome counts (ch.dC) added to the 32-bit totals (ch.cS); at most
 // FAST_MAX_PENDING sweeps may be drawn between two folds
-int launch_fast_fold(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err);
+int launch_fast_fold(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err, bool overwrite = false);
 constexpr uint32_t FAST_MAX_PENDING = 255;
 bool fast_supported(const DevNet &net, const char **why);
 
@@ -72,7 +72,8 @@ void launch_moment_devs(const DevNet &net, const DevChains &ch, double N, const 
 // discrete nodes: exact u64 sums of the STORED counts (layout in moments.cu; moment_isum_words() words per dataset);
 // after the all-reduces, launch_expand_counts fills sums / psums / dev / pdev of every statistic
 size_t moment_isum_words(const DevNet &net);
-void launch_count_sums(const DevNet &net, const DevChains &ch, unsigned long long *isums, cudaStream_t st, bool with_pending = false);
+void launch_count_sums(const DevNet &net, const DevChains &ch, unsigned long long *isums, cudaStream_t st, bool with_pending = false,
+                       bool totals_zero = false);
 void launch_expand_counts(const DevNet &net, double N, const unsigned long long *isums, const double *tsum, const double *tdev,
                           double *sums, double *psums, double *dev, double *pdev, cudaStream_t st);
 // finalize: Gelman-Rubin per node (random_nodes order) of dataset d, and its maximum

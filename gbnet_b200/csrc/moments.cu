@@ -167,7 +167,8 @@ __host__ __device__ inline size_t isum_words(const DevNet &n) { return n.sim ? (
 
 // with_pending: the fast path's per-batch byte counters (ch.dC) have not been folded into the totals: add them here
 // (the fold rewrites 2.5 MB of totals per chain; between folds the R-hat check only reads)
-__global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long *isums, int with_pending)
+// totals_zero: the totals of the fast path's S nodes are logically zero and were never written (capi.cu, cs_zero)
+__global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long *isums, int with_pending, int totals_zero)
 {
     const uint32_t d = blockIdx.y;
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;          // X_k for w < nX, then slots
@@ -203,7 +204,7 @@ __global__ void k_count_sums(DevNet net, DevChains ch, unsigned long long *isums
     }
     unsigned long long a1 = 0, a2 = 0, b1 = 0, b2 = 0, ab = 0, z = 0;
     for (uint32_t l = 0; l < net.n_graphs_local; l++) {
-        const uint2 cs = cnt[(size_t) (d * net.n_graphs_local + l) * stride + idx];
+        const uint2 cs = totals_zero ? make_uint2(0u, 0u) : cnt[(size_t) (d * net.n_graphs_local + l) * stride + idx];
         unsigned long long a = cs.x, b = cs.y;
         if (dC) {
             const uint2 dv = dC[(size_t) (d * net.n_graphs_local + l) * net.nD + didx];
@@ -318,10 +319,12 @@ void launch_moment_sums(const DevNet &net, const DevChains &ch, double N, double
 
 size_t moment_isum_words(const DevNet &net) { return isum_words(net); }
 
-void launch_count_sums(const DevNet &net, const DevChains &ch, unsigned long long *isums, cudaStream_t st, bool with_pending)
+void launch_count_sums(const DevNet &net, const DevChains &ch, unsigned long long *isums, cudaStream_t st, bool with_pending,
+                       bool totals_zero)
 {
     dim3 grid(((net.sim ? 2 * net.nH : net.nX + net.Ep) + 127) / 128, net.n_datasets);
-    k_count_sums<<<grid, 128, 0, st>>>(net, ch, isums, with_pending && !net.sim && ch.dC != nullptr ? 1 : 0);
+    const bool fast = !net.sim && ch.dC != nullptr;
+    k_count_sums<<<grid, 128, 0, st>>>(net, ch, isums, with_pending && fast ? 1 : 0, totals_zero && fast ? 1 : 0);
 }
 
 void launch_expand_counts(const DevNet &net, double N, const unsigned long long *isums, const double *tsum, const double *tdev,

@@ -1641,7 +1641,9 @@ __global__ void k_unpack_s(DevNet net, DevChains ch)
     }
 }
 
-// per-batch 8-bit counts -> 32-bit totals (Multinomial.cpp:101-105 as counts); dC is left at zero
+// per-batch 8-bit counts -> 32-bit totals (Multinomial.cpp:101-105 as counts); dC is left at zero.
+// OVERWRITE: the totals were never written (logically zero, capi.cu cs_zero): every slot of the block is set
+template <bool OVERWRITE>
 __global__ void k_fold_counts(DevNet net, DevChains ch)
 {
     const uint32_t c = blockIdx.y;
@@ -1649,7 +1651,7 @@ __global__ void k_fold_counts(DevNet net, DevChains ch)
     if (i >= net.nD) return;
     uint2 *pd = ch.dC + (size_t) c * net.nD + i;
     const uint2 dv = *pd;
-    if ((dv.x | dv.y) == 0) return;
+    if (!OVERWRITE && (dv.x | dv.y) == 0) return;
     const uint32_t row = i >> 5, lane = i & 31, g = net.dblk_grp[row];
     const uint32_t jb = row - (net.dbase[g] >> 5), gb = net.gbase[g], W = (net.gbase[g + 1] - gb) >> 5;
     uint2 *cS = ch.cS + (size_t) c * net.Ep + gb + lane;
@@ -1657,13 +1659,13 @@ __global__ void k_fold_counts(DevNet net, DevChains ch)
     for (uint32_t u = 0; u < 4; u++) {
         const uint32_t j = 4 * jb + u;
         const uint32_t d0 = (dv.x >> (8 * u)) & 0xffu, d2 = (dv.y >> (8 * u)) & 0xffu;
-        if (j < W && (d0 | d2)) {
-            uint2 t = cS[32 * j];
+        if (j < W && (OVERWRITE || (d0 | d2))) {
+            uint2 t = OVERWRITE ? make_uint2(0u, 0u) : cS[32 * j];
             t.x += d0; t.y += d2;
             cS[32 * j] = t;
         }
     }
-    *pd = make_uint2(0u, 0u);
+    if (dv.x | dv.y) *pd = make_uint2(0u, 0u);
 }
 
 // Stfp from S (refresh only): one thread per word of the by-TF list.  INITIAL: the network's initial words
@@ -1806,10 +1808,12 @@ int launch_fast_unpack(const DevNet &net, const DevChains &ch, cudaStream_t st, 
 }
 
 // per-batch 8-bit outcome counts of the S nodes -> the 32-bit totals in ch.cS
-int launch_fast_fold(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err)
+int launch_fast_fold(const DevNet &net, const DevChains &ch, cudaStream_t st, const char **err, bool overwrite)
 {
     if (ch.n_chains == 0) return 0;
-    k_fold_counts<<<dim3((net.nD + 255) / 256, ch.n_chains), 256, 0, st>>>(net, ch);
+    const dim3 grid((net.nD + 255) / 256, ch.n_chains);
+    if (overwrite) k_fold_counts<true><<<grid, 256, 0, st>>>(net, ch);
+    else k_fold_counts<false><<<grid, 256, 0, st>>>(net, ch);
     if (check(cudaGetLastError(), err)) return -1;
     return 1;
 }
