@@ -49,6 +49,9 @@
 #ifndef GBN_S2_PRIOR_SMEM
 #define GBN_S2_PRIOR_SMEM 1   // k_fast_s2: prior rows from shared memory (0: from the constant bank)
 #endif
+#ifndef GBN_S2_DC_PREFETCH
+#define GBN_S2_DC_PREFETCH 1  // k_fast_s2: the counters' lines are pulled into L2 before the barrier
+#endif
 #ifndef GBN_X1_AHEAD
 #define GBN_X1_AHEAD 3        // k_fast_x1: trips of look-ahead of the child-chunk loads (2 or 3)
 #endif
@@ -1397,7 +1400,9 @@ __global__ void __launch_bounds__(FS_NT, GBN_S_MINB) k_fast_s2(DevNet net, DevCh
     const uint32_t W4 = (W + 3) >> 2;                                // 4-step blocks (the last may hold pads)
     uint32_t swA = 0x55555555u, awA = 0, mwA = 0xffffffffu;
     if (W) { swA = ch.Sw[sw_off]; awA = ch.Aw[sw_off]; mwA = net.mor2[sb]; }
+#if GBN_S2_DC_PREFETCH
     for (uint32_t b = 0; b < W4; b++) asm volatile("prefetch.global.L2 [%0];" ::"l"(ch.dC + (dc_off + 32 * b)));
+#endif
     {
         // n never exceeds the in-degree: with groups in descending order of width the CTA's first group bounds it
         const uint32_t rows = net.groups_desc ? min(D, net.grec[g0].y + 2) : D;
