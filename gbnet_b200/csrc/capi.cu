@@ -342,16 +342,12 @@ int upload_evidence(gbn_model *m, const gbn_evidence *ev)
         const double ynoise[3][3] = { { 0.945, 0.050, 0.005 }, { 0.050, 0.900, 0.050 }, { 0.005, 0.050, 0.945 } };
         double lmin[3];
         for (int y = 0; y < 3; y++) lmin[y] = std::log(std::min(ynoise[0][y], std::min(ynoise[1][y], ynoise[2][y])));
-        std::vector<uint8_t> uf((size_t) m->n_datasets * tp.nX, 0);
-        for (uint32_t d = 0; d < m->n_datasets; d++)
-            for (uint32_t k = 0; k < tp.nX; k++) {
-                double bound = 0.;
-                for (uint32_t c = tp.tf_ptr[k]; c < tp.tf_ptr[k + 1]; c++) bound += lmin[m->h_y[(size_t) d * tp.nH + tp.tf_child[c]]];
-                uf[(size_t) d * tp.nX + k] = bound < -600. ? 1 : 0;                // -600 in natural logs ~ 2^-865
-            }
-        CUDA_TRY(cudaMemcpy(m->d_uf, uf.data(), uf.size(), cudaMemcpyHostToDevice));
+        // counted on the device (one warp per (dataset, TF) over the by-TF child list): on the host this loop over every
+        // edge was a third of a set_evidence call
+        CUDA_TRY(cudaMemcpy(m->d_y, m->h_y.data(), m->h_y.size(), cudaMemcpyHostToDevice));
+        launch_tf_underflow_flags(m->net, m->d_uf, lmin, -600., m->stream);       // -600 in natural logs ~ 2^-865
+        m->launches += 1;
     }
-    CUDA_TRY(cudaMemcpy(m->d_y, m->h_y.data(), m->h_y.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(m->d_yprob, m->h_yprob.data(), sizeof(double) * m->h_yprob.size(), cudaMemcpyHostToDevice));
     return 0;
 }

@@ -165,7 +165,28 @@ __global__ void k_init_chains(DevNet net, DevChains ch, double c00, double c01, 
     if (!skip_s && j < net.Ep) ch.S[(size_t) c * net.Ep + j] = net.mor_idx[j];     // pads: 1 = edge off
 }
 
+// one warp per (dataset, TF): the children counted by their evidence class, the bound from the three counts
+__global__ void k_tf_underflow_flags(DevNet net, uint8_t *uf, double l0, double l1, double l2, double threshold)
+{
+    const uint32_t d = blockIdx.y;
+    const uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= net.nX) return;
+    const uint8_t *y = net.y + (size_t) d * net.nH;
+    uint32_t n0 = 0, n2 = 0, n = 0;
+    for (uint32_t c = net.tf_ptr[k] + lane; c < net.tf_ptr[k + 1]; c += 32) {
+        const uint32_t v = y[net.tf_child[c]];
+        n0 += v == 0; n2 += v == 2; n += 1;
+    }
+    n0 = __reduce_add_sync(0xffffffffu, n0); n2 = __reduce_add_sync(0xffffffffu, n2); n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) uf[(size_t) d * net.nX + k] = ((double) n0 * l0 + (double) (n - n0 - n2) * l1 + (double) n2 * l2 < threshold) ? 1 : 0;
+}
+
 }  // namespace
+
+void launch_tf_underflow_flags(const DevNet &net, uint8_t *uf, const double lmin[3], double threshold, cudaStream_t st)
+{
+    k_tf_underflow_flags<<<dim3((net.nX + 7) / 8, net.n_datasets), 256, 0, st>>>(net, uf, lmin[0], lmin[1], lmin[2], threshold);
+}
 
 // skip_s_bytes: the fast path fills its packed views from the network's initial words (launch_fast_refresh, initial);
 // the byte view of S is then unpacked on demand

@@ -17,6 +17,9 @@ void launch_export_draws(const DevNet &net, uint32_t gchain, uint32_t sweep0, ui
                          double *flat_u, double *beta_v, double *exp_v, cudaStream_t st);
 
 // initial state of every local chain; cum[a][v] = cumulative prior likelihood of X (host libm)
+// uf[d][k] = 1 when sum over TF k's children of lmin[y of the child] < threshold (the product of the children's
+// likelihoods could underflow a double: capi.cu, upload_evidence)
+void launch_tf_underflow_flags(const DevNet &net, uint8_t *uf, const double lmin[3], double threshold, cudaStream_t st);
 void launch_init_chains(const DevNet &net, const DevChains &ch, const double cum[2][2], cudaStream_t st, bool skip_s_bytes = false);
 
 // ---- sweep_strict.cu: n_sweeps full sweeps X -> T -> S of every local chain, one CTA per chain,
