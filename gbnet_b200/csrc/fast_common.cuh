@@ -100,6 +100,44 @@ __device__ __forceinline__ double mh_decide_log(double prev, double proposal, do
     return proposal;
 }
 
+// One update of a T node whose blanket is its Beta prior alone (Beta::metropolis_hastings_with_prior_proposal,
+// Beta.cpp:60-91): prev -> the value the node keeps, given the prior draw of the proposal.  With the four density
+// arguments inside (0, 1) every density is positive and the log of the acceptance ratio is
+//   (a-1) log[prop q01 / (prev q10)] + (b-1) log[(1-prop)(1-q01) / ((1-prev)(1-q10))]
+// (lnB cancels): two logs and two divisions instead of the eight logs of four separate log-densities, at a difference
+// of a few ulps in the log-ratio (the size of the libm differences the fast path already has; the strict kernel keeps
+// the reference's form).  A proposal outside [0, 1], or a reverse-move argument q01 outside it, is rejected without
+// evaluating anything.  Anything else - an argument at an end point, or so small that a product could underflow, or a
+// current value with density zero - takes the general path with the densities' own special cases.
+__device__ __forceinline__ double mh_prior_step(double prev, double draw, double mean, double al, double be, double lnB,
+                                                bool have_expo, double expo_in,
+                                                uint64_t seed, uint32_t gchain, uint32_t sweep, uint32_t k)
+{
+    const double dx = draw - mean;
+    const double prop = prev + dx;
+    const double q01 = mean - dx, q10 = mean + dx;
+    constexpr double LO = 1e-150;
+    const bool in_prev = prev > LO && prev < 1., in_prop = prop > LO && prop < 1., in_q10 = q10 > LO && q10 < 1.;
+    // the proposal has density zero (gsl_ran_beta_pdf outside [0, 1]): kept at prev, Beta.cpp:66-68
+    if (in_prev && (prop < 0. || prop > 1.)) return prev;
+    // q01 = 0 with the other three densities positive: log(q01 / q10) = -inf, the proposal is rejected (Beta.cpp:80-90)
+    if (in_prev && in_prop && in_q10 && (q01 < 0. || q01 > 1.)) return prev;
+    if (in_prev && in_prop && in_q10 && q01 > LO && q01 < 1.) {
+        const double r1 = (prop * q01) / (prev * q10);
+        const double r2 = ((1. - prop) * (1. - q01)) / ((1. - prev) * (1. - q10));
+        const double logratio = log(r1) * (al - 1) + log(r2) * (be - 1);
+        bool accept = logratio >= 0.;
+        if (!accept) {
+            const double expo = have_expo ? expo_in : draw_exp(seed, gchain, sweep, k);
+            accept = logratio > -expo;
+        }
+        return accept ? prop : prev;
+    }
+    const double prev_ll = (0. + beta_logpdf(prev, al, be, lnB)) + 0.;
+    const double prop_ll = (0. + beta_logpdf(prop, al, be, lnB)) + 0.;
+    return mh_decide_log(prev, prop, prev_ll, prop_ll, mean, dx, al, be, lnB, have_expo, expo_in, seed, gchain, sweep, k);
+}
+
 // 2-bit S code at position pos of a packed array (16 codes per word)
 __device__ __forceinline__ uint32_t code_at(const uint32_t *w, uint32_t pos) { return (w[pos >> 4] >> (2 * (pos & 15))) & 3u; }
 

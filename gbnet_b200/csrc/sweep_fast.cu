@@ -932,42 +932,9 @@ __global__ void __launch_bounds__(FT_NT) k_fast_t(DevNet net, DevChains ch, Swee
         const uint32_t gchain = chain_global_id(net, c);
         const double al = net.t_a[k], be = net.t_b[k], mean = net.t_mean[k], lnB = net.t_lnB[k];
         const size_t row = ((size_t) c * ch.inj_sweeps + a.inj_row) * nX + k;
-        const double prev = t;
         const double draw = a.use_inj ? ch.inj_beta[row] : draw_beta(net.seed, gchain, a.sweep, k, al, be);
-        const double dx = draw - mean;
-        const double prop = prev + dx;
-        const double q01 = mean - dx, q10 = mean + dx;
-        // Beta::metropolis_hastings_with_prior_proposal (Beta.cpp:60-91).  With the four arguments inside (0, 1) every
-        // density is positive and the log of the acceptance ratio is
-        //   (a-1) log[prop q01 / (prev q10)] + (b-1) log[(1-prop)(1-q01) / ((1-prev)(1-q10))]
-        // (lnB cancels): two logs and two divisions instead of the eight logs of four separate log-densities, at a
-        // difference of a few ulps in the log-ratio (the size of the libm differences this path already has; the
-        // strict kernel keeps the reference's form).  A proposal outside [0, 1], or a reverse-move argument q01 outside it,
-        // is rejected without evaluating anything.  Anything else - an argument at an end point, or so small that a
-        // product could underflow, or a current value with density zero - takes the general path with the densities' own
-        // special cases.
-        constexpr double LO = 1e-150;
-        const bool in_prev = prev > LO && prev < 1., in_prop = prop > LO && prop < 1., in_q10 = q10 > LO && q10 < 1.;
-        if (in_prev && (prop < 0. || prop > 1.)) {
-            // the proposal has density zero (gsl_ran_beta_pdf outside [0, 1]): kept at prev, Beta.cpp:66-68 - no density needed
-        } else if (in_prev && in_prop && in_q10 && (q01 < 0. || q01 > 1.)) {
-            // q01 = 0 with the other three densities positive: log(q01 / q10) = -inf, the proposal is rejected (Beta.cpp:80-90)
-        } else if (in_prev && in_prop && in_q10 && q01 > LO && q01 < 1.) {
-            const double r1 = (prop * q01) / (prev * q10);
-            const double r2 = ((1. - prop) * (1. - q01)) / ((1. - prev) * (1. - q10));
-            const double logratio = log(r1) * (al - 1) + log(r2) * (be - 1);
-            bool accept = logratio >= 0.;
-            if (!accept) {
-                const double expo = a.use_inj ? ch.inj_exp[row] : draw_exp(net.seed, gchain, a.sweep, k);
-                accept = logratio > -expo;
-            }
-            if (accept) t = prop;
-        } else {
-            const double prev_ll = (0. + beta_logpdf(prev, al, be, lnB)) + 0.;
-            const double prop_ll = (0. + beta_logpdf(prop, al, be, lnB)) + 0.;
-            t = mh_decide_log(prev, prop, prev_ll, prop_ll, mean, dx, al, be, lnB,
-                              a.use_inj != 0, a.use_inj ? ch.inj_exp[row] : 0., net.seed, gchain, a.sweep, k);
-        }
+        t = mh_prior_step(t, draw, mean, al, be, lnB, a.use_inj != 0, a.use_inj ? ch.inj_exp[row] : 0.,
+                          net.seed, gchain, a.sweep, k);
         Tout[o] = t;
         if (t == 1.) *ch.flags = 1u;
         double m = ch.tMean[o], m2 = ch.tM2[o];

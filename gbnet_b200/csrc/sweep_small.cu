@@ -356,14 +356,8 @@ __global__ void __launch_bounds__(SM_NT, 1) k_small_sweep(DevNet net, DevChains 
             if (tupd) {
                 const double al = net.t_a[k], be = net.t_b[k], mean = net.t_mean[k], lnB = net.t_lnB[k];
                 const size_t row = inj_row * nX + k;
-                const double prev = t;
-                const double prev_ll = (0. + beta_logpdf(prev, al, be, lnB)) + 0.;
                 const double draw = use_inj ? ch.inj_beta[row] : draw_beta(net.seed, gchain, sweep, k, al, be);
-                const double dx = draw - mean;
-                const double prop = prev + dx;
-                const double prop_ll = (0. + beta_logpdf(prop, al, be, lnB)) + 0.;
-                t = mh_decide_log(prev, prop, prev_ll, prop_ll, mean, dx, al, be, lnB,
-                              use_inj, use_inj ? ch.inj_exp[row] : 0., net.seed, gchain, sweep, k);
+                t = mh_prior_step(t, draw, mean, al, be, lnB, use_inj, use_inj ? ch.inj_exp[row] : 0., net.seed, gchain, sweep, k);
                 sT[k] = t;
                 if (t == 1.) *ch.flags = 1u;
                 const size_t o = (size_t) c * nX + k;
