@@ -30,7 +30,6 @@ struct SweepArgs {
     uint32_t x_adapt;                // X kernel: adaptive window on (GBN_X_ADAPT=2 switches it off)
     uint32_t x1_force;               // single-chain X kernel: resolve every x1_force-th TF in fp64 whatever its draw (tests of
                                      // the resolve path: GBN_X1=3 every TF, GBN_X1=4 every eighth)
-    double one;                      // 1.0: a constant-bank operand the compiler cannot fold (copy_f64)
     uint32_t rk0[10], rk1[10];       // Philox round keys (seed words bumped by the Weyl constants): as kernel
                                      // parameters they are constant-bank operands of the round's XOR
 };
@@ -40,7 +39,6 @@ inline SweepArgs sweep_args(const DevNet &net)
     SweepArgs a{};
     uint32_t k0 = (uint32_t) net.seed, k1 = (uint32_t) (net.seed >> 32);
     for (int r = 0; r < 10; r++) { a.rk0[r] = k0; a.rk1[r] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
-    a.one = 1.;
     a.x_adapt = env_u32("GBN_X_ADAPT", 1) != 2;
     a.x1_force = env_u32("GBN_X1", 1) == 3 ? 1 : (env_u32("GBN_X1", 1) == 4 ? 8 : 0);
     return a;
